@@ -1,0 +1,526 @@
+// libisdf_b200.so — C-ABI layer (include/isdf.h) over the sm_100a kernels. No CPU fallback anywhere: every entry
+// point either runs CUDA kernels or fails with ISDF_ERR_CUDA / ISDF_ERR_STATE.
+#include "../../include/isdf.h"
+#include "isdf_types.cuh"
+#include "isdf_discrete.cuh"
+#include "isdf_swept.cuh"
+#include "isdf_host_mesh.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <limits>
+
+using namespace isdf;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            return fail(ISDF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+        }                                                                                             \
+    } while (0)
+
+struct isdf_ctx {
+    int device = 0;
+    isdf_config cfg;
+    DevCfg dcfg;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // map
+    bool have_map = false;
+    DevGrid grid;
+    DevBuf<uint32_t> d_bits;
+    // shape
+    bool have_shape = false;
+    DevShape shape;
+    DevBuf<BvhNode> d_nodes; DevBuf<double> d_tris, d_pn; DevBuf<uint32_t> d_inside;
+    // evaluation scratch
+    DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
+    DevBuf<int> d_tickets;       // N piece tickets + 1 pieces_done (+ swept counters)
+    DevBuf<unsigned long long> d_counter;
+    double *h_stage = nullptr;   // pinned
+    size_t h_stage_n = 0;
+    // swept volume
+    SweptState sv;
+    // shard
+    int rank = 0, world = 1;
+    isdf_stats stats;
+};
+
+static int set_device(isdf_ctx *c) { CU_TRY(cudaSetDevice(c->device)); return 0; }
+
+static int ensure_stage(isdf_ctx *c, size_t n) {
+    if (n <= c->h_stage_n) return 0;
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_n = 0;
+    CU_TRY(cudaMallocHost((void **)&c->h_stage, n * sizeof(double)));
+    c->h_stage_n = n;
+    return 0;
+}
+
+extern "C" const char *isdf_last_error(void) { return g_err.c_str(); }
+
+extern "C" int isdf_default_config(isdf_config *cfg) {
+    if (!cfg) return fail(ISDF_ERR_INVALID, "cfg is NULL");
+    // plan_manager/config/config_CappedCone.yaml
+    cfg->vehicle_mass = 0.61; cfg->grav_acc = 9.8; cfg->horiz_drag = 0.10; cfg->vert_drag = 0.10; cfg->paras_drag = 0.01; cfg->speed_eps = 0.0001;
+    cfg->vmax = 10; cfg->omgmax = 10; cfg->thetamax = 100.0;
+    cfg->weight_v = 1000.0; cfg->weight_p = 4000.0; cfg->weight_omg = 1000.0; cfg->weight_theta = 1000.0;
+    cfg->smoothing_eps = 1.0e-2; cfg->safety_hor = 0.866; cfg->occupancy_resolution = 1.0;
+    cfg->kernel_size = 13; cfg->integral_intervs = 64; cfg->threads_num = 30;
+    cfg->flags = ISDF_WITH_DYNAMICS | ISDF_WITH_COLLISION;
+    return 0;
+}
+
+extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
+    if (!cfg || !out) return fail(ISDF_ERR_INVALID, "cfg/out is NULL");
+    if (cfg->integral_intervs < 1 || cfg->kernel_size < 1 || !(cfg->occupancy_resolution > 0) || !(cfg->vehicle_mass > 0) ||
+        !(cfg->smoothing_eps > 0))
+        return fail(ISDF_ERR_INVALID, "config out of range");
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(ISDF_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    // fail loudly if the sm_100a image cannot run here
+    cudaFuncAttributes fa;
+    CU_TRY(cudaFuncGetAttributes(&fa, (const void *)k_discrete<false>));
+    isdf_ctx *c = new isdf_ctx();
+    c->device = device; c->cfg = *cfg;
+    std::memset(&c->stats, 0, sizeof(c->stats));
+    std::memset(&c->grid, 0, sizeof(c->grid));
+    std::memset(&c->shape, 0, sizeof(c->shape));
+    DevCfg &d = c->dcfg;
+    d.fp.mass = cfg->vehicle_mass; d.fp.grav = cfg->grav_acc; d.fp.dh_over_m = cfg->horiz_drag / cfg->vehicle_mass;
+    d.fp.cp = cfg->paras_drag; d.fp.veps = cfg->speed_eps;
+    d.vmax2 = cfg->vmax * cfg->vmax; d.omgmax2 = cfg->omgmax * cfg->omgmax; d.thetamax = cfg->thetamax;
+    d.wv = cfg->weight_v; d.wp = cfg->weight_p; d.womg = cfg->weight_omg; d.wtheta = cfg->weight_theta;
+    d.mu = cfg->smoothing_eps; d.safety = cfg->safety_hor;
+    d.half_bd = (cfg->kernel_size * cfg->occupancy_resolution) / 2;
+    d.K = cfg->integral_intervs; d.flags = cfg->flags;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = c->d_counter.ensure(4);
+    if (e == cudaSuccess) e = cudaMemset(c->d_counter.p, 0, 4 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { delete c; return fail(ISDF_ERR_CUDA, std::string("isdf_create: ") + cudaGetErrorString(e)); }
+    *out = c;
+    return 0;
+}
+
+extern "C" int isdf_destroy(isdf_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_bits.release(); c->d_nodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_inside.release();
+    c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
+    c->d_tickets.release(); c->d_counter.release();
+    c->sv.release();
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int isdf_get_stats(isdf_ctx *c, isdf_stats *out) {
+    if (!c || !out) return fail(ISDF_ERR_INVALID, "NULL argument");
+    *out = c->stats;
+    return 0;
+}
+
+extern "C" int isdf_set_shard(isdf_ctx *c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return fail(ISDF_ERR_INVALID, "bad shard");
+    if (world > c->cfg.integral_intervs + 1) return fail(ISDF_ERR_INVALID, "world larger than samples per piece");
+    c->rank = rank; c->world = world;
+    return 0;
+}
+
+// ---- shapes ---------------------------------------------------------------------------------------------------
+static void shape_common(isdf_ctx *c, const double *rot, const double *trans) {
+    DevShape &s = c->shape;
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; i++) s.rot[i] = rot ? rot[i] : I[i];
+    for (int i = 0; i < 3; i++) s.trans[i] = trans ? trans[i] : 0.0;
+    // CSG helper rotations: rotate(other, angle = acos(0), axis) of Shape.hpp:2021-2041 for axis = Y x X and Z x X
+    const double ang = std::acos(0.0), sn = std::sin(ang), cs = std::cos(ang), mm = 1 - cs;
+    auto fill = [&](double x, double y, double z, double *R) {
+        R[0] = mm * x * x + cs;     R[1] = mm * x * y + z * sn; R[2] = mm * z * x - y * sn;
+        R[3] = mm * x * y - z * sn; R[4] = mm * y * y + cs;     R[5] = mm * y * z + x * sn;
+        R[6] = mm * z * x + y * sn; R[7] = mm * y * z - x * sn; R[8] = mm * z * z + cs;
+    };
+    fill(0, 0, -1, s.csg_ry);  // (0,1,0) x (1,0,0)
+    fill(0, 1, 0, s.csg_rz);   // (0,0,1) x (1,0,0)
+}
+
+extern "C" int isdf_set_shape_analytic(isdf_ctx *c, int kind, const double *params, int nparams, const double *rot, const double *trans) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (kind < 0 || kind >= ISDF_SHAPE_MESH) return fail(ISDF_ERR_INVALID, "kind is not an analytic shape");
+    if (nparams < 0 || nparams > 12 || (nparams > 0 && !params)) return fail(ISDF_ERR_INVALID, "bad params");
+    std::memset(&c->shape, 0, sizeof(c->shape));
+    c->shape.kind = kind;
+    for (int i = 0; i < nparams; i++) c->shape.par[i] = params[i];
+    shape_common(c, rot, trans);
+    c->have_shape = true;
+    return 0;
+}
+
+extern "C" int isdf_set_shape_named(isdf_ctx *c, const char *name, const double *rot, const double *trans) {
+    if (!c || !name) return fail(ISDF_ERR_INVALID, "NULL argument");
+    struct Entry { const char *name; int kind; int n; double p[12]; };
+    // constants are the reference classes' hard-coded members (Shape.hpp:609,827,863,898-900,936,1003-1005,1052,1149,1214,
+    // 1239,1293,1346-1349,1520,1575,1630)
+    static const Entry table[] = {
+        {"Ball", ISDF_SHAPE_BALL, 1, {1.0}},
+        {"Point", ISDF_SHAPE_POINT, 0, {0}},
+        {"Torus", ISDF_SHAPE_TORUS, 2, {2.5, 0.3}},
+        {"Torus_big", ISDF_SHAPE_TORUS, 2, {3.5, 0.3}},
+        {"Cappedtorus", ISDF_SHAPE_CAPPED_TORUS, 4, {0, 0, 3.5, 0.3}},  // sc filled below: (sin 40, cos 40), radians
+        {"CappedCone", ISDF_SHAPE_CAPPED_CONE, 2, {2.0, 0.8}},
+        {"RoundedCone", ISDF_SHAPE_ROUNDED_CONE, 3, {1.5, 0.6, 4.5}},
+        {"WireframeBox", ISDF_SHAPE_WIREFRAME_BOX, 4, {1.8, 2.5, 3.5, 0.1}},
+        {"BendLinear", ISDF_SHAPE_BEND_LINEAR, 2, {2.0, 0.25}},
+        {"BendLinear_big", ISDF_SHAPE_BEND_LINEAR, 2, {3.2, 0.45}},
+        {"TwistBox", ISDF_SHAPE_TWIST_BOX, 4, {2.0, 2.0, 2.0, 3.14159265358979323846 / 6}},
+        {"BendBox", ISDF_SHAPE_BEND_BOX, 4, {2.0, 2.0, 2.0, 0.5}},
+        {"Table", ISDF_SHAPE_TABLE, 12, {0.0, 0.0, 0.0, 3.5, 1.75, 0.7, 2.8, 1.05, 0.0, 3.5, 1.75, 2.8}},
+        {"Trefoil", ISDF_SHAPE_TREFOIL, 0, {0}},
+        {"SmoothDifference", ISDF_SHAPE_SMOOTH_DIFFERENCE, 4, {3.0, 3.0, 0.5, 1.0}},
+        {"SmoothIntersection", ISDF_SHAPE_SMOOTH_INTERSECTION, 4, {3.0, 3.0, 0.5, 1.0}},
+        {"SmoothIntersection_big", ISDF_SHAPE_SMOOTH_INTERSECTION, 4, {9.0, 9.0, 1.5, 3.0}},
+        {"CSG", ISDF_SHAPE_CSG, 0, {0}},
+    };
+    for (const Entry &e : table) {
+        if (std::strcmp(e.name, name) == 0) {
+            double p[12];
+            for (int i = 0; i < 12; i++) p[i] = e.p[i];
+            if (e.kind == ISDF_SHAPE_CAPPED_TORUS) { p[0] = std::sin(40); p[1] = std::cos(40); }
+            return isdf_set_shape_analytic(c, e.kind, p, e.n, rot, trans);
+        }
+    }
+    // the reference falls back to the mesh Generalshape for unknown names (swm:269-274); a mesh needs its geometry
+    return fail(ISDF_ERR_INVALID, std::string("unknown analytic shape name '") + name + "' (use isdf_set_shape_mesh for OBJ bodies)");
+}
+
+extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const int32_t *F, int nF, const double *poly_params) {
+    if (!c || !V || !F) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    HostMesh hm; std::string err;
+    // the bitmap shortcut is sized for the smallest bound the kernels use: safety_hor (discrete) — the swept path uses
+    // 2*safety_hor + 0.1 >= safety_hor
+    if (!build_host_mesh(V, nV, F, nF, poly_params, c->cfg.safety_hor, hm, err)) return fail(ISDF_ERR_INVALID, err);
+    CU_TRY(c->d_nodes.upload(hm.nodes.data(), hm.nodes.size(), c->stream));
+    CU_TRY(c->d_tris.upload(hm.tris.data(), hm.tris.size(), c->stream));
+    CU_TRY(c->d_pn.upload(hm.pnormals.data(), hm.pnormals.size(), c->stream));
+    CU_TRY(c->d_inside.upload(hm.inside.data(), hm.inside.size(), c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    std::memset(&c->shape, 0, sizeof(c->shape));
+    c->shape.kind = ISDF_SHAPE_MESH;
+    shape_common(c, nullptr, nullptr);
+    DevMesh m = hm.view();
+    m.nodes = c->d_nodes.p; m.tris = c->d_tris.p; m.pnormals = c->d_pn.p; m.inside = c->d_inside.p;
+    c->shape.mesh = m;
+    c->have_shape = true;
+    return 0;
+}
+
+__global__ void k_shape_query(const __grid_constant__ DevShape S, const double *p, int n, double *sdf, double *grad, int what) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const d3 q = mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+    d3 g = mk3(0, 0, 0);
+    double s = 0;
+    if (what == ISDF_QUERY_SDF) s = shape_sdf(S, q);
+    else if (what == ISDF_QUERY_GRAD) g = shape_grad(S, q);
+    else s = shape_sdf_grad(S, q, g);
+    if (sdf && what != ISDF_QUERY_GRAD) sdf[i] = s;
+    if (grad && what != ISDF_QUERY_SDF) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+}
+
+extern "C" int isdf_shape_query(isdf_ctx *c, const double *p_rel, int n, double *sdf, double *grad, int what) {
+    if (!c || !p_rel || n < 0) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (!c->have_shape) return fail(ISDF_ERR_STATE, "shape not set");
+    if (what < 0 || what > 2) return fail(ISDF_ERR_INVALID, "bad query kind");
+    if (n == 0) return 0;
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    DevBuf<double> dp, ds, dg;
+    CU_TRY(dp.upload(p_rel, (size_t)3 * n, c->stream));
+    CU_TRY(ds.ensure(n)); CU_TRY(dg.ensure((size_t)3 * n));
+    k_shape_query<<<(n + 127) / 128, 128, 0, c->stream>>>(c->shape, dp.p, n, ds.p, dg.p, what);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    std::vector<double> hs(n), hg((size_t)3 * n);
+    CU_TRY(cudaMemcpyAsync(hs.data(), ds.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(hg.data(), dg.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (sdf && what != ISDF_QUERY_GRAD) std::memcpy(sdf, hs.data(), sizeof(double) * n);
+    if (grad && what != ISDF_QUERY_SDF) std::memcpy(grad, hg.data(), sizeof(double) * 3 * n);
+    dp.release(); ds.release(); dg.release();
+    return 0;
+}
+
+// ---- map ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack_bits(const T *occ, uint32_t *bits, int rows, int Z, int Zw) {
+    // one warp per 32-voxel word: ballot of "voxel != 0"
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const long long nwords = (long long)rows * Zw;
+    if (gw >= nwords) return;
+    const int row = gw / Zw, w = gw - row * Zw;
+    const int z = w * 32 + lane;
+    const bool o = (z < Z) && (occ[(size_t)row * Z + z] != (T)0);
+    const unsigned b = __ballot_sync(0xffffffffu, o);
+    if (lane == 0) bits[gw] = b;
+}
+
+template <typename T>
+static int set_map_impl(isdf_ctx *c, const T *occ, int X, int Y, int Z, const double *bmin, double res) {
+    if (!c || !occ || !bmin) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (X < 1 || Y < 1 || Z < 1 || !(res > 0)) return fail(ISDF_ERR_INVALID, "bad map size");
+    if ((long long)X * Y >= (1ll << 31) / ((Z + 31) / 32)) return fail(ISDF_ERR_INVALID, "map too large");
+    if (Z > 65535) return fail(ISDF_ERR_UNSUPPORTED, "Z > 65535");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    const size_t nvox = (size_t)X * Y * Z;
+    T *d_occ = nullptr;
+    CU_TRY(cudaMalloc((void **)&d_occ, nvox * sizeof(T)));
+    cudaError_t e = cudaMemcpyAsync(d_occ, occ, nvox * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+    const int Zw = (Z + 31) / 32;
+    const size_t nwords = (size_t)X * Y * Zw;
+    if (e == cudaSuccess) e = c->d_bits.ensure(nwords);
+    if (e == cudaSuccess) {
+        const long long threads = (long long)nwords * 32;
+        k_pack_bits<T><<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(d_occ, c->d_bits.p, X * Y, Z, Zw);
+        c->stats.kernel_launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_occ);
+    if (e != cudaSuccess) return fail(ISDF_ERR_CUDA, std::string("isdf_set_map: ") + cudaGetErrorString(e));
+    DevGrid &g = c->grid;
+    g.bits = c->d_bits.p; g.X = X; g.Y = Y; g.Z = Z; g.Zw = Zw; g.res = res;
+    const int dims[3] = {X, Y, Z};
+    for (int a = 0; a < 3; a++) { g.bmin[a] = bmin[a]; g.bmax[a] = bmin[a] + dims[a] * res; }
+    c->have_map = true;
+    return 0;
+}
+
+extern "C" int isdf_set_map_u8(isdf_ctx *c, const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res) {
+    return set_map_impl<uint8_t>(c, occ, X, Y, Z, bmin, res);
+}
+extern "C" int isdf_set_map_f64(isdf_ctx *c, const double *grid_map, int X, int Y, int Z, const double *bmin, double res) {
+    return set_map_impl<double>(c, grid_map, X, Y, Z, bmin, res);
+}
+
+// getPointsInAABB (pcs:148-170): one thread per voxel of the clamped index box, ordered output via a single-thread scan
+__global__ void k_points_in_aabb(const DevGrid G, double cx, double cy, double cz, double h, double *out, int cap, int *count) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int ix0 = grid_axis_index(cx - h, G.bmin[0], G.bmax[0], G.res, G.X), ix1 = grid_axis_index(cx + h, G.bmin[0], G.bmax[0], G.res, G.X);
+    const int iy0 = grid_axis_index(cy - h, G.bmin[1], G.bmax[1], G.res, G.Y), iy1 = grid_axis_index(cy + h, G.bmin[1], G.bmax[1], G.res, G.Y);
+    const int iz0 = grid_axis_index(cz - h, G.bmin[2], G.bmax[2], G.res, G.Z), iz1 = grid_axis_index(cz + h, G.bmin[2], G.bmax[2], G.res, G.Z);
+    int n = 0;
+    for (int i = ix0; i <= ix1; i++)
+        for (int j = iy0; j <= iy1; j++)
+            for (int k = iz0; k <= iz1; k++) {
+                const uint32_t w = G.bits[((size_t)i * G.Y + j) * G.Zw + (k >> 5)];
+                if ((w >> (k & 31)) & 1u) {
+                    if (n < cap) { out[3 * n] = (i + 0.5) * G.res + G.bmin[0]; out[3 * n + 1] = (j + 0.5) * G.res + G.bmin[1]; out[3 * n + 2] = (k + 0.5) * G.res + G.bmin[2]; }
+                    n++;
+                }
+            }
+    *count = n;
+}
+
+extern "C" int isdf_points_in_aabb(isdf_ctx *c, const double *centre, double half_extent, double *out_points, int cap, int *n) {
+    if (!c || !centre || !n || cap < 0 || (cap > 0 && !out_points)) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (!c->have_map) return fail(ISDF_ERR_STATE, "map not set");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    DevBuf<double> d; DevBuf<int> dn;
+    CU_TRY(d.ensure((size_t)3 * (cap > 0 ? cap : 1))); CU_TRY(dn.ensure(1));
+    k_points_in_aabb<<<1, 32, 0, c->stream>>>(c->grid, centre[0], centre[1], centre[2], half_extent, d.p, cap, dn.p);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    int cnt = 0;
+    CU_TRY(cudaMemcpyAsync(&cnt, dn.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const int m = cnt < cap ? cnt : cap;
+    if (m > 0) CU_TRY(cudaMemcpy(out_points, d.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    d.release(); dn.release();
+    return 0;
+}
+
+// ---- discrete evaluation ------------------------------------------------------------------------------------
+static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *d_C, double *d_out, cudaStream_t st) {
+    const int K = c->cfg.integral_intervs;
+    const long long S = (long long)N * (K + 1);
+    CU_TRY(c->d_partial.ensure((size_t)S * PARTIAL_STRIDE));
+    CU_TRY(c->d_piece_cost.ensure(N));
+    if (c->d_tickets.n < (size_t)N + 1) {
+        CU_TRY(c->d_tickets.ensure((size_t)N + 1));
+        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int) * (N + 1), st));
+    }
+    DiscArgs A;
+    A.cfg = c->dcfg; A.grid = c->grid; A.shape = c->shape; A.N = N; A.T = d_T; A.C = d_C;
+    A.partial = c->d_partial.p; A.piece_ticket = c->d_tickets.p; A.pieces_done = c->d_tickets.p + c->d_tickets.n - 1;
+    A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
+    A.rank = c->rank; A.world = c->world;
+    const long long M = (S - c->rank + c->world - 1) / c->world;
+    const unsigned grid = (unsigned)((M + DISC_WARPS - 1) / DISC_WARPS);
+    CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
+    if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete<true><<<grid, DISC_THREADS, 0, st>>>(A);
+    else k_discrete<false><<<grid, DISC_THREADS, 0, st>>>(A);
+    c->stats.kernel_launches++;
+    c->stats.evals_discrete++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int check_eval_state(isdf_ctx *c, int N, bool need_map) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (N < 1) return fail(ISDF_ERR_INVALID, "N < 1");
+    const bool coll = (c->cfg.flags & ISDF_WITH_COLLISION) != 0;
+    if (coll && !c->have_shape) return fail(ISDF_ERR_STATE, "shape not set");
+    if (need_map && coll && !c->have_map) return fail(ISDF_ERR_STATE, "map not set");
+    return 0;
+}
+
+extern "C" int isdf_eval_discrete_device(isdf_ctx *c, int N, const double *d_T, const double *d_coeffs, double *d_out, void *cuda_stream) {
+    int r = check_eval_state(c, N, true);
+    if (r) return r;
+    if (!d_T || !d_coeffs || !d_out) return fail(ISDF_ERR_INVALID, "NULL device pointer");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    return launch_discrete(c, N, d_T, d_coeffs, d_out, (cudaStream_t)cuda_stream);
+}
+
+static void poison(double *cost) { if (cost) *cost = std::numeric_limits<double>::quiet_NaN(); }
+
+extern "C" int isdf_eval_discrete(isdf_ctx *c, int N, const double *T, const double *coeffs, double *cost, double *gradC, double *gradT) {
+    int r = check_eval_state(c, N, true);
+    if (r) { poison(cost); return r; }
+    if (!T || !coeffs || !cost || !gradC || !gradT) { poison(cost); return fail(ISDF_ERR_INVALID, "NULL argument"); }
+    auto body = [&]() -> int {
+        if (set_device(c)) return ISDF_ERR_CUDA;
+        const size_t nin = (size_t)19 * N, nout = (size_t)19 * N + 1;
+        if (ensure_stage(c, nin + nout)) return ISDF_ERR_CUDA;
+        CU_TRY(c->d_T.ensure(N)); CU_TRY(c->d_C.ensure((size_t)18 * N)); CU_TRY(c->d_out.ensure(nout));
+        std::memcpy(c->h_stage, T, sizeof(double) * N);
+        std::memcpy(c->h_stage + N, coeffs, sizeof(double) * 18 * N);
+        CU_TRY(cudaMemcpyAsync(c->d_T.p, c->h_stage, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage + N, sizeof(double) * 18 * N, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaEventRecord(c->ev0, c->stream));
+        int rr = launch_discrete(c, N, c->d_T.p, c->d_C.p, c->d_out.p, c->stream);
+        if (rr) return rr;
+        CU_TRY(cudaEventRecord(c->ev1, c->stream));
+        double *h_out = c->h_stage + nin;
+        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long pairs = 0;
+        CU_TRY(cudaMemcpyAsync(&pairs, c->d_counter.p, sizeof(pairs), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->stats.last_kernel_ms = ms; c->stats.last_pairs = (int64_t)pairs;
+        *cost += h_out[0];                                   // accumulate like hpp:539-550
+        for (size_t k = 0; k < (size_t)18 * N; k++) gradC[k] += h_out[1 + k];
+        for (int k = 0; k < N; k++) gradT[k] += h_out[1 + 18 * N + k];
+        return 0;
+    };
+    r = body();
+    if (r) poison(cost);
+    return r;
+}
+
+// ---- swept volume -------------------------------------------------------------------------------------------
+extern "C" int isdf_set_points(isdf_ctx *c, const double *pts, int P) {
+    if (!c || P < 0 || (P > 0 && !pts)) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    CU_TRY(c->sv.set_points(pts, P, c->stream));
+    return 0;
+}
+
+static int swept_common(isdf_ctx *c, int N, const double *d_T, const double *d_C, double *d_out, cudaStream_t st,
+                        const double *g_t, const double *g_s, const double *g_g) {
+    if (c->sv.P <= 0) return fail(ISDF_ERR_STATE, "obstacle points not set (isdf_set_points)");
+    int launches = 0;
+    cudaError_t e = c->sv.launch(c->dcfg, c->shape, N, d_T, d_C, d_out, c->rank, c->world, st, g_t, g_s, g_g, &launches);
+    c->stats.kernel_launches += launches;
+    c->stats.evals_swept++;
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? ISDF_ERR_INVALID : ISDF_ERR_CUDA, std::string("swept: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int isdf_eval_swept_device(isdf_ctx *c, int N, const double *d_T, const double *d_coeffs, double *d_out, void *cuda_stream) {
+    int r = check_eval_state(c, N, false);
+    if (r) return r;
+    if (!c->have_shape) return fail(ISDF_ERR_STATE, "shape not set");
+    if (!d_T || !d_coeffs || !d_out) return fail(ISDF_ERR_INVALID, "NULL device pointer");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    return swept_common(c, N, d_T, d_coeffs, d_out, (cudaStream_t)cuda_stream, nullptr, nullptr, nullptr);
+}
+
+static int eval_swept_host(isdf_ctx *c, int N, const double *T, const double *coeffs, const double *g_t, const double *g_s,
+                           const double *g_g, double *cost, double *gradC, double *gradT) {
+    int r = check_eval_state(c, N, false);
+    if (r) { poison(cost); return r; }
+    if (!c->have_shape) { poison(cost); return fail(ISDF_ERR_STATE, "shape not set"); }
+    if (!T || !coeffs || !cost || !gradC || !gradT) { poison(cost); return fail(ISDF_ERR_INVALID, "NULL argument"); }
+    auto body = [&]() -> int {
+        if (set_device(c)) return ISDF_ERR_CUDA;
+        const size_t nin = (size_t)19 * N, nout = (size_t)19 * N + 1;
+        if (ensure_stage(c, nin + nout)) return ISDF_ERR_CUDA;
+        CU_TRY(c->d_T.ensure(N)); CU_TRY(c->d_C.ensure((size_t)18 * N)); CU_TRY(c->d_out.ensure(nout));
+        std::memcpy(c->h_stage, T, sizeof(double) * N);
+        std::memcpy(c->h_stage + N, coeffs, sizeof(double) * 18 * N);
+        CU_TRY(cudaMemcpyAsync(c->d_T.p, c->h_stage, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage + N, sizeof(double) * 18 * N, cudaMemcpyHostToDevice, c->stream));
+        DevBuf<double> dgt, dgs, dgg;
+        if (g_t) {
+            CU_TRY(dgt.upload(g_t, c->sv.P, c->stream)); CU_TRY(dgs.upload(g_s, c->sv.P, c->stream));
+            CU_TRY(dgg.upload(g_g, (size_t)3 * c->sv.P, c->stream));
+        }
+        CU_TRY(cudaEventRecord(c->ev0, c->stream));
+        int rr = swept_common(c, N, c->d_T.p, c->d_C.p, c->d_out.p, c->stream, dgt.p, dgs.p, dgg.p);
+        if (rr) return rr;
+        CU_TRY(cudaEventRecord(c->ev1, c->stream));
+        double *h_out = c->h_stage + nin;
+        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long nsdf = 0;
+        CU_TRY(cudaMemcpyAsync(&nsdf, c->sv.d_counter.p, sizeof(nsdf), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        dgt.release(); dgs.release(); dgg.release();
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->stats.last_kernel_ms = ms; c->stats.last_sdf_evals = (int64_t)nsdf;
+        *cost += h_out[0];                                   // accumulate like hpp:640-645
+        for (size_t k = 0; k < (size_t)18 * N; k++) gradC[k] += h_out[1 + k];
+        for (int k = 0; k < N; k++) gradT[k] += h_out[1 + 18 * N + k];
+        return 0;
+    };
+    r = body();
+    if (r) poison(cost);
+    return r;
+}
+
+extern "C" int isdf_eval_swept(isdf_ctx *c, int N, const double *T, const double *coeffs, double *cost, double *gradC, double *gradT) {
+    return eval_swept_host(c, N, T, coeffs, nullptr, nullptr, nullptr, cost, gradC, gradT);
+}
+
+extern "C" int isdf_eval_swept_given(isdf_ctx *c, int N, const double *T, const double *coeffs, const double *tstar, const double *sdf,
+                          const double *grel, double *cost, double *gradC, double *gradT) {
+    if (!tstar || !sdf || !grel) { poison(cost); return fail(ISDF_ERR_INVALID, "NULL argument"); }
+    return eval_swept_host(c, N, T, coeffs, tstar, sdf, grel, cost, gradC, gradT);
+}
+
+extern "C" int isdf_get_swept_results(isdf_ctx *c, double *tstar, double *sdf, double *grel) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (c->sv.P <= 0) return fail(ISDF_ERR_STATE, "obstacle points not set");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    const size_t P = c->sv.P;
+    if (tstar) CU_TRY(cudaMemcpy(tstar, c->sv.d_tstar.p, sizeof(double) * P, cudaMemcpyDeviceToHost));
+    if (sdf) CU_TRY(cudaMemcpy(sdf, c->sv.d_sdf.p, sizeof(double) * P, cudaMemcpyDeviceToHost));
+    if (grel) CU_TRY(cudaMemcpy(grel, c->sv.d_grel.p, sizeof(double) * 3 * P, cudaMemcpyDeviceToHost));
+    return 0;
+}
+

@@ -1,0 +1,192 @@
+// Host-side, one-off construction of the device mesh structure at isdf_set_shape_mesh time:
+// the counterpart of the Generalshape constructor (Shape.cpp:27-103: read mesh, pre-transform by poly_params,
+// tree.init(V,F), fast_winding_number precompute). Produces the BVH, leaf-ordered triangles, pseudonormals and the
+// inside/outside bitmap described in isdf_mesh.cuh.
+#pragma once
+#include "isdf_mesh.cuh"
+#include <vector>
+#include <map>
+#include <array>
+#include <string>
+#include <algorithm>
+#include <numeric>
+#include <cmath>
+
+namespace isdf {
+
+struct HostMesh {
+    std::vector<BvhNode> nodes;
+    std::vector<double> tris, pnormals;
+    std::vector<uint32_t> inside;
+    int ntris = 0;
+    int gdim[3] = {0, 0, 0};
+    double glo[3] = {0, 0, 0}, gcell = 0, sign_radius = 0;
+    double blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
+    DevMesh view() const {  // host pointers; same code path as the device for the bitmap construction
+        DevMesh m;
+        m.nodes = nodes.data(); m.tris = tris.data(); m.pnormals = pnormals.data(); m.inside = inside.data();
+        m.ntris = ntris;
+        for (int a = 0; a < 3; a++) { m.gdim[a] = gdim[a]; m.glo[a] = glo[a]; m.blo[a] = blo[a]; m.bhi[a] = bhi[a]; }
+        m.gcell = gcell; m.sign_radius = sign_radius;
+        return m;
+    }
+};
+
+namespace detail {
+struct BuildNode { double lo[3], hi[3]; int left = -1, right = -1, first = 0, count = 0; };
+constexpr int LEAF_MAX = 4;
+
+inline int build_rec(std::vector<BuildNode> &bn, std::vector<int> &order, int b, int e, const std::vector<std::array<double, 9>> &tv,
+                     const std::vector<std::array<double, 3>> &cen) {
+    BuildNode nd;
+    double clo[3], chi[3];
+    for (int a = 0; a < 3; a++) { nd.lo[a] = clo[a] = 1e300; nd.hi[a] = chi[a] = -1e300; }
+    for (int i = b; i < e; i++) {
+        const auto &t = tv[order[i]];
+        for (int k = 0; k < 3; k++)
+            for (int a = 0; a < 3; a++) { nd.lo[a] = std::min(nd.lo[a], t[3 * k + a]); nd.hi[a] = std::max(nd.hi[a], t[3 * k + a]); }
+        for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], cen[order[i]][a]); chi[a] = std::max(chi[a], cen[order[i]][a]); }
+    }
+    nd.first = b; nd.count = e - b;
+    const int me = (int)bn.size();
+    bn.push_back(nd);
+    if (e - b <= LEAF_MAX) return me;
+    int ax = 0;
+    if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+    if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+    const int mid = (b + e) / 2;
+    std::nth_element(order.begin() + b, order.begin() + mid, order.begin() + e, [&](int x, int y) { return cen[x][ax] < cen[y][ax]; });
+    const int l = build_rec(bn, order, b, mid, tv, cen);
+    const int r = build_rec(bn, order, mid, e, tv, cen);
+    bn[me].left = l; bn[me].right = r;
+    return me;
+}
+}  // namespace detail
+
+// V: nV x 3, F: nF x 3 (row-major). poly_params {tx,ty,tz, roll,pitch,yaw [deg]} or nullptr (Shape.cpp:38-50).
+// sign_reach: smallest query bound the kernels will use with the bitmap shortcut (safety_hor).
+inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF, const double *poly_params, double sign_reach,
+                            HostMesh &out, std::string &err) {
+    if (nV < 3 || nF < 1) { err = "mesh needs at least 3 vertices and 1 face"; return false; }
+    for (int i = 0; i < 3 * nF; i++) if (F[i] < 0 || F[i] >= nV) { err = "face index out of range"; return false; }
+    std::vector<std::array<double, 3>> V(nV);
+    for (int i = 0; i < nV; i++) V[i] = {Vin[3 * i], Vin[3 * i + 1], Vin[3 * i + 2]};
+    if (poly_params) {  // V <- Rz(yaw) Ry(pitch) Rx(roll) V + t
+        const double PI = 3.14159265358979323846;
+        const double r = poly_params[3] * PI / 180.0, p = poly_params[4] * PI / 180.0, y = poly_params[5] * PI / 180.0;
+        const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
+        for (auto &v : V) {
+            const double x1 = v[0], y1 = cr * v[1] - sr * v[2], z1 = sr * v[1] + cr * v[2];           // Rx
+            const double x2 = cp * x1 + sp * z1, y2 = y1, z2 = -sp * x1 + cp * z1;                    // Ry
+            const double x3 = cy * x2 - sy * y2, y3 = sy * x2 + cy * y2, z3 = z2;                     // Rz
+            v = {x3 + poly_params[0], y3 + poly_params[1], z3 + poly_params[2]};
+        }
+    }
+    // weld vertices that coincide exactly so adjacency survives unindexed input
+    std::map<std::array<double, 3>, int> weld;
+    std::vector<int> canon(nV);
+    for (int i = 0; i < nV; i++) { auto it = weld.find(V[i]); if (it == weld.end()) { weld[V[i]] = i; canon[i] = i; } else canon[i] = it->second; }
+
+    std::vector<std::array<double, 9>> tv(nF);
+    std::vector<std::array<double, 3>> cen(nF), fn(nF);
+    std::vector<std::array<int, 3>> fi(nF);
+    for (int t = 0; t < nF; t++) {
+        for (int k = 0; k < 3; k++) { fi[t][k] = canon[F[3 * t + k]]; for (int a = 0; a < 3; a++) tv[t][3 * k + a] = V[F[3 * t + k]][a]; }
+        for (int a = 0; a < 3; a++) cen[t][a] = (tv[t][a] + tv[t][3 + a] + tv[t][6 + a]) / 3.0;
+        const d3 A = mk3(tv[t][0], tv[t][1], tv[t][2]), B = mk3(tv[t][3], tv[t][4], tv[t][5]), C = mk3(tv[t][6], tv[t][7], tv[t][8]);
+        const d3 n = unit3(cross3(B - A, C - A));
+        fn[t] = {n.x, n.y, n.z};
+    }
+    // pseudonormals: edges = sum of adjacent unit face normals, vertices = incident-angle-weighted sum
+    std::map<std::pair<int, int>, std::array<double, 3>> en;
+    std::vector<std::array<double, 3>> vn(nV, {0, 0, 0});
+    for (int t = 0; t < nF; t++) {
+        for (int k = 0; k < 3; k++) {
+            const int u = fi[t][k], v = fi[t][(k + 1) % 3];
+            auto &e = en[{std::min(u, v), std::max(u, v)}];
+            for (int a = 0; a < 3; a++) e[a] += fn[t][a];
+            const d3 P0 = mk3(tv[t][3 * k], tv[t][3 * k + 1], tv[t][3 * k + 2]);
+            const d3 P1 = mk3(tv[t][3 * ((k + 1) % 3)], tv[t][3 * ((k + 1) % 3) + 1], tv[t][3 * ((k + 1) % 3) + 2]);
+            const d3 P2 = mk3(tv[t][3 * ((k + 2) % 3)], tv[t][3 * ((k + 2) % 3) + 1], tv[t][3 * ((k + 2) % 3) + 2]);
+            const d3 e1 = unit3(P1 - P0), e2 = unit3(P2 - P0);
+            const double ang = std::acos(std::max(-1.0, std::min(1.0, dot3(e1, e2))));
+            for (int a = 0; a < 3; a++) vn[u][a] += ang * fn[t][a];
+        }
+    }
+    // BVH
+    std::vector<int> order(nF);
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<detail::BuildNode> bn;
+    bn.reserve(2 * nF);
+    detail::build_rec(bn, order, 0, nF, tv, cen);
+    // leaf-ordered triangle + pseudonormal arrays
+    out.ntris = nF;
+    out.tris.resize((size_t)9 * nF); out.pnormals.resize((size_t)21 * nF);
+    for (int pos = 0; pos < nF; pos++) {
+        const int t = order[pos];
+        double *T = &out.tris[(size_t)9 * pos];
+        for (int a = 0; a < 3; a++) { T[a] = tv[t][a]; T[3 + a] = tv[t][3 + a] - tv[t][a]; T[6 + a] = tv[t][6 + a] - tv[t][a]; }
+        double *Pn = &out.pnormals[(size_t)21 * pos];
+        for (int a = 0; a < 3; a++) Pn[a] = fn[t][a];
+        for (int k = 0; k < 3; k++) {  // edges ab, bc, ca
+            const int u = fi[t][k], v = fi[t][(k + 1) % 3];
+            const auto &e = en[{std::min(u, v), std::max(u, v)}];
+            for (int a = 0; a < 3; a++) Pn[3 + 3 * k + a] = e[a];
+        }
+        for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) Pn[12 + 3 * k + a] = vn[fi[t][k]][a];
+    }
+    // fat nodes: every internal node carries both children's boxes
+    auto code_of = [&](int bi, const std::vector<int> &fat_index) -> int {
+        const auto &b = bn[bi];
+        if (b.left < 0) return ~(b.first * 4 + (b.count - 1));
+        return fat_index[bi];
+    };
+    std::vector<int> fat_index(bn.size(), -1);
+    int nfat = 0;
+    for (size_t i = 0; i < bn.size(); i++) if (bn[i].left >= 0) fat_index[i] = nfat++;
+    if (nfat == 0) {  // whole mesh is one leaf
+        out.nodes.resize(1);
+        BvhNode &n = out.nodes[0];
+        for (int a = 0; a < 3; a++) { n.lbox[a] = n.rbox[a] = bn[0].lo[a]; n.lbox[3 + a] = n.rbox[3 + a] = bn[0].hi[a]; }
+        n.left = n.right = code_of(0, fat_index); n.pad0 = n.pad1 = 0;
+    } else {
+        out.nodes.resize(nfat);
+        for (size_t i = 0; i < bn.size(); i++) {
+            if (bn[i].left < 0) continue;
+            BvhNode &n = out.nodes[fat_index[i]];
+            const auto &L = bn[bn[i].left], &R = bn[bn[i].right];
+            for (int a = 0; a < 3; a++) { n.lbox[a] = L.lo[a]; n.lbox[3 + a] = L.hi[a]; n.rbox[a] = R.lo[a]; n.rbox[3 + a] = R.hi[a]; }
+            n.left = code_of(bn[i].left, fat_index); n.right = code_of(bn[i].right, fat_index); n.pad0 = n.pad1 = 0;
+        }
+    }
+    for (int a = 0; a < 3; a++) { out.blo[a] = bn[0].lo[a]; out.bhi[a] = bn[0].hi[a]; }
+    // inside/outside bitmap over the mesh AABB: cell diagonal = 0.9 * sign_reach (so < sign_reach), capped at 160^3 cells
+    out.sign_radius = 0; out.gcell = 1.0; out.inside.assign(1, 0u);
+    for (int a = 0; a < 3; a++) { out.gdim[a] = 0; out.glo[a] = out.blo[a]; }
+    if (sign_reach > 0) {
+        const double cell = 0.9 * sign_reach / std::sqrt(3.0);
+        long long dims[3]; bool ok = true;
+        for (int a = 0; a < 3; a++) { dims[a] = (long long)std::ceil((out.bhi[a] - out.blo[a]) / cell) + 1; if (dims[a] > 160) ok = false; }
+        if (ok) {
+            out.gcell = cell; out.sign_radius = sign_reach;
+            for (int a = 0; a < 3; a++) out.gdim[a] = (int)dims[a];
+            const size_t nb = (size_t)dims[0] * dims[1] * dims[2];
+            out.inside.assign((nb + 31) / 32, 0u);
+            HostMesh tmp = out; tmp.sign_radius = 0;  // unbounded queries while filling
+            const DevMesh mv = tmp.view();
+            for (int ix = 0; ix < out.gdim[0]; ix++)
+                for (int iy = 0; iy < out.gdim[1]; iy++)
+                    for (int iz = 0; iz < out.gdim[2]; iz++) {
+                        const d3 c = mk3(out.glo[0] + (ix + 0.5) * cell, out.glo[1] + (iy + 0.5) * cell, out.glo[2] + (iz + 0.5) * cell);
+                        d3 g;
+                        if (mesh_sdf_grad(mv, c, 1e300, g) < 0.0) {
+                            const size_t bit = ((size_t)ix * out.gdim[1] + iy) * out.gdim[2] + iz;
+                            out.inside[bit >> 5] |= (1u << (bit & 31));
+                        }
+                    }
+        }
+    }
+    return true;
+}
+
+}  // namespace isdf

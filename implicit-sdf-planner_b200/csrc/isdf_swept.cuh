@@ -1,0 +1,514 @@
+// Swept-volume collision term: addSaftyPenaOnSweptVolumeParallel (back_end_optimizer.hpp:557-649) and the SV-SDF query
+// getSDFofSweptVolume<true>(p, t, g, set_ts=false) (sw_manager.hpp:710-747) with choiceTInit (:367-445),
+// gradientDescent (:1000-1062), getSDFAtTimeStamp (:550-556), getSDF_DOTAtTimeStampOptimized (:593-662),
+// getGradPrelAtTimeStamp (:566-572), Trajectory::locatePieceIdx / getPos_Vel_Acc_Jerk (trajectory.hpp:105-149, 545-570).
+//
+// B200 mapping — the reference runs one OpenMP thread per obstacle point through a long scalar search; here
+//   k_sv_table : the coarse time grid t = 0, 0.2, ... (same running sum as the reference's for-loop) and the robot
+//                pose at each coarse time are computed ONCE per evaluation and shared by every point (the reference
+//                recomputes the pose per point per sample);
+//   k_sv_points: one WARP per obstacle point. Lanes split the coarse scan (ballot -> in-range bitmap -> intervals via
+//                bit scans), split each fine scan, and run the sign-descent SPECULATIVELY: in one pass the 32 lanes
+//                evaluate f(x), the six finite-difference samples of the gradient and all 18 candidate steps
+//                x -/+ 0.02/2^d, so an outer iteration costs one SDF latency instead of up to 9 + 7 dependent ones.
+//                Accept/reject decisions replay the reference's sequential logic exactly (same comparisons, same
+//                iteration accounting);
+//   k_sv_reduce / k_sv_finish: deterministic per-piece reduction (fixed thread->point map, fixed trees) and the
+//                gradT(j<i) prefix of hpp:642-645 as a suffix sum.
+#pragma once
+#include "isdf_types.cuh"
+
+namespace isdf {
+
+constexpr int SV_WARPS = 4;
+constexpr int SV_THREADS = SV_WARPS * 32;
+constexpr int SV_MAX_COARSE = 1536;  // traj_duration < 300 s (updateTraj ignores longer ones, swm:291) at 0.2 s
+constexpr int SV_FLAG_WORDS = SV_MAX_COARSE / 32;
+
+struct TrajView { const double *T; const double *C; int N; };
+
+// locatePieceIdx (trajectory.hpp:545-563): sequential subtraction, strict '>', clamps past the end
+__device__ __forceinline__ int traj_locate(const TrajView &tr, double &t) {
+    int idx = 0;
+    for (; idx < tr.N; idx++) {
+        const double dur = tr.T[idx];
+        if (!(t > dur)) break;
+        t -= dur;
+    }
+    if (idx == tr.N) { idx--; t += tr.T[idx]; }
+    return idx;
+}
+
+// Piece::getPos_Vel_Acc_Jerk (trajectory.hpp:105-149): running powers, integer factors multiplied first
+__device__ __forceinline__ void traj_pvaj(const TrajView &tr, double tabs, d3 &p, d3 &v, d3 &a, d3 &j) {
+    double t = tabs;
+    const int i = traj_locate(tr, t);
+    const double *cx = tr.C + 6 * i, *cy = tr.C + 6 * tr.N + 6 * i, *cz = tr.C + 12 * tr.N + 6 * i;
+    double px = 0, py = 0, pz = 0, vx = 0, vy = 0, vz = 0, ax = 0, ay = 0, az = 0, jx = 0, jy = 0, jz = 0;
+    double ptn = 1.0, vtn = 1.0, atn = 1.0, jtn = 1.0;
+    int vn = 1, am = 1, an = 2, jl = 1, jm = 2, jn = 3;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const double x = cx[k], y = cy[k], z = cz[k];
+        px += ptn * x; py += ptn * y; pz += ptn * z; ptn *= t;
+        if (k >= 1) { const double f = vn * vtn; vx += f * x; vy += f * y; vz += f * z; vtn *= t; vn++; }
+        if (k >= 2) { const double f = (am * an) * atn; ax += f * x; ay += f * y; az += f * z; atn *= t; am++; an++; }
+        if (k >= 3) { const double f = (jl * jm * jn) * jtn; jx += f * x; jy += f * y; jz += f * z; jtn *= t; jl++; jm++; jn++; }
+    }
+    p = mk3(px, py, pz); v = mk3(vx, vy, vz); a = mk3(ax, ay, az); j = mk3(jx, jy, jz);
+}
+
+struct SvArgs {
+    DevCfg cfg;
+    DevShape shape;
+    int N;
+    const double *T, *C;
+    int P;
+    const double *pts;
+    double *tstar, *sdf, *grel;   // per point (in/out, out, out)
+    double *times;                // coarse time grid
+    double *poses;                // 12 per coarse time: x(3), R rows(9)
+    int *meta;                    // [0] = number of coarse samples
+    double *state;                // [0] = traj_duration (persists across evaluations like the SweptVolumeManager member)
+    double *partial;              // P x PARTIAL_STRIDE
+    int *piece;                   // P (piece of t*, -1 = no contribution)
+    double *piece_gdt, *piece_cost;  // N each
+    double *out;                  // 19N+1
+    unsigned long long *counter;  // reference-equivalent SDF evaluation count
+    int rank, world;
+    const double *g_t, *g_s, *g_g;  // tier-T1: given t*, sdf*, g_rel (null = search)
+};
+
+// ---- k_sv_table ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sv_table(const __grid_constant__ SvArgs A) {
+    extern __shared__ double smem[];
+    double *sT = smem, *sC = smem + A.N;
+    for (int k = threadIdx.x; k < A.N; k += blockDim.x) sT[k] = A.T[k];
+    for (int k = threadIdx.x; k < 18 * A.N; k += blockDim.x) sC[k] = A.C[k];
+    __shared__ int s_nc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double td = 0.0;
+        for (int k = 0; k < A.N; k++) td += sT[k];         // getTotalDuration (trajectory.hpp:457-466)
+        if (td < 3 * 1e2) A.state[0] = td;                 // updateTraj (swm:287-296)
+        const double dur = A.state[0];
+        int nc = 0;
+        for (double t = 0; t < dur && nc < SV_MAX_COARSE; t += 0.2) A.times[nc++] = t;  // choiceTInit's coarse loop (swm:392)
+        A.meta[0] = nc; s_nc = nc;
+    }
+    __syncthreads();
+    const TrajView tr = {sT, sC, A.N};
+    for (int k = threadIdx.x; k < s_nc; k += blockDim.x) {
+        d3 x, v, a, j;
+        traj_pvaj(tr, A.times[k], x, v, a, j);
+        const rot3 R = quat_rot(flat_quat_only(A.cfg.fp, v, a));
+        double *o = A.poses + 12 * (size_t)k;
+        o[0] = x.x; o[1] = x.y; o[2] = x.z;
+        o[3] = R.r0.x; o[4] = R.r0.y; o[5] = R.r0.z; o[6] = R.r1.x; o[7] = R.r1.y; o[8] = R.r1.z; o[9] = R.r2.x; o[10] = R.r2.y; o[11] = R.r2.z;
+    }
+}
+
+// ---- helpers for k_sv_points ------------------------------------------------------------------------------------
+template <bool MESH>
+__device__ __forceinline__ double sv_sdf_bounded(const DevShape &S, d3 prel, double reach) {
+    if (MESH) { d3 g; return mesh_sdf_grad(S.mesh, prel, reach, g); }
+    return shape_sdf_analytic(S, prel);
+}
+
+// getSDFAtTimeStamp (swm:550-556)
+template <bool MESH>
+__device__ __forceinline__ double sv_sdf_at(const SvArgs &A, const TrajView &tr, d3 p, double t, double reach) {
+    d3 x, v, a, j;
+    traj_pvaj(tr, t, x, v, a, j);
+    const rot3 R = quat_rot(flat_quat_only(A.cfg.fp, v, a));
+    return sv_sdf_bounded<MESH>(A.shape, rot_applyT(R, p - x), reach);
+}
+
+__device__ __forceinline__ d3 shfl3(d3 v, int src) {
+    return mk3(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src));
+}
+
+// Warp-cooperative getonlyGrad1 at a body-frame point known to every lane.
+template <bool MESH>
+__device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane) {
+    if (MESH) { d3 g = mk3(0, 0, 0); mesh_sdf_grad(S.mesh, tmp, 1e300, g); return g; }
+    if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) return unit3(tmp);
+    d3 q = tmp;
+    if (S.kind == ISDF_SHAPE_BOX) {
+        if (lane == 1) q.x += 0.01; else if (lane == 2) q.y += 0.01; else if (lane == 3) q.z += 0.01;
+        const double val = shape_sdf_analytic(S, q);
+        const double f0 = __shfl_sync(0xffffffffu, val, 0);
+        return mk3((__shfl_sync(0xffffffffu, val, 1) - f0) / 0.01, (__shfl_sync(0xffffffffu, val, 2) - f0) / 0.01,
+                   (__shfl_sync(0xffffffffu, val, 3) - f0) / 0.01);
+    }
+    const double dx = 0.000005;
+    if (lane < 6) {
+        const int ax = lane >> 1;
+        double c = (ax == 0 ? tmp.x : (ax == 1 ? tmp.y : tmp.z)) - dx;
+        if (lane & 1) c = c + 2 * dx;
+        if (ax == 0) q.x = c; else if (ax == 1) q.y = c; else q.z = c;
+    }
+    const double val = shape_sdf_analytic(S, q);
+    const double gx = __shfl_sync(0xffffffffu, val, 1) - __shfl_sync(0xffffffffu, val, 0);
+    const double gy = __shfl_sync(0xffffffffu, val, 3) - __shfl_sync(0xffffffffu, val, 2);
+    const double gz = __shfl_sync(0xffffffffu, val, 5) - __shfl_sync(0xffffffffu, val, 4);
+    return unit3(mk3(gx / (2 * dx), gy / (2 * dx), gz / (2 * dx)));
+}
+
+// gradientDescent (swm:1000-1062), one speculative warp pass per outer iteration.
+// lanes 0..8: x - tau_d (taken when g > 0), lanes 9..17: x + tau_d (g < 0), lane 18: f(x), lanes 19..24: FD samples.
+template <bool MESH>
+__device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0,
+                                    double &fx, double &x, unsigned &nevals, int lane) {
+    const DevShape &S = A.shape;
+    const double alpha = 0.02, tol = 1e-5;
+    int iter = 0; bool stop = false;
+    double prev_x = 10000000.0;
+    x = x0;
+    const bool central = !MESH && S.kind != ISDF_SHAPE_BALL && S.kind != ISDF_SHAPE_POINT && S.kind != ISDF_SHAPE_BOX;
+    while (iter < 300 && !stop && fabs(x - prev_x) > tol) {
+        double t = x;
+        if (lane < 18) {
+            const int d = (lane % 9) + 1;
+            double tau = alpha;
+            for (int q = 1; q < d; q++) tau = 0.5 * tau;
+            const double xc = (lane < 9) ? (x - tau * 1) : (x - tau * (-1));
+            t = fmax(fmin(xc, t_max), t_min);
+        }
+        d3 xt, v, a, j;
+        traj_pvaj(tr, t, xt, v, a, j);
+        FlatState fs;
+        flat_state(A.cfg.fp, v, a, j, fs);
+        const rot3 R = quat_rot(flat_quat(fs));
+        const d3 tmp = rot_applyT(R, p - xt);
+        d3 q = tmp;
+        if (central && lane >= 19 && lane < 25) {
+            const double dx = 0.000005;
+            const int ax = (lane - 19) >> 1;
+            double c = (ax == 0 ? tmp.x : (ax == 1 ? tmp.y : tmp.z)) - dx;
+            if ((lane - 19) & 1) c = c + 2 * dx;
+            if (ax == 0) q.x = c; else if (ax == 1) q.y = c; else q.z = c;
+        } else if (!MESH && S.kind == ISDF_SHAPE_BOX && lane >= 19 && lane < 22) {
+            if (lane == 19) q.x += 0.01; else if (lane == 20) q.y += 0.01; else q.z += 0.01;
+        }
+        double val; d3 gm = mk3(0, 0, 0);
+        if (MESH) val = mesh_sdf_grad(S.mesh, q, 1e300, gm);
+        else val = shape_sdf_analytic(S, q);
+        if (iter == 0) { fx = __shfl_sync(0xffffffffu, val, 18); nevals++; }
+        // gradient of the SDF at (x, tmp@lane18)
+        d3 g;
+        if (MESH) g = shfl3(gm, 18);
+        else if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) g = shfl3(unit3(tmp), 18);
+        else if (S.kind == ISDF_SHAPE_BOX) {
+            const double f0 = __shfl_sync(0xffffffffu, val, 18);
+            g = mk3((__shfl_sync(0xffffffffu, val, 19) - f0) / 0.01, (__shfl_sync(0xffffffffu, val, 20) - f0) / 0.01,
+                    (__shfl_sync(0xffffffffu, val, 21) - f0) / 0.01);
+        } else {
+            const double dx = 0.000005;
+            const double gx = __shfl_sync(0xffffffffu, val, 20) - __shfl_sync(0xffffffffu, val, 19);
+            const double gy = __shfl_sync(0xffffffffu, val, 22) - __shfl_sync(0xffffffffu, val, 21);
+            const double gz = __shfl_sync(0xffffffffu, val, 24) - __shfl_sync(0xffffffffu, val, 23);
+            g = unit3(mk3(gx / (2 * dx), gy / (2 * dx), gz / (2 * dx)));
+        }
+        // d/dt of the SDF: grad . point_velocity, point_velocity = -(R^T v + omega x tmp)  (swm:655-661), on lane 18's pose
+        const d3 omg = flat_omega(fs);
+        const d3 rv = rot_applyT(R, v), wx = cross3(omg, tmp);
+        const d3 pv = mk3(-(rv.x + wx.x), -(rv.y + wx.y), -(rv.z + wx.z));
+        const double gd = __shfl_sync(0xffffffffu, dot3(g, pv), 18);
+        const int sgn = (int)(gd > 0) - (int)(gd < 0);
+        const unsigned ok = __ballot_sync(0xffffffffu, lane < 18 && (val - fx) < 0);
+        const unsigned m = sgn > 0 ? (ok & 0x1ffu) : (sgn < 0 ? ((ok >> 9) & 0x1ffu) : 0u);
+        prev_x = x;
+        if (m) {
+            const int d = __ffs(m);
+            const int src = (sgn > 0 ? 0 : 9) + d - 1;
+            x = __shfl_sync(0xffffffffu, t, src);
+            fx = __shfl_sync(0xffffffffu, val, src);
+            iter += d; nevals += d;
+        } else {
+            iter += 9; nevals += 9; stop = true;
+        }
+    }
+}
+
+// ---- k_sv_points: one warp per obstacle point -------------------------------------------------------------------------
+template <bool MESH>
+__global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant__ SvArgs A) {
+    extern __shared__ double smem[];
+    double *sT = smem, *sC = smem + A.N;
+    __shared__ uint32_t sflags[SV_WARPS][SV_FLAG_WORDS];
+    for (int k = threadIdx.x; k < A.N; k += blockDim.x) sT[k] = A.T[k];
+    for (int k = threadIdx.x; k < 18 * A.N; k += blockDim.x) sC[k] = A.C[k];
+    __syncthreads();
+    const TrajView tr = {sT, sC, A.N};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Mloc = (A.P - A.rank + A.world - 1) / A.world;
+    const int m = blockIdx.x * SV_WARPS + warp;
+    if (m >= Mloc) return;
+    const int pk = A.rank + A.world * m;
+    const d3 p = mk3(A.pts[3 * pk], A.pts[3 * pk + 1], A.pts[3 * pk + 2]);
+    const DevCfg &cfg = A.cfg;
+    const double dur = A.state[0];
+    const int nc = A.meta[0];
+    const double inf = 2 * cfg.safety + 0.1;   // safty_hor_inf (swm:383)
+
+    double sdf_value = 1e1, tstar = A.tstar[pk];
+    d3 grel = mk3(0, 0, 0);
+    unsigned nevals = 0;
+    bool found = false;
+
+    if (A.g_t) {
+        sdf_value = A.g_s[pk]; tstar = A.g_t[pk]; grel = mk3(A.g_g[3 * pk], A.g_g[3 * pk + 1], A.g_g[3 * pk + 2]);
+        found = true;
+    } else {
+        // ---- coarse scan: in-range bitmap -------------------------------------------------------------------------
+        uint32_t *fl = sflags[warp];
+        for (int base = 0; base < nc; base += 32) {
+            const int k = base + lane;
+            bool in = false;
+            if (k < nc) {
+                const double *o = A.poses + 12 * (size_t)k;
+                const d3 d = mk3(p.x - __ldg(o), p.y - __ldg(o + 1), p.z - __ldg(o + 2));
+                const d3 prel = mk3(__ldg(o + 3) * d.x + __ldg(o + 6) * d.y + __ldg(o + 9) * d.z,
+                                    __ldg(o + 4) * d.x + __ldg(o + 7) * d.y + __ldg(o + 10) * d.z,
+                                    __ldg(o + 5) * d.x + __ldg(o + 8) * d.y + __ldg(o + 11) * d.z);
+                in = sv_sdf_bounded<MESH>(A.shape, prel, inf) < inf;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            if (lane == 0) fl[base >> 5] = b;
+        }
+        __syncwarp();
+        nevals += nc;
+        const int nwords = (nc + 31) >> 5;
+        // last run entry (in-range sample whose predecessor is out of range): its SDF initialises range_mindis (quirk Q2)
+        int last_entry = -1;
+        for (int w = nwords - 1; w >= 0 && last_entry < 0; w--) {
+            const uint32_t cur = fl[w];
+            const uint32_t prevbit = (w > 0) ? (fl[w - 1] >> 31) : 0u;
+            const uint32_t starts = cur & ~((cur << 1) | prevbit);
+            if (starts) last_entry = w * 32 + (31 - __clz(starts));
+        }
+        if (last_entry >= 0) {
+            double range_mindis = sv_sdf_at<MESH>(A, tr, p, A.times[last_entry], inf);  // same value the coarse pass saw
+            double range_time_seed = 0.0;
+            double min_sdf_star = 1e1;
+            // walk the closed runs in order
+            int pos = 0;
+            while (pos < nc) {
+                // next set bit at or after pos
+                int kin = -1;
+                for (int w = pos >> 5; w < nwords; w++) {
+                    uint32_t cur = fl[w];
+                    if (w == (pos >> 5)) cur &= ~((1u << (pos & 31)) - 1u);
+                    if (cur) { kin = w * 32 + __ffs(cur) - 1; break; }
+                }
+                if (kin < 0) break;
+                // next clear bit after kin
+                int kout = -1;
+                for (int w = kin >> 5; w < nwords; w++) {
+                    uint32_t cur = ~fl[w];
+                    if (w == (kin >> 5)) cur &= ~((1u << (kin & 31)) - 1u);
+                    if (w == nwords - 1 && (nc & 31)) cur &= (1u << (nc & 31)) - 1u;
+                    if (cur) { kout = w * 32 + __ffs(cur) - 1; break; }
+                }
+                if (kout < 0) break;  // run still open at the end of the scan: dropped (quirk Q2)
+                const double lb = fmax(0.0, A.times[kin] - 0.2);
+                const double ub = fmin(dur, A.times[kout] + 0.2);
+                // ---- fine scan of [lb, ub) at dt = 0.02 (swm:423-438): t advances by repeated addition ----------------
+                {
+                    double t = lb;
+                    for (int q = 0; q < lane; q++) t += 0.02;
+                    int mi = lane;
+                    while (__any_sync(0xffffffffu, t < ub)) {
+                        const bool valid = t < ub;
+                        double dis = 1e300;
+                        if (valid) dis = sv_sdf_at<MESH>(A, tr, p, t, inf);
+                        nevals += __popc(__ballot_sync(0xffffffffu, valid));
+                        // warp argmin, ties -> smaller sample index (first occurrence wins under the strict '<')
+                        double bd = dis; int bi = mi; double bt = t;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            const double otm = __shfl_xor_sync(0xffffffffu, bt, o);
+                            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = otm; }
+                        }
+                        if (bd < range_mindis) { range_mindis = bd; range_time_seed = bt; }
+                        for (int q = 0; q < 32; q++) t += 0.02;
+                        mi += 32;
+                    }
+                }
+                // ---- descent inside the interval (swm:730-734) ---------------------------------------------------------
+                const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
+                double sdf_star = 1e1, t_star = 0;
+                sv_gradient_descent<MESH>(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
+                if (sdf_star < min_sdf_star) { min_sdf_star = sdf_star; tstar = t_star; found = true; }
+                pos = kout;
+            }
+            if (found) {
+                sdf_value = min_sdf_star;
+                // getGradPrelAtTimeStamp (swm:566-572) at the winning t*
+                d3 x, v, a, j;
+                traj_pvaj(tr, tstar, x, v, a, j);
+                const rot3 R = quat_rot(flat_quat_only(cfg.fp, v, a));
+                grel = warp_grad<MESH>(A.shape, rot_applyT(R, p - x), lane);
+            }
+        }
+    }
+
+    // ---- chain-rule tail (hpp:578-636) ----------------------------------------------------------------------------------
+    int piece = -1;
+    if (lane == 0) {
+        A.tstar[pk] = tstar; A.sdf[pk] = sdf_value;
+        A.grel[3 * pk] = grel.x; A.grel[3 * pk + 1] = grel.y; A.grel[3 * pk + 2] = grel.z;
+        if (A.counter && nevals) atomicAdd(A.counter, (unsigned long long)nevals);
+        double f, df;
+        hinge(cfg.safety - sdf_value, 0.01, f, df);   // mu hard-coded 0.01 (hpp:851)
+        if (found && f > 2.220446049250313e-16) {     // returns costp > DBL_EPSILON (hpp:865)
+            double tl = tstar;
+            const int i = traj_locate(tr, tl);
+            PieceEval pe;
+            piece_eval(sC + 6 * i, sC + 6 * A.N + 6 * i, sC + 12 * A.N + 6 * i, tl, pe);
+            FlatState fs;
+            flat_state(cfg.fp, pe.vel, pe.acc, pe.jer, fs);
+            const quat4 q = flat_quat(fs);
+            const rot3 R = quat_rot(q);
+            const d3 wg = rot_apply(R, grel);
+            const d3 dd = p - pe.pos;
+            double jq[4];
+            quat_pull(q, grel, dd, jq);
+            const d3 gP = mk3(cfg.wp * (df * wg.x), cfg.wp * (df * wg.y), cfg.wp * (df * wg.z));
+            const double gQ[4] = {cfg.wp * (-df * jq[0]), cfg.wp * (-df * jq[1]), cfg.wp * (-df * jq[2]), cfg.wp * (-df * jq[3])};
+            const double pena = cfg.wp * f;
+            d3 gV, gA, gJ;
+            flat_adjoint(cfg.fp, fs, pe.vel, pe.acc, gQ, mk3(0, 0, 0), mk3(0, 0, 0), gV, gA, gJ);
+            double *o = A.partial + (size_t)pk * PARTIAL_STRIDE;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                o[k] = pe.b0[k] * gP.x + pe.b1[k] * gV.x + pe.b2[k] * gA.x + pe.b3[k] * gJ.x;
+                o[6 + k] = pe.b0[k] * gP.y + pe.b1[k] * gV.y + pe.b2[k] * gA.y + pe.b3[k] * gJ.y;
+                o[12 + k] = pe.b0[k] * gP.z + pe.b1[k] * gV.z + pe.b2[k] * gA.z + pe.b3[k] * gJ.z;
+            }
+            o[18] = (-dot3(gP, pe.vel) + -dot3(gV, pe.acc) + -dot3(gA, pe.jer) + -dot3(gJ, pe.sna));
+            o[19] = pena;
+            piece = i;
+        }
+        A.piece[pk] = piece;
+    }
+}
+
+// ---- reductions --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sv_reduce(const __grid_constant__ SvArgs A) {
+    const int i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Mloc = (A.P - A.rank + A.world - 1) / A.world;
+    double acc[PARTIAL_STRIDE];
+#pragma unroll
+    for (int q = 0; q < PARTIAL_STRIDE; q++) acc[q] = 0.0;
+    for (int m = threadIdx.x; m < Mloc; m += blockDim.x) {
+        const int pk = A.rank + A.world * m;
+        if (A.piece[pk] == i) {
+            const double *o = A.partial + (size_t)pk * PARTIAL_STRIDE;
+#pragma unroll
+            for (int q = 0; q < PARTIAL_STRIDE; q++) acc[q] += o[q];
+        }
+    }
+    __shared__ double red[8][PARTIAL_STRIDE];
+#pragma unroll
+    for (int q = 0; q < PARTIAL_STRIDE; q++) { const double s = warp_sum(acc[q]); if (lane == 0) red[warp][q] = s; }
+    __syncthreads();
+    if (threadIdx.x < PARTIAL_STRIDE) {
+        const int q = threadIdx.x;
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += red[w][q];
+        if (q < 18) { const int ax = q / 6, k = q - 6 * ax; A.out[1 + (size_t)ax * 6 * A.N + 6 * i + k] = s; }
+        else if (q == 18) A.piece_gdt[i] = s;
+        else A.piece_cost[i] = s;
+    }
+}
+
+__global__ void k_sv_finish(const __grid_constant__ SvArgs A) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double c = 0.0;
+    for (int i = 0; i < A.N; i++) c += A.piece_cost[i];
+    A.out[0] = c;
+    double run = 0.0;  // gradT(j) += gdT for all j < i (hpp:642-645)  <=>  gradT(j) = sum over pieces i > j
+    for (int i = A.N - 1; i >= 0; i--) { A.out[1 + 18 * A.N + i] = run; run += A.piece_gdt[i]; }
+}
+
+// ---- host-side state ----------------------------------------------------------------------------------------------
+struct SweptState {
+    int P = 0;
+    DevBuf<double> d_pts, d_tstar, d_sdf, d_grel, d_times, d_poses, d_state, d_partial, d_piece_gdt, d_piece_cost;
+    DevBuf<int> d_piece, d_meta;
+    DevBuf<unsigned long long> d_counter;
+
+    cudaError_t set_points(const double *pts, int n, cudaStream_t st) {
+        cudaError_t e = cudaSuccess;
+        P = 0;
+        if (n == 0) return e;
+        if ((e = d_pts.upload(pts, (size_t)3 * n, st)) != cudaSuccess) return e;
+        if ((e = d_tstar.ensure(n)) != cudaSuccess) return e;
+        if ((e = d_sdf.ensure(n)) != cudaSuccess) return e;
+        if ((e = d_grel.ensure((size_t)3 * n)) != cudaSuccess) return e;
+        if ((e = d_partial.ensure((size_t)n * PARTIAL_STRIDE)) != cudaSuccess) return e;
+        if ((e = d_piece.ensure(n)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(d_tstar.p, 0, sizeof(double) * n, st)) != cudaSuccess) return e;  // lastTstar := zeros (plan_manager.cpp:254)
+        if ((e = cudaMemsetAsync(d_sdf.p, 0, sizeof(double) * n, st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(d_grel.p, 0, sizeof(double) * 3 * n, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        P = n;
+        return e;
+    }
+    cudaError_t ensure_common() {
+        cudaError_t e;
+        if ((e = d_times.ensure(SV_MAX_COARSE)) != cudaSuccess) return e;
+        if ((e = d_poses.ensure((size_t)12 * SV_MAX_COARSE)) != cudaSuccess) return e;
+        if ((e = d_meta.ensure(4)) != cudaSuccess) return e;
+        if (d_state.n == 0) {
+            if ((e = d_state.ensure(4)) != cudaSuccess) return e;
+            if ((e = cudaMemset(d_state.p, 0, 4 * sizeof(double))) != cudaSuccess) return e;
+        }
+        if (d_counter.n == 0) {
+            if ((e = d_counter.ensure(2)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    cudaError_t launch(const DevCfg &cfg, const DevShape &shape, int N, const double *d_T, const double *d_C, double *d_out,
+                       int rank, int world, cudaStream_t st, const double *g_t, const double *g_s, const double *g_g, int *launches) {
+        cudaError_t e;
+        if ((e = ensure_common()) != cudaSuccess) return e;
+        if ((e = d_piece_gdt.ensure(N)) != cudaSuccess) return e;
+        if ((e = d_piece_cost.ensure(N)) != cudaSuccess) return e;
+        SvArgs A;
+        A.cfg = cfg; A.shape = shape; A.N = N; A.T = d_T; A.C = d_C; A.P = P; A.pts = d_pts.p;
+        A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
+        A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
+        A.out = d_out; A.counter = d_counter.p; A.rank = rank; A.world = world; A.g_t = g_t; A.g_s = g_s; A.g_g = g_g;
+        const size_t sm = sizeof(double) * 19 * (size_t)N;
+        if (sm > 200 * 1024) return cudaErrorInvalidValue;
+        if ((e = cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
+        if (sm > 48 * 1024) {
+            cudaFuncSetAttribute(k_sv_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        }
+        k_sv_table<<<1, 256, sm, st>>>(A);
+        const int Mloc = (P - rank + world - 1) / world;
+        const unsigned grid = (unsigned)((Mloc + SV_WARPS - 1) / SV_WARPS);
+        if (grid > 0) {
+            if (shape.kind == ISDF_SHAPE_MESH) k_sv_points<true><<<grid, SV_THREADS, sm, st>>>(A);
+            else k_sv_points<false><<<grid, SV_THREADS, sm, st>>>(A);
+        }
+        k_sv_reduce<<<N, 256, 0, st>>>(A);
+        k_sv_finish<<<1, 32, 0, st>>>(A);
+        *launches = 3 + (grid > 0 ? 1 : 0);
+        return cudaGetLastError();
+    }
+    void release() {
+        d_pts.release(); d_tstar.release(); d_sdf.release(); d_grel.release(); d_times.release(); d_poses.release(); d_state.release();
+        d_partial.release(); d_piece_gdt.release(); d_piece_cost.release(); d_piece.release(); d_meta.release(); d_counter.release();
+    }
+};
+
+}  // namespace isdf

@@ -1,0 +1,143 @@
+/* isdf.h — C ABI of libisdf_b200.so: B200-native (sm_100a) collision cost/gradient evaluator for the
+ * Implicit-SDF-Planner back end. Plain pointers and sizes only; no torch / Eigen / ROS types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to /root/reference/src):
+ *   hpp   = planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp
+ *   swm   = swept_volume/include/swept_volume/sw_manager.hpp
+ *   Shape = utils/include/utils/Shape.hpp, utils/src/Shape.cpp
+ *   pcs   = map_manager/include/map_manager/PCSmap_manager.h ; grid = map_manager/src/Gridmap3D.cpp
+ *   minco = utils/include/utils/minco.hpp ; lmbm = utils/include/lmbm/lmbm.h ; lbfgs = utils/include/utils/lbfgs.hpp
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative isdf_status on failure; isdf_last_error() gives the message.
+ *     On failure every output cost is set to NaN so that either optimiser driver terminates
+ *     (the LMBM callback has no error channel, lmbm_call.f:125; L-BFGS aborts on NaN, lbfgs.hpp:148-197).
+ *   - Matrices follow Eigen's defaults: `coeffs`/`gradC` are MatrixX3d (6N x 3) COLUMN-major:
+ *     element (6*i + k, axis) at [axis*6N + 6*i + k] = t^k coefficient of piece i (hpp:434,460).
+ *   - There is no CPU fallback: if no CUDA device / kernel image is usable, isdf_create fails.
+ */
+#ifndef ISDF_H
+#define ISDF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct isdf_ctx isdf_ctx;
+
+typedef enum isdf_status {
+    ISDF_OK = 0,
+    ISDF_ERR_INVALID = -1,   /* bad argument */
+    ISDF_ERR_STATE = -2,     /* map / shape / points not set */
+    ISDF_ERR_CUDA = -3,      /* CUDA runtime or launch failure (message has the CUDA error string) */
+    ISDF_ERR_UNSUPPORTED = -4
+} isdf_status;
+
+/* Subset of struct Config (utils/include/utils/config.hpp:13-203) that the hot path reads, in the units of
+ * plan_manager/config/ *.yaml. Same field order as oracle/oracle_capi.cpp::orc_config. */
+typedef struct isdf_config {
+    double vehicle_mass, grav_acc, horiz_drag, vert_drag, paras_drag, speed_eps; /* FlatnessMap::reset, flatness.hpp:36-51 */
+    double vmax, omgmax, thetamax;                                               /* hpp:678-680 */
+    double weight_v, weight_p, weight_omg, weight_theta;                         /* hpp:683-687 */
+    double smoothing_eps;        /* smooth_fac, hpp:689 */
+    double safety_hor;           /* hpp:691 */
+    double occupancy_resolution; /* bd = kernel_size * occupancy_resolution, hpp:692 */
+    int32_t kernel_size;
+    int32_t integral_intervs;    /* integralRes K, hpp:690: K+1 trapezoid nodes per piece */
+    int32_t threads_num;         /* kept for interface parity (config.hpp:16); ignored by the GPU path */
+    int32_t flags;               /* isdf_flags */
+} isdf_config;
+
+typedef enum isdf_flags {
+    ISDF_WITH_DYNAMICS = 1,   /* velocity / body-rate / tilt penalties of addTimeIntPenaltyParallel (hpp:505-534) */
+    ISDF_WITH_COLLISION = 2   /* grad_cost_p (hpp:766-824) wired into the sample loop as hpp:619-626 wires its SV sibling */
+} isdf_flags;
+
+/* Numeric ids shared with oracle/oracle_shapes.hpp::ShapeKind. params[] layout per kind is documented in
+ * implicit-sdf-planner_b200/csrc/isdf_shapes.cuh; isdf_set_shape_named() fills the reference's hard-coded constants. */
+typedef enum isdf_shape_kind {
+    ISDF_SHAPE_BALL = 0, ISDF_SHAPE_POINT = 1, ISDF_SHAPE_TORUS = 2, ISDF_SHAPE_CAPPED_TORUS = 3,
+    ISDF_SHAPE_CAPPED_CONE = 4, ISDF_SHAPE_ROUNDED_CONE = 5, ISDF_SHAPE_WIREFRAME_BOX = 6,
+    ISDF_SHAPE_BEND_LINEAR = 7, ISDF_SHAPE_TWIST_BOX = 8, ISDF_SHAPE_BEND_BOX = 9, ISDF_SHAPE_TABLE = 10,
+    ISDF_SHAPE_TREFOIL = 11, ISDF_SHAPE_SMOOTH_DIFFERENCE = 12, ISDF_SHAPE_SMOOTH_INTERSECTION = 13,
+    ISDF_SHAPE_CSG = 14, ISDF_SHAPE_BOX = 15, ISDF_SHAPE_MESH = 16
+} isdf_shape_kind;
+
+/* What isdf_shape_query computes — the four BasicShape virtuals (Shape.hpp:469-472). */
+typedef enum isdf_query {
+    ISDF_QUERY_SDF = 0,       /* getonlySDF(pos_rel) */
+    ISDF_QUERY_GRAD = 1,      /* getonlyGrad1(pos_rel) */
+    ISDF_QUERY_SDF_GRAD = 2   /* getSDFwithGrad1(pos_rel, grad) */
+} isdf_query;
+
+typedef struct isdf_stats {
+    int64_t kernel_launches;   /* kernels of this library launched since isdf_create */
+    int64_t evals_discrete;    /* isdf_eval_discrete* calls */
+    int64_t evals_swept;       /* isdf_eval_swept* calls */
+    int64_t last_pairs;        /* (sample, voxel) pairs that reached the SDF in the last discrete evaluation */
+    int64_t last_sdf_evals;    /* SDF evaluations in the last swept-volume evaluation */
+    double last_kernel_ms;     /* device time of the last evaluation's kernels (CUDA events on the launch stream) */
+} isdf_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+/* values of plan_manager/config/config_CappedCone.yaml; flags = DYNAMICS|COLLISION */
+int isdf_default_config(isdf_config *cfg);
+/* replaces TrajOptimizer::setParam (hpp:667-722) + SweptVolumeManager ctor (swm:135-150). device = CUDA ordinal. */
+int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out);
+int isdf_destroy(isdf_ctx *ctx);
+const char *isdf_last_error(void);
+int isdf_get_stats(isdf_ctx *ctx, isdf_stats *out);
+/* Shard the evaluation: this context evaluates samples / obstacle points with index % world == rank and returns
+ * partial sums (caller all-reduces 19N+1 doubles). Default rank 0 / world 1. */
+int isdf_set_shard(isdf_ctx *ctx, int rank, int world);
+
+/* ---- robot shape: replaces SweptVolumeManager::initShape (swm:255-275) and the Generalshape ctor (Shape.cpp:27-103) */
+/* rotate_rowmajor / trans = Generalshape::Rotate / trans from poly_params (Shape.hpp:776-780); NULL = identity / zero */
+int isdf_set_shape_analytic(isdf_ctx *ctx, int kind, const double *params, int nparams,
+                            const double *rotate_rowmajor, const double *trans);
+/* factory keyed by the OBJ basename like shapeConstructors (swm:74-123): "Torus", "CSG", ...; plus "Ball", "Point" */
+int isdf_set_shape_named(isdf_ctx *ctx, const char *name, const double *rotate_rowmajor, const double *trans);
+/* triangle mesh (V: nV x 3 row-major, F: nF x 3 row-major, consistently outward-oriented, closed);
+ * poly_params = {tx,ty,tz, roll,pitch,yaw in degrees} pre-transform as Shape.cpp:38-50, NULL = none.
+ * SDF = s * dist (Shape.cpp:105-151) with s = ±1 the exact inside/outside sign (see DESIGN.md "mesh sign"). */
+int isdf_set_shape_mesh(isdf_ctx *ctx, const double *V, int nV, const int32_t *F, int nF, const double *poly_params);
+/* the BasicShape virtual surface (Shape.hpp:469-472) for n body-frame points (n x 3 row-major); sdf/grad may be NULL */
+int isdf_shape_query(isdf_ctx *ctx, const double *p_rel, int n, double *sdf, double *grad, int what);
+
+/* ---- occupancy map: replaces GridMap3D::createGridMap + the fill in PCSmap_manager.cpp:148-181 ------------ */
+/* occ: X*Y*Z bytes, address ix*Y*Z + iy*Z + iz (GridMap3D.h:194-195), non-zero = occupied.
+ * boundary_xyzmax is taken as bmin + size*res. */
+int isdf_set_map_u8(isdf_ctx *ctx, const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res);
+/* the reference's own storage: one double per voxel (GridMap3D.h:215) */
+int isdf_set_map_f64(isdf_ctx *ctx, const double *grid_map, int X, int Y, int Z, const double *bmin, double res);
+/* PCSmapManager::getPointsInAABB (pcs:148-170) on the device map; writes up to cap centres (cap x 3), returns count in *n */
+int isdf_points_in_aabb(isdf_ctx *ctx, const double *centre, double half_extent, double *out_points, int cap, int *n);
+
+/* ---- discrete collision term: addTimeIntPenaltyParallel (hpp:432-554) with grad_cost_p (hpp:766-824) wired in */
+/* ACCUMULATES into *cost, gradC (6N x 3 col-major), gradT (N) exactly like the reference's reference arguments. */
+int isdf_eval_discrete(isdf_ctx *ctx, int N, const double *T, const double *coeffs,
+                       double *cost, double *gradC, double *gradT);
+/* device-resident variant: d_T (N), d_coeffs (18N) and d_out (19N+1 = [cost | gradC 18N | gradT N], OVERWRITTEN)
+ * are device pointers on ctx's device; cuda_stream is a cudaStream_t (NULL = default stream). Asynchronous. */
+int isdf_eval_discrete_device(isdf_ctx *ctx, int N, const double *d_T, const double *d_coeffs, double *d_out,
+                              void *cuda_stream);
+
+/* ---- swept-volume term: addSaftyPenaOnSweptVolumeParallel (hpp:557-649) + getSDFofSweptVolume (swm:710-747) --- */
+/* parallel_points (plan_manager.cpp:246-254): P x 3 row-major world-frame voxel centres; resets lastTstar to 0 */
+int isdf_set_points(isdf_ctx *ctx, const double *pts, int P);
+int isdf_eval_swept(isdf_ctx *ctx, int N, const double *T, const double *coeffs,
+                    double *cost, double *gradC, double *gradT);
+int isdf_eval_swept_device(isdf_ctx *ctx, int N, const double *d_T, const double *d_coeffs, double *d_out,
+                           void *cuda_stream);
+/* per-point results of the last swept evaluation: t* (lastTstar, hpp:59), SV-SDF value, g_rel (3 per point); any may be NULL */
+int isdf_get_swept_results(isdf_ctx *ctx, double *tstar, double *sdf, double *grel);
+/* tier-T1 tail parity: evaluate the chain-rule tail at caller-supplied t*, sdf*, g_rel instead of searching */
+int isdf_eval_swept_given(isdf_ctx *ctx, int N, const double *T, const double *coeffs, const double *tstar,
+                          const double *sdf, const double *grel, double *cost, double *gradC, double *gradT);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISDF_H */

@@ -1,0 +1,192 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_math.hpp header).
+// Flat C entry points so tests/ and bench.py's cpu_baseline leg can drive the oracle through ctypes.
+// Built by oracle/Makefile into oracle/liboracle.so (serial + OpenMP variants live in the same library;
+// `use_omp` selects the reference's `parallel for schedule(dynamic)` + `critical` structure).
+#include "oracle_planner.hpp"
+#include "oracle_minco.hpp"
+#include <cstdio>
+
+using namespace orc;
+
+extern "C" {
+
+// Same field order as isdf_config in include/isdf.h (tests assert sizeof equality).
+struct orc_config {
+    double vehicle_mass, grav_acc, horiz_drag, vert_drag, paras_drag, speed_eps;
+    double vmax, omgmax, thetamax;
+    double weight_v, weight_p, weight_omg, weight_theta;
+    double smoothing_eps, safety_hor;
+    double occupancy_resolution;
+    int kernel_size, integral_intervs, threads_num, flags;
+};
+
+static Params to_params(const orc_config *c) {
+    Params P;
+    P.mass = c->vehicle_mass; P.grav = c->grav_acc; P.dh = c->horiz_drag; P.dv = c->vert_drag; P.cp = c->paras_drag;
+    P.veps = c->speed_eps; P.vmax = c->vmax; P.omgmax = c->omgmax; P.thetamax = c->thetamax;
+    P.weight_v = c->weight_v; P.weight_p = c->weight_p; P.weight_omg = c->weight_omg; P.weight_theta = c->weight_theta;
+    P.smooth_fac = c->smoothing_eps; P.safety_hor = c->safety_hor; P.integral_res = c->integral_intervs;
+    P.bd = c->kernel_size * c->occupancy_resolution;  // hpp:692
+    P.threads = c->threads_num > 0 ? c->threads_num : 1;
+    P.with_dynamics = (c->flags & 1) ? 1 : 0;
+    P.with_collision = (c->flags & 2) ? 1 : 0;
+    return P;
+}
+
+struct OrcShape { Shape s; Mesh mesh; };
+
+void *orc_shape_create(int kind, const double *par, int npar, const double *rot_rowmajor, const double *trans) {
+    OrcShape *o = new OrcShape();
+    o->s.kind = kind;
+    for (int i = 0; i < npar && i < 12; i++) o->s.par[i] = par[i];
+    if (rot_rowmajor) for (int i = 0; i < 9; i++) o->s.Rotate.m[i] = rot_rowmajor[i];
+    if (trans) o->s.trans = V3(trans[0], trans[1], trans[2]);
+    return o;
+}
+void *orc_shape_create_named(const char *name, const double *rot_rowmajor, const double *trans) {
+    OrcShape *o = new OrcShape();
+    if (!make_named_shape(name, o->s)) { delete o; return nullptr; }
+    if (rot_rowmajor) for (int i = 0; i < 9; i++) o->s.Rotate.m[i] = rot_rowmajor[i];
+    if (trans) o->s.trans = V3(trans[0], trans[1], trans[2]);
+    return o;
+}
+// V: nV x 3 row-major, F: nF x 3 row-major; poly_params may be NULL (no pre-transform)
+void *orc_shape_create_mesh(const double *V, int nV, const int *F, int nF, const double *poly_params, int wn_mode) {
+    OrcShape *o = new OrcShape();
+    o->mesh.V.resize(nV);
+    for (int i = 0; i < nV; i++) o->mesh.V[i] = V3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
+    o->mesh.F.assign(F, F + 3 * (size_t)nF);
+    if (poly_params) o->mesh.pretransform(poly_params);
+    o->mesh.wn_mode = wn_mode;
+    o->mesh.build();
+    o->s.kind = SK_MESH;
+    o->s.mesh = &o->mesh;
+    return o;
+}
+void orc_shape_destroy(void *h) { delete (OrcShape *)h; }
+int orc_shape_kind(void *h) { return ((OrcShape *)h)->s.kind; }
+void orc_shape_params(void *h, double *par12) { for (int i = 0; i < 12; i++) par12[i] = ((OrcShape *)h)->s.par[i]; }
+
+// what: 0 = getonlySDF, 1 = getonlyGrad1, 2 = getSDFwithGrad1
+void orc_shape_query(void *h, const double *p, int n, double *sdf, double *grad, int what) {
+    const Shape &s = ((OrcShape *)h)->s;
+    for (int i = 0; i < n; i++) {
+        const V3 q(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        V3 g;
+        if (what == 0) sdf[i] = s.sdf(q);
+        else if (what == 1) g = s.grad(q);
+        else sdf[i] = s.sdf_grad(q, g);
+        if (what) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+    }
+}
+// mesh internals for known-answer tests
+void orc_mesh_query(void *h, const double *p, int n, double *d2_bvh, double *d2_brute, double *closest, double *w_exact, double *w_bh) {
+    const Mesh &m = ((OrcShape *)h)->mesh;
+    for (int i = 0; i < n; i++) {
+        const V3 q(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        V3 c; int t;
+        if (d2_bvh) { d2_bvh[i] = m.closest(q, c, t); if (closest) { closest[3 * i] = c.x; closest[3 * i + 1] = c.y; closest[3 * i + 2] = c.z; } }
+        if (d2_brute) d2_brute[i] = m.closest_brute(q, c, t);
+        if (w_exact) w_exact[i] = m.winding_exact(q);
+        if (w_bh) w_bh[i] = m.winding_bh(q);
+    }
+}
+
+void orc_flat_forward(const orc_config *c, const double *v, const double *a, const double *j, double *quat, double *omg) {
+    Params P = to_params(c); Flat F; F.reset(P.mass, P.grav, P.dh, P.dv, P.cp, P.veps);
+    V3 o; F.forward(V3(v[0], v[1], v[2]), V3(a[0], a[1], a[2]), V3(j[0], j[1], j[2]), quat, o);
+    omg[0] = o.x; omg[1] = o.y; omg[2] = o.z;
+}
+void orc_flat_backward(const orc_config *c, const double *v, const double *a, const double *j, const double *pos_grad,
+                       const double *vel_grad, const double *quat_grad, const double *omg_grad, double *out12) {
+    Params P = to_params(c); Flat F; F.reset(P.mass, P.grav, P.dh, P.dv, P.cp, P.veps);
+    V3 gp, gv, ga, gj;
+    F.backward(V3(v[0], v[1], v[2]), V3(a[0], a[1], a[2]), V3(j[0], j[1], j[2]), V3(pos_grad[0], pos_grad[1], pos_grad[2]),
+               V3(vel_grad[0], vel_grad[1], vel_grad[2]), quat_grad, V3(omg_grad[0], omg_grad[1], omg_grad[2]), gp, gv, ga, gj);
+    const V3 *o[4] = {&gp, &gv, &ga, &gj};
+    for (int i = 0; i < 4; i++) { out12[3 * i] = o[i]->x; out12[3 * i + 1] = o[i]->y; out12[3 * i + 2] = o[i]->z; }
+}
+
+// Discrete path. occ: X*Y*Z bytes, z fastest. Accumulates nothing: outputs are overwritten.
+int orc_eval_discrete(const orc_config *c, const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res,
+                      void *shape, int N, const double *T, const double *C, double *cost, double *gradC, double *gradT,
+                      long long *npairs, int use_omp, int rank, int world) {
+    Params P = to_params(c);
+    Grid G; G.X = X; G.Y = Y; G.Z = Z; G.res = res; G.occ = occ;
+    G.bmin = V3(bmin[0], bmin[1], bmin[2]);
+    G.bmax = V3(bmin[0] + X * res, bmin[1] + Y * res, bmin[2] + Z * res);
+    Traj tr; tr.N = N; tr.T = T; tr.C = C;
+    EvalOut out;
+    eval_discrete(P, occ ? &G : nullptr, shape ? &((OrcShape *)shape)->s : nullptr, tr, out, use_omp != 0, rank, world > 0 ? world : 1);
+    *cost = out.cost;
+    std::memcpy(gradC, out.gradC.data(), sizeof(double) * 18 * N);
+    std::memcpy(gradT, out.gradT.data(), sizeof(double) * N);
+    if (npairs) *npairs = out.n_pairs;
+    return 0;
+}
+
+// Swept-volume path. tstar in/out (lastTstar). sdf_out / grel_out optional. given_* optional (tier-T1 tail parity).
+int orc_eval_swept(const orc_config *c, void *shape, int N, const double *T, const double *C, int npts, const double *pts,
+                   double *tstar, double *cost, double *gradC, double *gradT, double *sdf_out, double *grel_out,
+                   long long *nsdf, int use_omp, const double *given_tstar, const double *given_sdf, const double *given_grel) {
+    Params P = to_params(c);
+    Traj tr; tr.N = N; tr.T = T; tr.C = C;
+    EvalOut out;
+    SweptGiven gv{given_tstar, given_sdf, given_grel};
+    eval_swept(P, ((OrcShape *)shape)->s, tr, npts, pts, tstar, out, use_omp != 0, sdf_out, grel_out, given_tstar ? &gv : nullptr);
+    *cost = out.cost;
+    std::memcpy(gradC, out.gradC.data(), sizeof(double) * 18 * N);
+    std::memcpy(gradT, out.gradT.data(), sizeof(double) * N);
+    if (nsdf) *nsdf = out.n_sdf;
+    return 0;
+}
+
+// Single swept-volume SDF query (getSDFofSweptVolume<true>(p, t, g, false), swm:710-747)
+double orc_sdf_swept(const orc_config *c, void *shape, int N, const double *T, const double *C, const double *p, double *tstar, double *grel) {
+    Params P = to_params(c);
+    Traj tr; tr.N = N; tr.T = T; tr.C = C;
+    SweptVolume sv; sv.P = &P; sv.S = &((OrcShape *)shape)->s; sv.tr = &tr; sv.F.reset(P.mass, P.grav, P.dh, P.dv, P.cp, P.veps); sv.update();
+    V3 g; const double s = sv.sdf_swept(V3(p[0], p[1], p[2]), *tstar, g);
+    grel[0] = g.x; grel[1] = g.y; grel[2] = g.z;
+    return s;
+}
+
+// getPointsInAABB (pcs:148-170) exposed for grid tests; returns count, writes up to cap centres
+int orc_points_in_aabb(const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res, const double *centre,
+                       double half, double *out, int cap) {
+    Grid G; G.X = X; G.Y = Y; G.Z = Z; G.res = res; G.occ = occ;
+    G.bmin = V3(bmin[0], bmin[1], bmin[2]); G.bmax = V3(bmin[0] + X * res, bmin[1] + Y * res, bmin[2] + Z * res);
+    std::vector<V3> v; G.points_in_aabb(V3(centre[0], centre[1], centre[2]), half, half, half, v);
+    for (int i = 0; i < (int)v.size() && i < cap; i++) { out[3 * i] = v[i].x; out[3 * i + 1] = v[i].y; out[3 * i + 2] = v[i].z; }
+    return (int)v.size();
+}
+
+// ---- MINCO S3NU (adjacent step) --------------------------------------------------
+// headPVA/tailPVA: 3x3 column-major (columns = pos, vel, acc). inPs: 3 x (N-1) column-major. coeffs out: 6N x 3 col-major.
+int orc_minco_forward(int N, const double *headPVA, const double *tailPVA, const double *inPs, const double *T,
+                      double *coeffs, double *energy, double *gradC_energy, double *gradT_energy) {
+    MincoS3 m; m.set_conditions(headPVA, tailPVA, N);
+    m.set_parameters(inPs, T);
+    std::memcpy(coeffs, m.b.data(), sizeof(double) * 18 * N);
+    if (energy) *energy = m.energy();
+    if (gradC_energy) m.energy_grad_coeffs(gradC_energy);
+    if (gradT_energy) m.energy_grad_times(gradT_energy);
+    return 0;
+}
+int orc_minco_backward(int N, const double *headPVA, const double *tailPVA, const double *inPs, const double *T,
+                       const double *gradC, const double *gradT, double *gradP_out, double *gradT_out) {
+    MincoS3 m; m.set_conditions(headPVA, tailPVA, N);
+    m.set_parameters(inPs, T);
+    m.propagate_grad(gradC, gradT, gradP_out, gradT_out);
+    return 0;
+}
+
+int orc_omp_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
