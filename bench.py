@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — collision cost+gradient evaluations/s of the discrete hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through libisdf_b200.so)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (OpenMP structure) on host cores
+
+Workload (N=1 and every N: strong scaling, total work fixed): BASELINE.json configs[2] — the configuration the
+north_star target is quoted on: 512^3 random voxel map (Bernoulli 5 % + wall slabs), 64-piece MINCO trajectory,
+256 samples/piece (S = 16448 pose samples), robot = 3900-triangle closed mesh (rounded cone, the mesh-SDF path).
+One "step" = one cost + gradC (6N x 3) + gradT (N) evaluation of the collision term over the whole trajectory.
+At N > 1 every rank evaluates the pose samples s % N == rank and the 19N+1 doubles are all-reduced over NCCL.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "implicit-sdf-planner_b200", "py"))
+
+METRIC = "collision_cost_grad_evals_per_s"
+UNIT = "evals/s"
+WORKLOAD = dict(map_dim=512, occupancy=0.05, pieces=64, samples_per_piece=256, kernel_size=13, mesh="rounded_cone_3900tri",
+                poly_params=[0.0, 0.0, 0.0, 120.0, 0.0, 0.0])
+
+
+# ---- distributed helpers (also exercised by tests/test_multi_rank_gloo.py on CPU/gloo) ------------------------------
+def dist_ready():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized()
+
+
+def allreduce_partials(t):
+    """sum the per-rank partial [cost | gradC | gradT] vectors in place (NCCL over NVLink on GPU tensors, gloo on CPU)."""
+    if dist_ready():
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def max_over_ranks(x):
+    if not dist_ready():
+        return float(x)
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if dist_ready():
+        import torch.distributed as dist
+        dist.barrier()
+
+
+# ---- workload ------------------------------------------------------------------------------------------------------------
+def make_workload(small=False):
+    import isdf_b200 as I
+    import workloads as W
+    w = dict(WORKLOAD)
+    if small:
+        w.update(map_dim=128, pieces=8, samples_per_piece=32)
+    X = w["map_dim"]
+    occ = W.random_map(X, X, X, p=w["occupancy"], seed=1, slabs=3)
+    cfg = I.default_config_values()
+    cfg.integral_intervs = w["samples_per_piece"]
+    cfg.kernel_size = w["kernel_size"]
+    cfg.flags = I.WITH_COLLISION | I.WITH_DYNAMICS
+    T, Cc, wp = W.make_trajectory(w["pieces"], [0, 0, 0], [X, X, X], seed=11, jitter=0.2)
+    V, F = W.rounded_cone_mesh()
+    return w, cfg, occ, T, Cc, V, F
+
+
+def algorithmic_bytes(w):
+    """S*W^3 bytes of occupancy (1 B/voxel, each sample's window counted once) + coeff/T read + grads written."""
+    N, K, Wk = w["pieces"], w["samples_per_piece"], w["kernel_size"]
+    S = N * (K + 1)
+    return S * Wk ** 3 + 8 * 19 * N + 8 * (19 * N + 1)
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            txt, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in txt.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_discrete_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ---- CPU arm: the reference's algorithm (oracle port, OpenMP `parallel for schedule(dynamic)` + `critical`) -----------------
+def cpu_sample_eval(w, cfg, occ, T, Cc, V, F, pieces, threads):
+    """one evaluation restricted to the first `pieces` pieces (a bounded sample of the same workload); returns seconds"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O     # bench's CPU legs are one of the three places allowed to execute oracle/
+    N = w["pieces"]
+    sub = np.concatenate([Cc.reshape(3, 6 * N)[ax, :6 * pieces] for ax in range(3)])
+    oc = O.config_from(cfg)
+    oc.threads_num = threads
+    if not hasattr(cpu_sample_eval, "shape"):
+        cpu_sample_eval.shape = O.Shape.mesh(V, F, w["poly_params"], wn_mode=O.WN_BH)
+    t0 = time.perf_counter()
+    r = O.eval_discrete(oc, occ, [0, 0, 0], 1.0, cpu_sample_eval.shape, T[:pieces], sub, use_omp=True)
+    return time.perf_counter() - t0, r
+
+
+def cpu_baseline(w, cfg, occ, T, Cc, V, F, budget_s=20.0):
+    cores = os.cpu_count() or 1
+    pieces = 1
+    dt, _ = cpu_sample_eval(w, cfg, occ, T, Cc, V, F, pieces, cores)
+    # grow the sample until it is worth ~budget/2 of CPU time, never beyond the full trajectory
+    while dt < budget_s / 4 and pieces < w["pieces"]:
+        pieces = min(w["pieces"], pieces * 2)
+        dt, _ = cpu_sample_eval(w, cfg, occ, T, Cc, V, F, pieces, cores)
+    evals_per_s = 1.0 / (dt * w["pieces"] / pieces)
+    return {"value": evals_per_s, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {pieces} of {w['pieces']} pieces ({pieces * (w['samples_per_piece'] + 1)} pose samples) of the same workload, "
+                      f"{dt:.2f} s wall with {cores} OpenMP threads (schedule(dynamic) + critical, g++ -O3), scaled by pieces"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, cfg, occ, T, Cc, V, F = make_workload(args.small)
+    cores = os.cpu_count() or 1
+    pieces = args.ref_pieces
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_sample_eval(w, cfg, occ, T, Cc, V, F, pieces, cores)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = cpu_sample_eval(w, cfg, occ, T, Cc, V, F, pieces, cores)
+        times.append(dt)
+    ms = 1e3 * statistics.mean(times) * w["pieces"] / pieces
+    val = 1e3 / ms
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(w), **w},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"each step = first {pieces} of {w['pieces']} pieces, time scaled by {w['pieces']}/{pieces}; "
+                                       f"{cores} OpenMP threads, reference loop structure (parallel for dynamic + critical)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(w):
+    return (f"BASELINE configs[2]: random {w['map_dim']}^3 voxel map (p={w['occupancy']}, wall slabs), {w['pieces']}-piece MINCO traj, "
+            f"{w['samples_per_piece']} samples/piece, mesh-SDF robot ({w['mesh']}), discrete collision cost+grad")
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import isdf_b200 as I
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, cfg, occ, T, Cc, V, F = make_workload(args.small)
+    N = w["pieces"]
+    ev = I.Evaluator(cfg, device=local)
+    ev.set_map_u8(occ, [0, 0, 0], 1.0)
+    ev.set_shape_mesh(V, F, w["poly_params"])
+    ev.set_shard(rank, world)
+    dev = torch.device("cuda", local)
+    d_T = torch.from_numpy(T).to(dev)
+    d_C = torch.from_numpy(Cc).to(dev)
+    d_out = torch.zeros(19 * N + 1, dtype=torch.float64, device=dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        ev.eval_discrete_device(N, d_T.data_ptr(), d_C.data_ptr(), d_out.data_ptr(), stream)
+        if world > 1:
+            allreduce_partials(d_out)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ev.stats().kernel_launches
+    ev_pairs = []
+    times = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        barrier()
+        e0.record()
+        step_device()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(max_over_ranks(e0.elapsed_time(e1)))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = ev.stats().kernel_launches - l0
+    # warm-L2 figure for context (steady state of an optimiser loop: map stays L2 resident)
+    warm = []
+    for _ in range(min(args.steps, 10)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); barrier()
+        e0.record(); step_device(); e1.record()
+        torch.cuda.synchronize()
+        warm.append(max_over_ranks(e0.elapsed_time(e1)))
+    clocks = sampler.stop() if sampler else None
+    ms = statistics.mean(times)
+    result = d_out.cpu().numpy().copy()
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D + kernel + D2H inside the timed region) ---------
+    e2e_times = []
+    h_part = torch.empty(19 * N + 1, dtype=torch.float64).pin_memory()
+    for it in range(3 + args.steps):
+        flush.zero_()
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        c, gC, gT = ev.eval_discrete(T, Cc)               # isdf_eval_discrete: pinned staging, H2D, kernel, D2H, sync
+        if world > 1:
+            h_part[0] = c; h_part[1:1 + 18 * N] = torch.from_numpy(gC); h_part[1 + 18 * N:] = torch.from_numpy(gT)
+            d_tmp = h_part.to(dev, non_blocking=True)
+            allreduce_partials(d_tmp)
+            h_part.copy_(d_tmp)
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if it >= 3:
+            e2e_times.append(max_over_ranks(dt))
+    pairs = ev.stats().last_pairs
+    kernel_ms_alone = ev.stats().last_kernel_ms
+    ms_e2e = statistics.mean(e2e_times)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        ab = algorithmic_bytes(w)
+        achieved = ab / (ms * 1e-3) / 1e9 if world == 1 else ab / world / (ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(w), **w, "l2": "flushed (512 MiB write) between timed steps",
+                           "parallelism": f"sample-interleaved shards x{world} + 1 NCCL all-reduce of {19 * N + 1} doubles" if world > 1 else "1 GPU"},
+                "clocks": clocks,
+                "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * 19 * N, "d2h_bytes_per_step": 8 * (19 * N + 1) + 8,
+                        "ms_per_step": ms_e2e, "api": "isdf_eval_discrete (host buffers)"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                             "peak_source": peak_src, "kernel": "k_discrete<MESH>", "algorithmic_bytes_per_launch": ab // world,
+                             "note": "window bytes counted at 1 B/voxel per sample (SURVEY §8d); the kernel is FP64/latency bound, see DESIGN.md"},
+                "extra": {"pairs_per_eval": int(pairs), "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step_warm_l2": statistics.mean(warm),
+                          "evals_per_s_warm_l2": 1e3 / statistics.mean(warm), "ms_min": min(times), "ms_max": max(times),
+                          "kernel_ms_in_host_call": kernel_ms_alone, "wall_s_timed_loop": wall,
+                          "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:]))}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w, cfg, occ, T, Cc, V, F, budget_s=args.cpu_budget)
+            line["extra"]["speedup_kernel_vs_cpu"] = line["value"] / line["cpu_baseline"]["value"]
+            line["extra"]["speedup_e2e_vs_cpu"] = line["e2e"]["value"] / line["cpu_baseline"]["value"]
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-pieces", type=int, default=2, help="--impl reference: pieces per step sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,349 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every call goes through the C-ABI of libisdf_b200.so and is
+compared with the oracle on identical seeded inputs.
+
+Tolerances (stated, FP64 path):
+  * SDF values: 1e-12 (abs/rel). Arithmetic is FP64 add/mul/div/sqrt with FMA contraction off on both sides; only libm
+    (sin/cos/atan2/acos) may differ in the last ulp.
+  * FD gradients (getonlyGrad1): 1e-8 — the reference's dx = 5e-6 central difference amplifies 1-ulp SDF differences by 1e5.
+  * cost / gradC / gradT: <= 1e-6 relative (cost) and rel-L2 (gradients) — BASELINE.json north_star; typically ~1e-13.
+"""
+import ctypes as C
+import math
+import os
+import numpy as np
+import pytest
+import isdf_b200 as I
+import oracle_lib as O
+import workloads as W
+from common import small_case, rel_l2, BMIN, tilted, MESHES
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-6
+
+
+def grads(gC, gT):
+    return np.concatenate([gC, gT])
+
+
+def check_eval(got, exp, tol=TOL, what=""):
+    c, gC, gT = got
+    oc, ogC, ogT = exp[0], exp[1], exp[2]
+    if abs(oc) > 0:
+        assert abs(c - oc) <= tol * abs(oc), f"{what}: cost {c} vs {oc}"
+    else:
+        assert c == 0
+    r = rel_l2(grads(gC, gT), grads(ogC, ogT))
+    assert r <= tol, f"{what}: gradient rel-L2 {r:.3e}"
+    return r
+
+
+# ---- the BasicShape plug-in surface ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", I.NAMED_SHAPES)
+def test_shape_query_named(name):
+    R, t = tilted()
+    ev = I.Evaluator()
+    ev.set_shape_named(name, R, t)
+    osh = O.Shape.named(name, R, t)
+    p = np.random.default_rng(11).uniform(-6, 6, size=(2000, 3))
+    s, g = ev.shape_query(p, I.QUERY_SDF_GRAD)
+    os_, og = osh.query(p, 2)
+    assert np.allclose(s, os_, rtol=1e-12, atol=1e-12), np.abs(s - os_).max()
+    bad = np.abs(g - og).max(axis=1) > 1e-8
+    assert bad.mean() <= 0.002, (bad.sum(), np.abs(g - og).max())   # FD across a non-smooth seam can flip branch within ±dx
+    s0, _ = ev.shape_query(p, I.QUERY_SDF)
+    _, g1 = ev.shape_query(p, I.QUERY_GRAD)
+    assert np.array_equal(s0, s) and np.array_equal(g1, g)
+    ev.close()
+
+
+def test_shape_query_box_and_golden():
+    R, t = tilted()
+    ev = I.Evaluator()
+    ev.set_shape_analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.15, 0.15], R, t)
+    z = np.load(os.path.join(G, "shapes.npz"))
+    s, g = ev.shape_query(z["p"])
+    assert np.allclose(s, z["Box_sdf"], rtol=1e-12, atol=1e-12) and np.allclose(g, z["Box_grad"], atol=1e-9)
+    for name in I.NAMED_SHAPES:
+        ev.set_shape_named(name, z["R"], z["t"])
+        s, g = ev.shape_query(z["p"])
+        assert np.allclose(s, z[f"{name}_sdf"], rtol=1e-12, atol=1e-12), name
+    ev.close()
+
+
+@pytest.mark.parametrize("mesh", list(MESHES))
+def test_shape_query_mesh(mesh):
+    V, F = MESHES[mesh]()
+    pp = [0.2, -0.1, 0.3, 120.0, 10.0, -30.0]
+    ev = I.Evaluator()
+    ev.set_shape_mesh(V, F, pp)
+    osh = O.Shape.mesh(V, F, pp)
+    p = np.random.default_rng(5).uniform(-5, 6, size=(3000, 3))
+    s, g = ev.shape_query(p)
+    os_, og = osh.query(p)
+    assert np.array_equal(np.sign(s), np.sign(os_)), "inside/outside classification differs from the exact winding number"
+    assert np.allclose(s, os_, rtol=1e-12, atol=1e-12), np.abs(s - os_).max()
+    bad = np.abs(g - og).max(axis=1) > 1e-9
+    assert bad.mean() <= 0.002   # equidistant-triangle ties
+    ev.close()
+
+
+def test_points_in_aabb_matches_reference_semantics():
+    rng = np.random.default_rng(3)
+    occ = (rng.random((40, 33, 70)) < 0.2).astype(np.uint8)     # Z > 64: rows span three bit-words
+    bmin, res = np.array([-3.0, 1.0, 0.5]), 0.5
+    ev = I.Evaluator()
+    ev.set_map_u8(occ, bmin, res)
+    bmax = bmin + np.array(occ.shape) * res
+    for _ in range(40):
+        c = bmin + (bmax - bmin) * (rng.random(3) * 1.6 - 0.3)
+        half = rng.uniform(0.3, 3.0)
+        a, na = ev.points_in_aabb(c, half)
+        b, nb = O.points_in_aabb(occ, bmin, res, c, half)
+        assert na == nb and np.array_equal(a, b)
+    ev.set_map_f64(occ.astype(np.float64) * 3.0, bmin, res)      # reference storage: double per voxel, non-zero = occupied
+    a, na = ev.points_in_aabb(bmin + 5, 2.0)
+    b, nb = O.points_in_aabb(occ, bmin, res, bmin + 5, 2.0)
+    assert na == nb and np.array_equal(a, b)
+    ev.close()
+
+
+# ---- discrete path ------------------------------------------------------------------------------------------------------------
+DISCRETE_SHAPES = ["Ball", "Torus_big", "RoundedCone", "CappedCone", "WireframeBox", "BendLinear_big", "TwistBox", "Table", "Trefoil",
+                   "SmoothDifference", "SmoothIntersection_big", "CSG"]
+
+
+@pytest.mark.parametrize("name", DISCRETE_SHAPES)
+def test_discrete_parity_analytic(name):
+    cfg, occ, T, Cc, _ = small_case(N=4, K=16, seed=3)
+    R, t = tilted()
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    ev.set_shape_named(name, R, t)
+    exp = O.eval_discrete(O.config_from(cfg), occ, BMIN, 1.0, O.Shape.named(name, R, t), T, Cc)
+    got = ev.eval_discrete(T, Cc)
+    r = check_eval(got, exp, what=name)
+    assert ev.stats().last_pairs == exp[3]
+    print(f"{name}: cost {got[0]:.6g} grad rel-L2 {r:.2e} pairs {exp[3]}")
+    ev.close()
+
+
+def test_discrete_parity_box_shape():
+    cfg, occ, T, Cc, _ = small_case(N=3, K=12, seed=8)
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    ev.set_shape_analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.3, 0.3])
+    exp = O.eval_discrete(O.config_from(cfg), occ, BMIN, 1.0, O.Shape.analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.3, 0.3]), T, Cc)
+    check_eval(ev.eval_discrete(T, Cc), exp, what="Box")
+    ev.close()
+
+
+@pytest.mark.parametrize("mesh", list(MESHES))
+def test_discrete_parity_mesh(mesh):
+    cfg, occ, T, Cc, _ = small_case(N=4, K=16, seed=6)
+    V, F = MESHES[mesh]()
+    pp = [0.0, 0.0, 0.0, 120.0, 0.0, 0.0]        # config_CappedCone.yaml poly_params
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    ev.set_shape_mesh(V, F, pp)
+    exp = O.eval_discrete(O.config_from(cfg), occ, BMIN, 1.0, O.Shape.mesh(V, F, pp), T, Cc)
+    got = ev.eval_discrete(T, Cc)
+    r = check_eval(got, exp, what=mesh)
+    assert got[0] > 0 and ev.stats().last_pairs == exp[3]
+    print(f"mesh {mesh}: cost {got[0]:.6g} grad rel-L2 {r:.2e}")
+    ev.close()
+
+
+@pytest.mark.parametrize("case", ["N1", "K1", "res05", "ks17", "dense", "outside", "collision_only", "dynamics_only", "empty_map"])
+def test_discrete_edge_cases(case):
+    N, K, seed, noise, ks, res, flags = 3, 12, 9, 0.03, 13, 1.0, None
+    if case == "N1": N = 1
+    if case == "K1": K = 1
+    if case == "ks17": ks = 17
+    if case == "dense": noise = 0.6
+    if case == "collision_only": flags = I.WITH_COLLISION
+    if case == "dynamics_only": flags = I.WITH_DYNAMICS
+    cfg, occ, T, Cc, wp = small_case(N=N, K=K, seed=seed, noise=noise, flags=flags, kernel_size=ks)
+    bmin = list(BMIN)
+    if case == "res05":
+        res, cfg.occupancy_resolution = 0.5, 0.5
+        Cc = Cc * 0.5     # shrink the trajectory into the 32 m map
+    if case == "outside":
+        bmin = [30.0, -10.0, 5.0]   # most of the trajectory lies outside the map: windows clamp to the border (quirk Q6)
+    if case == "empty_map":
+        occ = np.zeros_like(occ)
+    if case == "dynamics_only":
+        cfg.vmax, cfg.omgmax, cfg.thetamax = 0.8, 0.3, 0.2
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, bmin, res)
+    ev.set_shape_named("SmoothIntersection")
+    exp = O.eval_discrete(O.config_from(cfg), occ, bmin, res, O.Shape.named("SmoothIntersection"), T, Cc)
+    got = ev.eval_discrete(T, Cc)
+    check_eval(got, exp, what=case)
+    assert ev.stats().last_pairs == (exp[3] if (cfg.flags & I.WITH_COLLISION) else 0)
+    ev.close()
+
+
+def test_discrete_accumulates_into_caller_buffers_and_is_deterministic():
+    cfg, occ, T, Cc, _ = small_case(N=4, K=16, seed=3)
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    ev.set_shape_named("Torus")
+    c1, gC1, gT1 = ev.eval_discrete(T, Cc)
+    c2, gC2, gT2 = ev.eval_discrete(T, Cc)
+    assert c1 == c2 and np.array_equal(gC1, gC2) and np.array_equal(gT1, gT2)      # bit-reproducible
+    c3, gC3, gT3 = ev.eval_discrete(T, Cc, cost=5.0, gradC=np.ones(18 * 4), gradT=2 * np.ones(4))
+    assert c3 == 5.0 + c1 and np.array_equal(gC3, 1.0 + gC1) and np.array_equal(gT3, 2.0 + gT1)   # hpp:539-550 semantics
+    ev.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_discrete_shards_sum_to_full(world):
+    cfg, occ, T, Cc, _ = small_case(N=4, K=16, seed=3)
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    ev.set_shape_named("RoundedCone")
+    full = ev.eval_discrete(T, Cc)
+    acc = [0.0, np.zeros(72), np.zeros(4)]
+    for r in range(world):
+        ev.set_shard(r, world)
+        c, gC, gT = ev.eval_discrete(T, Cc)
+        exp = O.eval_discrete(O.config_from(cfg), occ, BMIN, 1.0, O.Shape.named("RoundedCone"), T, Cc, rank=r, world=world)
+        check_eval((c, gC, gT), exp, what=f"shard {r}/{world}")
+        acc[0] += c; acc[1] += gC; acc[2] += gT
+    assert abs(acc[0] - full[0]) <= 1e-12 * abs(full[0]) and rel_l2(grads(acc[1], acc[2]), grads(full[1], full[2])) < 1e-12
+    ev.close()
+
+
+def test_errors_surface_as_status_and_nan_cost():
+    cfg, occ, T, Cc, _ = small_case(N=2, K=4)
+    ev = I.Evaluator(cfg)
+    lib = ev.lib
+    c = C.c_double(1.0)
+    gC, gT = np.zeros(36), np.zeros(2)
+    dp = C.POINTER(C.c_double)
+    r = lib.isdf_eval_discrete(ev.h, 2, T.ctypes.data_as(dp), Cc.ctypes.data_as(dp), C.byref(c), gC.ctypes.data_as(dp), gT.ctypes.data_as(dp))
+    assert r == -2 and math.isnan(c.value) and b"shape" in lib.isdf_last_error()     # ISDF_ERR_STATE, NaN so the optimiser stops
+    ev.set_shape_named("Ball")
+    r = lib.isdf_eval_discrete(ev.h, 2, T.ctypes.data_as(dp), Cc.ctypes.data_as(dp), C.byref(c), gC.ctypes.data_as(dp), gT.ctypes.data_as(dp))
+    assert r == -2 and b"map" in lib.isdf_last_error()
+    with pytest.raises(I.IsdfError):
+        ev.set_shape_named("NoSuchShape")
+    with pytest.raises(I.IsdfError):
+        ev.set_shard(3, 2)
+    ev.close()
+
+
+def test_discrete_golden_fixture():
+    z = np.load(os.path.join(G, "discrete.npz"))
+    occ = np.unpackbits(z["occ_bits"])[:np.prod(z["occ_shape"])].reshape(z["occ_shape"]).astype(np.uint8)
+    cfg = I.default_config_values()
+    cfg.integral_intervs = int(z["K"])
+    s = np.load(os.path.join(G, "shapes.npz"))
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    for name in ["Ball", "CSG", "Trefoil", "SmoothIntersection"]:
+        ev.set_shape_named(name, s["R"], s["t"])
+        check_eval(ev.eval_discrete(z["T"], z["C"]), (float(z[f"{name}_cost"]), z[f"{name}_gradC"], z[f"{name}_gradT"]), what=name)
+    V, F = MESHES["lprism"]()
+    ev.set_shape_mesh(V, F, [0, 0, 0, 120, 0, 0])
+    check_eval(ev.eval_discrete(z["T"], z["C"]), (float(z["mesh_cost"]), z["mesh_gradC"], z["mesh_gradT"]), what="mesh")
+    ev.close()
+
+
+# ---- swept-volume path -----------------------------------------------------------------------------------------------------------
+def sv_case(N=4, seed=3, npts=400):
+    cfg, occ, T, Cc, wp = small_case(N=N, K=16, seed=seed, noise=0.05)
+    pts = W.gather_obstacle_points(occ, BMIN, 1.0, wp, cfg.kernel_size * cfg.occupancy_resolution / 3.0)[:npts]
+    return cfg, T, Cc, pts
+
+
+@pytest.mark.parametrize("name", ["Ball", "Torus", "RoundedCone", "SmoothIntersection", "CSG", "TwistBox"])
+def test_swept_tail_parity_given_tstar(name):
+    """tier T1: chain-rule tail at the oracle's t*, sdf*, g_rel"""
+    cfg, T, Cc, pts = sv_case()
+    osh = O.Shape.named(name)
+    ref = O.eval_swept(O.config_from(cfg), osh, T, Cc, pts)
+    ev = I.Evaluator(cfg)
+    ev.set_shape_named(name)
+    ev.set_points(pts)
+    got = ev.eval_swept_given(T, Cc, ref["tstar"], ref["sdf"], ref["grel"])
+    check_eval(got, (ref["cost"], ref["gradC"], ref["gradT"]), tol=1e-9, what=f"T1 {name}")
+    ev.close()
+
+
+@pytest.mark.parametrize("name", ["Ball", "Torus", "RoundedCone", "SmoothIntersection", "Box"])
+def test_swept_end_to_end_parity(name):
+    """tier T2: device-side search. Same accept/reject decisions => same t* to rounding."""
+    cfg, T, Cc, pts = sv_case(seed=5)
+    if name == "Box":
+        osh = O.Shape.analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.3, 0.3])
+    else:
+        osh = O.Shape.named(name)
+    ref = O.eval_swept(O.config_from(cfg), osh, T, Cc, pts)
+    ev = I.Evaluator(cfg)
+    if name == "Box":
+        ev.set_shape_analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.3, 0.3])
+    else:
+        ev.set_shape_named(name)
+    ev.set_points(pts)
+    got = ev.eval_swept(T, Cc)
+    ts, sd, gr = ev.swept_results()
+    hit = ref["sdf"] < 9.99
+    assert np.array_equal(sd < 9.99, hit)
+    dt = np.abs(ts - ref["tstar"])[hit]
+    print(f"{name}: points {len(pts)} hits {hit.sum()} max|dt*| {dt.max() if dt.size else 0:.3e} cost {got[0]:.6g} vs {ref['cost']:.6g}")
+    assert (dt <= 8e-5).mean() >= 0.99, f"t* mismatch on {(dt > 8e-5).sum()} points"
+    assert np.allclose(sd[hit], ref["sdf"][hit], rtol=0, atol=1e-6)
+    check_eval(got, (ref["cost"], ref["gradC"], ref["gradT"]), tol=1e-6, what=f"T2 {name}")
+    assert ev.stats().last_sdf_evals == ref["nsdf"]
+    ev.close()
+
+
+@pytest.mark.parametrize("mesh", ["lprism", "rcone"])
+def test_swept_end_to_end_mesh(mesh):
+    cfg, T, Cc, pts = sv_case(seed=7, npts=200)
+    V, F = MESHES[mesh]()
+    osh = O.Shape.mesh(V, F)
+    ref = O.eval_swept(O.config_from(cfg), osh, T, Cc, pts)
+    ev = I.Evaluator(cfg)
+    ev.set_shape_mesh(V, F)
+    ev.set_points(pts)
+    got = ev.eval_swept(T, Cc)
+    ts, sd, gr = ev.swept_results()
+    hit = ref["sdf"] < 9.99
+    assert np.array_equal(sd < 9.99, hit)
+    dt = np.abs(ts - ref["tstar"])[hit]
+    assert (dt <= 8e-5).mean() >= 0.99
+    check_eval(got, (ref["cost"], ref["gradC"], ref["gradT"]), tol=1e-6, what=f"T2 mesh {mesh}")
+    ev.close()
+
+
+def test_swept_shards_sum_to_full_and_tstar_persists():
+    cfg, T, Cc, pts = sv_case(seed=5)
+    ev = I.Evaluator(cfg)
+    ev.set_shape_named("Torus")
+    ev.set_points(pts)
+    full = ev.eval_swept(T, Cc)
+    t_full, _, _ = ev.swept_results()
+    acc = [0.0, np.zeros(72), np.zeros(4)]
+    for r in range(3):
+        ev.set_shard(r, 3)
+        c, gC, gT = ev.eval_swept(T, Cc)
+        acc[0] += c; acc[1] += gC; acc[2] += gT
+    assert abs(acc[0] - full[0]) <= 1e-12 * max(abs(full[0]), 1) and rel_l2(grads(acc[1], acc[2]), grads(full[1], full[2])) < 1e-12
+    t2, _, _ = ev.swept_results()
+    assert np.array_equal(t2, t_full)
+    ev.close()
+
+
+def test_swept_golden_fixture():
+    z = np.load(os.path.join(G, "swept.npz"))
+    cfg, *_ = small_case(N=4, K=16, seed=3)
+    ev = I.Evaluator(cfg)
+    ev.set_points(z["pts"])
+    for name in ["Ball", "Torus", "SmoothIntersection"]:
+        ev.set_shape_named(name)
+        got = ev.eval_swept(z["T"], z["C"])
+        check_eval(got, (float(z[f"{name}_cost"]), z[f"{name}_gradC"], z[f"{name}_gradT"]), what=name)
+    ev.close()
