@@ -14,6 +14,9 @@
 
 using namespace isdf;
 
+__global__ void k_mesh_cells(const __grid_constant__ DevMesh M, int nx, int ny, int nz, double lx, double ly, double lz, double cell,
+                             float *dist, uint32_t *seed);
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
@@ -38,11 +41,14 @@ struct isdf_ctx {
     // shape
     bool have_shape = false;
     DevShape shape;
-    DevBuf<BvhNode> d_nodes; DevBuf<double> d_tris, d_pn; DevBuf<uint32_t> d_inside;
+    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
     DevBuf<int> d_tickets;       // N piece tickets + 1 pieces_done (+ swept counters)
-    DevBuf<unsigned long long> d_counter;
+    DevBuf<int> d_order; DevBuf<unsigned> d_work;   // longest-first sample order (from the previous evaluation's work)
+    long long order_for = -1;    // (N, rank, world) signature the order array is valid for
+    DevBuf<unsigned long long> d_counter, d_dbg;
+    bool dbg_on = false;
     double *h_stage = nullptr;   // pinned
     size_t h_stage_n = 0;
     // swept volume
@@ -88,7 +94,7 @@ extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
     CU_TRY(cudaSetDevice(device));
     // fail loudly if the sm_100a image cannot run here
     cudaFuncAttributes fa;
-    CU_TRY(cudaFuncGetAttributes(&fa, (const void *)k_discrete<false>));
+    CU_TRY(cudaFuncGetAttributes(&fa, (const void *)k_discrete_analytic));
     isdf_ctx *c = new isdf_ctx();
     c->device = device; c->cfg = *cfg;
     std::memset(&c->stats, 0, sizeof(c->stats));
@@ -116,9 +122,9 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->d_bits.release(); c->d_nodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_inside.release();
+    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_cell_dist.release(); c->d_cell_seed.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
-    c->d_tickets.release(); c->d_counter.release();
+    c->d_tickets.release(); c->d_counter.release(); c->d_order.release(); c->d_work.release(); c->d_dbg.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -137,7 +143,7 @@ extern "C" int isdf_get_stats(isdf_ctx *c, isdf_stats *out) {
 extern "C" int isdf_set_shard(isdf_ctx *c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return fail(ISDF_ERR_INVALID, "bad shard");
     if (world > c->cfg.integral_intervs + 1) return fail(ISDF_ERR_INVALID, "world larger than samples per piece");
-    c->rank = rank; c->world = world;
+    c->rank = rank; c->world = world; c->order_for = -1;
     return 0;
 }
 
@@ -215,18 +221,50 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
     // 2*safety_hor + 0.1 >= safety_hor
     if (!build_host_mesh(V, nV, F, nF, poly_params, c->cfg.safety_hor, hm, err)) return fail(ISDF_ERR_INVALID, err);
     CU_TRY(c->d_nodes.upload(hm.nodes.data(), hm.nodes.size(), c->stream));
+    CU_TRY(c->d_wnodes.upload(hm.wnodes.data(), hm.wnodes.size(), c->stream));
     CU_TRY(c->d_tris.upload(hm.tris.data(), hm.tris.size(), c->stream));
     CU_TRY(c->d_pn.upload(hm.pnormals.data(), hm.pnormals.size(), c->stream));
-    CU_TRY(c->d_inside.upload(hm.inside.data(), hm.inside.size(), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     std::memset(&c->shape, 0, sizeof(c->shape));
     c->shape.kind = ISDF_SHAPE_MESH;
     shape_common(c, nullptr, nullptr);
     DevMesh m = hm.view();
-    m.nodes = c->d_nodes.p; m.tris = c->d_tris.p; m.pnormals = c->d_pn.p; m.inside = c->d_inside.p;
+    m.nodes = c->d_nodes.p; m.wnodes = c->d_wnodes.p; m.tris = c->d_tris.p; m.pnormals = c->d_pn.p;
+    // per-cell signed distance + seed triangle, computed on the device with the freshly uploaded BVH
+    const size_t ncell = (size_t)m.gdim[0] * m.gdim[1] * m.gdim[2];
+    CU_TRY(c->d_cell_dist.ensure(ncell));
+    CU_TRY(c->d_cell_seed.ensure(ncell));
+    {
+        DevMesh build = m;
+        build.gdim[0] = 0;            // no grid while it is being built: plain unbounded BVH queries
+        build.cell_dist = nullptr; build.cell_seed = nullptr;
+        k_mesh_cells<<<(unsigned)((ncell + 127) / 128), 128, 0, c->stream>>>(build, m.gdim[0], m.gdim[1], m.gdim[2], m.glo[0], m.glo[1], m.glo[2],
+                                                                           m.gcell, c->d_cell_dist.p, c->d_cell_seed.p);
+        c->stats.kernel_launches++;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    m.cell_dist = c->d_cell_dist.p; m.cell_seed = c->d_cell_seed.p;
     c->shape.mesh = m;
     c->have_shape = true;
     return 0;
+}
+
+// signed distance + nearest triangle at every cell centre of the body-frame grid (one thread per cell)
+__global__ void k_mesh_cells(const __grid_constant__ DevMesh M, int nx, int ny, int nz, double lx, double ly, double lz, double cell,
+                             float *dist, uint32_t *seed) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nx * ny * nz) return;
+    const int iz = (int)(idx % nz), iy = (int)((idx / nz) % ny), ix = (int)(idx / ((size_t)nz * ny));
+    const d3 p = mk3(lx + (ix + 0.5) * cell, ly + (iy + 0.5) * cell, lz + (iz + 0.5) * cell);
+    d3 c = mk3(0, 0, 0); int tri, feat;
+    const double d2 = mesh_closest(M, p, 1e300, c, tri, feat);
+    const d3 e = p - c;
+    const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
+    double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
+    if (side == 0.0) { const double *fn = M.pnormals + 21 * (size_t)tri; side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2]; }
+    dist[idx] = (float)((side < 0.0 ? -1.0 : 1.0) * sqrt(d2));
+    seed[idx] = (uint32_t)tri;
 }
 
 __global__ void k_shape_query(const __grid_constant__ DevShape S, const double *p, int n, double *sdf, double *grad, int what) {
@@ -369,11 +407,22 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     A.partial = c->d_partial.p; A.piece_ticket = c->d_tickets.p; A.pieces_done = c->d_tickets.p + c->d_tickets.n - 1;
     A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
     A.rank = c->rank; A.world = c->world;
+    A.dbg = nullptr;
+    if (c->dbg_on) { CU_TRY(c->d_dbg.ensure((size_t)3 * S)); CU_TRY(cudaMemsetAsync(c->d_dbg.p, 0, sizeof(unsigned long long) * 3 * S, st)); A.dbg = c->d_dbg.p; }
     const long long M = (S - c->rank + c->world - 1) / c->world;
-    const unsigned grid = (unsigned)((M + DISC_WARPS - 1) / DISC_WARPS);
     CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
-    if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete<true><<<grid, DISC_THREADS, 0, st>>>(A);
-    else k_discrete<false><<<grid, DISC_THREADS, 0, st>>>(A);
+    // longest-first order from the previous evaluation of the same problem shape (first evaluation: natural order)
+    const long long sig = ((long long)N << 20) ^ ((long long)c->rank << 10) ^ c->world ^ ((long long)K << 40);
+    CU_TRY(c->d_work.ensure((size_t)S)); CU_TRY(c->d_order.ensure((size_t)M));
+    A.work = c->d_work.p;
+    A.order = (c->order_for == sig) ? c->d_order.p : nullptr;
+    const unsigned grid = (unsigned)((M + DISC_WARPS - 1) / DISC_WARPS);
+    if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
+    else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
+    // off the result's critical path: the caller can already read d_out when this finishes on the same stream
+    k_order_samples<<<1, 1024, 0, st>>>(c->d_work.p, c->rank, c->world, (int)M, c->d_order.p);
+    c->order_for = sig;
+    c->stats.kernel_launches++;
     c->stats.kernel_launches++;
     c->stats.evals_discrete++;
     CU_TRY(cudaGetLastError());
@@ -524,3 +573,11 @@ extern "C" int isdf_get_swept_results(isdf_ctx *c, double *tstar, double *sdf, d
     return 0;
 }
 
+
+// ---- internal diagnostics (not part of include/isdf.h) ------------------------------------------------------------
+extern "C" int isdf_dbg_enable(isdf_ctx *c, int on) { if (!c) return -1; c->dbg_on = on != 0; return 0; }
+extern "C" int isdf_dbg_sample_stats(isdf_ctx *c, unsigned long long *out, long long n) {
+    if (!c || !out || (size_t)n > c->d_dbg.n) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -3;
+    return cudaMemcpy(out, c->d_dbg.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}

@@ -1,22 +1,26 @@
-// Fused discrete collision cost/gradient kernel: ONE launch per optimiser step.
+// Fused discrete collision cost/gradient kernels: ONE launch per optimiser step.
 //
 // Reference semantics: addTimeIntPenaltyParallel (back_end_optimizer.hpp:432-554) with grad_cost_p (hpp:766-824)
 // wired into the sample loop exactly as hpp:619-626 wires its swept-volume sibling; PCSmapManager::getPointsInAABB
 // (PCSmap_manager.h:148-170); getSDFWithGradWhenRobotAtState (sw_manager.hpp:537-541).
 //
 // Mapping (B200-first, not the reference's OpenMP-over-samples + critical section):
-//   * one warp per pose sample; a CTA owns DISC_WARPS consecutive samples, the hardware CTA scheduler balances
-//     the heavy (near-obstacle) stretches of the trajectory across the 148 SMs;
 //   * the pose window is read from the BIT-packed occupancy: lane = (x,y) row, one or two 32-bit loads + funnel
 //     shift give the row's z-run; a warp prefix sum over popcounts enumerates only the occupied voxels
 //     (the reference tests every voxel and heap-allocates a vector per sample, hpp:787);
-//   * two warp-level compaction queues keep lanes dense: queue A = voxels inside the body-frame cull box,
-//     queue B = voxels whose hinge is active (sdf < safety_hor) and therefore need the 6 extra finite-difference
-//     SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87) — evaluating those only for active voxels is exact
+//   * one WARP per pose sample, processed in longest-first order: the per-sample work measured in the previous
+//     evaluation (an optimiser moves the trajectory only a little between steps) sorts the samples so the heavy ones —
+//     poses grazing an obstacle — start first and the tail of the launch is made of cheap samples;
+//   * k_discrete_analytic — two warp-level compaction queues keep lanes dense: queue A = voxels inside the body-frame
+//     cull box, queue B = voxels whose hinge is active (sdf < safety_hor) and therefore need the 6 extra finite-
+//     difference SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87). Evaluating those only for active voxels is exact
 //     because an inactive voxel contributes nothing (hpp:809-821);
-//   * per-lane FP64 accumulators, xor-butterfly warp reduction, flatness adjoint, then a deterministic two-level
+//   * k_discrete_mesh — voxels that survive the exact culls (body-frame box, inflated mesh AABB, per-cell distance lower
+//     bound) are answered by WARP-COOPERATIVE nearest-triangle searches (32-ary tree, lane = child / triangle slot),
+//     seeded with the cell's nearest triangle;
+//   * sample epilogue (penalties, flatness adjoint, beta-basis outer products), then a deterministic two-level
 //     reduction: per-sample partials in HBM, and the LAST warp to finish a piece (ticket counter) sums that piece
-//     in ascending sample order — the same order as the serial oracle, independent of scheduling.
+//     in ascending sample order — independent of scheduling, so results are bit-reproducible run to run.
 #pragma once
 #include "isdf_types.cuh"
 
@@ -25,6 +29,10 @@ namespace isdf {
 constexpr int DISC_WARPS = 4;
 constexpr int DISC_THREADS = DISC_WARPS * 32;
 constexpr int QCAP = 64;
+// CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md): the analytic kernel
+// is fastest at 4 (128 regs), the mesh kernel at 3 (168 regs; forcing more spills the cooperative BVH search and is slower)
+constexpr int ANALYTIC_MIN_BLOCKS = 4;
+constexpr int MESH_MIN_BLOCKS = 3;
 
 struct DiscArgs {
     DevCfg cfg;
@@ -39,6 +47,9 @@ struct DiscArgs {
     double *piece_cost;    // N
     double *out;           // 19N+1: cost | gradC | gradT
     unsigned long long *pair_counter;  // may be null
+    unsigned long long *dbg;           // may be null: per sample {cycles, pairs, queries}
+    const int *order;                  // may be null: order[m] = local sample index processed by warp m (longest first)
+    unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
     int rank, world;       // this launch evaluates samples s with s % world == rank
 };
 
@@ -67,8 +78,218 @@ __device__ __forceinline__ int grid_axis_index(double coord, double bmin, double
     return clampi((int)floor((c - bmin) / res), 0, size - 1);
 }
 
-template <bool MESH>
-__global__ void __launch_bounds__(DISC_THREADS) k_discrete(const __grid_constant__ DiscArgs A) {
+struct Window { int ix0, ix1, iy0, iy1, iz0, iz1; };
+
+__device__ __forceinline__ Window window_of(const DevGrid &G, d3 pos, double h) {
+    Window w;
+    w.ix0 = grid_axis_index(pos.x - h, G.bmin[0], G.bmax[0], G.res, G.X);
+    w.ix1 = grid_axis_index(pos.x + h, G.bmin[0], G.bmax[0], G.res, G.X);
+    w.iy0 = grid_axis_index(pos.y - h, G.bmin[1], G.bmax[1], G.res, G.Y);
+    w.iy1 = grid_axis_index(pos.y + h, G.bmin[1], G.bmax[1], G.res, G.Y);
+    w.iz0 = grid_axis_index(pos.z - h, G.bmin[2], G.bmax[2], G.res, G.Z);
+    w.iz1 = grid_axis_index(pos.z + h, G.bmin[2], G.bmax[2], G.res, G.Z);
+    return w;
+}
+__device__ __forceinline__ d3 voxel_centre(const DevGrid &G, int ix, int iy, int iz) {   // getGridCubeCenter (Gridmap3D.cpp:177-194)
+    return mk3((ix + 0.5) * G.res + G.bmin[0], (iy + 0.5) * G.res + G.bmin[1], (iz + 0.5) * G.res + G.bmin[2]);
+}
+
+// Enumerate the occupied voxels of a window, 32 at a time, in the reference's order (x, then y, then z ascending).
+// visit(valid, ix, iy, iz) is called by the whole warp; lanes without a voxel pass valid = false.
+// The row batches are dealt round-robin: this warp takes batches first_batch, first_batch + batch_stride, ...
+template <class Visit>
+__device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, int lane, int first_batch, int batch_stride, Visit &&visit) {
+    const int ny = W.iy1 - W.iy0 + 1;
+    const int nrows = (W.ix1 - W.ix0 + 1) * ny;
+    for (int zs = W.iz0; zs <= W.iz1; zs += 32) {
+        const int nzc = min(32, W.iz1 - zs + 1);
+        const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
+        const int wz = zs >> 5, sh = zs & 31;
+        for (int rb = 32 * first_batch; rb < nrows; rb += 32 * batch_stride) {
+            const int r = rb + lane;
+            uint32_t bits = 0;
+            int rx = 0, ry = 0;
+            if (r < nrows) {
+                rx = r / ny; ry = r - rx * ny;
+                const uint32_t *row = G.bits + ((size_t)(W.ix0 + rx) * G.Y + (W.iy0 + ry)) * G.Zw;
+                const uint32_t lo = __ldg(row + wz);
+                const uint32_t hi = (sh != 0 && wz + 1 < G.Zw) ? __ldg(row + wz + 1) : 0u;
+                bits = __funnelshift_r(lo, hi, sh) & zmask;
+            }
+            const int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int base = 0; base < total; base += 32) {
+                const int kk = base + lane;
+                // source lane = number of lanes whose inclusive count is <= kk (binary search over the scan)
+                int src = 0;
+#pragma unroll
+                for (int stp = 16; stp > 0; stp >>= 1) {
+                    const int probe = src + stp - 1;
+                    const int v = __shfl_sync(0xffffffffu, incl, probe & 31);
+                    if (probe < 32 && v <= kk) src += stp;
+                }
+                src = min(src, 31);
+                const int s_incl = __shfl_sync(0xffffffffu, incl, src);
+                const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
+                uint32_t s_bits = __shfl_sync(0xffffffffu, bits, src);
+                const int s_rx = __shfl_sync(0xffffffffu, rx, src), s_ry = __shfl_sync(0xffffffffu, ry, src);
+                const bool valid = kk < total;
+                int bz = 0;
+                if (valid) {
+                    // position of the nth set bit: clear the n lowest set bits, then find-first-set
+                    int nth = kk - (s_incl - s_cnt);
+                    while (nth-- > 0) s_bits &= s_bits - 1;
+                    bz = __ffs(s_bits) - 1;
+                }
+                visit(valid, W.ix0 + s_rx, W.iy0 + s_ry, zs + bz);
+            }
+        }
+    }
+}
+
+// pose of sample (i, j): position, flatness quaternion, rotation (hpp:456-492)
+__device__ __forceinline__ void sample_pose(const DiscArgs &A, int i, int j, double step, d3 &pos, quat4 &q, rot3 &R) {
+    double cx[6], cy[6], cz[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        cx[k] = __ldg(A.C + 6 * i + k);
+        cy[k] = __ldg(A.C + 6 * A.N + 6 * i + k);
+        cz[k] = __ldg(A.C + 12 * A.N + 6 * i + k);
+    }
+    PieceEval pe;
+    piece_eval(cx, cy, cz, j * step, pe);
+    q = flat_quat_only(A.cfg.fp, pe.vel, pe.acc);
+    pos = pe.pos;
+    R = quat_rot(q);
+}
+
+// hpp:505-551 for one sample given the reduced collision sums; writes the 20 per-sample partials to st[]
+__device__ __forceinline__ void sample_epilogue(const DiscArgs &A, int i, int j, double Ti, double costp, d3 gp,
+                                                double gq0, double gq1, double gq2, double gq3, double *st) {
+    const DevCfg &cfg = A.cfg;
+    const int K = cfg.K;
+    const double frac = 1.0 / K;
+    const double step = Ti * frac;
+    double cx[6], cy[6], cz[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        cx[k] = __ldg(A.C + 6 * i + k);
+        cy[k] = __ldg(A.C + 6 * A.N + 6 * i + k);
+        cz[k] = __ldg(A.C + 12 * A.N + 6 * i + k);
+    }
+    PieceEval pe;
+    piece_eval(cx, cy, cz, j * step, pe);
+    FlatState fs;
+    flat_state(cfg.fp, pe.vel, pe.acc, pe.jer, fs);
+    const quat4 q = flat_quat(fs);
+    const d3 omg = flat_omega(fs);
+    double pena = 0.0;
+    d3 gradVel = mk3(0, 0, 0), gradOmg = mk3(0, 0, 0), gradPos = mk3(0, 0, 0);
+    double gradQuat[4] = {0, 0, 0, 0};
+    if (cfg.flags & ISDF_WITH_DYNAMICS) {
+        const double cos_theta = 1.0 - 2.0 * (q.x * q.x + q.y * q.y);
+        double f, df;
+        if (hinge(dot3(pe.vel, pe.vel) - cfg.vmax2, cfg.mu, f, df)) {
+            const double sc = cfg.wv * df * 2.0;
+            gradVel = mk3(sc * pe.vel.x, sc * pe.vel.y, sc * pe.vel.z); pena += cfg.wv * f;
+        }
+        if (hinge(dot3(omg, omg) - cfg.omgmax2, cfg.mu, f, df)) {
+            const double sc = cfg.womg * df * 2.0;
+            gradOmg = mk3(sc * omg.x, sc * omg.y, sc * omg.z); pena += cfg.womg * f;
+        }
+        if (hinge(acos(cos_theta) - cfg.thetamax, cfg.mu, f, df)) {
+            const double sc = cfg.wtheta * df / sqrt(1.0 - cos_theta * cos_theta) * 4.0;
+            gradQuat[1] += sc * q.x; gradQuat[2] += sc * q.y; pena += cfg.wtheta * f;
+        }
+    }
+    if (costp > 0.0) {  // grad_cost_p returns (costp > 0), hpp:823
+        gradPos = mk3(cfg.wp * gp.x, cfg.wp * gp.y, cfg.wp * gp.z);
+        gradQuat[0] += cfg.wp * gq0; gradQuat[1] += cfg.wp * gq1; gradQuat[2] += cfg.wp * gq2; gradQuat[3] += cfg.wp * gq3;
+        pena += cfg.wp * costp;
+    }
+    d3 gV, gA, gJ;
+    flat_adjoint(cfg.fp, fs, pe.vel, pe.acc, gradQuat, gradOmg, gradVel, gV, gA, gJ);
+    const d3 gP = gradPos;
+    const double node = (j == 0 || j == K) ? 0.5 : 1.0;
+    const double alpha = j * frac;
+    const double w = node * step;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        st[k] = (pe.b0[k] * gP.x + pe.b1[k] * gV.x + pe.b2[k] * gA.x + pe.b3[k] * gJ.x) * w;
+        st[6 + k] = (pe.b0[k] * gP.y + pe.b1[k] * gV.y + pe.b2[k] * gA.y + pe.b3[k] * gJ.y) * w;
+        st[12 + k] = (pe.b0[k] * gP.z + pe.b1[k] * gV.z + pe.b2[k] * gA.z + pe.b3[k] * gJ.z) * w;
+    }
+    st[18] = (dot3(gP, pe.vel) + dot3(gV, pe.acc) + dot3(gA, pe.jer) + dot3(gJ, pe.sna)) * alpha * node * step + node * frac * pena;
+    st[19] = node * step * pena;
+}
+
+// Called by a full warp after the partials of sample s (piece i) are in HBM: take a ticket; the last warp of the
+// piece sums it in ascending sample order, the last piece sums the costs. Deterministic regardless of scheduling.
+__device__ __forceinline__ void piece_finish(const DiscArgs &A, int i, int lane) {
+    const int K = A.cfg.K, N = A.N;
+    __threadfence();
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(A.piece_ticket + i, 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const int first_s = i * (K + 1), last_s = first_s + K;
+    const int f0 = first_s + ((A.rank - first_s) % A.world + A.world) % A.world;  // first local sample >= first_s
+    const int local_cnt = (f0 > last_s) ? 0 : ((last_s - f0) / A.world + 1);
+    if (ticket != local_cnt - 1) return;
+    __threadfence();
+    if (lane < PARTIAL_STRIDE) {
+        double sum = 0.0;
+        int ss = f0;
+        // 8 independent loads in flight per step; the additions stay in ascending-sample order
+        for (; ss + 7 * A.world <= last_s; ss += 8 * A.world) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcg(A.partial + (size_t)(ss + u * A.world) * PARTIAL_STRIDE + lane);
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum += v[u];
+        }
+        for (; ss <= last_s; ss += A.world) sum += __ldcg(A.partial + (size_t)ss * PARTIAL_STRIDE + lane);
+        if (lane < 18) { const int ax = lane / 6, k = lane - 6 * ax; A.out[1 + (size_t)ax * 6 * N + 6 * i + k] = sum; }
+        else if (lane == 18) A.out[1 + 18 * N + i] = sum;
+        else A.piece_cost[i] = sum;
+    }
+    if (lane == 0) A.piece_ticket[i] = 0;
+    __threadfence();
+    int done = 0;
+    if (lane == 0) done = atomicAdd(A.pieces_done, 1);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != N - 1) return;
+    __threadfence();
+    // cost = sum over pieces in ascending order: lanes fetch, every lane adds in the same order
+    double c = 0.0;
+    for (int base = 0; base < N; base += 32) {
+        const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
+        for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
+    }
+    if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; }
+}
+
+// ============================================================================================================================
+// Shared tail of both kernels (one warp = one sample): epilogue on lane 0, publish the partial row, piece ticket.
+__device__ __forceinline__ void sample_finish(const DiscArgs &A, int s, int i, int j, double Ti, const double wsum[8], unsigned npairs,
+                                              double *stage, long long t_begin, unsigned work) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
+        sample_epilogue(A, i, j, Ti, wsum[0], mk3(wsum[1], wsum[2], wsum[3]), wsum[4], wsum[5], wsum[6], wsum[7], stage);
+        if (A.work) A.work[s] = work;       // cost estimate for the next evaluation's longest-first order
+    }
+    __syncwarp();
+    if (lane < PARTIAL_STRIDE) A.partial[(size_t)s * PARTIAL_STRIDE + lane] = stage[lane];
+    if (A.dbg && lane == 0) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = work; }
+    piece_finish(A, i, lane);
+}
+
+// ============================================================================================================================
+// analytic shapes
+__global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_analytic(const __grid_constant__ DiscArgs A) {
     __shared__ uint32_t qA[DISC_WARPS][QCAP];
     __shared__ uint32_t qB[DISC_WARPS][QCAP];
     __shared__ double qBs[DISC_WARPS][QCAP];
@@ -77,35 +298,19 @@ __global__ void __launch_bounds__(DISC_THREADS) k_discrete(const __grid_constant
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const DevCfg &cfg = A.cfg;
-    const int K = cfg.K, N = A.N;
-    const int S = N * (K + 1);
-    // local sample index m -> global sample s = rank + world * m
-    const int M = (S - A.rank + A.world - 1) / A.world;
-    const int m = blockIdx.x * DISC_WARPS + warp;
-    if (m >= M) return;
-    const int s = A.rank + A.world * m;
+    const int K = cfg.K;
+    const int S = A.N * (K + 1);
+    const int M = (S - A.rank + A.world - 1) / A.world;   // local samples; local m -> global s = rank + world * m
+    const int slot = blockIdx.x * DISC_WARPS + warp;
+    if (slot >= M) return;
+    const int s = A.rank + A.world * (A.order ? A.order[slot] : slot);
     const int i = s / (K + 1), j = s - i * (K + 1);
-
-    // ---- pose of this sample (every lane, redundantly: ~300 FP64 ops, no divergence). Only pos / q / R stay live
-    // across the window scan; the epilogue re-derives the rest on one lane to keep register pressure low. -------------
     const double Ti = __ldg(A.T + i);
-    const double frac = 1.0 / K;
-    const double step = Ti * frac;
+    const double step = Ti * (1.0 / K);
+    const long long t_begin = A.dbg ? clock64() : 0;
+
     d3 pos; quat4 q; rot3 R;
-    {
-        double cx[6], cy[6], cz[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            cx[k] = __ldg(A.C + 6 * i + k);
-            cy[k] = __ldg(A.C + 6 * N + 6 * i + k);
-            cz[k] = __ldg(A.C + 12 * N + 6 * i + k);
-        }
-        PieceEval pe;
-        piece_eval(cx, cy, cz, j * step, pe);
-        q = flat_quat_only(cfg.fp, pe.vel, pe.acc);
-        pos = pe.pos;
-        R = quat_rot(q);
-    }
+    sample_pose(A, i, j, step, pos, q, R);
 
     PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned npairs = 0;
@@ -113,25 +318,15 @@ __global__ void __launch_bounds__(DISC_THREADS) k_discrete(const __grid_constant
     if (cfg.flags & ISDF_WITH_COLLISION) {
         const DevGrid &G = A.grid;
         const double h = cfg.half_bd;
-        const int ix0 = grid_axis_index(pos.x - h, G.bmin[0], G.bmax[0], G.res, G.X);
-        const int ix1 = grid_axis_index(pos.x + h, G.bmin[0], G.bmax[0], G.res, G.X);
-        const int iy0 = grid_axis_index(pos.y - h, G.bmin[1], G.bmax[1], G.res, G.Y);
-        const int iy1 = grid_axis_index(pos.y + h, G.bmin[1], G.bmax[1], G.res, G.Y);
-        const int iz0 = grid_axis_index(pos.z - h, G.bmin[2], G.bmax[2], G.res, G.Z);
-        const int iz1 = grid_axis_index(pos.z + h, G.bmin[2], G.bmax[2], G.res, G.Z);
-        const int ny = iy1 - iy0 + 1;
-        const int nrows = (ix1 - ix0 + 1) * ny;
+        const Window W = window_of(G, pos, h);
         int nA = 0, nB = 0;  // queue fill (warp-uniform)
 
+        auto entry_centre = [&](uint32_t e) { return voxel_centre(G, W.ix0 + (int)(e & 0xffu), W.iy0 + (int)((e >> 8) & 0xffu), (int)(e >> 16)); };
         // queue B consumer: finite-difference gradient + accumulation for `cnt` active voxels
         auto drain_B = [&](int cnt) {
             if (lane < cnt) {
-                const uint32_t e = qB[warp][lane];
                 const double sdf = qBs[warp][lane];
-                const d3 ctr = mk3((ix0 + (int)(e & 0xffu) + 0.5) * G.res + G.bmin[0],
-                                   (iy0 + (int)((e >> 8) & 0xffu) + 0.5) * G.res + G.bmin[1],
-                                   ((int)(e >> 16) + 0.5) * G.res + G.bmin[2]);
-                const d3 d = ctr - pos;
+                const d3 d = entry_centre(qB[warp][lane]) - pos;
                 const d3 prel = rot_applyT(R, d);
                 const d3 g = shape_grad_analytic(A.shape, prel, sdf);
                 pair_accumulate(cfg, R, q, d, sdf, g, acc);
@@ -150,19 +345,9 @@ __global__ void __launch_bounds__(DISC_THREADS) k_discrete(const __grid_constant
             bool active = false; uint32_t e = 0; double sdf = 0.0;
             if (lane < cnt) {
                 e = qA[warp][lane];
-                const d3 ctr = mk3((ix0 + (int)(e & 0xffu) + 0.5) * G.res + G.bmin[0],
-                                   (iy0 + (int)((e >> 8) & 0xffu) + 0.5) * G.res + G.bmin[1],
-                                   ((int)(e >> 16) + 0.5) * G.res + G.bmin[2]);
-                const d3 d = ctr - pos;
-                const d3 prel = rot_applyT(R, d);
-                if (MESH) {
-                    d3 g = mk3(0, 0, 0);
-                    sdf = mesh_sdf_grad(A.shape.mesh, prel, cfg.safety, g);
-                    pair_accumulate(cfg, R, q, d, sdf, g, acc);
-                } else {
-                    sdf = shape_sdf_analytic(A.shape, prel);
-                    active = (cfg.safety - sdf) > 0.0;
-                }
+                const d3 prel = rot_applyT(R, entry_centre(e) - pos);
+                sdf = shape_sdf_analytic(A.shape, prel);
+                active = (cfg.safety - sdf) > 0.0;
             }
             __syncwarp();
             const int rest = nA - cnt;
@@ -171,180 +356,118 @@ __global__ void __launch_bounds__(DISC_THREADS) k_discrete(const __grid_constant
             __syncwarp();
             if (lane < rest) qA[warp][lane] = e2;
             nA = rest;
-            if (!MESH) {
-                const unsigned bal = __ballot_sync(0xffffffffu, active);
-                if (active) { const int p = nB + __popc(bal & lt_mask); qB[warp][p] = e; qBs[warp][p] = sdf; }
-                nB += __popc(bal);
-                __syncwarp();
-                if (nB >= 32) drain_B(32);
-            } else {
-                __syncwarp();
-            }
+            const unsigned bal = __ballot_sync(0xffffffffu, active);
+            if (active) { const int p = nB + __popc(bal & lt_mask); qB[warp][p] = e; qBs[warp][p] = sdf; }
+            nB += __popc(bal);
+            __syncwarp();
+            if (nB >= 32) drain_B(32);
         };
 
-        for (int zs = iz0; zs <= iz1; zs += 32) {
-            const int nzc = min(32, iz1 - zs + 1);
-            const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
-            const int wz = zs >> 5, sh = zs & 31;
-            for (int rb = 0; rb < nrows; rb += 32) {
-                const int r = rb + lane;
-                uint32_t bits = 0;
-                int rx = 0, ry = 0;
-                if (r < nrows) {
-                    rx = r / ny; ry = r - rx * ny;
-                    const uint32_t *row = G.bits + ((size_t)(ix0 + rx) * G.Y + (iy0 + ry)) * G.Zw;
-                    const uint32_t lo = __ldg(row + wz);
-                    const uint32_t hi = (sh != 0 && wz + 1 < G.Zw) ? __ldg(row + wz + 1) : 0u;
-                    bits = __funnelshift_r(lo, hi, sh) & zmask;
-                }
-                const int cnt = __popc(bits);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                for (int base = 0; base < total; base += 32) {
-                    const int kk = base + lane;
-                    // source lane = number of lanes whose inclusive count is <= kk (binary search over the scan)
-                    int src = 0;
-#pragma unroll
-                    for (int stp = 16; stp > 0; stp >>= 1) {
-                        const int probe = src + stp - 1;
-                        const int v = __shfl_sync(0xffffffffu, incl, probe & 31);
-                        if (probe < 32 && v <= kk) src += stp;
-                    }
-                    src = min(src, 31);
-                    const int s_incl = __shfl_sync(0xffffffffu, incl, src);
-                    const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
-                    const uint32_t s_bits = __shfl_sync(0xffffffffu, bits, src);
-                    const int s_rx = __shfl_sync(0xffffffffu, rx, src), s_ry = __shfl_sync(0xffffffffu, ry, src);
-                    bool pass = false; uint32_t entry = 0;
-                    if (kk < total) {
-                        const int nth = kk - (s_incl - s_cnt);                 // 0-based rank inside the source row
-                        const int bz = __fns(s_bits, 0, nth + 1);              // position of the nth set bit
-                        const int lz = (zs - 0) + bz;                          // absolute z index
-                        const d3 ctr = mk3((ix0 + s_rx + 0.5) * G.res + G.bmin[0], (iy0 + s_ry + 0.5) * G.res + G.bmin[1],
-                                           (lz + 0.5) * G.res + G.bmin[2]);
-                        const d3 prel = rot_applyT(R, ctr - pos);
-                        pass = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
-                        if (pass) npairs++;
-                        if (MESH && pass) {
-                            // outside the mesh AABB inflated by safety_hor => sdf >= safety_hor => hinge inactive (exact skip)
-                            const DevMesh &Mh = A.shape.mesh;
-                            const double sf = cfg.safety;
-                            if (prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
-                                prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf) pass = false;
-                        }
-                        entry = (uint32_t)s_rx | ((uint32_t)s_ry << 8) | ((uint32_t)lz << 16);
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                    if (pass) qA[warp][nA + __popc(bal & lt_mask)] = entry;
-                    nA += __popc(bal);
-                    __syncwarp();
-                    if (nA >= 32) drain_A(32);
-                }
+        scan_window(G, W, lane, 0, 1, [&](bool valid, int vx, int vy, int vz) {
+            bool pass = false;
+            if (valid) {
+                const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
+                pass = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
             }
-        }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            npairs += __popc(bal);
+            if (pass) qA[warp][nA + __popc(bal & lt_mask)] = (uint32_t)(vx - W.ix0) | ((uint32_t)(vy - W.iy0) << 8) | ((uint32_t)vz << 16);
+            nA += __popc(bal);
+            __syncwarp();
+            if (nA >= 32) drain_A(32);
+        });
         if (nA > 0) drain_A(nA);
-        if (!MESH && nB > 0) drain_B(nB);
+        if (nB > 0) drain_B(nB);
     }
+    // per-warp sums (xor butterfly: fixed order)
+    const double wsum[8] = {warp_sum(acc.c), warp_sum(acc.gx), warp_sum(acc.gy), warp_sum(acc.gz),
+                            warp_sum(acc.q0), warp_sum(acc.q1), warp_sum(acc.q2), warp_sum(acc.q3)};
+    sample_finish(A, s, i, j, Ti, wsum, npairs, stage[warp], t_begin, npairs);
+}
 
-    // ---- reduce the pair sums over the warp ----------------------------------------------------------------------
-    const double costp = warp_sum(acc.c);
-    const d3 gp = mk3(warp_sum(acc.gx), warp_sum(acc.gy), warp_sum(acc.gz));
-    const double gq0 = warp_sum(acc.q0), gq1 = warp_sum(acc.q1), gq2 = warp_sum(acc.q2), gq3 = warp_sum(acc.q3);
-    if (A.pair_counter) {
-        const unsigned tot = __reduce_add_sync(0xffffffffu, npairs);
-        if (lane == 0 && tot) atomicAdd(A.pair_counter, (unsigned long long)tot);
-    }
+// ============================================================================================================================
+// mesh shapes
+__global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
+    __shared__ double stage[DISC_WARPS][PARTIAL_STRIDE];
+    __shared__ WideStack wstack[DISC_WARPS];
 
-    // ---- sample epilogue (hpp:505-551) ----------------------------------------------------------------------------
-    if (lane == 0) {
-        double cx[6], cy[6], cz[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            cx[k] = __ldg(A.C + 6 * i + k);
-            cy[k] = __ldg(A.C + 6 * N + 6 * i + k);
-            cz[k] = __ldg(A.C + 12 * N + 6 * i + k);
-        }
-        PieceEval pe;
-        piece_eval(cx, cy, cz, j * step, pe);
-        FlatState fs;
-        flat_state(cfg.fp, pe.vel, pe.acc, pe.jer, fs);
-        const d3 omg = flat_omega(fs);
-        double pena = 0.0;
-        d3 gradVel = mk3(0, 0, 0), gradOmg = mk3(0, 0, 0), gradPos = mk3(0, 0, 0);
-        double gradQuat[4] = {0, 0, 0, 0};
-        if (cfg.flags & ISDF_WITH_DYNAMICS) {
-            const double cos_theta = 1.0 - 2.0 * (q.x * q.x + q.y * q.y);
-            double f, df;
-            if (hinge(dot3(pe.vel, pe.vel) - cfg.vmax2, cfg.mu, f, df)) {
-                const double sc = cfg.wv * df * 2.0;
-                gradVel = mk3(sc * pe.vel.x, sc * pe.vel.y, sc * pe.vel.z); pena += cfg.wv * f;
-            }
-            if (hinge(dot3(omg, omg) - cfg.omgmax2, cfg.mu, f, df)) {
-                const double sc = cfg.womg * df * 2.0;
-                gradOmg = mk3(sc * omg.x, sc * omg.y, sc * omg.z); pena += cfg.womg * f;
-            }
-            if (hinge(acos(cos_theta) - cfg.thetamax, cfg.mu, f, df)) {
-                const double sc = cfg.wtheta * df / sqrt(1.0 - cos_theta * cos_theta) * 4.0;
-                gradQuat[1] += sc * q.x; gradQuat[2] += sc * q.y; pena += cfg.wtheta * f;
-            }
-        }
-        if (costp > 0.0) {  // grad_cost_p returns (costp > 0), hpp:823
-            gradPos = mk3(cfg.wp * gp.x, cfg.wp * gp.y, cfg.wp * gp.z);
-            gradQuat[0] += cfg.wp * gq0; gradQuat[1] += cfg.wp * gq1; gradQuat[2] += cfg.wp * gq2; gradQuat[3] += cfg.wp * gq3;
-            pena += cfg.wp * costp;
-        }
-        d3 gV, gA, gJ;
-        flat_adjoint(cfg.fp, fs, pe.vel, pe.acc, gradQuat, gradOmg, gradVel, gV, gA, gJ);
-        const d3 gP = gradPos;
-        const double node = (j == 0 || j == K) ? 0.5 : 1.0;
-        const double alpha = j * frac;
-        const double w = node * step;
-        double *st = stage[warp];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            st[k] = (pe.b0[k] * gP.x + pe.b1[k] * gV.x + pe.b2[k] * gA.x + pe.b3[k] * gJ.x) * w;
-            st[6 + k] = (pe.b0[k] * gP.y + pe.b1[k] * gV.y + pe.b2[k] * gA.y + pe.b3[k] * gJ.y) * w;
-            st[12 + k] = (pe.b0[k] * gP.z + pe.b1[k] * gV.z + pe.b2[k] * gA.z + pe.b3[k] * gJ.z) * w;
-        }
-        st[18] = (dot3(gP, pe.vel) + dot3(gV, pe.acc) + dot3(gA, pe.jer) + dot3(gJ, pe.sna)) * alpha * node * step + node * frac * pena;
-        st[19] = node * step * pena;
-    }
-    __syncwarp();
-    if (lane < PARTIAL_STRIDE) A.partial[(size_t)s * PARTIAL_STRIDE + lane] = stage[warp][lane];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const DevCfg &cfg = A.cfg;
+    const DevMesh &Mh = A.shape.mesh;
+    const int K = cfg.K;
+    const int S = A.N * (K + 1);
+    const int M = (S - A.rank + A.world - 1) / A.world;
+    const int slot = blockIdx.x * DISC_WARPS + warp;
+    if (slot >= M) return;
+    const int s = A.rank + A.world * (A.order ? A.order[slot] : slot);
+    const int i = s / (K + 1), j = s - i * (K + 1);
+    const double Ti = __ldg(A.T + i);
+    const double step = Ti * (1.0 / K);
+    const long long t_begin = A.dbg ? clock64() : 0;
 
-    // ---- deterministic reduction: last warp of a piece sums it in ascending-sample order ------------------------
-    __threadfence();
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(A.piece_ticket + i, 1);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    // number of this rank's samples in piece i
-    const int first_s = i * (K + 1), last_s = first_s + K;
-    int f0 = first_s + ((A.rank - first_s) % A.world + A.world) % A.world;  // first local sample >= first_s
-    const int local_cnt = (f0 > last_s) ? 0 : ((last_s - f0) / A.world + 1);
-    if (ticket != local_cnt - 1) return;
-    __threadfence();
-    if (lane < PARTIAL_STRIDE) {
-        double sum = 0.0;
-        for (int ss = f0; ss <= last_s; ss += A.world) sum += __ldcg(A.partial + (size_t)ss * PARTIAL_STRIDE + lane);
-        if (lane < 18) { const int ax = lane / 6, k = lane - 6 * ax; A.out[1 + (size_t)ax * 6 * N + 6 * i + k] = sum; }
-        else if (lane == 18) A.out[1 + 18 * N + i] = sum;
-        else A.piece_cost[i] = sum;
+    d3 pos; quat4 q; rot3 R;
+    sample_pose(A, i, j, step, pos, q, R);
+
+    PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};   // warp-uniform: every lane of a cooperative query holds the same result
+    unsigned npairs = 0, nquery = 0;
+
+    if (cfg.flags & ISDF_WITH_COLLISION) {
+        const DevGrid &G = A.grid;
+        const double h = cfg.half_bd, sf = cfg.safety;
+        const Window W = window_of(G, pos, h);
+        scan_window(G, W, lane, 0, 1, [&](bool valid, int vx, int vy, int vz) {
+            bool pass = false, box = false;
+            if (valid) {
+                const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
+                box = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
+                // exact skips: outside the mesh AABB inflated by safety_hor, or in a cell whose every point is >= safety_hor away
+                int cell;
+                pass = box && !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
+                                prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf) && !mesh_far(Mh, prel, sf, cell);
+            }
+            npairs += __popc(__ballot_sync(0xffffffffu, box));
+            unsigned bal = __ballot_sync(0xffffffffu, pass);
+            while (bal) {   // one surviving voxel at a time, in voxel order
+                const int sl = __ffs(bal) - 1;
+                bal &= bal - 1;
+                nquery++;
+                const int ox = __shfl_sync(0xffffffffu, vx, sl), oy = __shfl_sync(0xffffffffu, vy, sl), oz = __shfl_sync(0xffffffffu, vz, sl);
+                const d3 d = voxel_centre(G, ox, oy, oz) - pos;
+                d3 g = mk3(0, 0, 0);
+                const double sdf = mesh_sdf_grad_warp(Mh, rot_applyT(R, d), sf, g, lane, &wstack[warp]);
+                pair_accumulate(cfg, R, q, d, sdf, g, acc);
+            }
+        });
     }
-    if (lane == 0) A.piece_ticket[i] = 0;
-    __threadfence();
-    int done = 0;
-    if (lane == 0) done = atomicAdd(A.pieces_done, 1);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != N - 1) return;
-    __threadfence();
-    if (lane == 0) {
-        double c = 0.0;
-        for (int p = 0; p < N; p++) c += __ldcg(A.piece_cost + p);
-        A.out[0] = c;
-        *A.pieces_done = 0;
+    const double wsum[8] = {acc.c, acc.gx, acc.gy, acc.gz, acc.q0, acc.q1, acc.q2, acc.q3};
+    sample_finish(A, s, i, j, Ti, wsum, npairs, stage[warp], t_begin, 64u * nquery + npairs);
+}
+
+
+// Longest-first order for the next evaluation: bucket sort of the local samples by the work they reported (descending).
+// Placement inside a bucket uses shared-memory atomics: the order only decides WHICH warp takes WHICH sample, never the
+// arithmetic (partials are reduced in a fixed order), so results stay bit-reproducible. One CTA, ~10 us, off the critical path.
+constexpr int ORDER_BUCKETS = 1024;
+__device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 3, (unsigned)ORDER_BUCKETS - 1u); }
+__global__ void __launch_bounds__(1024) k_order_samples(const unsigned *work, int rank, int world, int M, int *order) {
+    __shared__ int hist[ORDER_BUCKETS];
+    __shared__ int cursor[ORDER_BUCKETS];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int m = threadIdx.x; m < M; m += blockDim.x) atomicAdd(&hist[order_bucket(work[rank + world * m])], 1);
+    __syncthreads();
+    // exclusive scan over buckets in DESCENDING bucket order (warp 0: 32 lanes x 32 buckets each)
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int local = 0;
+        for (int k = 0; k < 32; k++) local += hist[ORDER_BUCKETS - 1 - (lane * 32 + k)];
+        int incl = local;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int run = incl - local;
+        for (int k = 0; k < 32; k++) { const int b = ORDER_BUCKETS - 1 - (lane * 32 + k); cursor[b] = run; run += hist[b]; }
     }
+    __syncthreads();
+    for (int m = threadIdx.x; m < M; m += blockDim.x) order[atomicAdd(&cursor[order_bucket(work[rank + world * m])], 1)] = m;
 }
 
 }  // namespace isdf

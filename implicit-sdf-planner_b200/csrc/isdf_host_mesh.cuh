@@ -16,18 +16,18 @@ namespace isdf {
 
 struct HostMesh {
     std::vector<BvhNode> nodes;
+    std::vector<WideNode> wnodes;
     std::vector<double> tris, pnormals;
-    std::vector<uint32_t> inside;
     int ntris = 0;
     int gdim[3] = {0, 0, 0};
-    double glo[3] = {0, 0, 0}, gcell = 0, sign_radius = 0;
+    double glo[3] = {0, 0, 0}, gcell = 0, ghd = 0, gpad = 0, sign_radius = 0;
     double blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
     DevMesh view() const {  // host pointers; same code path as the device for the bitmap construction
         DevMesh m;
-        m.nodes = nodes.data(); m.tris = tris.data(); m.pnormals = pnormals.data(); m.inside = inside.data();
+        m.nodes = nodes.data(); m.wnodes = wnodes.data(); m.tris = tris.data(); m.pnormals = pnormals.data(); m.cell_dist = nullptr; m.cell_seed = nullptr;
         m.ntris = ntris;
         for (int a = 0; a < 3; a++) { m.gdim[a] = gdim[a]; m.glo[a] = glo[a]; m.blo[a] = blo[a]; m.bhi[a] = bhi[a]; }
-        m.gcell = gcell; m.sign_radius = sign_radius;
+        m.gcell = gcell; m.ghd = ghd; m.gpad = gpad; m.sign_radius = sign_radius;
         return m;
     }
 };
@@ -159,32 +159,63 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
             n.left = code_of(bn[i].left, fat_index); n.right = code_of(bn[i].right, fat_index); n.pad0 = n.pad1 = 0;
         }
     }
-    for (int a = 0; a < 3; a++) { out.blo[a] = bn[0].lo[a]; out.bhi[a] = bn[0].hi[a]; }
-    // inside/outside bitmap over the mesh AABB: cell diagonal = 0.9 * sign_reach (so < sign_reach), capped at 160^3 cells
-    out.sign_radius = 0; out.gcell = 1.0; out.inside.assign(1, 0u);
-    for (int a = 0; a < 3; a++) { out.gdim[a] = 0; out.glo[a] = out.blo[a]; }
-    if (sign_reach > 0) {
-        const double cell = 0.9 * sign_reach / std::sqrt(3.0);
-        long long dims[3]; bool ok = true;
-        for (int a = 0; a < 3; a++) { dims[a] = (long long)std::ceil((out.bhi[a] - out.blo[a]) / cell) + 1; if (dims[a] > 160) ok = false; }
-        if (ok) {
-            out.gcell = cell; out.sign_radius = sign_reach;
-            for (int a = 0; a < 3; a++) out.gdim[a] = (int)dims[a];
-            const size_t nb = (size_t)dims[0] * dims[1] * dims[2];
-            out.inside.assign((nb + 31) / 32, 0u);
-            HostMesh tmp = out; tmp.sign_radius = 0;  // unbounded queries while filling
-            const DevMesh mv = tmp.view();
-            for (int ix = 0; ix < out.gdim[0]; ix++)
-                for (int iy = 0; iy < out.gdim[1]; iy++)
-                    for (int iz = 0; iz < out.gdim[2]; iz++) {
-                        const d3 c = mk3(out.glo[0] + (ix + 0.5) * cell, out.glo[1] + (iy + 0.5) * cell, out.glo[2] + (iz + 0.5) * cell);
-                        d3 g;
-                        if (mesh_sdf_grad(mv, c, 1e300, g) < 0.0) {
-                            const size_t bit = ((size_t)ix * out.gdim[1] + iy) * out.gdim[2] + iz;
-                            out.inside[bit >> 5] |= (1u << (bit & 31));
-                        }
+    // 32-ary nodes: collapse five binary levels per wide level (same leaves, same triangle order)
+    {
+        out.wnodes.clear();
+        struct Job { int bin; int wide; int depth; };
+        std::vector<Job> jobs;
+        out.wnodes.emplace_back();
+        jobs.push_back({0, 0, 1});
+        int max_depth = 1;
+        for (size_t j = 0; j < jobs.size(); j++) {
+            const Job job = jobs[j];
+            max_depth = std::max(max_depth, job.depth);
+            std::vector<int> frontier{job.bin};
+            if (bn[job.bin].left >= 0) {
+                for (int lvl = 0; lvl < 5; lvl++) {
+                    std::vector<int> nxt;
+                    for (int f : frontier) {
+                        if (bn[f].left >= 0) { nxt.push_back(bn[f].left); nxt.push_back(bn[f].right); }
+                        else nxt.push_back(f);
                     }
+                    frontier.swap(nxt);
+                }
+            }
+            WideNode w;
+            for (int k = 0; k < 32; k++) {
+                for (int a = 0; a < 3; a++) { w.lo[a][k] = 1e300; w.hi[a][k] = -1e300; }
+                w.child[k] = WIDE_EMPTY;
+            }
+            for (size_t k = 0; k < frontier.size(); k++) {
+                const auto &b = bn[frontier[k]];
+                for (int a = 0; a < 3; a++) { w.lo[a][k] = b.lo[a]; w.hi[a][k] = b.hi[a]; }
+                if (b.left < 0) w.child[k] = ~(b.first * 8 + (b.count - 1));
+                else {
+                    w.child[k] = (int)out.wnodes.size();
+                    out.wnodes.emplace_back();
+                    jobs.push_back({frontier[k], w.child[k], job.depth + 1});
+                }
+            }
+            out.wnodes[job.wide] = w;
         }
+        if (max_depth > 3) { err = "mesh too large for the 3-level 32-ary tree (more than ~130k triangles)"; return false; }
+    }
+    for (int a = 0; a < 3; a++) { out.blo[a] = bn[0].lo[a]; out.bhi[a] = bn[0].hi[a]; }
+    // cell grid geometry (the per-cell distance / seed arrays are filled by k_mesh_cells on the device):
+    // AABB padded by `pad`, cell edge 0.1 (body-frame metres) or coarser so that no axis exceeds 160 cells.
+    {
+        const double pad = 2.0 * sign_reach + 0.1;   // covers the discrete reach (safety_hor) and the swept one (2*safety_hor+0.1)
+        double ext = 0;
+        for (int a = 0; a < 3; a++) ext = std::max(ext, out.bhi[a] - out.blo[a] + 2 * pad);
+        const double cell = std::max(0.1, ext / 160.0);
+        out.gcell = cell; out.gpad = pad;
+        for (int a = 0; a < 3; a++) {
+            out.glo[a] = out.blo[a] - pad;
+            out.gdim[a] = (int)std::ceil((out.bhi[a] - out.blo[a] + 2 * pad) / cell) + 1;
+        }
+        const double hd = 0.5 * std::sqrt(3.0) * cell;
+        out.ghd = hd * (1.0 + 1e-6) + 1e-5 * std::max(1.0, ext);   // + float rounding of cell_dist
+        out.sign_radius = (2.0 * hd < 0.9 * sign_reach) ? sign_reach : 0.0;
     }
     return true;
 }

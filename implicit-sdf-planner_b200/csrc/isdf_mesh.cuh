@@ -21,16 +21,30 @@ struct BvhNode {       // 112 bytes
     int pad0, pad1;
 };
 
+// 32-ary node for WARP-COOPERATIVE queries: lane i owns child i (SoA boxes => one coalesced 256-byte load per plane).
+// Built by collapsing five levels of the same binary tree, so leaves (<= 4 triangles) and triangle order are shared.
+constexpr int WIDE_EMPTY = 0x7fffffff;
+struct WideNode {           // 1664 bytes
+    double lo[3][32];
+    double hi[3][32];
+    int child[32];          // >= 0: WideNode index; < 0: leaf, ~code with code = first_tri*8 + (count-1); WIDE_EMPTY: unused slot
+};
+
 struct DevMesh {
     const BvhNode *nodes;   // nodes[0] is the root (a single-leaf mesh still gets one node with right = left)
+    const WideNode *wnodes; // wnodes[0] is the root of the 32-ary tree
     const double *tris;     // 9 doubles per triangle in leaf order: a, ab, ac
     const double *pnormals; // 21 doubles per triangle: face, edge ab, edge bc, edge ca, vertex a, b, c
-    const uint32_t *inside; // sign bitmap over [glo, glo + gdim*gcell), bit = 1 -> cell centre inside
+    // body-frame cell grid over the mesh AABB padded by gpad (filled on the device at isdf_set_shape_mesh time):
+    const float *cell_dist;     // signed distance of the cell CENTRE to the mesh
+    const uint32_t *cell_seed;  // triangle (leaf order) nearest to the cell centre: a tight initial bound for queries in the cell
     int ntris;
     int gdim[3];
     double glo[3];
-    double gcell;           // cell edge; cell diagonal < sign_radius
-    double sign_radius;     // a point with no triangle within this distance shares its cell's sign (0 = bitmap unusable)
+    double gcell;           // cell edge
+    double ghd;             // half cell diagonal plus float-rounding slack: sdf(p) >= cell_dist - ghd for every p in the cell
+    double gpad;            // padding of the grid around the AABB: a point outside the grid is at least gpad away
+    double sign_radius;     // a point with no triangle within this distance shares its cell centre's sign (0 = unusable)
     double blo[3], bhi[3];  // mesh AABB
 };
 
@@ -68,26 +82,33 @@ ISDF_HD d3 tri_closest(d3 p, d3 a, d3 ab, d3 ac, int &feat) {
 }
 
 // Exact nearest triangle within sqrt(bound2). Returns squared distance (bound2 if none found; tri = -1).
+// "while-while" traversal: every lane first descends through internal nodes until it holds a leaf, then all lanes of the
+// warp test their leaves together — the long triangle test is not serialised against other lanes' box tests.
 __host__ __device__ inline double mesh_closest(const DevMesh &M, d3 p, double bound2, d3 &cbest, int &tri, int &feat) {
+    constexpr int DONE = 0x7fffffff;
     double best = bound2;
     tri = -1; feat = 0;
-    int stack[48];
-    double stack_d2[48];
+    int stack[40];
+    double stack_d2[40];
     int sp = 0;
-    int cur = 0;
+    int cur = 0;   // node index (>= 0), leaf code (< 0) or DONE
     for (;;) {
-        if (cur >= 0) {
+        while (cur >= 0 && cur != DONE) {
             const BvhNode *nd = M.nodes + cur;
             const double dl = box_dist2(nd->lbox, p), dr = box_dist2(nd->rbox, p);
             const int l = nd->left, r = nd->right;
             const bool hl = dl < best, hr = (dr < best) && (r != l);
             if (hl && hr) {
                 if (dl <= dr) { stack[sp] = r; stack_d2[sp++] = dr; cur = l; } else { stack[sp] = l; stack_d2[sp++] = dl; cur = r; }
-                continue;
+            } else if (hl) cur = l;
+            else if (hr) cur = r;
+            else {
+                cur = DONE;
+                while (sp > 0) { --sp; if (stack_d2[sp] < best) { cur = stack[sp]; break; } }
             }
-            if (hl) { cur = l; continue; }
-            if (hr) { cur = r; continue; }
-        } else {
+        }
+        if (cur == DONE) return best;
+        {
             const int code = ~cur;
             const int first = code >> 2, cnt = (code & 3) + 1;
             for (int t = first; t < first + cnt; t++) {
@@ -99,20 +120,24 @@ __host__ __device__ inline double mesh_closest(const DevMesh &M, d3 p, double bo
                 if (dd < best) { best = dd; cbest = q; tri = t; feat = f; }
             }
         }
-        // pop the next subtree that can still beat the current best
-        do {
-            if (sp == 0) return best;
-            cur = stack[--sp];
-        } while (!(stack_d2[sp] < best));
+        cur = DONE;
+        while (sp > 0) { --sp; if (stack_d2[sp] < best) { cur = stack[sp]; break; } }
     }
 }
 
-ISDF_HD bool mesh_cell_inside(const DevMesh &M, d3 p) {
+ISDF_HD int mesh_cell_index(const DevMesh &M, d3 p) {
     const int ix = (int)floor((p.x - M.glo[0]) / M.gcell), iy = (int)floor((p.y - M.glo[1]) / M.gcell), iz = (int)floor((p.z - M.glo[2]) / M.gcell);
-    if (ix < 0 || iy < 0 || iz < 0 || ix >= M.gdim[0] || iy >= M.gdim[1] || iz >= M.gdim[2]) return false;
-    const size_t bit = ((size_t)ix * M.gdim[1] + iy) * M.gdim[2] + iz;
-    return (M.inside[bit >> 5] >> (bit & 31)) & 1u;
+    if (ix < 0 || iy < 0 || iz < 0 || ix >= M.gdim[0] || iy >= M.gdim[1] || iz >= M.gdim[2]) return -1;
+    return (ix * M.gdim[1] + iy) * M.gdim[2] + iz;
 }
+// true when sdf(q) >= reach for EVERY q in p's cell (SDF is 1-Lipschitz), i.e. a hinge / range test with that reach is
+// exactly inactive. `cell` returns the cell index (-1 outside the grid).
+ISDF_HD bool mesh_far(const DevMesh &M, d3 p, double reach, int &cell) {
+    cell = (M.gdim[0] > 0) ? mesh_cell_index(M, p) : -1;
+    if (cell < 0) return (M.gdim[0] > 0) && (reach <= M.gpad);
+    return (double)M.cell_dist[cell] - M.ghd >= reach;
+}
+ISDF_HD bool mesh_cell_inside(const DevMesh &M, int cell) { return cell >= 0 && M.cell_dist[cell] < 0.0f; }
 
 // getSDFwithGrad1 for the mesh shape (Shape.cpp:139-151): sdf = s * dist, grad = normalise(s * (p - c)).
 // `reach` prunes the search: the caller only needs the value when sdf < reach (pass 1e300 for "always").
@@ -120,15 +145,38 @@ ISDF_HD bool mesh_cell_inside(const DevMesh &M, d3 p) {
 // hinge is inactive) or deep inside (full search).
 __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double reach, d3 &g) {
     d3 c = mk3(0, 0, 0);
-    int tri, feat;
-    double d2;
+    int tri = -1, feat = 0, cell;
     const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+    const bool far = mesh_far(M, p, reach, cell);
+    if (bounded && far) return reach;                                  // exact: every point of this cell is >= reach away
+    // seed: the triangle nearest to the cell centre gives a tight starting bound
+    double seed_d2 = 1e300;
+    if (cell >= 0) {
+        const int st = (int)M.cell_seed[cell];
+        const double *T = M.tris + 9 * (size_t)st;
+        const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), feat);
+        const d3 e = p - q;
+        seed_d2 = dot3(e, e); c = q; tri = st;
+    }
+    double d2;
     if (bounded) {
-        d2 = mesh_closest(M, p, reach * reach, c, tri, feat);
-        if (tri < 0) {
-            if (!mesh_cell_inside(M, p)) return reach;   // outside and at least `reach` away
-            d2 = mesh_closest(M, p, 1e300, c, tri, feat); // deep inside: rare
+        const double r2 = reach * reach;
+        if (seed_d2 < r2) {
+            d3 c2; int t2, f2;
+            d2 = mesh_closest(M, p, seed_d2, c2, t2, f2);
+            if (t2 >= 0) { c = c2; tri = t2; feat = f2; } else d2 = seed_d2;
+        } else {
+            tri = -1;
+            d2 = mesh_closest(M, p, r2, c, tri, feat);
+            if (tri < 0) {
+                if (!mesh_cell_inside(M, cell)) return reach;          // outside and at least `reach` away
+                d2 = mesh_closest(M, p, 1e300, c, tri, feat);          // deep inside: rare
+            }
         }
+    } else if (tri >= 0) {
+        d3 c2; int t2, f2;
+        d2 = mesh_closest(M, p, seed_d2, c2, t2, f2);
+        if (t2 >= 0) { c = c2; tri = t2; feat = f2; } else d2 = seed_d2;
     } else {
         d2 = mesh_closest(M, p, 1e300, c, tri, feat);
     }
@@ -136,6 +184,126 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
     const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
     double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
     if (side == 0.0) {  // on the surface or numerically tangent: fall back to the face normal
+        const double *fn = M.pnormals + 21 * (size_t)tri;
+        side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2];
+    }
+    const double s = (side < 0.0) ? -1.0 : 1.0;
+    g = unit3(s * e);
+    return s * sqrt(d2);
+}
+
+// ---- warp-cooperative exact nearest triangle --------------------------------------------------------------------------
+// Every lane passes the SAME query point; lane i tests child i of the current 32-ary node, leaf triangles are tested
+// 32 at a time (8 leaves x 4 slots), the winner is found with a butterfly arg-min. All lanes return identical results.
+// `stk` is a per-warp shared-memory scratch of WIDE_STACK (node, d2) pairs.
+constexpr int WIDE_STACK = 96;
+struct WideStack { int node[WIDE_STACK]; double d2[WIDE_STACK]; };
+
+__device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bound2, int seed, d3 &cbest, int &tri, int &feat,
+                                               int lane, WideStack *stk) {
+    double best = bound2;
+    tri = -1; feat = 0;
+    if (seed >= 0) {   // every lane evaluates the seed triangle (uniform): a tight bound before the first node is opened
+        const double *T = M.tris + 9 * (size_t)seed;
+        int f;
+        const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+        const d3 e = p - q;
+        const double dd = dot3(e, e);
+        if (dd < best) { best = dd; cbest = q; tri = seed; feat = f; }
+    }
+    int sp = 0;
+    int cur = 0; double cur_d2 = 0.0;
+    for (;;) {
+        if (cur_d2 < best) {
+            const WideNode *nd = M.wnodes + cur;
+            const int ch = nd->child[lane];
+            const double ex = fmax(fmax(nd->lo[0][lane] - p.x, p.x - nd->hi[0][lane]), 0.0);
+            const double ey = fmax(fmax(nd->lo[1][lane] - p.y, p.y - nd->hi[1][lane]), 0.0);
+            const double ez = fmax(fmax(nd->lo[2][lane] - p.z, p.z - nd->hi[2][lane]), 0.0);
+            const double d2 = ex * ex + ey * ey + ez * ez;
+            const bool alive = (ch != WIDE_EMPTY) && (d2 < best);
+            // ---- leaves: 8 per pass, 4 triangle slots each ----------------------------------------------------------------
+            unsigned leafmask = __ballot_sync(0xffffffffu, alive && ch < 0);
+            while (leafmask) {
+                const int grp = lane >> 2, slot = lane & 3;
+                const unsigned src = __fns(leafmask, 0, grp + 1);
+                const int scode = __shfl_sync(0xffffffffu, ch, src & 31);
+                const double sd2 = __shfl_sync(0xffffffffu, d2, src & 31);
+                double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0, t = -1;
+                if (src < 32u) {
+                    const int code = ~scode;
+                    const int first = code >> 3, cnt = (code & 7) + 1;
+                    // leaves of up to 8 triangles: slots 0..3 take triangle slot and slot+4
+                    for (int k = slot; k < cnt; k += 4) {
+                        if (!(sd2 < best)) break;
+                        const double *T = M.tris + 9 * (size_t)(first + k);
+                        int ff;
+                        const d3 qq = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ff);
+                        const d3 e = p - qq;
+                        const double d = dot3(e, e);
+                        if (d < dd) { dd = d; q = qq; f = ff; t = first + k; }
+                    }
+                }
+                if (__any_sync(0xffffffffu, dd < best)) {
+                    double bd = dd; int bl = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                        if (od < bd || (od == bd && ol < bl)) { bd = od; bl = ol; }
+                    }
+                    best = bd;
+                    cbest = mk3(__shfl_sync(0xffffffffu, q.x, bl), __shfl_sync(0xffffffffu, q.y, bl), __shfl_sync(0xffffffffu, q.z, bl));
+                    tri = __shfl_sync(0xffffffffu, t, bl);
+                    feat = __shfl_sync(0xffffffffu, f, bl);
+                }
+                // drop the (up to) 8 leaves just processed
+                const unsigned eighth = __fns(leafmask, 0, 8);
+                leafmask = (eighth >= 32u) ? 0u : (leafmask & ~((2u << eighth) - 1u));
+            }
+            // ---- internal children: push farthest first so the nearest is popped next ---------------------------------
+            unsigned imask = __ballot_sync(0xffffffffu, alive && ch >= 0 && ch != WIDE_EMPTY && d2 < best);
+            while (imask) {
+                const unsigned key = ((imask >> lane) & 1u) ? ((__float_as_uint((float)d2) & ~31u) | (unsigned)lane) : 0u;
+                const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+                const int sl = (int)(kmax & 31u);
+                const int snode = __shfl_sync(0xffffffffu, ch, sl);
+                const double sd2 = __shfl_sync(0xffffffffu, d2, sl);
+                if (lane == 0 && sp < WIDE_STACK) { stk->node[sp] = snode; stk->d2[sp] = sd2; }
+                sp = min(sp + 1, WIDE_STACK);
+                imask &= ~(1u << sl);
+            }
+            __syncwarp();
+        }
+        if (sp == 0) return best;
+        --sp;
+        cur = stk->node[sp]; cur_d2 = stk->d2[sp];
+        __syncwarp();
+    }
+}
+
+// Warp-cooperative getSDFwithGrad1 for the mesh shape — same contract as mesh_sdf_grad, all lanes get the same answer.
+__device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk) {
+    d3 c = mk3(0, 0, 0);
+    int tri, feat, cell;
+    double d2;
+    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+    const bool far = mesh_far(M, p, reach, cell);
+    if (bounded && far) return reach;
+    const int seed = (cell >= 0) ? (int)M.cell_seed[cell] : -1;
+    if (bounded) {
+        d2 = wide_closest(M, p, reach * reach, seed, c, tri, feat, lane, stk);
+        if (tri < 0) {
+            if (!mesh_cell_inside(M, cell)) return reach;
+            d2 = wide_closest(M, p, 1e300, seed, c, tri, feat, lane, stk);
+        }
+    } else {
+        d2 = wide_closest(M, p, 1e300, seed, c, tri, feat, lane, stk);
+    }
+    const d3 e = p - c;
+    const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
+    double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
+    if (side == 0.0) {
         const double *fn = M.pnormals + 21 * (size_t)tri;
         side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2];
     }
