@@ -45,7 +45,8 @@ struct isdf_ctx {
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
     DevBuf<int> d_tickets;       // N piece tickets + 1 pieces_done (+ swept counters)
-    DevBuf<int> d_order; DevBuf<unsigned> d_work;   // longest-first sample order (from the previous evaluation's work)
+    DevBuf<int> d_items, d_item_count, d_split_ticket; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
+    int warp_slots = 148 * 12;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
     DevBuf<unsigned long long> d_counter, d_dbg;
     bool dbg_on = false;
@@ -97,6 +98,12 @@ extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
     CU_TRY(cudaFuncGetAttributes(&fa, (const void *)k_discrete_analytic));
     isdf_ctx *c = new isdf_ctx();
     c->device = device; c->cfg = *cfg;
+    {
+        cudaDeviceProp prop; int nb = 0;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_discrete_mesh, DISC_THREADS, 0) == cudaSuccess && nb > 0)
+            c->warp_slots = prop.multiProcessorCount * nb * DISC_WARPS;
+    }
     std::memset(&c->stats, 0, sizeof(c->stats));
     std::memset(&c->grid, 0, sizeof(c->grid));
     std::memset(&c->shape, 0, sizeof(c->shape));
@@ -124,7 +131,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     cudaStreamSynchronize(c->stream);
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_cell_dist.release(); c->d_cell_seed.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
-    c->d_tickets.release(); c->d_counter.release(); c->d_order.release(); c->d_work.release(); c->d_dbg.release();
+    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_split_ticket.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -173,6 +180,7 @@ extern "C" int isdf_set_shape_analytic(isdf_ctx *c, int kind, const double *para
     for (int i = 0; i < nparams; i++) c->shape.par[i] = params[i];
     shape_common(c, rot, trans);
     c->have_shape = true;
+    c->order_for = -1;   // work items of another shape class may carry split slots
     return 0;
 }
 
@@ -247,6 +255,7 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
     m.cell_dist = c->d_cell_dist.p; m.cell_seed = c->d_cell_seed.p;
     c->shape.mesh = m;
     c->have_shape = true;
+    c->order_for = -1;
     return 0;
 }
 
@@ -413,14 +422,26 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
     // longest-first order from the previous evaluation of the same problem shape (first evaluation: natural order)
     const long long sig = ((long long)N << 20) ^ ((long long)c->rank << 10) ^ c->world ^ ((long long)K << 40);
-    CU_TRY(c->d_work.ensure((size_t)S)); CU_TRY(c->d_order.ensure((size_t)M));
+    const int max_split = (c->shape.kind == ISDF_SHAPE_MESH) ? (int)(M / 8 + 1) : 0;   // only mesh samples have a heavy tail worth splitting
+    const size_t max_items = (size_t)M + (size_t)(ROW_CLASSES - 1) * max_split;
+    CU_TRY(c->d_work.ensure((size_t)S));
+    if (c->d_items.n < 3 * max_items + (size_t)M) { CU_TRY(c->d_items.ensure(3 * max_items + (size_t)M)); c->order_for = -1; }   // a regrown table holds no items yet
+    CU_TRY(c->d_item_count.ensure(1));
+    CU_TRY(c->d_subsum.ensure((size_t)max_split * ROW_CLASSES * 8));
+    if (c->d_split_ticket.n < (size_t)max_split) {
+        CU_TRY(c->d_split_ticket.ensure((size_t)max_split)); CU_TRY(c->d_split_work.ensure((size_t)max_split));
+        CU_TRY(cudaMemsetAsync(c->d_split_ticket.p, 0, sizeof(int) * max_split, st));
+        CU_TRY(cudaMemsetAsync(c->d_split_work.p, 0, sizeof(unsigned) * max_split, st));
+    }
     A.work = c->d_work.p;
-    A.order = (c->order_for == sig) ? c->d_order.p : nullptr;
-    const unsigned grid = (unsigned)((M + DISC_WARPS - 1) / DISC_WARPS);
+    const bool have_items = (c->order_for == sig);
+    A.items = have_items ? c->d_items.p : nullptr;
+    A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_ticket = c->d_split_ticket.p; A.split_work = c->d_split_work.p;
+    const unsigned grid = (unsigned)(((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS);
     if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
     else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
     // off the result's critical path: the caller can already read d_out when this finishes on the same stream
-    k_order_samples<<<1, 1024, 0, st>>>(c->d_work.p, c->rank, c->world, (int)M, c->d_order.p);
+    k_build_items<<<1, 1024, 0, st>>>(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots, c->d_items.p, c->d_item_count.p);
     c->order_for = sig;
     c->stats.kernel_launches++;
     c->stats.kernel_launches++;

@@ -8,9 +8,11 @@
 //   * the pose window is read from the BIT-packed occupancy: lane = (x,y) row, one or two 32-bit loads + funnel
 //     shift give the row's z-run; a warp prefix sum over popcounts enumerates only the occupied voxels
 //     (the reference tests every voxel and heap-allocates a vector per sample, hpp:787);
-//   * one WARP per pose sample, processed in longest-first order: the per-sample work measured in the previous
-//     evaluation (an optimiser moves the trajectory only a little between steps) sorts the samples so the heavy ones —
-//     poses grazing an obstacle — start first and the tail of the launch is made of cheap samples;
+//   * work items, longest first: the per-sample work measured in the previous evaluation (an optimiser moves the
+//     trajectory only a little between steps) sorts the samples, and a sample that grazes an obstacle (dozens of mesh
+//     queries) is split into ROW_CLASSES items — window rows r with r % ROW_CLASSES == c — taken by different warps.
+//     The per-sample sum is ALWAYS formed class by class in the same order, whether one warp walks all classes or
+//     eight warps take one each, so the split never changes a bit of the result;
 //   * k_discrete_analytic — two warp-level compaction queues keep lanes dense: queue A = voxels inside the body-frame
 //     cull box, queue B = voxels whose hinge is active (sdf < safety_hor) and therefore need the 6 extra finite-
 //     difference SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87). Evaluating those only for active voxels is exact
@@ -29,6 +31,8 @@ namespace isdf {
 constexpr int DISC_WARPS = 4;
 constexpr int DISC_THREADS = DISC_WARPS * 32;
 constexpr int QCAP = 64;
+constexpr int ROW_CLASSES = 8;          // a pose window's rows are summed in 8 interleaved classes (canonical order)
+constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than this (work units: 64 per mesh query + 1 per culled pair)
 // CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md): the analytic kernel
 // is fastest at 4 (128 regs), the mesh kernel at 3 (168 regs; forcing more spills the cooperative BVH search and is slower)
 constexpr int ANALYTIC_MIN_BLOCKS = 4;
@@ -48,7 +52,11 @@ struct DiscArgs {
     double *out;           // 19N+1: cost | gradC | gradT
     unsigned long long *pair_counter;  // may be null
     unsigned long long *dbg;           // may be null: per sample {cycles, pairs, queries}
-    const int *order;                  // may be null: order[m] = local sample index processed by warp m (longest first)
+    const int *items;                  // may be null: 3 ints per work item {local sample m, row class or -1 = all, split slot or -1}
+    const int *item_count;             // number of valid items (device)
+    double *subsum;                    // split slot x ROW_CLASSES x 8 class sums
+    int *split_ticket;                 // split slot -> arrivals (zero on entry, zero on exit)
+    unsigned *split_work;              // split slot -> work accumulated by the parts
     unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
     int rank, world;       // this launch evaluates samples s with s % world == rank
 };
@@ -96,17 +104,19 @@ __device__ __forceinline__ d3 voxel_centre(const DevGrid &G, int ix, int iy, int
 
 // Enumerate the occupied voxels of a window, 32 at a time, in the reference's order (x, then y, then z ascending).
 // visit(valid, ix, iy, iz) is called by the whole warp; lanes without a voxel pass valid = false.
-// The row batches are dealt round-robin: this warp takes batches first_batch, first_batch + batch_stride, ...
+// cls >= 0: only the rows of that class are visited (row r = cls + ROW_CLASSES * k); cls < 0: every row.
+// visit additionally receives the row index r (row class = r % ROW_CLASSES).
 template <class Visit>
-__device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, int lane, int first_batch, int batch_stride, Visit &&visit) {
+__device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, int lane, int cls, Visit &&visit) {
     const int ny = W.iy1 - W.iy0 + 1;
     const int nrows = (W.ix1 - W.ix0 + 1) * ny;
     for (int zs = W.iz0; zs <= W.iz1; zs += 32) {
         const int nzc = min(32, W.iz1 - zs + 1);
         const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
         const int wz = zs >> 5, sh = zs & 31;
-        for (int rb = 32 * first_batch; rb < nrows; rb += 32 * batch_stride) {
-            const int r = rb + lane;
+        const int rstep = cls < 0 ? 1 : ROW_CLASSES, rfirst = cls < 0 ? 0 : cls;
+        for (int rb = 0; rfirst + rstep * rb < nrows; rb += 32) {
+            const int r = rfirst + rstep * (rb + lane);
             uint32_t bits = 0;
             int rx = 0, ry = 0;
             if (r < nrows) {
@@ -136,6 +146,7 @@ __device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, i
                 const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
                 uint32_t s_bits = __shfl_sync(0xffffffffu, bits, src);
                 const int s_rx = __shfl_sync(0xffffffffu, rx, src), s_ry = __shfl_sync(0xffffffffu, ry, src);
+                const int s_r = __shfl_sync(0xffffffffu, r, src);
                 const bool valid = kk < total;
                 int bz = 0;
                 if (valid) {
@@ -144,7 +155,7 @@ __device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, i
                     while (nth-- > 0) s_bits &= s_bits - 1;
                     bz = __ffs(s_bits) - 1;
                 }
-                visit(valid, W.ix0 + s_rx, W.iy0 + s_ry, zs + bz);
+                visit(valid, W.ix0 + s_rx, W.iy0 + s_ry, zs + bz, s_r);
             }
         }
     }
@@ -272,13 +283,51 @@ __device__ __forceinline__ void piece_finish(const DiscArgs &A, int i, int lane)
 }
 
 // ============================================================================================================================
-// Shared tail of both kernels (one warp = one sample): epilogue on lane 0, publish the partial row, piece ticket.
-__device__ __forceinline__ void sample_finish(const DiscArgs &A, int s, int i, int j, double Ti, const double wsum[8], unsigned npairs,
+// Work item of this warp: {global sample, first class, one-past-last class, split slot}. Returns false when there is none.
+struct Item { int s, c0, c1, hslot; };
+__device__ __forceinline__ bool fetch_item(const DiscArgs &A, Item &it) {
+    const int K = A.cfg.K;
+    const int S = A.N * (K + 1);
+    const int M = (S - A.rank + A.world - 1) / A.world;   // local samples; local m -> global s = rank + world * m
+    const int slot = blockIdx.x * DISC_WARPS + (threadIdx.x >> 5);
+    if (A.items) {
+        if (slot >= __ldg(A.item_count)) return false;
+        const int m = __ldg(A.items + 3 * slot), part = __ldg(A.items + 3 * slot + 1);
+        it.s = A.rank + A.world * m;
+        it.c0 = part < 0 ? 0 : part; it.c1 = part < 0 ? ROW_CLASSES : part + 1;
+        it.hslot = __ldg(A.items + 3 * slot + 2);
+        return true;
+    }
+    if (slot >= M) return false;
+    it.s = A.rank + A.world * slot; it.c0 = 0; it.c1 = ROW_CLASSES; it.hslot = -1;
+    return true;
+}
+
+// Shared tail of both kernels. Whole-sample item: `tot` already holds the class sums added in class order. Split item:
+// publish this class's sums; the LAST part to arrive adds the ROW_CLASSES class sums in the same order and finishes.
+__device__ __forceinline__ void sample_finish(const DiscArgs &A, const Item &it, int i, int j, double Ti, double tot[8], unsigned npairs,
                                               double *stage, long long t_begin, unsigned work) {
     const int lane = threadIdx.x & 31;
+    const int s = it.s;
+    if (lane == 0 && A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
+    if (it.hslot >= 0) {
+        double *sub = A.subsum + ((size_t)it.hslot * ROW_CLASSES + it.c0) * 8;
+        if (lane < 8) sub[lane] = tot[lane];
+        if (lane == 0) atomicAdd(A.split_work + it.hslot, work);
+        __threadfence();
+        int t = 0;
+        if (lane == 0) t = atomicAdd(A.split_ticket + it.hslot, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t != ROW_CLASSES - 1) return;
+        __threadfence();
+        const double *all = A.subsum + (size_t)it.hslot * ROW_CLASSES * 8;
+#pragma unroll
+        for (int v = 0; v < 8; v++) { double a = 0.0; for (int c = 0; c < ROW_CLASSES; c++) a += __ldcg(all + c * 8 + v); tot[v] = a; }
+        work = __ldcg(A.split_work + it.hslot);
+        if (lane == 0) { A.split_ticket[it.hslot] = 0; A.split_work[it.hslot] = 0; }
+    }
     if (lane == 0) {
-        if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
-        sample_epilogue(A, i, j, Ti, wsum[0], mk3(wsum[1], wsum[2], wsum[3]), wsum[4], wsum[5], wsum[6], wsum[7], stage);
+        sample_epilogue(A, i, j, Ti, tot[0], mk3(tot[1], tot[2], tot[3]), tot[4], tot[5], tot[6], tot[7], stage);
         if (A.work) A.work[s] = work;       // cost estimate for the next evaluation's longest-first order
     }
     __syncwarp();
@@ -299,11 +348,9 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
     const unsigned lt_mask = (1u << lane) - 1u;
     const DevCfg &cfg = A.cfg;
     const int K = cfg.K;
-    const int S = A.N * (K + 1);
-    const int M = (S - A.rank + A.world - 1) / A.world;   // local samples; local m -> global s = rank + world * m
-    const int slot = blockIdx.x * DISC_WARPS + warp;
-    if (slot >= M) return;
-    const int s = A.rank + A.world * (A.order ? A.order[slot] : slot);
+    Item it;
+    if (!fetch_item(A, it)) return;
+    const int s = it.s;
     const int i = s / (K + 1), j = s - i * (K + 1);
     const double Ti = __ldg(A.T + i);
     const double step = Ti * (1.0 / K);
@@ -312,13 +359,14 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
     d3 pos; quat4 q; rot3 R;
     sample_pose(A, i, j, step, pos, q, R);
 
-    PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};
+    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned npairs = 0;
 
     if (cfg.flags & ISDF_WITH_COLLISION) {
         const DevGrid &G = A.grid;
         const double h = cfg.half_bd;
         const Window W = window_of(G, pos, h);
+        PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};
         int nA = 0, nB = 0;  // queue fill (warp-uniform)
 
         auto entry_centre = [&](uint32_t e) { return voxel_centre(G, W.ix0 + (int)(e & 0xffu), W.iy0 + (int)((e >> 8) & 0xffu), (int)(e >> 16)); };
@@ -363,7 +411,7 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
             if (nB >= 32) drain_B(32);
         };
 
-        scan_window(G, W, lane, 0, 1, [&](bool valid, int vx, int vy, int vz) {
+        scan_window(G, W, lane, -1, [&](bool valid, int vx, int vy, int vz, int) {
             bool pass = false;
             if (valid) {
                 const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
@@ -378,11 +426,11 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
         });
         if (nA > 0) drain_A(nA);
         if (nB > 0) drain_B(nB);
+        // xor butterfly: fixed order (analytic samples are never split: their work is near-uniform)
+        tot[0] = warp_sum(acc.c); tot[1] = warp_sum(acc.gx); tot[2] = warp_sum(acc.gy); tot[3] = warp_sum(acc.gz);
+        tot[4] = warp_sum(acc.q0); tot[5] = warp_sum(acc.q1); tot[6] = warp_sum(acc.q2); tot[7] = warp_sum(acc.q3);
     }
-    // per-warp sums (xor butterfly: fixed order)
-    const double wsum[8] = {warp_sum(acc.c), warp_sum(acc.gx), warp_sum(acc.gy), warp_sum(acc.gz),
-                            warp_sum(acc.q0), warp_sum(acc.q1), warp_sum(acc.q2), warp_sum(acc.q3)};
-    sample_finish(A, s, i, j, Ti, wsum, npairs, stage[warp], t_begin, npairs);
+    sample_finish(A, it, i, j, Ti, tot, npairs, stage[warp], t_begin, npairs);
 }
 
 // ============================================================================================================================
@@ -390,16 +438,15 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
 __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
     __shared__ double stage[DISC_WARPS][PARTIAL_STRIDE];
     __shared__ WideStack wstack[DISC_WARPS];
+    __shared__ double cacc[DISC_WARPS][ROW_CLASSES][8];   // per-warp class accumulators
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const DevCfg &cfg = A.cfg;
     const DevMesh &Mh = A.shape.mesh;
     const int K = cfg.K;
-    const int S = A.N * (K + 1);
-    const int M = (S - A.rank + A.world - 1) / A.world;
-    const int slot = blockIdx.x * DISC_WARPS + warp;
-    if (slot >= M) return;
-    const int s = A.rank + A.world * (A.order ? A.order[slot] : slot);
+    Item it;
+    if (!fetch_item(A, it)) return;
+    const int s = it.s;
     const int i = s / (K + 1), j = s - i * (K + 1);
     const double Ti = __ldg(A.T + i);
     const double step = Ti * (1.0 / K);
@@ -408,14 +455,19 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
     d3 pos; quat4 q; rot3 R;
     sample_pose(A, i, j, step, pos, q, R);
 
-    PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};   // warp-uniform: every lane of a cooperative query holds the same result
+    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned npairs = 0, nquery = 0;
 
     if (cfg.flags & ISDF_WITH_COLLISION) {
         const DevGrid &G = A.grid;
         const double h = cfg.half_bd, sf = cfg.safety;
         const Window W = window_of(G, pos, h);
-        scan_window(G, W, lane, 0, 1, [&](bool valid, int vx, int vy, int vz) {
+        const bool whole = (it.c1 - it.c0) == ROW_CLASSES;
+        if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) cacc[warp][c][lane] = 0.0;
+        __syncwarp();
+        // whole sample: one pass over all rows, contributions filed by row class; split part: only this class's rows.
+        // Either way a class sum adds the same terms in the same (row, z) order.
+        scan_window(G, W, lane, whole ? -1 : it.c0, [&](bool valid, int vx, int vy, int vz, int vr) {
             bool pass = false, box = false;
             if (valid) {
                 const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
@@ -432,32 +484,72 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 bal &= bal - 1;
                 nquery++;
                 const int ox = __shfl_sync(0xffffffffu, vx, sl), oy = __shfl_sync(0xffffffffu, vy, sl), oz = __shfl_sync(0xffffffffu, vz, sl);
+                const int cls = __shfl_sync(0xffffffffu, vr, sl) % ROW_CLASSES;
                 const d3 d = voxel_centre(G, ox, oy, oz) - pos;
                 d3 g = mk3(0, 0, 0);
                 const double sdf = mesh_sdf_grad_warp(Mh, rot_applyT(R, d), sf, g, lane, &wstack[warp]);
-                pair_accumulate(cfg, R, q, d, sdf, g, acc);
+                PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};   // identical on every lane
+                pair_accumulate(cfg, R, q, d, sdf, g, one);
+                if (lane < 8 && one.c > 0.0) {
+                    const double v = lane == 0 ? one.c : lane == 1 ? one.gx : lane == 2 ? one.gy : lane == 3 ? one.gz :
+                                     lane == 4 ? one.q0 : lane == 5 ? one.q1 : lane == 6 ? one.q2 : one.q3;
+                    cacc[warp][cls][lane] += v;
+                }
             }
         });
+        __syncwarp();
+        // sample (or part) total: class sums added in class order
+        double mine = 0.0;
+        if (lane < 8) for (int c = it.c0; c < it.c1; c++) mine += cacc[warp][c][lane];
+#pragma unroll
+        for (int v = 0; v < 8; v++) tot[v] = __shfl_sync(0xffffffffu, mine, v);
     }
-    const double wsum[8] = {acc.c, acc.gx, acc.gy, acc.gz, acc.q0, acc.q1, acc.q2, acc.q3};
-    sample_finish(A, s, i, j, Ti, wsum, npairs, stage[warp], t_begin, 64u * nquery + npairs);
+    sample_finish(A, it, i, j, Ti, tot, npairs, stage[warp], t_begin, 64u * nquery + npairs);
 }
 
 
-// Longest-first order for the next evaluation: bucket sort of the local samples by the work they reported (descending).
-// Placement inside a bucket uses shared-memory atomics: the order only decides WHICH warp takes WHICH sample, never the
-// arithmetic (partials are reduced in a fixed order), so results stay bit-reproducible. One CTA, ~10 us, off the critical path.
+// Work items for the next evaluation: bucket sort by reported work, descending. A sample is split into ROW_CLASSES items
+// (work/ROW_CLASSES each) only when it alone would outlast the launch's balanced share: work > 0.7 * total / warp_slots —
+// with one GPU almost nothing is split (splitting costs redundant pose + sparse row scans), with the samples sharded
+// over 8 GPUs the same trajectory has 8x less work per GPU and its heavy samples are spread over 8 warps each. Placement inside a bucket uses
+// shared-memory atomics: the order only decides WHICH warp takes WHICH item, never the arithmetic, so results stay
+// bit-reproducible. One CTA, ~10 us, off the critical path of the evaluation that produced `work`.
 constexpr int ORDER_BUCKETS = 1024;
 __device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 3, (unsigned)ORDER_BUCKETS - 1u); }
-__global__ void __launch_bounds__(1024) k_order_samples(const unsigned *work, int rank, int world, int M, int *order) {
+__global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots,
+                                                      int *items, int *item_count) {
     __shared__ int hist[ORDER_BUCKETS];
     __shared__ int cursor[ORDER_BUCKETS];
+    __shared__ int nsplit;
+    __shared__ unsigned long long total_work;
+    __shared__ unsigned split_work;
     hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { nsplit = 0; total_work = 0ull; }
     __syncthreads();
-    for (int m = threadIdx.x; m < M; m += blockDim.x) atomicAdd(&hist[order_bucket(work[rank + world * m])], 1);
+    {
+        unsigned long long mine = 0ull;
+        for (int m = threadIdx.x; m < M; m += blockDim.x) mine += work[rank + world * m];
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&total_work, mine);
+    }
     __syncthreads();
-    // exclusive scan over buckets in DESCENDING bucket order (warp 0: 32 lanes x 32 buckets each)
-    if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+        const unsigned long long t = (total_work * 7ull) / (10ull * (unsigned long long)max(warp_slots, 1));
+        split_work = (unsigned)min(max(t, (unsigned long long)SPLIT_WORK_MIN), 0xffffffffull);
+    }
+    __syncthreads();
+    const unsigned SPLIT_WORK = split_work;
+    // pass 1: decide splits (first come first served up to max_split), histogram the item keys
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const unsigned w = work[rank + world * m];
+        int hs = -1;
+        if (w >= SPLIT_WORK) { hs = atomicAdd(&nsplit, 1); if (hs >= max_split) hs = -1; }
+        if (hs >= 0) atomicAdd(&hist[order_bucket(w / ROW_CLASSES)], ROW_CLASSES);
+        else atomicAdd(&hist[order_bucket(w)], 1);
+        items[3 * (size_t)(M + (ROW_CLASSES - 1) * max_split) + m] = hs;   // scratch behind the item table
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {   // exclusive scan over buckets in DESCENDING bucket order
         const int lane = threadIdx.x;
         int local = 0;
         for (int k = 0; k < 32; k++) local += hist[ORDER_BUCKETS - 1 - (lane * 32 + k)];
@@ -465,9 +557,20 @@ __global__ void __launch_bounds__(1024) k_order_samples(const unsigned *work, in
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         int run = incl - local;
         for (int k = 0; k < 32; k++) { const int b = ORDER_BUCKETS - 1 - (lane * 32 + k); cursor[b] = run; run += hist[b]; }
+        if (lane == 31) *item_count = run;
     }
     __syncthreads();
-    for (int m = threadIdx.x; m < M; m += blockDim.x) order[atomicAdd(&cursor[order_bucket(work[rank + world * m])], 1)] = m;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const unsigned w = work[rank + world * m];
+        const int hs = items[3 * (size_t)(M + (ROW_CLASSES - 1) * max_split) + m];
+        if (hs >= 0) {
+            const int pos = atomicAdd(&cursor[order_bucket(w / ROW_CLASSES)], ROW_CLASSES);
+            for (int c = 0; c < ROW_CLASSES; c++) { items[3 * (pos + c)] = m; items[3 * (pos + c) + 1] = c; items[3 * (pos + c) + 2] = hs; }
+        } else {
+            const int pos = atomicAdd(&cursor[order_bucket(w)], 1);
+            items[3 * pos] = m; items[3 * pos + 1] = -1; items[3 * pos + 2] = -1;
+        }
+    }
 }
 
 }  // namespace isdf

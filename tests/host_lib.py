@@ -1,0 +1,64 @@
+"""ctypes binding of implicit-sdf-planner_b200/host/libisdf_host.so (the C++ host adapters' test hooks)."""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "implicit-sdf-planner_b200", "host", "libisdf_host.so")
+dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        import isdf_b200 as I
+        I.load_library()   # libisdf_b200.so first (rpath also finds it)
+        L = C.CDLL(LIB)
+        L.isdf_host_minco_forward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
+        L.isdf_host_minco_backward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
+        L.isdf_host_backend_create.restype = C.c_void_p
+        L.isdf_host_backend_create.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_double, C.c_int, C.c_int]
+        L.isdf_host_backend_cost.restype = C.c_double
+        L.isdf_host_backend_cost.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.isdf_host_backend_last.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_int)]
+        L.isdf_host_backend_destroy.argtypes = [C.c_void_p]
+        L.isdf_host_tau_maps.argtypes = [dp, C.c_int, dp, dp]
+        L.isdf_host_shape_sdf_grad.restype = C.c_double
+        L.isdf_host_shape_sdf_grad.argtypes = [C.c_void_p, dp, dp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def minco_forward(head, tail, inPs, T):
+    T = f(T).reshape(-1)
+    N = T.size
+    h, t, ip = np.asfortranarray(f(head)), np.asfortranarray(f(tail)), np.asfortranarray(f(inPs).reshape(3, -1))
+    co, gc, gt, e = np.zeros(18 * N), np.zeros(18 * N), np.zeros(N), C.c_double(0)
+    lib().isdf_host_minco_forward(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(co), C.byref(e), _p(gc), _p(gt))
+    return co, e.value, gc, gt
+
+
+def minco_backward(head, tail, inPs, T, gradC, gradT):
+    T = f(T).reshape(-1)
+    N = T.size
+    h, t, ip = np.asfortranarray(f(head)), np.asfortranarray(f(tail)), np.asfortranarray(f(inPs).reshape(3, -1))
+    gp, gt = np.zeros((3, N - 1), order="F"), np.zeros(N)
+    lib().isdf_host_minco_backward(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(f(gradC)), _p(f(gradT)),
+                                   gp.ctypes.data_as(dp), _p(gt))
+    return gp, gt
+
+
+def tau_maps(tau):
+    tau = f(tau)
+    T, back = np.zeros_like(tau), np.zeros_like(tau)
+    lib().isdf_host_tau_maps(_p(tau), tau.size, _p(T), _p(back))
+    return T, back

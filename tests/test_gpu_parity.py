@@ -347,3 +347,56 @@ def test_swept_golden_fixture():
         got = ev.eval_swept(z["T"], z["C"])
         check_eval(got, (float(z[f"{name}_cost"]), z[f"{name}_gradC"], z[f"{name}_gradT"]), what=name)
     ev.close()
+
+
+# ---- host adapters: the reference's callback / plug-in surface on top of the C ABI ------------------------------------------------
+def test_lmbm_callback_matches_oracle_composition():
+    """BackEnd::costFunctionLmbm (lmbm_evaluate_t) == forwardT/P -> MINCO -> energy -> swept + time-integral -> propogateGrad ->
+    rho*sum(T) -> backwardGradT/P assembled from the oracle's pieces (back_end_optimizer.hpp:358-430)."""
+    import ctypes as CT
+    import host_lib as H
+    cfg, T0, Cc, pts = sv_case(seed=5, npts=300)
+    cfg.flags = I.WITH_DYNAMICS                       # the live reference: collision only through the swept-volume term
+    cfg.vmax, cfg.omgmax = 1.2, 0.5                   # make the dynamic penalties active
+    N = T0.size
+    wp = W.random_walk_waypoints(N, [0, 0, 0], [50, 50, 34], seed=5)
+    head, tail = np.zeros((3, 3)), np.zeros((3, 3))
+    head[:, 0], tail[:, 0] = wp[0], wp[-1]
+    rng = np.random.default_rng(1)
+    tau = rng.normal(size=N) * 0.5 + 1.0
+    x = np.concatenate([tau, wp[1:-1].reshape(-1)])
+    rho = 20.0
+    # oracle composition
+    Tt = np.where(tau > 0, (0.5 * tau + 1) * tau + 1, 1 / ((0.5 * tau - 1) * tau + 1))
+    co, energy, gC, gT = O.minco_forward(head, tail, wp[1:-1].T, Tt)
+    osh = O.Shape.named("Torus")
+    sv = O.eval_swept(O.config_from(cfg), osh, Tt, co, pts)
+    di = O.eval_discrete(O.config_from(cfg), None, BMIN, 1.0, None, Tt, co)
+    cost = energy + sv["cost"] + di[0] + rho * Tt.sum()
+    gp, gt = O.minco_backward(head, tail, wp[1:-1].T, Tt, gC + sv["gradC"] + di[1], gT + sv["gradT"] + di[2])
+    gt = gt + rho
+    gtau = np.where(tau > 0, gt * (tau + 1), gt * (1 - tau) / ((0.5 * tau - 1) * tau + 1) ** 2)
+    g_ref = np.concatenate([gtau, gp.T.reshape(-1)])
+    # product
+    ev = I.Evaluator(cfg)
+    ev.set_shape_named("Torus")
+    ev.set_points(pts)
+    L = H.lib()
+    hh, tt = np.asfortranarray(head), np.asfortranarray(tail)
+    be = L.isdf_host_backend_create(ev.h, N, hh.ctypes.data_as(H.dp), tt.ctypes.data_as(H.dp), rho, 1, 1)
+    g = np.zeros_like(x)
+    c = L.isdf_host_backend_cost(be, x.ctypes.data_as(H.dp), g.ctypes.data_as(H.dp), x.size)
+    cp, cother, ctot, st = CT.c_double(), CT.c_double(), CT.c_double(), CT.c_int()
+    L.isdf_host_backend_last(be, CT.byref(cp), CT.byref(cother), CT.byref(ctot), CT.byref(st))
+    L.isdf_host_backend_destroy(be)
+    assert st.value == 0 and ctot.value == c
+    assert abs(c - cost) <= 1e-6 * abs(cost), (c, cost)
+    assert abs(cp.value - sv["cost"]) <= 1e-6 * max(abs(sv["cost"]), 1.0)
+    assert rel_l2(g, g_ref) <= 1e-6
+    # the single-point plug-in call goes through the same device SDF
+    gr = np.zeros(3)
+    p = np.array([1.0, 0.4, -0.2])
+    s = L.isdf_host_shape_sdf_grad(ev.h, p.ctypes.data_as(H.dp), gr.ctypes.data_as(H.dp))
+    os_, og = osh.query(p[None])
+    assert abs(s - os_[0]) < 1e-12 and np.allclose(gr, og[0], atol=1e-8)
+    ev.close()

@@ -1,0 +1,40 @@
+"""Host-side C++ adapters (no GPU needed): the product's MINCO port against the oracle's and a dense numpy solve, and the
+tau <-> T decision-variable maps (back_end_optimizer.hpp:214-256)."""
+import numpy as np
+import host_lib as H
+import oracle_lib as O
+import workloads as W
+from common import rel_l2
+
+
+def _problem(N=6, seed=0):
+    rng = np.random.default_rng(seed)
+    wp = W.random_walk_waypoints(N, [0, 0, 0], [40, 40, 30], seed=seed + 1)
+    T = 2.5 * (1 + 0.4 * (rng.random(N) - 0.5))
+    head, tail = np.zeros((3, 3)), np.zeros((3, 3))
+    head[:, 0], tail[:, 0] = wp[0], wp[-1]
+    head[:, 1], head[:, 2], tail[:, 1] = rng.normal(size=3) * 0.3, rng.normal(size=3) * 0.1, rng.normal(size=3) * 0.2
+    return wp, T, head, tail, rng
+
+
+def test_host_minco_equals_oracle_and_dense_solve():
+    for N in (1, 2, 6, 17):
+        wp, T, head, tail, rng = _problem(N, seed=N)
+        inP = wp[1:-1].T if N > 1 else np.zeros((3, 0))
+        co, e, gc, gt = H.minco_forward(head, tail, inP, T)
+        ref = W.minco_s3(wp, T, head_va=[head[:, 1], head[:, 2]], tail_va=[tail[:, 1], tail[:, 2]])
+        assert rel_l2(co, ref) < 1e-9
+        oco, oe, ogc, ogt = O.minco_forward(head, tail, inP, T)
+        assert rel_l2(co, oco) < 1e-12 and abs(e - oe) <= 1e-12 * abs(oe) and rel_l2(gc, ogc) < 1e-12 and rel_l2(gt, ogt) < 1e-12
+        if N > 1:
+            gC, gT = rng.normal(size=18 * N), rng.normal(size=N)
+            gp, gtt = H.minco_backward(head, tail, inP, T, gC, gT)
+            ogp, ogtt = O.minco_backward(head, tail, inP, T, gC, gT)
+            assert rel_l2(gp, ogp) < 1e-11 and rel_l2(gtt, ogtt) < 1e-11
+
+
+def test_tau_maps_round_trip():
+    tau = np.array([-3.0, -0.5, 0.0, 0.2, 1.7, 4.0])
+    T, back = H.tau_maps(tau)
+    exp = np.where(tau > 0, (0.5 * tau + 1) * tau + 1, 1 / ((0.5 * tau - 1) * tau + 1))
+    assert np.allclose(T, exp, rtol=1e-15) and np.allclose(back, tau, atol=1e-12) and np.all(T > 0)
