@@ -32,8 +32,9 @@ struct isdf_ctx {
     int device = 0;
     isdf_config cfg;
     DevCfg dcfg;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, aux_stream = nullptr;   // aux: work-item build, off the evaluation's critical path
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_main_done = nullptr, ev_items_done = nullptr;
+    bool items_pending = false;
     // map
     bool have_map = false;
     DevGrid grid;
@@ -116,6 +117,9 @@ extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
     d.half_bd = (cfg->kernel_size * cfg->occupancy_resolution) / 2;
     d.K = cfg->integral_intervs; d.flags = cfg->flags;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_items_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = c->d_counter.ensure(4);
@@ -129,6 +133,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_cell_dist.release(); c->d_cell_seed.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_split_ticket.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
@@ -136,6 +141,9 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_main_done) cudaEventDestroy(c->ev_main_done);
+    if (c->ev_items_done) cudaEventDestroy(c->ev_items_done);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -422,7 +430,7 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
     // longest-first order from the previous evaluation of the same problem shape (first evaluation: natural order)
     const long long sig = ((long long)N << 20) ^ ((long long)c->rank << 10) ^ c->world ^ ((long long)K << 40);
-    const int max_split = (c->shape.kind == ISDF_SHAPE_MESH) ? (int)(M / 8 + 1) : 0;   // only mesh samples have a heavy tail worth splitting
+    const int max_split = (c->shape.kind == ISDF_SHAPE_MESH) ? (int)(M / 4 + 1) : 0;   // only mesh samples have a heavy tail worth splitting
     const size_t max_items = (size_t)M + (size_t)(ROW_CLASSES - 1) * max_split;
     CU_TRY(c->d_work.ensure((size_t)S));
     if (c->d_items.n < 3 * max_items + (size_t)M) { CU_TRY(c->d_items.ensure(3 * max_items + (size_t)M)); c->order_for = -1; }   // a regrown table holds no items yet
@@ -438,10 +446,15 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     A.items = have_items ? c->d_items.p : nullptr;
     A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_ticket = c->d_split_ticket.p; A.split_work = c->d_split_work.p;
     const unsigned grid = (unsigned)(((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS);
+    if (c->items_pending) CU_TRY(cudaStreamWaitEvent(st, c->ev_items_done, 0));   // the table this launch reads (or overwrites next)
     if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
     else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
-    // off the result's critical path: the caller can already read d_out when this finishes on the same stream
-    k_build_items<<<1, 1024, 0, st>>>(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots, c->d_items.p, c->d_item_count.p);
+    // build the next evaluation's work items on the aux stream: overlaps the caller's D2H / all-reduce / host work
+    CU_TRY(cudaEventRecord(c->ev_main_done, st));
+    CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_main_done, 0));
+    k_build_items<<<1, 1024, 0, c->aux_stream>>>(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots, c->d_items.p, c->d_item_count.p);
+    CU_TRY(cudaEventRecord(c->ev_items_done, c->aux_stream));
+    c->items_pending = true;
     c->order_for = sig;
     c->stats.kernel_launches++;
     c->stats.kernel_launches++;

@@ -523,20 +523,32 @@ __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int 
     __shared__ int nsplit;
     __shared__ unsigned long long total_work;
     __shared__ unsigned split_work;
-    hist[threadIdx.x] = 0;
+    hist[threadIdx.x] = 0; cursor[threadIdx.x] = 0;
     if (threadIdx.x == 0) { nsplit = 0; total_work = 0ull; }
     __syncthreads();
     {
         unsigned long long mine = 0ull;
-        for (int m = threadIdx.x; m < M; m += blockDim.x) mine += work[rank + world * m];
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            const unsigned w = work[rank + world * m];
+            mine += w;
+            atomicAdd(&cursor[order_bucket(w)], 1);          // cursor[] doubles as the per-sample work histogram here
+        }
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
         if ((threadIdx.x & 31) == 0) atomicAdd(&total_work, mine);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // balanced-share threshold, raised if needed so that only the max_split HEAVIEST samples qualify
         const unsigned long long t = (total_work * 7ull) / (10ull * (unsigned long long)max(warp_slots, 1));
-        split_work = (unsigned)min(max(t, (unsigned long long)SPLIT_WORK_MIN), 0xffffffffull);
+        unsigned thr = (unsigned)min(max(t, (unsigned long long)SPLIT_WORK_MIN), 0xffffffffull);
+        int cum = 0, b = ORDER_BUCKETS - 1;
+        for (; b >= 0; b--) { if (cum + cursor[b] > max_split) break; cum += cursor[b]; }
+        if (b >= 0) thr = max(thr, (unsigned)(b + 1) << 3);   // buckets above b fit into the split slots
+        if (b == ORDER_BUCKETS - 1) thr = 0xffffffffu;        // even the top bucket alone overflows: no splitting
+        split_work = thr;
     }
+    __syncthreads();
+    cursor[threadIdx.x] = 0;
     __syncthreads();
     const unsigned SPLIT_WORK = split_work;
     // pass 1: decide splits (first come first served up to max_split), histogram the item keys
