@@ -179,6 +179,81 @@ def cpu_baseline(w, cfg, occ, T, Cc, V, F, budget_s=20.0):
                       f"{dt:.2f} s wall with {cores} OpenMP threads (schedule(dynamic) + critical, g++ -O3), scaled by pieces"}
 
 
+# ---- secondary metric: L-BFGS iterations/s over the whole callback (MINCO -> swept-volume term -> time integral -> adjoint) -------
+def lbfgs_workload():
+    import isdf_b200 as I
+    import workloads as W
+    X = 256
+    occ = W.random_map(X, X, X, p=0.05, seed=2, slabs=3)
+    cfg = I.default_config_values()
+    cfg.flags = I.WITH_DYNAMICS                      # the live reference callback: collision through the swept-volume term
+    N = 64
+    wp = W.random_walk_waypoints(N, [0, 0, 0], [X, X, X], seed=11)
+    pts = W.gather_obstacle_points(occ, [0, 0, 0], 1.0, wp, cfg.kernel_size * cfg.occupancy_resolution / 3.0)
+    head, tail = np.zeros((3, 3)), np.zeros((3, 3))
+    head[:, 0], tail[:, 0] = wp[0], wp[-1]
+    x0 = np.concatenate([np.full(N, 1.2), wp[1:-1].reshape(-1)])   # tau = 1.2 -> T = 2.92 s per piece
+    return cfg, N, wp, pts, head, tail, x0, "Torus_big"
+
+
+def lbfgs_ours(device, max_iterations=40):
+    import ctypes as CT
+    import isdf_b200 as I
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import host_lib as H
+    cfg, N, wp, pts, head, tail, x0, shape = lbfgs_workload()
+    ev = I.Evaluator(cfg, device=device)
+    ev.set_shape_named(shape)
+    ev.set_points(pts)
+    L = H.lib()
+    hh, tt = np.asfortranarray(head), np.asfortranarray(tail)
+    out = {}
+    for rep in range(2):                                           # first run warms up allocations / work-item tables
+        be = L.isdf_host_backend_create(ev.h, N, hh.ctypes.data_as(H.dp), tt.ctypes.data_as(H.dp), 20.0, 1, 1)
+        x = x0.copy()
+        fx, it, evs = CT.c_double(0), CT.c_int(0), CT.c_int(0)
+        t0 = time.perf_counter()
+        r = L.isdf_host_lbfgs_backend(be, x.ctypes.data_as(H.dp), x.size, CT.byref(fx), 16, 10, 1e-6, 0.0, max_iterations, CT.byref(it), CT.byref(evs))
+        dt = time.perf_counter() - t0
+        L.isdf_host_backend_destroy(be)
+        out = {"iters_per_s": it.value / dt, "callback_evals_per_s": evs.value / dt, "iterations": it.value, "evaluations": evs.value,
+               "seconds": dt, "ret": r, "final_cost": fx.value,
+               "config": f"256^3 map p=0.05, 64 pieces, {len(pts)} obstacle points, robot {shape}, callback = MINCO + swept-volume term + "
+                         "time-integral dynamics + adjoint (back_end_optimizer.hpp:358-430), L-BFGS mem 16 past 10 (config_CappedCone.yaml:99-102)"}
+    ev.close()
+    return out
+
+
+def lbfgs_cpu(max_iterations=2):
+    """same driver, callback assembled from the oracle (OpenMP, all host threads)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import host_lib as H
+    import oracle_lib as O
+    cfg, N, wp, pts, head, tail, x0, shape = lbfgs_workload()
+    oc = O.config_from(cfg)
+    oc.threads_num = os.cpu_count() or 1
+    sh = O.Shape.named(shape)
+    rho = 20.0
+
+    def fun(x):
+        tau = x[:N]
+        T = np.where(tau > 0, (0.5 * tau + 1) * tau + 1, 1 / ((0.5 * tau - 1) * tau + 1))
+        inP = x[N:].reshape(-1, 3).T
+        co, energy, gC, gT = O.minco_forward(head, tail, inP, T)
+        sv = O.eval_swept(oc, sh, T, co, pts, use_omp=True)
+        di = O.eval_discrete(oc, None, [0, 0, 0], 1.0, None, T, co, use_omp=True)
+        cost = energy + sv["cost"] + di[0] + rho * T.sum()
+        gp, gt = O.minco_backward(head, tail, inP, T, gC + sv["gradC"] + di[1], gT + sv["gradT"] + di[2])
+        gt = gt + rho
+        gtau = np.where(tau > 0, gt * (tau + 1), gt * (1 - tau) / ((0.5 * tau - 1) * tau + 1) ** 2)
+        return cost, np.concatenate([gtau, gp.T.reshape(-1)])
+    t0 = time.perf_counter()
+    r = H.lbfgs_minimize(fun, x0, mem_size=16, past=10, delta=1e-6, g_epsilon=0.0, max_iterations=max_iterations)
+    dt = time.perf_counter() - t0
+    return {"iters_per_s": r["iterations"] / dt, "callback_evals_per_s": r["evaluations"] / dt, "iterations": r["iterations"],
+            "evaluations": r["evaluations"], "seconds": dt, "cores": oc.threads_num}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -328,6 +403,13 @@ def run_ours(args):
                           "evals_per_s_warm_l2": 1e3 / statistics.mean(warm), "ms_min": min(times), "ms_max": max(times),
                           "kernel_ms_in_host_call": kernel_ms_alone, "wall_s_timed_loop": wall,
                           "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:]))}}
+        if world == 1 and not args.no_lbfgs:
+            try:
+                line["extra"]["lbfgs"] = lbfgs_ours(local)
+                if not args.no_cpu_baseline:
+                    line["extra"]["lbfgs"]["cpu"] = lbfgs_cpu()
+            except Exception as e:   # secondary metric must never take the headline line down
+                line["extra"]["lbfgs"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, cfg, occ, T, Cc, V, F, budget_s=args.cpu_budget)
             line["extra"]["speedup_kernel_vs_cpu"] = line["value"] / line["cpu_baseline"]["value"]
@@ -348,6 +430,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lbfgs", action="store_true", help="skip the secondary L-BFGS iterations/s measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-pieces", type=int, default=2, help="--impl reference: pieces per step sample")
     ap.add_argument("--robot", default="mesh", help="mesh (headline) or an analytic shape name, e.g. SmoothIntersection (diagnostic runs)")

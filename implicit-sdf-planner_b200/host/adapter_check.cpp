@@ -2,6 +2,7 @@
 // them: the MINCO port against the oracle / numpy, and the full LMBM-signature callback on the GPU box.
 #include "isdf_shape_adapter.hpp"
 #include "isdf_cost_callback.hpp"
+#include "isdf_lbfgs.hpp"
 #include <cstring>
 
 using namespace isdf_host;
@@ -41,5 +42,21 @@ void isdf_host_backend_last(void *be, double *cost_pos, double *cost_other, doub
 void isdf_host_backend_destroy(void *be) { delete (BackEnd *)be; }
 void isdf_host_tau_maps(const double *tau, int n, double *T, double *tau_back) { BackEnd::forwardT(tau, T, n); BackEnd::backwardT(T, tau_back, n); }
 double isdf_host_shape_sdf_grad(isdf_ctx *ctx, const double *p, double *grad) { DeviceShape s(ctx); return s.getSDFwithGrad1(p, grad); }
+
+// L-BFGS on any raw callback (known-answer tests, CPU baseline with the oracle as the callback) ...
+int isdf_host_lbfgs_generic(int n, double *x, double *f, lbfgs_eval_raw_t eval, void *instance, int mem_size, int past, double delta,
+                            double g_epsilon, int max_iterations, int *iterations, int *evaluations) {
+    LbfgsParams pr; pr.mem_size = mem_size; pr.past = past; pr.delta = delta; pr.g_epsilon = g_epsilon; pr.max_iterations = max_iterations;
+    pr.min_step = 1.0e-32;                                   // config_CappedCone.yaml:101
+    LbfgsStats st; double fx = 0;
+    const int r = lbfgs_optimize(n, x, fx, eval, nullptr, nullptr, instance, pr, &st);
+    *f = fx; if (iterations) *iterations = st.iterations; if (evaluations) *evaluations = st.evaluations;
+    return r;
+}
+// ... and on the GPU-backed callback (BackEnd::costFunctionLbfgs)
+int isdf_host_lbfgs_backend(void *be, double *x, int n, double *f, int mem_size, int past, double delta, double g_epsilon, int max_iterations,
+                            int *iterations, int *evaluations) {
+    return isdf_host_lbfgs_generic(n, x, f, &BackEnd::costFunctionLbfgs, be, mem_size, past, delta, g_epsilon, max_iterations, iterations, evaluations);
+}
 
 }  // extern "C"

@@ -26,8 +26,34 @@ def lib():
         L.isdf_host_tau_maps.argtypes = [dp, C.c_int, dp, dp]
         L.isdf_host_shape_sdf_grad.restype = C.c_double
         L.isdf_host_shape_sdf_grad.argtypes = [C.c_void_p, dp, dp]
+        L.isdf_host_lbfgs_generic.argtypes = [C.c_int, dp, dp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.isdf_host_lbfgs_backend.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _lib = L
     return _lib
+
+
+EVAL_T = C.CFUNCTYPE(C.c_double, C.c_void_p, dp, dp, C.c_int, dp)   # lbfgs_eval_raw_t
+
+
+def lbfgs_minimize(fun, x0, mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_iterations=0):
+    """fun(x) -> (f, grad). Runs the product's L-BFGS driver on a python callback (KATs, CPU baseline)."""
+    x = f(x0).copy()
+    n = x.size
+    count = [0]
+
+    def cb(_inst, xp, gp, nn, pc):
+        xv = np.ctypeslib.as_array(xp, shape=(nn,))
+        fv, gv = fun(xv.copy())
+        np.ctypeslib.as_array(gp, shape=(nn,))[:] = gv
+        count[0] += 1
+        return float(fv)
+    cfn = EVAL_T(cb)
+    fx, it, ev = C.c_double(0), C.c_int(0), C.c_int(0)
+    r = lib().isdf_host_lbfgs_generic(n, _p(x), C.byref(fx), C.cast(cfn, C.c_void_p), None, mem_size, past, delta, g_epsilon, max_iterations,
+                                      C.byref(it), C.byref(ev))
+    return dict(ret=r, x=x, f=fx.value, iterations=it.value, evaluations=ev.value)
 
 
 def _p(a):

@@ -400,3 +400,31 @@ def test_lmbm_callback_matches_oracle_composition():
     os_, og = osh.query(p[None])
     assert abs(s - os_[0]) < 1e-12 and np.allclose(gr, og[0], atol=1e-8)
     ev.close()
+
+
+def test_lbfgs_driver_on_gpu_callback_decreases_cost():
+    """L-BFGS (reference fork semantics) over the full callback: MINCO -> swept-volume term -> time integral -> adjoint."""
+    import ctypes as CT
+    import host_lib as H
+    cfg, T0, Cc, pts = sv_case(seed=5, npts=300)
+    cfg.flags = I.WITH_DYNAMICS
+    N = T0.size
+    wp = W.random_walk_waypoints(N, [0, 0, 0], [50, 50, 34], seed=5)
+    head, tail = np.zeros((3, 3)), np.zeros((3, 3))
+    head[:, 0], tail[:, 0] = wp[0], wp[-1]
+    x = np.concatenate([np.full(N, 1.2), wp[1:-1].reshape(-1)])
+    ev = I.Evaluator(cfg)
+    ev.set_shape_named("Torus")
+    ev.set_points(pts)
+    L = H.lib()
+    hh, tt = np.asfortranarray(head), np.asfortranarray(tail)
+    be = L.isdf_host_backend_create(ev.h, N, hh.ctypes.data_as(H.dp), tt.ctypes.data_as(H.dp), 20.0, 1, 1)
+    g = np.zeros_like(x)
+    c0 = L.isdf_host_backend_cost(be, x.ctypes.data_as(H.dp), g.ctypes.data_as(H.dp), x.size)
+    fx, it, evs = CT.c_double(0), CT.c_int(0), CT.c_int(0)
+    r = L.isdf_host_lbfgs_backend(be, x.ctypes.data_as(H.dp), x.size, CT.byref(fx), 16, 10, 1e-6, 0.0, 60, CT.byref(it), CT.byref(evs))
+    L.isdf_host_backend_destroy(be)
+    print("lbfgs ret", r, "cost", c0, "->", fx.value, "iterations", it.value, "evaluations", evs.value)
+    assert r in (0, 1, -1008) or r <= -1009          # converged / stopped / max iterations / line-search limits: all leave the last iterate
+    assert np.isfinite(fx.value) and fx.value < c0 and it.value >= 1 and evs.value >= it.value
+    ev.close()

@@ -38,3 +38,23 @@ def test_tau_maps_round_trip():
     T, back = H.tau_maps(tau)
     exp = np.where(tau > 0, (0.5 * tau + 1) * tau + 1, 1 / ((0.5 * tau - 1) * tau + 1))
     assert np.allclose(T, exp, rtol=1e-15) and np.allclose(back, tau, atol=1e-12) and np.all(T > 0)
+
+
+def test_lbfgs_driver_known_answers():
+    """Rosenbrock (minimum 0 at (1,..,1)) and a convex quadratic: the driver with the reference fork's semantics converges."""
+    def rosen(x):
+        f = np.sum(100 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2)
+        g = np.zeros_like(x)
+        g[:-1] = -400 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+        g[1:] += 200 * (x[1:] - x[:-1] ** 2)
+        return f, g
+    r = H.lbfgs_minimize(rosen, np.array([-1.2, 1.0, -0.5, 0.8]), past=0, g_epsilon=1e-8, max_iterations=5000)
+    assert r["ret"] in (0, 1) and np.allclose(r["x"], 1.0, atol=1e-4) and r["f"] < 1e-8
+    assert r["evaluations"] >= r["iterations"] >= 5
+    A = np.diag([1.0, 10.0, 100.0]); b = np.array([1.0, -2.0, 3.0])
+    r = H.lbfgs_minimize(lambda x: (0.5 * x @ A @ x - b @ x, A @ x - b), np.zeros(3), past=0, g_epsilon=1e-10, max_iterations=500)
+    assert np.allclose(r["x"], np.linalg.solve(A, b), atol=1e-6)
+    # argument validation mirrors the reference's return codes
+    assert H.lbfgs_minimize(rosen, np.zeros(2), mem_size=0)["ret"] == -1022    # LBFGSERR_INVALID_MEMSIZE
+    # NaN cost aborts with LBFGSERR_INVALID_FUNCVAL: what the C ABI's NaN-on-error relies on
+    assert H.lbfgs_minimize(lambda x: (float("nan"), x), np.ones(2))["ret"] == -1012
