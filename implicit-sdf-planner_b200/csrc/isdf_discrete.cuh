@@ -332,7 +332,11 @@ __device__ __forceinline__ void sample_finish(const DiscArgs &A, const Item &it,
     }
     __syncwarp();
     if (lane < PARTIAL_STRIDE) A.partial[(size_t)s * PARTIAL_STRIDE + lane] = stage[lane];
+#ifdef ISDF_PHASE_TIMING
+    if (A.dbg && lane == 0) A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin);
+#else
     if (A.dbg && lane == 0) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = work; }
+#endif
     piece_finish(A, i, lane);
 }
 
@@ -451,9 +455,15 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
     const double Ti = __ldg(A.T + i);
     const double step = Ti * (1.0 / K);
     const long long t_begin = A.dbg ? clock64() : 0;
+#ifdef ISDF_PHASE_TIMING
+    long long t_query = 0, t_pose = 0;
+#endif
 
     d3 pos; quat4 q; rot3 R;
     sample_pose(A, i, j, step, pos, q, R);
+#ifdef ISDF_PHASE_TIMING
+    t_pose = clock64() - t_begin;
+#endif
 
     double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned npairs = 0, nquery = 0;
@@ -469,25 +479,29 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
         // Either way a class sum adds the same terms in the same (row, z) order.
         scan_window(G, W, lane, whole ? -1 : it.c0, [&](bool valid, int vx, int vy, int vz, int vr) {
             bool pass = false, box = false;
+            int cell = -1;
             if (valid) {
                 const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
                 box = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
                 // exact skips: outside the mesh AABB inflated by safety_hor, or in a cell whose every point is >= safety_hor away
-                int cell;
                 pass = box && !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
                                 prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf) && !mesh_far(Mh, prel, sf, cell);
             }
             npairs += __popc(__ballot_sync(0xffffffffu, box));
             unsigned bal = __ballot_sync(0xffffffffu, pass);
+#ifdef ISDF_PHASE_TIMING
+            const long long tq0 = clock64();
+#endif
             while (bal) {   // one surviving voxel at a time, in voxel order
                 const int sl = __ffs(bal) - 1;
                 bal &= bal - 1;
                 nquery++;
                 const int ox = __shfl_sync(0xffffffffu, vx, sl), oy = __shfl_sync(0xffffffffu, vy, sl), oz = __shfl_sync(0xffffffffu, vz, sl);
                 const int cls = __shfl_sync(0xffffffffu, vr, sl) % ROW_CLASSES;
+                const int qcell = __shfl_sync(0xffffffffu, cell, sl);
                 const d3 d = voxel_centre(G, ox, oy, oz) - pos;
                 d3 g = mk3(0, 0, 0);
-                const double sdf = mesh_sdf_grad_warp(Mh, rot_applyT(R, d), sf, g, lane, &wstack[warp]);
+                const double sdf = mesh_sdf_grad_warp(Mh, rot_applyT(R, d), sf, g, lane, &wstack[warp], qcell);
                 PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};   // identical on every lane
                 pair_accumulate(cfg, R, q, d, sdf, g, one);
                 if (lane < 8 && one.c > 0.0) {
@@ -496,6 +510,9 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                     cacc[warp][cls][lane] += v;
                 }
             }
+#ifdef ISDF_PHASE_TIMING
+            t_query += clock64() - tq0;
+#endif
         });
         __syncwarp();
         // sample (or part) total: class sums added in class order
@@ -504,6 +521,14 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
 #pragma unroll
         for (int v = 0; v < 8; v++) tot[v] = __shfl_sync(0xffffffffu, mine, v);
     }
+#ifdef ISDF_PHASE_TIMING
+    if (A.dbg && lane == 0 && it.hslot < 0) {   // whole samples only: {total set later, pose+scan cycles, query cycles} and counts in the upper bits
+        const long long t_scan_end = clock64() - t_begin;
+        A.dbg[3 * (size_t)s + 1] = ((unsigned long long)nquery << 40) | (unsigned long long)(t_scan_end - t_query);
+        A.dbg[3 * (size_t)s + 2] = ((unsigned long long)npairs << 40) | (unsigned long long)t_query;
+        (void)t_pose;
+    }
+#endif
     sample_finish(A, it, i, j, Ti, tot, npairs, stage[warp], t_begin, 64u * nquery + npairs);
 }
 

@@ -55,30 +55,30 @@ ISDF_HD double box_dist2(const double *b, d3 p) {
     return ex * ex + ey * ey + ez * ez;
 }
 
-// Closest point on triangle (a, a+ab, a+ac) by Voronoi-region classification; feat: 0 face, 1 ab, 2 bc, 3 ca, 4 a, 5 b, 6 c
+// Closest point on triangle (a, a+ab, a+ac) by Voronoi-region classification (Ericson's regions and priorities);
+// feat: 0 face, 1 ab, 2 bc, 3 ca, 4 a, 5 b, 6 c. Written branch-free: every region's barycentric candidate is computed
+// from independent dot products / divisions and the winner is picked by predicated selects in reverse priority order,
+// so the FP64 dependency chain is ~15 operations + one division instead of ~100 — the search kernels are bound by
+// exactly this latency.
 ISDF_HD d3 tri_closest(d3 p, d3 a, d3 ab, d3 ac, int &feat) {
     const d3 ap = p - a;
+    const d3 bp = ap - ab, cp = ap - ac;
     const double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
-    if (d1 <= 0.0 && d2 <= 0.0) { feat = 4; return a; }
-    const d3 bp = ap - ab;
     const double d3_ = dot3(ab, bp), d4 = dot3(ac, bp);
-    if (d3_ >= 0.0 && d4 <= d3_) { feat = 5; return a + ab; }
-    const double vc = d1 * d4 - d3_ * d2;
-    if (vc <= 0.0 && d1 >= 0.0 && d3_ <= 0.0) { feat = 1; return a + (d1 / (d1 - d3_)) * ab; }
-    const d3 cp = ap - ac;
     const double d5 = dot3(ab, cp), d6 = dot3(ac, cp);
-    if (d6 >= 0.0 && d5 <= d6) { feat = 6; return a + ac; }
-    const double vb = d5 * d2 - d1 * d6;
-    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { feat = 3; return a + (d2 / (d2 - d6)) * ac; }
-    const double va = d3_ * d6 - d5 * d4;
-    if (va <= 0.0 && (d4 - d3_) >= 0.0 && (d5 - d6) >= 0.0) {
-        feat = 2;
-        const double w = (d4 - d3_) / ((d4 - d3_) + (d5 - d6));
-        return (a + ab) + w * (ac - ab);
-    }
-    feat = 0;
-    const double den = 1.0 / (va + vb + vc);
-    return a + (vb * den) * ab + (vc * den) * ac;
+    const double vc = d1 * d4 - d3_ * d2, vb = d5 * d2 - d1 * d6, va = d3_ * d6 - d5 * d4;
+    const double e43 = d4 - d3_, e56 = d5 - d6;
+    const double tab = d1 / (d1 - d3_), tac = d2 / (d2 - d6), tbc = e43 / (e43 + e56), den = 1.0 / (va + vb + vc);
+    double s = vb * den, t = vc * den;
+    int f = 0;
+    if (va <= 0.0 && e43 >= 0.0 && e56 >= 0.0) { s = 1.0 - tbc; t = tbc; f = 2; }
+    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { s = 0.0; t = tac; f = 3; }
+    if (d6 >= 0.0 && d5 <= d6) { s = 0.0; t = 1.0; f = 6; }
+    if (vc <= 0.0 && d1 >= 0.0 && d3_ <= 0.0) { s = tab; t = 0.0; f = 1; }
+    if (d3_ >= 0.0 && d4 <= d3_) { s = 1.0; t = 0.0; f = 5; }
+    if (d1 <= 0.0 && d2 <= 0.0) { s = 0.0; t = 0.0; f = 4; }
+    feat = f;
+    return mk3(a.x + (s * ab.x + t * ac.x), a.y + (s * ab.y + t * ac.y), a.z + (s * ab.z + t * ac.z));
 }
 
 // Exact nearest triangle within sqrt(bound2). Returns squared distance (bound2 if none found; tri = -1).
@@ -197,12 +197,13 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
 // 32 at a time (8 leaves x 4 slots), the winner is found with a butterfly arg-min. All lanes return identical results.
 // `stk` is a per-warp shared-memory scratch of WIDE_STACK (node, d2) pairs.
 constexpr int WIDE_STACK = 96;
-struct WideStack { int node[WIDE_STACK]; double d2[WIDE_STACK]; };
+struct WideStack { int node[WIDE_STACK]; double d2[WIDE_STACK]; int leaf[32]; double leaf_d2[32]; };
 
 __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bound2, int seed, d3 &cbest, int &tri, int &feat,
                                                int lane, WideStack *stk) {
     double best = bound2;
     tri = -1; feat = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
     if (seed >= 0) {   // every lane evaluates the seed triangle (uniform): a tight bound before the first node is opened
         const double *T = M.tris + 9 * (size_t)seed;
         int f;
@@ -222,20 +223,19 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
             const double ez = fmax(fmax(nd->lo[2][lane] - p.z, p.z - nd->hi[2][lane]), 0.0);
             const double d2 = ex * ex + ey * ey + ez * ez;
             const bool alive = (ch != WIDE_EMPTY) && (d2 < best);
-            // ---- leaves: 8 per pass, 4 triangle slots each ----------------------------------------------------------------
-            unsigned leafmask = __ballot_sync(0xffffffffu, alive && ch < 0);
-            while (leafmask) {
-                const int grp = lane >> 2, slot = lane & 3;
-                const unsigned src = __fns(leafmask, 0, grp + 1);
-                const int scode = __shfl_sync(0xffffffffu, ch, src & 31);
-                const double sd2 = __shfl_sync(0xffffffffu, d2, src & 31);
+            // ---- leaves: compacted into a shared list, then 8 per pass x 4 triangle slots ------------------------------
+            const bool is_leaf = alive && ch < 0;
+            const unsigned leafmask = __ballot_sync(0xffffffffu, is_leaf);
+            const int nleaf = __popc(leafmask);
+            if (is_leaf) { const int r = __popc(leafmask & lt_mask); stk->leaf[r] = ch; stk->leaf_d2[r] = d2; }
+            __syncwarp();
+            for (int base = 0; base < nleaf; base += 8) {
+                const int idx = base + (lane >> 2), slot = lane & 3;
                 double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0, t = -1;
-                if (src < 32u) {
-                    const int code = ~scode;
+                if (idx < nleaf && stk->leaf_d2[idx] < best) {
+                    const int code = ~stk->leaf[idx];
                     const int first = code >> 3, cnt = (code & 7) + 1;
-                    // leaves of up to 8 triangles: slots 0..3 take triangle slot and slot+4
-                    for (int k = slot; k < cnt; k += 4) {
-                        if (!(sd2 < best)) break;
+                    for (int k = slot; k < cnt; k += 4) {   // leaves of up to 8 triangles: slots take triangle k and k+4
                         const double *T = M.tris + 9 * (size_t)(first + k);
                         int ff;
                         const d3 qq = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ff);
@@ -244,22 +244,26 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
                         if (d < dd) { dd = d; q = qq; f = ff; t = first + k; }
                     }
                 }
-                if (__any_sync(0xffffffffu, dd < best)) {
-                    double bd = dd; int bl = lane;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                        if (od < bd || (od == bd && ol < bl)) { bd = od; bl = ol; }
+                // arg-min: 32-bit order-preserving key (float rounded down) + one REDUX; exact tie-break among equal keys
+                const bool cand = dd < best;
+                const unsigned key = cand ? __float_as_uint(__double2float_rd(dd)) : 0xffffffffu;
+                const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+                if (kmin != 0xffffffffu) {
+                    unsigned tied = __ballot_sync(0xffffffffu, cand && key == kmin);
+                    int win = __ffs(tied) - 1;
+                    double wd = __shfl_sync(0xffffffffu, dd, win);
+                    tied &= tied - 1;
+                    while (tied) {   // rare: several lanes within one float ulp
+                        const int o = __ffs(tied) - 1;
+                        tied &= tied - 1;
+                        const double od = __shfl_sync(0xffffffffu, dd, o);
+                        if (od < wd) { wd = od; win = o; }
                     }
-                    best = bd;
-                    cbest = mk3(__shfl_sync(0xffffffffu, q.x, bl), __shfl_sync(0xffffffffu, q.y, bl), __shfl_sync(0xffffffffu, q.z, bl));
-                    tri = __shfl_sync(0xffffffffu, t, bl);
-                    feat = __shfl_sync(0xffffffffu, f, bl);
+                    best = wd;
+                    cbest = mk3(__shfl_sync(0xffffffffu, q.x, win), __shfl_sync(0xffffffffu, q.y, win), __shfl_sync(0xffffffffu, q.z, win));
+                    tri = __shfl_sync(0xffffffffu, t, win);
+                    feat = __shfl_sync(0xffffffffu, f, win);
                 }
-                // drop the (up to) 8 leaves just processed
-                const unsigned eighth = __fns(leafmask, 0, 8);
-                leafmask = (eighth >= 32u) ? 0u : (leafmask & ~((2u << eighth) - 1u));
             }
             // ---- internal children: push farthest first so the nearest is popped next ---------------------------------
             unsigned imask = __ballot_sync(0xffffffffu, alive && ch >= 0 && ch != WIDE_EMPTY && d2 < best);
@@ -283,13 +287,16 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
 }
 
 // Warp-cooperative getSDFwithGrad1 for the mesh shape — same contract as mesh_sdf_grad, all lanes get the same answer.
-__device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk) {
+// known_cell: cell index already looked up by the caller (and known not to be "far"), or -2 to look it up here.
+__device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk, int known_cell = -2) {
     d3 c = mk3(0, 0, 0);
-    int tri, feat, cell;
+    int tri, feat, cell = known_cell;
     double d2;
     const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
-    const bool far = mesh_far(M, p, reach, cell);
-    if (bounded && far) return reach;
+    if (known_cell == -2) {
+        const bool far = mesh_far(M, p, reach, cell);
+        if (bounded && far) return reach;
+    }
     const int seed = (cell >= 0) ? (int)M.cell_seed[cell] : -1;
     if (bounded) {
         d2 = wide_closest(M, p, reach * reach, seed, c, tri, feat, lane, stk);
