@@ -17,6 +17,9 @@ using namespace isdf;
 __global__ void k_mesh_cells(const __grid_constant__ DevMesh M, int nx, int ny, int nz, double lx, double ly, double lz, double cell,
                              float *dist, uint32_t *seed);
 
+__global__ void k_mesh_cell_lists(const __grid_constant__ DevMesh M, long long ncell, double hd, double list_reach, uint16_t *cnt,
+                                  const uint32_t *off, uint32_t *cand);
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
@@ -42,7 +45,7 @@ struct isdf_ctx {
     // shape
     bool have_shape = false;
     DevShape shape;
-    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed;
+    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
     DevBuf<int> d_tickets;       // N piece tickets + 1 pieces_done (+ swept counters)
@@ -134,7 +137,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
-    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_cell_dist.release(); c->d_cell_seed.release();
+    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_split_ticket.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
     c->sv.release();
@@ -253,7 +256,7 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
     {
         DevMesh build = m;
         build.gdim[0] = 0;            // no grid while it is being built: plain unbounded BVH queries
-        build.cell_dist = nullptr; build.cell_seed = nullptr;
+        build.cell_dist = nullptr; build.cell_seed = nullptr; build.cell_off = nullptr; build.cell_cnt = nullptr; build.cand = nullptr;
         k_mesh_cells<<<(unsigned)((ncell + 127) / 128), 128, 0, c->stream>>>(build, m.gdim[0], m.gdim[1], m.gdim[2], m.glo[0], m.glo[1], m.glo[2],
                                                                            m.gcell, c->d_cell_dist.p, c->d_cell_seed.p);
         c->stats.kernel_launches++;
@@ -261,6 +264,32 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
         CU_TRY(cudaStreamSynchronize(c->stream));
     }
     m.cell_dist = c->d_cell_dist.p; m.cell_seed = c->d_cell_seed.p;
+    m.cell_off = nullptr; m.cell_cnt = nullptr; m.cand = nullptr;
+    // exact candidate lists for the cells the discrete path queries (centre within safety_hor + a cell diagonal of the surface)
+    {
+        const double hd = 0.5 * std::sqrt(3.0) * m.gcell;
+        const double list_reach = c->cfg.safety_hor + 2.0 * m.ghd;
+        CU_TRY(c->d_cell_cnt.ensure(ncell)); CU_TRY(c->d_cell_off.ensure(ncell));
+        const unsigned warps_grid = (unsigned)((ncell + 3) / 4);
+        k_mesh_cell_lists<<<warps_grid, 128, 0, c->stream>>>(m, (long long)ncell, hd, list_reach, c->d_cell_cnt.p, nullptr, nullptr);
+        c->stats.kernel_launches++;
+        CU_TRY(cudaGetLastError());
+        std::vector<uint16_t> cnt(ncell);
+        CU_TRY(cudaMemcpyAsync(cnt.data(), c->d_cell_cnt.p, sizeof(uint16_t) * ncell, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        std::vector<uint32_t> off(ncell);
+        size_t total = 0;
+        for (size_t i = 0; i < ncell; i++) { off[i] = (uint32_t)total; total += cnt[i]; }
+        if (total > 0 && total < (1ull << 31)) {
+            CU_TRY(c->d_cand.ensure(total));
+            CU_TRY(cudaMemcpyAsync(c->d_cell_off.p, off.data(), sizeof(uint32_t) * ncell, cudaMemcpyHostToDevice, c->stream));
+            k_mesh_cell_lists<<<warps_grid, 128, 0, c->stream>>>(m, (long long)ncell, hd, list_reach, c->d_cell_cnt.p, c->d_cell_off.p, c->d_cand.p);
+            c->stats.kernel_launches++;
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            m.cell_off = c->d_cell_off.p; m.cell_cnt = c->d_cell_cnt.p; m.cand = c->d_cand.p;
+        }
+    }
     c->shape.mesh = m;
     c->have_shape = true;
     c->order_for = -1;
@@ -282,6 +311,35 @@ __global__ void k_mesh_cells(const __grid_constant__ DevMesh M, int nx, int ny, 
     if (side == 0.0) { const double *fn = M.pnormals + 21 * (size_t)tri; side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2]; }
     dist[idx] = (float)((side < 0.0 ? -1.0 : 1.0) * sqrt(d2));
     seed[idx] = (uint32_t)tri;
+}
+
+// Candidate lists (one warp per cell). Pass 1 (cand == nullptr): count the triangles within d_c + 2 hd of the cell centre and
+// store the count (0 for cells that are too far, too deep or whose list would exceed LIST_CAP). Pass 2: fill the lists.
+constexpr int LIST_CAP = 160;
+__global__ void __launch_bounds__(128) k_mesh_cell_lists(const __grid_constant__ DevMesh M, long long ncell, double hd, double list_reach,
+                                                         uint16_t *cnt, const uint32_t *off, uint32_t *cand) {
+    __shared__ WideStack stk[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long cell = (long long)blockIdx.x * 4 + warp;
+    if (cell >= ncell) return;
+    const double dc = fabs((double)M.cell_dist[cell]);
+    if (cand == nullptr) { if (lane == 0) cnt[cell] = 0; }
+    else if (cnt[cell] == 0) return;
+    if (dc > list_reach) return;
+    const int nz = M.gdim[2], ny = M.gdim[1];
+    const int iz = (int)(cell % nz), iy = (int)((cell / nz) % ny), ix = (int)(cell / ((long long)nz * ny));
+    const d3 ctr = mk3(M.glo[0] + (ix + 0.5) * M.gcell, M.glo[1] + (iy + 0.5) * M.gcell, M.glo[2] + (iz + 0.5) * M.gcell);
+    // radius: centre distance (float-rounded: add its slack) + two half diagonals, then a relative safety margin
+    const double R = (dc + (M.ghd - hd) + 2.0 * hd) * (1.0 + 1e-9) + 1e-12;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int n = 0;
+    const uint32_t base = cand ? off[cell] : 0u;
+    wide_range(M, ctr, R * R, lane, &stk[warp], [&](bool hit, int t) {
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (cand && hit) cand[base + n + __popc(bal & lt_mask)] = (uint32_t)t;
+        n += __popc(bal);
+    });
+    if (cand == nullptr && lane == 0) cnt[cell] = (n <= LIST_CAP) ? (uint16_t)n : (uint16_t)0;
 }
 
 __global__ void k_shape_query(const __grid_constant__ DevShape S, const double *p, int n, double *sdf, double *grad, int what) {

@@ -38,6 +38,12 @@ struct DevMesh {
     // body-frame cell grid over the mesh AABB padded by gpad (filled on the device at isdf_set_shape_mesh time):
     const float *cell_dist;     // signed distance of the cell CENTRE to the mesh
     const uint32_t *cell_seed;  // triangle (leaf order) nearest to the cell centre: a tight initial bound for queries in the cell
+    // exact candidate lists: for a cell with centre c and centre distance d_c, EVERY triangle that can be the closest one for
+    // some point of the cell lies within d_c + 2*half_diag of c. Cells near the surface store that set (cell_cnt > 0) and a
+    // query in such a cell is a flat, traversal-free loop over it; cell_cnt == 0 means "search the tree" (far or deep cells).
+    const uint32_t *cell_off;   // offset into cand
+    const uint16_t *cell_cnt;   // number of candidates (0 = no list)
+    const uint32_t *cand;       // triangle indices (leaf order)
     int ntris;
     int gdim[3];
     double glo[3];
@@ -149,6 +155,28 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
     const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
     const bool far = mesh_far(M, p, reach, cell);
     if (bounded && far) return reach;                                  // exact: every point of this cell is >= reach away
+    if (cell >= 0 && M.cell_cnt && M.cell_cnt[cell] != 0) {
+        // flat loop over the cell's exact candidate list: no traversal, no stack, identical code on every lane
+        const uint32_t off = M.cell_off[cell];
+        const int cnt = (int)M.cell_cnt[cell];
+        double bd = 1e300;
+        for (int k = 0; k < cnt; k++) {
+            const int t = (int)M.cand[off + k];
+            const double *T = M.tris + 9 * (size_t)t;
+            int f;
+            const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+            const d3 e = p - q;
+            const double dd = dot3(e, e);
+            if (dd < bd) { bd = dd; c = q; tri = t; feat = f; }
+        }
+        const d3 e = p - c;
+        const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
+        double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
+        if (side == 0.0) { const double *fn = M.pnormals + 21 * (size_t)tri; side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2]; }
+        const double s = (side < 0.0) ? -1.0 : 1.0;
+        g = unit3(s * e);
+        return s * sqrt(bd);
+    }
     // seed: the triangle nearest to the cell centre gives a tight starting bound
     double seed_d2 = 1e300;
     if (cell >= 0) {
@@ -286,6 +314,94 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
     }
 }
 
+// Warp-cooperative range query on the 32-ary tree: calls emit(valid, tri) for every triangle whose exact distance to c is
+// <= sqrt(R2), 32 triangles per call (lanes without one pass valid = false). Used to build the per-cell candidate lists.
+template <class Emit>
+__device__ __forceinline__ void wide_range(const DevMesh &M, d3 c, double R2, int lane, WideStack *stk, Emit &&emit) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int sp = 0, cur = 0;
+    for (;;) {
+        const WideNode *nd = M.wnodes + cur;
+        const int ch = nd->child[lane];
+        const double ex = fmax(fmax(nd->lo[0][lane] - c.x, c.x - nd->hi[0][lane]), 0.0);
+        const double ey = fmax(fmax(nd->lo[1][lane] - c.y, c.y - nd->hi[1][lane]), 0.0);
+        const double ez = fmax(fmax(nd->lo[2][lane] - c.z, c.z - nd->hi[2][lane]), 0.0);
+        const bool alive = (ch != WIDE_EMPTY) && (ex * ex + ey * ey + ez * ez <= R2);
+        const bool is_leaf = alive && ch < 0;
+        const unsigned leafmask = __ballot_sync(0xffffffffu, is_leaf);
+        const int nleaf = __popc(leafmask);
+        if (is_leaf) stk->leaf[__popc(leafmask & lt_mask)] = ch;
+        __syncwarp();
+        for (int base = 0; base < nleaf; base += 4) {      // 4 leaves x 8 triangle slots
+            const int idx = base + (lane >> 3), slot = lane & 7;
+            bool hit = false; int t = -1;
+            if (idx < nleaf) {
+                const int code = ~stk->leaf[idx];
+                const int first = code >> 3, cnt = (code & 7) + 1;
+                if (slot < cnt) {
+                    t = first + slot;
+                    const double *T = M.tris + 9 * (size_t)t;
+                    int ff;
+                    const d3 q = tri_closest(c, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ff);
+                    const d3 e = c - q;
+                    hit = dot3(e, e) <= R2;
+                }
+            }
+            emit(hit, t);
+        }
+        unsigned imask = __ballot_sync(0xffffffffu, alive && ch >= 0);
+        while (imask) {
+            const int sl = __ffs(imask) - 1;
+            imask &= imask - 1;
+            const int snode = __shfl_sync(0xffffffffu, ch, sl);
+            if (lane == 0 && sp < WIDE_STACK) stk->node[sp] = snode;
+            sp = min(sp + 1, WIDE_STACK);
+        }
+        __syncwarp();
+        if (sp == 0) return;
+        cur = stk->node[--sp];
+        __syncwarp();
+    }
+}
+
+// Warp-cooperative nearest triangle from a cell's candidate list: lanes test 32 candidates per pass, REDUX arg-min.
+__device__ __forceinline__ double list_closest(const DevMesh &M, d3 p, int cell, d3 &cbest, int &tri, int &feat, int lane) {
+    const uint32_t off = M.cell_off[cell];
+    const int cnt = (int)M.cell_cnt[cell];
+    double best = 1e300;
+    tri = -1; feat = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0, t = -1;
+        if (base + lane < cnt) {
+            t = (int)__ldg(M.cand + off + base + lane);
+            const double *T = M.tris + 9 * (size_t)t;
+            q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+            const d3 e = p - q;
+            dd = dot3(e, e);
+        }
+        const bool candd = dd < best;
+        const unsigned key = candd ? __float_as_uint(__double2float_rd(dd)) : 0xffffffffu;
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        if (kmin != 0xffffffffu) {
+            unsigned tied = __ballot_sync(0xffffffffu, candd && key == kmin);
+            int win = __ffs(tied) - 1;
+            double wd = __shfl_sync(0xffffffffu, dd, win);
+            tied &= tied - 1;
+            while (tied) {
+                const int o = __ffs(tied) - 1;
+                tied &= tied - 1;
+                const double od = __shfl_sync(0xffffffffu, dd, o);
+                if (od < wd) { wd = od; win = o; }
+            }
+            best = wd;
+            cbest = mk3(__shfl_sync(0xffffffffu, q.x, win), __shfl_sync(0xffffffffu, q.y, win), __shfl_sync(0xffffffffu, q.z, win));
+            tri = __shfl_sync(0xffffffffu, t, win);
+            feat = __shfl_sync(0xffffffffu, f, win);
+        }
+    }
+    return best;
+}
+
 // Warp-cooperative getSDFwithGrad1 for the mesh shape — same contract as mesh_sdf_grad, all lanes get the same answer.
 // known_cell: cell index already looked up by the caller (and known not to be "far"), or -2 to look it up here.
 __device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk, int known_cell = -2) {
@@ -298,7 +414,9 @@ __device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, dou
         if (bounded && far) return reach;
     }
     const int seed = (cell >= 0) ? (int)M.cell_seed[cell] : -1;
-    if (bounded) {
+    if (cell >= 0 && M.cell_cnt && M.cell_cnt[cell] != 0) {
+        d2 = list_closest(M, p, cell, c, tri, feat, lane);       // exact: the list holds every possible closest triangle
+    } else if (bounded) {
         d2 = wide_closest(M, p, reach * reach, seed, c, tri, feat, lane, stk);
         if (tri < 0) {
             if (!mesh_cell_inside(M, cell)) return reach;
