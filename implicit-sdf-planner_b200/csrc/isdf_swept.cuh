@@ -17,8 +17,36 @@
 //                gradT(j<i) prefix of hpp:642-645 as a suffix sum.
 #pragma once
 #include "isdf_types.cuh"
+#include <cuda/barrier>
+#include <cuda/ptx>
 
 namespace isdf {
+
+// Stage the MINCO block [C (18N doubles) | T (N doubles)] into shared memory with the TMA bulk-copy engine
+// (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP) — one elected thread issues the copies,
+// every thread waits on the barrier. Falls back to a cooperative loop when the 16-byte alignment rules do not hold.
+__device__ __forceinline__ void stage_traj_block(double *sC, double *sT, const double *gC, const double *gT, int N,
+                                                 cuda::barrier<cuda::thread_scope_block> *bar) {
+    const bool tma_ok = ((reinterpret_cast<unsigned long long>(gC) & 15ull) == 0) && ((reinterpret_cast<unsigned long long>(gT) & 15ull) == 0) &&
+                        ((N & 1) == 0);
+    if (tma_ok) {
+        if (threadIdx.x == 0) {
+            init(bar, blockDim.x);
+            cuda::ptx::fence_proxy_async(cuda::ptx::space_shared);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            cuda::memcpy_async(sC, gC, cuda::aligned_size_t<16>(sizeof(double) * 18 * (size_t)N), *bar);
+            cuda::memcpy_async(sT, gT, cuda::aligned_size_t<16>(sizeof(double) * (size_t)N), *bar);
+        }
+        cuda::barrier<cuda::thread_scope_block>::arrival_token tok = bar->arrive();
+        bar->wait(std::move(tok));
+    } else {
+        for (int k = threadIdx.x; k < 18 * N; k += blockDim.x) sC[k] = gC[k];
+        for (int k = threadIdx.x; k < N; k += blockDim.x) sT[k] = gT[k];
+        __syncthreads();
+    }
+}
 
 constexpr int SV_WARPS = 4;
 constexpr int SV_THREADS = SV_WARPS * 32;
@@ -81,12 +109,12 @@ struct SvArgs {
 
 // ---- k_sv_table ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sv_table(const __grid_constant__ SvArgs A) {
-    extern __shared__ double smem[];
-    double *sT = smem, *sC = smem + A.N;
-    for (int k = threadIdx.x; k < A.N; k += blockDim.x) sT[k] = A.T[k];
-    for (int k = threadIdx.x; k < 18 * A.N; k += blockDim.x) sC[k] = A.C[k];
+    extern __shared__ __align__(16) double smem[];
+    double *sC = smem, *sT = smem + 18 * A.N;
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+    stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
     __shared__ int s_nc;
-    __syncthreads();
     if (threadIdx.x == 0) {
         double td = 0.0;
         for (int k = 0; k < A.N; k++) td += sT[k];         // getTotalDuration (trajectory.hpp:457-466)
@@ -131,7 +159,7 @@ __device__ __forceinline__ d3 shfl3(d3 v, int src) {
 // Warp-cooperative getonlyGrad1 at a body-frame point known to every lane.
 template <bool MESH>
 __device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane) {
-    if (MESH) { d3 g = mk3(0, 0, 0); mesh_sdf_grad(S.mesh, tmp, 1e300, g); return g; }
+    if (MESH) { d3 g = mk3(0, 0, 0); mesh_sdf_grad(S.mesh, tmp, 1e300, g); return g; }   // every lane the same point: uniform control flow
     if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) return unit3(tmp);
     d3 q = tmp;
     if (S.kind == ISDF_SHAPE_BOX) {
@@ -157,6 +185,46 @@ __device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane) {
 
 // gradientDescent (swm:1000-1062), one speculative warp pass per outer iteration.
 // lanes 0..8: x - tau_d (taken when g > 0), lanes 9..17: x + tau_d (g < 0), lane 18: f(x), lanes 19..24: FD samples.
+// Mesh robots: a speculative pass would cost 25 independent BVH searches; instead the descent runs in the reference's
+// sequential order and every SDF evaluation is ONE warp-cooperative search (lane = candidate triangle / child box).
+__device__ void sv_gradient_descent_mesh(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0,
+                                         double &fx, double &x, unsigned &nevals, int lane, WideStack *stk) {
+    const DevMesh &M = A.shape.mesh;
+    const double alpha = 0.02, tol = 1e-5;
+    int iter = 0; bool stop = false;
+    double prev_x = 10000000.0;
+    x = x0;
+    while (iter < 300 && !stop && fabs(x - prev_x) > tol) {
+        d3 xt, v, a, j;
+        traj_pvaj(tr, x, xt, v, a, j);
+        FlatState fs;
+        flat_state(A.cfg.fp, v, a, j, fs);
+        const rot3 R = quat_rot(flat_quat(fs));
+        const d3 tmp = rot_applyT(R, p - xt);
+        d3 g = mk3(0, 0, 0);
+        const double f_here = mesh_sdf_grad_warp(M, tmp, 1e300, g, lane, stk);
+        if (iter == 0) { fx = f_here; nevals++; }
+        const d3 omg = flat_omega(fs);
+        const d3 rv = rot_applyT(R, v), wx = cross3(omg, tmp);
+        const double gd = g.x * -(rv.x + wx.x) + g.y * -(rv.y + wx.y) + g.z * -(rv.z + wx.z);
+        const int sgn = (int)(gd > 0) - (int)(gd < 0);
+        double tau = alpha;
+        prev_x = x;
+        for (int div = 1; div < 10; div++) {
+            iter = iter + 1; nevals++;
+            const double xc = fmax(fmin(x - tau * sgn, t_max), t_min);
+            d3 x2, v2, a2, j2;
+            traj_pvaj(tr, xc, x2, v2, a2, j2);
+            const rot3 R2 = quat_rot(flat_quat_only(A.cfg.fp, v2, a2));
+            d3 g2 = mk3(0, 0, 0);
+            const double fc = mesh_sdf_grad_warp(M, rot_applyT(R2, p - x2), 1e300, g2, lane, stk);
+            if ((fc - fx) < 0) { x = xc; fx = fc; break; }
+            tau = 0.5 * tau;
+            if (div == 9) stop = true;
+        }
+    }
+}
+
 template <bool MESH>
 __device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0,
                                     double &fx, double &x, unsigned &nevals, int lane) {
@@ -234,12 +302,13 @@ __device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, d
 // ---- k_sv_points: one warp per obstacle point -------------------------------------------------------------------------
 template <bool MESH>
 __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant__ SvArgs A) {
-    extern __shared__ double smem[];
-    double *sT = smem, *sC = smem + A.N;
+    extern __shared__ __align__(16) double smem[];
+    double *sC = smem, *sT = smem + 18 * A.N;
     __shared__ uint32_t sflags[SV_WARPS][SV_FLAG_WORDS];
-    for (int k = threadIdx.x; k < A.N; k += blockDim.x) sT[k] = A.T[k];
-    for (int k = threadIdx.x; k < 18 * A.N; k += blockDim.x) sC[k] = A.C[k];
-    __syncthreads();
+    __shared__ WideStack wstk[MESH ? SV_WARPS : 1];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+    stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
     const TrajView tr = {sT, sC, A.N};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Mloc = (A.P - A.rank + A.world - 1) / A.world;
@@ -341,7 +410,8 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                 // ---- descent inside the interval (swm:730-734) ---------------------------------------------------------
                 const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
                 double sdf_star = 1e1, t_star = 0;
-                sv_gradient_descent<MESH>(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
+                if (MESH) sv_gradient_descent_mesh(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane, &wstk[MESH ? warp : 0]);
+                else sv_gradient_descent<MESH>(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
                 if (sdf_star < min_sdf_star) { min_sdf_star = sdf_star; tstar = t_star; found = true; }
                 pos = kout;
             }
