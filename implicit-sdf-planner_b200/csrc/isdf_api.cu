@@ -467,6 +467,94 @@ extern "C" int isdf_points_in_aabb(isdf_ctx *c, const double *centre, double hal
     return 0;
 }
 
+// ---- obstacle gather (plan_manager.cpp:232-254 / pcs:182-216) -------------------------------------------------------------
+struct GatherBox { int a0[3], a1[3], l0[3], l1[3]; };
+__device__ __forceinline__ bool gather_includes(const DevGrid &G, const GatherBox &b, int i, int j, int k) {
+    if (i < b.a0[0] || i > b.a1[0] || j < b.a0[1] || j > b.a1[1] || k < b.a0[2] || k > b.a1[2]) return false;
+    if (!(i > b.l1[0] || i < b.l0[0] || j > b.l1[1] || j < b.l0[1] || k > b.l1[2] || k < b.l0[2])) return false;
+    return (G.bits[((size_t)i * G.Y + j) * G.Zw + (k >> 5)] >> (k & 31)) & 1u;
+}
+// one CTA; waypoints processed in order, a voxel is emitted by the FIRST waypoint that includes it; block-level ordered compaction
+__global__ void __launch_bounds__(256) k_gather_points(const DevGrid G, const double *wps, int nQ, double h, double ox, double oy, double oz,
+                                                       GatherBox *boxes, double *out, int cap, int *count) {
+    __shared__ int warp_cnt[8];
+    __shared__ int running;
+    for (int q = threadIdx.x; q < nQ; q += blockDim.x) {
+        GatherBox b;
+        const double c[3] = {wps[3 * q] + ox, wps[3 * q + 1] + oy, wps[3 * q + 2] + oz};
+        const double l[3] = {q == 0 ? 999.0 : wps[3 * (q - 1)], q == 0 ? 999.0 : wps[3 * (q - 1) + 1], q == 0 ? 999.0 : wps[3 * (q - 1) + 2]};
+        const int dims[3] = {G.X, G.Y, G.Z};
+        for (int a = 0; a < 3; a++) {
+            b.a0[a] = grid_axis_index(c[a] - h, G.bmin[a], G.bmax[a], G.res, dims[a]); b.a1[a] = grid_axis_index(c[a] + h, G.bmin[a], G.bmax[a], G.res, dims[a]);
+            b.l0[a] = grid_axis_index(l[a] - h, G.bmin[a], G.bmax[a], G.res, dims[a]); b.l1[a] = grid_axis_index(l[a] + h, G.bmin[a], G.bmax[a], G.res, dims[a]);
+        }
+        boxes[q] = b;
+    }
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < nQ; q++) {
+        const GatherBox b = boxes[q];
+        const int ny = b.a1[1] - b.a0[1] + 1, nz = b.a1[2] - b.a0[2] + 1;
+        const int nvox = (b.a1[0] - b.a0[0] + 1) * ny * nz;
+        for (int base = 0; base < nvox; base += blockDim.x) {
+            const int v = base + threadIdx.x;
+            bool emit = false; int i = 0, j = 0, k = 0;
+            if (v < nvox) {
+                i = b.a0[0] + v / (ny * nz); j = b.a0[1] + (v / nz) % ny; k = b.a0[2] + v % nz;
+                emit = gather_includes(G, b, i, j, k);
+                for (int p = 0; emit && p < q; p++) if (gather_includes(G, boxes[p], i, j, k)) emit = false;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, emit);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = running;
+            for (int w = 0; w < warp; w++) off += warp_cnt[w];
+            if (emit) {
+                const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                if (pos < cap) { out[3 * pos] = (i + 0.5) * G.res + G.bmin[0]; out[3 * pos + 1] = (j + 0.5) * G.res + G.bmin[1]; out[3 * pos + 2] = (k + 0.5) * G.res + G.bmin[2]; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_cnt[w]; running += t; }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) *count = running;
+}
+
+extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints, int nQ, double half_extent, const double *offset,
+                                           double *out_points, int cap, int *n, int set_as_points) {
+    if (!c || !waypoints || nQ < 1 || !n || cap < 0 || (cap > 0 && !out_points && !set_as_points)) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (!c->have_map) return fail(ISDF_ERR_STATE, "map not set");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    DevBuf<double> dw, dout; DevBuf<GatherBox> db; DevBuf<int> dn;
+    const int capd = cap > 0 ? cap : 1;
+    CU_TRY(dw.upload(waypoints, (size_t)3 * nQ, c->stream));
+    CU_TRY(dout.ensure((size_t)3 * capd)); CU_TRY(db.ensure(nQ)); CU_TRY(dn.ensure(1));
+    const double ox = offset ? offset[0] : 0.0, oy = offset ? offset[1] : 0.0, oz = offset ? offset[2] : 0.0;
+    k_gather_points<<<1, 256, 0, c->stream>>>(c->grid, dw.p, nQ, half_extent, ox, oy, oz, db.p, dout.p, capd, dn.p);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    int cnt = 0;
+    CU_TRY(cudaMemcpyAsync(&cnt, dn.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *n = cnt;
+    const int m = cnt < cap ? cnt : cap;
+    int rc = 0;
+    if (m > 0 && out_points) CU_TRY(cudaMemcpy(out_points, dout.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+    if (set_as_points) {
+        if (cnt > cap) rc = fail(ISDF_ERR_INVALID, "cap smaller than the obstacle list");
+        else {
+            std::vector<double> tmp((size_t)3 * (m > 0 ? m : 1));
+            if (m > 0) CU_TRY(cudaMemcpy(tmp.data(), dout.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+            cudaError_t e = c->sv.set_points(tmp.data(), m, c->stream);
+            if (e != cudaSuccess) rc = fail(ISDF_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    dw.release(); dout.release(); db.release(); dn.release();
+    return rc;
+}
+
 // ---- discrete evaluation ------------------------------------------------------------------------------------
 static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *d_C, double *d_out, cudaStream_t st) {
     const int K = c->cfg.integral_intervs;
@@ -572,6 +660,15 @@ extern "C" int isdf_eval_discrete(isdf_ctx *c, int N, const double *T, const dou
     r = body();
     if (r) poison(cost);
     return r;
+}
+
+extern "C" int isdf_get_piece_costs(isdf_ctx *c, double *piece_cost, int n) {
+    if (!c || !piece_cost || n < 0) return fail(ISDF_ERR_INVALID, "bad argument");
+    if ((size_t)n > c->d_piece_cost.n) return fail(ISDF_ERR_STATE, "no discrete evaluation with that many pieces yet");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaMemcpy(piece_cost, c->d_piece_cost.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 // ---- swept volume -------------------------------------------------------------------------------------------

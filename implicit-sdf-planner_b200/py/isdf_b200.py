@@ -26,7 +26,8 @@ ABI_SYMBOLS = ["isdf_default_config", "isdf_create", "isdf_destroy", "isdf_last_
                "isdf_set_shape_analytic", "isdf_set_shape_named", "isdf_set_shape_mesh", "isdf_shape_query",
                "isdf_set_map_u8", "isdf_set_map_f64", "isdf_points_in_aabb", "isdf_eval_discrete",
                "isdf_eval_discrete_device", "isdf_set_points", "isdf_eval_swept", "isdf_eval_swept_device",
-               "isdf_get_swept_results", "isdf_eval_swept_given"]
+               "isdf_get_swept_results", "isdf_eval_swept_given", "isdf_get_piece_costs",
+               "isdf_gather_obstacle_points"]
 
 
 class Config(C.Structure):
@@ -89,6 +90,8 @@ def load_library(path=None):
     lib.isdf_eval_swept.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp]
     lib.isdf_eval_swept_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     lib.isdf_get_swept_results.argtypes = [vp, dp, dp, dp]
+    lib.isdf_get_piece_costs.argtypes = [vp, dp, C.c_int]
+    lib.isdf_gather_obstacle_points.argtypes = [vp, dp, C.c_int, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int), C.c_int]
     lib.isdf_eval_swept_given.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
     for s in ABI_SYMBOLS:
         if s != "isdf_last_error":
@@ -195,6 +198,21 @@ class Evaluator:
         c = C.c_double(cost)
         self._check(self.lib.isdf_eval_discrete(self.h, N, _dp(T), _dp(Cc), C.byref(c), _dp(gC), _dp(gT)))
         return c.value, gC, gT
+
+    def gather_obstacle_points(self, waypoints, half, offset=(0.0, 0.0, 0.0), cap=1000000, set_as_points=False):
+        wp = _f64(waypoints).reshape(-1, 3)
+        off = _f64(offset).reshape(3)
+        out = np.zeros((cap, 3))
+        n = C.c_int(0)
+        self._check(self.lib.isdf_gather_obstacle_points(self.h, _dp(wp), wp.shape[0], float(half), _dp(off), _dp(out), cap, C.byref(n), int(set_as_points)))
+        if set_as_points:
+            self.n_points = n.value
+        return out[:min(n.value, cap)].copy(), n.value
+
+    def piece_costs(self, n):
+        out = np.zeros(n)
+        self._check(self.lib.isdf_get_piece_costs(self.h, _dp(out), n))
+        return out
 
     def set_points(self, pts):
         pts = _f64(pts).reshape(-1, 3)

@@ -115,6 +115,13 @@ int isdf_set_map_f64(isdf_ctx *ctx, const double *grid_map, int X, int Y, int Z,
 /* PCSmapManager::getPointsInAABB (pcs:148-170) on the device map; writes up to cap centres (cap x 3), returns count in *n */
 int isdf_points_in_aabb(isdf_ctx *ctx, const double *centre, double half_extent, double *out_points, int cap, int *n);
 
+/* The obstacle list of PlannerManager::generateTraj (plan_manager.cpp:232-254): for every waypoint in order, the occupied voxels of
+ * box(wp + offset, half) that are not in box(previous wp, half) (PCSmapManager::getPointsInAABBOutOfLastOne, pcs:182-216),
+ * de-duplicated by voxel. waypoints: nQ x 3 row-major. Writes up to cap centres in (first-including waypoint, voxel address)
+ * order and the total in *n. If set_as_points != 0 the list also becomes the swept-volume point set (== isdf_set_points). */
+int isdf_gather_obstacle_points(isdf_ctx *ctx, const double *waypoints, int nQ, double half_extent, const double *offset,
+                                double *out_points, int cap, int *n, int set_as_points);
+
 /* ---- discrete collision term: addTimeIntPenaltyParallel (hpp:432-554) with grad_cost_p (hpp:766-824) wired in */
 /* ACCUMULATES into *cost, gradC (6N x 3 col-major), gradT (N) exactly like the reference's reference arguments. */
 int isdf_eval_discrete(isdf_ctx *ctx, int N, const double *T, const double *coeffs,
@@ -123,6 +130,11 @@ int isdf_eval_discrete(isdf_ctx *ctx, int N, const double *T, const double *coef
  * are device pointers on ctx's device; cuda_stream is a cudaStream_t (NULL = default stream). Asynchronous. */
 int isdf_eval_discrete_device(isdf_ctx *ctx, int N, const double *d_T, const double *d_coeffs, double *d_out,
                               void *cuda_stream);
+
+/* per-piece cost terms of the last discrete evaluation (n <= N doubles). With B independent trajectories concatenated into one
+ * call (pieces b*N0 .. b*N0+N0-1 belong to trajectory b — the discrete term couples nothing across pieces, so a batch of
+ * random restarts is simply a longer coefficient block) the cost of trajectory b is the sum of its N0 entries. */
+int isdf_get_piece_costs(isdf_ctx *ctx, double *piece_cost, int n);
 
 /* ---- swept-volume term: addSaftyPenaOnSweptVolumeParallel (hpp:557-649) + getSDFofSweptVolume (swm:710-747) --- */
 /* parallel_points (plan_manager.cpp:246-254): P x 3 row-major world-frame voxel centres; resets lastTstar to 0 */

@@ -161,6 +161,18 @@ int orc_points_in_aabb(const uint8_t *occ, int X, int Y, int Z, const double *bm
     return (int)v.size();
 }
 
+// obstacle list (plan_manager.cpp:232-254); wps: nQ x 3; returns count, writes up to cap points
+int orc_gather_obstacle_points(const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res, const double *wps, int nQ,
+                               double half, const double *offset, double *out, int cap) {
+    Grid G; G.X = X; G.Y = Y; G.Z = Z; G.res = res; G.occ = occ;
+    G.bmin = V3(bmin[0], bmin[1], bmin[2]); G.bmax = V3(bmin[0] + X * res, bmin[1] + Y * res, bmin[2] + Z * res);
+    std::vector<V3> w(nQ), v;
+    for (int i = 0; i < nQ; i++) w[i] = V3(wps[3 * i], wps[3 * i + 1], wps[3 * i + 2]);
+    G.gather_obstacle_points(w, half, V3(offset[0], offset[1], offset[2]), v);
+    for (int i = 0; i < (int)v.size() && i < cap; i++) { out[3 * i] = v[i].x; out[3 * i + 1] = v[i].y; out[3 * i + 2] = v[i].z; }
+    return (int)v.size();
+}
+
 // ---- MINCO S3NU (adjacent step) --------------------------------------------------
 // headPVA/tailPVA: 3x3 column-major (columns = pos, vel, acc). inPs: 3 x (N-1) column-major. coeffs out: 6N x 3 col-major.
 int orc_minco_forward(int N, const double *headPVA, const double *tailPVA, const double *inPs, const double *T,

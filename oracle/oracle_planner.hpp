@@ -50,6 +50,36 @@ struct Grid {
     void proj_in_map(V3 &p) const {  // projInMap (pcs:130-137)
         for (int a = 0; a < 3; a++) { if (p[a] < bmin[a]) p[a] = bmin[a]; if (p[a] > bmax[a]) p[a] = bmax[a]; }
     }
+    // index box of an AABB after projInMap (pcs:184-197)
+    void index_box(const V3 &c, double h, int lo[3], int hi[3]) const {
+        V3 c1 = c - V3(h, h, h), c2 = c + V3(h, h, h);
+        proj_in_map(c1); proj_in_map(c2);
+        grid_index(c1, lo); grid_index(c2, hi);
+    }
+    // The obstacle list of plan_manager.cpp:232-254: for every waypoint in order, getPointsInAABBOutOfLastOne (pcs:182-216)
+    // inserts the occupied voxels of box(wp + offset) that are NOT in box(previous wp) into a map keyed by voxel id.
+    // Output order here: first-inserting waypoint, then the reference's loop order (x, y, z ascending); the reference's own
+    // order is the iteration order of an unordered_map (unspecified).
+    void gather_obstacle_points(const std::vector<V3> &wps, double h, const V3 &offset, std::vector<V3> &out) const {
+        std::vector<char> seen((size_t)X * Y * Z, 0);
+        V3 last(999, 999, 999);                                     // tmp_pos initial value (plan_manager.cpp:228)
+        for (const V3 &wp : wps) {
+            int a0[3], a1[3], l0[3], l1[3];
+            index_box(wp + offset, h, a0, a1);
+            index_box(last, h, l0, l1);
+            for (int i = a0[0]; i <= a1[0]; i++)
+                for (int j = a0[1]; j <= a1[1]; j++)
+                    for (int k = a0[2]; k <= a1[2]; k++) {
+                        if (i > l1[0] || i < l0[0] || j > l1[1] || j < l0[1] || k > l1[2] || k < l0[2]) {
+                            if (occupied(i, j, k)) {
+                                char &sn = seen[((size_t)i * Y + j) * Z + k];
+                                if (!sn) { sn = 1; out.push_back(centre(i, j, k)); }
+                            }
+                        }
+                    }
+            last = wp;
+        }
+    }
     // getPointsInAABB (pcs:148-170)
     void points_in_aabb(const V3 &c, double hx, double hy, double hz, std::vector<V3> &out) const {
         V3 c1 = c - V3(hx, hy, hz), c2 = c + V3(hx, hy, hz);

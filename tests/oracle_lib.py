@@ -57,6 +57,7 @@ def lib():
         L.orc_sdf_swept.restype = C.c_double
         L.orc_sdf_swept.argtypes = [C.POINTER(OrcConfig), C.c_void_p, C.c_int, dp, dp, dp, dp, dp]
         L.orc_points_in_aabb.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, dp, C.c_double, dp, C.c_double, dp, C.c_int]
+        L.orc_gather_obstacle_points.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, dp, C.c_double, dp, C.c_int, C.c_double, dp, dp, C.c_int]
         L.orc_minco_forward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         L.orc_minco_backward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         _lib = L
@@ -186,6 +187,16 @@ def points_in_aabb(occ, bmin, res, centre, half, cap=100000):
     X, Y, Z = occ.shape
     out = np.zeros((cap, 3))
     n = lib().orc_points_in_aabb(occ.ctypes.data_as(C.POINTER(C.c_uint8)), X, Y, Z, _p(f64(bmin)), float(res), _p(f64(centre)), float(half), _p(out), cap)
+    return out[:min(n, cap)].copy(), n
+
+
+def gather_obstacle_points(occ, bmin, res, wps, half, offset=(0, 0, 0), cap=2000000):
+    occ = np.ascontiguousarray(occ, dtype=np.uint8)
+    X, Y, Z = occ.shape
+    wps = f64(wps).reshape(-1, 3)
+    out = np.zeros((cap, 3))
+    n = lib().orc_gather_obstacle_points(occ.ctypes.data_as(C.POINTER(C.c_uint8)), X, Y, Z, _p(f64(bmin)), float(res), _p(wps), wps.shape[0],
+                                         float(half), _p(f64(offset)), _p(out), cap)
     return out[:min(n, cap)].copy(), n
 
 

@@ -428,3 +428,49 @@ def test_lbfgs_driver_on_gpu_callback_decreases_cost():
     assert r in (0, 1, -1008) or r <= -1009          # converged / stopped / max iterations / line-search limits: all leave the last iterate
     assert np.isfinite(fx.value) and fx.value < c0 and it.value >= 1 and evs.value >= it.value
     ev.close()
+
+
+def test_batch_of_trajectories_as_one_concatenated_block():
+    """BASELINE configs[4] in miniature: B random-restart trajectories evaluated in ONE call by concatenating their pieces;
+    per-trajectory gradients are bit-identical to separate evaluations, per-trajectory costs come from the piece costs."""
+    cfg, occ, _, _, _ = small_case(N=4, K=16, seed=3)
+    B, N0 = 5, 4
+    trajs = [W.make_trajectory(N0, [0, 0, 0], [50, 50, 34], seed=100 + b, jitter=0.3) for b in range(B)]
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    V, F = MESHES["rcone"]()
+    ev.set_shape_mesh(V, F, [0, 0, 0, 120, 0, 0])
+    singles = [ev.eval_discrete(T, Cc) for (T, Cc, _) in trajs]
+    # column-major 6*(B*N0) x 3 block: per axis, the B trajectories' 6*N0 coefficients back to back
+    Tall = np.concatenate([T for (T, _, _) in trajs])
+    Call = np.concatenate([np.concatenate([Cc.reshape(3, 6 * N0)[ax] for (_, Cc, _) in trajs]) for ax in range(3)])
+    c, gC, gT = ev.eval_discrete(Tall, Call)
+    pc = ev.piece_costs(B * N0)
+    gCm = gC.reshape(3, 6 * B * N0)
+    for b in range(B):
+        sc, sgC, sgT = singles[b]
+        assert np.array_equal(gCm[:, 6 * N0 * b:6 * N0 * (b + 1)].reshape(-1), sgC)
+        assert np.array_equal(gT[N0 * b:N0 * (b + 1)], sgT)
+        assert abs(pc[N0 * b:N0 * (b + 1)].sum() - sc) <= 1e-12 * max(abs(sc), 1.0)
+    assert abs(c - sum(s[0] for s in singles)) <= 1e-12 * abs(c)
+    ev.close()
+
+
+def test_obstacle_gather_matches_reference_semantics():
+    """plan_manager.cpp:232-254 + getPointsInAABBOutOfLastOne (pcs:182-216): same set, same (waypoint, address) order as the oracle."""
+    cfg, occ, T, Cc, wp = small_case(N=6, K=8, seed=4, noise=0.08)
+    half = cfg.kernel_size * cfg.occupancy_resolution / 3.0
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    for off in ([0.0, 0.0, 0.0], [0.5, -0.3, 1.2]):
+        a, na = ev.gather_obstacle_points(wp[1:-1], half, off)
+        b, nb = O.gather_obstacle_points(occ, BMIN, 1.0, wp[1:-1], half, off)
+        assert na == nb and na > 50 and np.array_equal(a, b)
+        assert len(np.unique(a, axis=0)) == na                     # de-duplicated
+    # and it can feed the swept-volume path directly
+    pts, n = ev.gather_obstacle_points(wp[1:-1], half, set_as_points=True)
+    ev.set_shape_named("Torus")
+    got = ev.eval_swept(T, Cc)
+    ref = O.eval_swept(O.config_from(cfg), O.Shape.named("Torus"), T, Cc, pts)
+    check_eval(got, (ref["cost"], ref["gradC"], ref["gradT"]), what="gather->swept")
+    ev.close()
