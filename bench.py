@@ -384,6 +384,27 @@ def run_ours(args):
     kernel_ms_alone = ev.stats().last_kernel_ms
     ms_e2e = statistics.mean(e2e_times)
 
+    # ---- context for N > 1: batch of random restarts, one trajectory per GPU, no collective (BASELINE configs[4] in miniature) ----
+    batch_weak = None
+    if world > 1:
+        import workloads as W
+        Tb, Cb, _ = W.make_trajectory(N, [0, 0, 0], [w["map_dim"]] * 3, seed=11 + rank, jitter=0.2)
+        ev.set_shard(0, 1)
+        d_Tb, d_Cb = torch.from_numpy(Tb).to(dev), torch.from_numpy(Cb).to(dev)
+        for _ in range(4):
+            ev.eval_discrete_device(N, d_Tb.data_ptr(), d_Cb.data_ptr(), d_out.data_ptr(), stream)
+        tb = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); barrier()
+            e0.record(); ev.eval_discrete_device(N, d_Tb.data_ptr(), d_Cb.data_ptr(), d_out.data_ptr(), stream); e1.record()
+            torch.cuda.synchronize()
+            tb.append(max_over_ranks(e0.elapsed_time(e1)))
+        ev.set_shard(rank, world)
+        batch_weak = {"evals_per_s": world * 1e3 / statistics.mean(tb), "ms_per_step_max_over_ranks": statistics.mean(tb), "scaling": "weak",
+                      "what": f"{world} different trajectories (seed 11+rank), one per GPU, evaluated concurrently; no collective"}
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         ab = algorithmic_bytes(w)
@@ -402,7 +423,7 @@ def run_ours(args):
                 "extra": {"pairs_per_eval": int(pairs), "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step_warm_l2": statistics.mean(warm),
                           "evals_per_s_warm_l2": 1e3 / statistics.mean(warm), "ms_min": min(times), "ms_max": max(times),
                           "kernel_ms_in_host_call": kernel_ms_alone, "wall_s_timed_loop": wall,
-                          "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:]))}}
+                          "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:])), "batch_weak": batch_weak}}
         if world == 1 and not args.no_lbfgs:
             try:
                 line["extra"]["lbfgs"] = lbfgs_ours(local)
