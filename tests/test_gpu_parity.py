@@ -154,12 +154,13 @@ def test_discrete_parity_mesh(mesh):
     ev.close()
 
 
-@pytest.mark.parametrize("case", ["N1", "K1", "res05", "ks17", "dense", "outside", "collision_only", "dynamics_only", "empty_map"])
+@pytest.mark.parametrize("case", ["N1", "K1", "res05", "ks17", "ks40", "dense", "outside", "collision_only", "dynamics_only", "empty_map"])
 def test_discrete_edge_cases(case):
     N, K, seed, noise, ks, res, flags = 3, 12, 9, 0.03, 13, 1.0, None
     if case == "N1": N = 1
     if case == "K1": K = 1
     if case == "ks17": ks = 17
+    if case == "ks40": ks, N, K = 40, 2, 4      # window taller than 32 voxels: exercises the z-chunk loop of the bit scan
     if case == "dense": noise = 0.6
     if case == "collision_only": flags = I.WITH_COLLISION
     if case == "dynamics_only": flags = I.WITH_DYNAMICS
