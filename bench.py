@@ -453,7 +453,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lbfgs", action="store_true", help="skip the secondary L-BFGS iterations/s measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
-    ap.add_argument("--ref-pieces", type=int, default=2, help="--impl reference: pieces per step sample")
+    ap.add_argument("--ref-pieces", type=int, default=16, help="--impl reference: pieces per step sample (of 64)")
     ap.add_argument("--robot", default="mesh", help="mesh (headline) or an analytic shape name, e.g. SmoothIntersection (diagnostic runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -238,7 +238,8 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
     HostMesh hm; std::string err;
     // the bitmap shortcut is sized for the smallest bound the kernels use: safety_hor (discrete) — the swept path uses
     // 2*safety_hor + 0.1 >= safety_hor
-    if (!build_host_mesh(V, nV, F, nF, poly_params, c->cfg.safety_hor, hm, err)) return fail(ISDF_ERR_INVALID, err);
+    if (!build_host_mesh(V, nV, F, nF, poly_params, c->cfg.safety_hor, hm, err))
+        return fail(err.find("not a closed") != std::string::npos ? ISDF_ERR_UNSUPPORTED : ISDF_ERR_INVALID, err);
     CU_TRY(c->d_nodes.upload(hm.nodes.data(), hm.nodes.size(), c->stream));
     CU_TRY(c->d_wnodes.upload(hm.wnodes.data(), hm.wnodes.size(), c->stream));
     CU_TRY(c->d_tris.upload(hm.tris.data(), hm.tris.size(), c->stream));

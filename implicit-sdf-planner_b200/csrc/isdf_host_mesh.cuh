@@ -113,6 +113,21 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
             for (int a = 0; a < 3; a++) vn[u][a] += ang * fn[t][a];
         }
     }
+    // The ±1 sign from pseudonormals is the generalised winding number's 0/1 only for a CLOSED, consistently oriented surface:
+    // every undirected edge must be used exactly twice, once in each direction.
+    {
+        std::map<std::pair<int, int>, int> directed;
+        for (int t = 0; t < nF; t++)
+            for (int k = 0; k < 3; k++) directed[{fi[t][k], fi[t][(k + 1) % 3]}]++;
+        for (const auto &e : directed) {
+            const auto rev = directed.find({e.first.second, e.first.first});
+            if (e.first.first == e.first.second || e.second != 1 || rev == directed.end() || rev->second != 1) {
+                err = "mesh is not a closed, consistently oriented 2-manifold (open, duplicated or flipped edge); the winding-number "
+                      "sign of soups / open meshes is not supported by this build";
+                return false;
+            }
+        }
+    }
     // BVH
     std::vector<int> order(nF);
     std::iota(order.begin(), order.end(), 0);

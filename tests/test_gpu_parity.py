@@ -232,6 +232,14 @@ def test_errors_surface_as_status_and_nan_cost():
         ev.set_shape_named("NoSuchShape")
     with pytest.raises(I.IsdfError):
         ev.set_shard(3, 2)
+    V, F = W.box_mesh()
+    with pytest.raises(I.IsdfError) as e:      # open mesh: the winding-number sign is not defined by a closed surface
+        ev.set_shape_mesh(V, F[:-1])
+    assert e.value.code == -4
+    with pytest.raises(I.IsdfError) as e:      # one flipped triangle: inconsistent orientation
+        F2 = F.copy(); F2[0] = F2[0][::-1]
+        ev.set_shape_mesh(V, F2)
+    assert e.value.code == -4
     ev.close()
 
 
