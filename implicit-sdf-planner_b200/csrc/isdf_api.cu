@@ -45,7 +45,7 @@ struct isdf_ctx {
     // shape
     bool have_shape = false;
     DevShape shape;
-    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt;
+    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
     DevBuf<int> d_tickets;       // N piece tickets + 1 pieces_done (+ swept counters)
@@ -137,7 +137,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
-    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
+    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_split_ticket.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
     c->sv.release();
@@ -244,12 +244,13 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
     CU_TRY(c->d_wnodes.upload(hm.wnodes.data(), hm.wnodes.size(), c->stream));
     CU_TRY(c->d_tris.upload(hm.tris.data(), hm.tris.size(), c->stream));
     CU_TRY(c->d_pn.upload(hm.pnormals.data(), hm.pnormals.size(), c->stream));
+    CU_TRY(c->d_obb.upload(hm.leaf_obb.data(), hm.leaf_obb.size(), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     std::memset(&c->shape, 0, sizeof(c->shape));
     c->shape.kind = ISDF_SHAPE_MESH;
     shape_common(c, nullptr, nullptr);
     DevMesh m = hm.view();
-    m.nodes = c->d_nodes.p; m.wnodes = c->d_wnodes.p; m.tris = c->d_tris.p; m.pnormals = c->d_pn.p;
+    m.nodes = c->d_nodes.p; m.wnodes = c->d_wnodes.p; m.tris = c->d_tris.p; m.pnormals = c->d_pn.p; m.leaf_obb = c->d_obb.p;
     // per-cell signed distance + seed triangle, computed on the device with the freshly uploaded BVH
     const size_t ncell = (size_t)m.gdim[0] * m.gdim[1] * m.gdim[2];
     CU_TRY(c->d_cell_dist.ensure(ncell));
@@ -765,7 +766,12 @@ extern "C" int isdf_get_swept_results(isdf_ctx *c, double *tstar, double *sdf, d
 
 
 // ---- internal diagnostics (not part of include/isdf.h) ------------------------------------------------------------
-extern "C" int isdf_dbg_enable(isdf_ctx *c, int on) { if (!c) return -1; c->dbg_on = on != 0; return 0; }
+extern "C" int isdf_dbg_enable(isdf_ctx *c, int on) { if (!c) return -1; c->dbg_on = on != 0; c->sv.dbg_on = on != 0; return 0; }
+extern "C" int isdf_dbg_swept_stats(isdf_ctx *c, unsigned long long *out, long long n) {
+    if (!c || !out || (size_t)n > c->sv.d_dbg.n) return -1;
+    cudaStreamSynchronize(c->stream);
+    return cudaMemcpy(out, c->sv.d_dbg.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
 extern "C" int isdf_dbg_sample_stats(isdf_ctx *c, unsigned long long *out, long long n) {
     if (!c || !out || (size_t)n > c->d_dbg.n) return -1;
     if (cudaSetDevice(c->device) != cudaSuccess) return -3;

@@ -17,14 +17,14 @@ namespace isdf {
 struct HostMesh {
     std::vector<BvhNode> nodes;
     std::vector<WideNode> wnodes;
-    std::vector<double> tris, pnormals;
+    std::vector<double> tris, pnormals, leaf_obb;
     int ntris = 0;
     int gdim[3] = {0, 0, 0};
     double glo[3] = {0, 0, 0}, gcell = 0, ghd = 0, gpad = 0, sign_radius = 0;
     double blo[3] = {0, 0, 0}, bhi[3] = {0, 0, 0};
     DevMesh view() const {  // host pointers; same code path as the device for the bitmap construction
         DevMesh m;
-        m.nodes = nodes.data(); m.wnodes = wnodes.data(); m.tris = tris.data(); m.pnormals = pnormals.data(); m.cell_dist = nullptr; m.cell_seed = nullptr; m.cell_off = nullptr; m.cell_cnt = nullptr; m.cand = nullptr;
+        m.nodes = nodes.data(); m.wnodes = wnodes.data(); m.tris = tris.data(); m.pnormals = pnormals.data(); m.leaf_obb = leaf_obb.empty() ? nullptr : leaf_obb.data(); m.cell_dist = nullptr; m.cell_seed = nullptr; m.cell_off = nullptr; m.cell_cnt = nullptr; m.cand = nullptr;
         m.ntris = ntris;
         for (int a = 0; a < 3; a++) { m.gdim[a] = gdim[a]; m.glo[a] = glo[a]; m.blo[a] = blo[a]; m.bhi[a] = bhi[a]; }
         m.gcell = gcell; m.ghd = ghd; m.gpad = gpad; m.sign_radius = sign_radius;
@@ -212,6 +212,56 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
                 }
             }
             out.wnodes[job.wide] = w;
+        }
+        // oriented boxes of the leaves (see DevMesh::leaf_obb): axis 0 = area-weighted mean normal of the leaf's triangles,
+        // axis 1 = its longest edge projected into the plane, axis 2 = their cross product; extents from the vertices,
+        // padded so that rounding can never put a vertex outside the box
+        out.leaf_obb.assign((size_t)15 * nF, 0.0);
+        for (const auto &b : bn) {
+            if (b.left >= 0) continue;
+            double n[3] = {0, 0, 0}, le[3] = {0, 0, 0}, le2 = -1.0;
+            std::vector<std::array<double, 3>> pts;
+            for (int t = b.first; t < b.first + b.count; t++) {
+                const double *T = &out.tris[(size_t)9 * t];
+                const double A[3] = {T[0], T[1], T[2]}, B[3] = {T[0] + T[3], T[1] + T[4], T[2] + T[5]}, Cc[3] = {T[0] + T[6], T[1] + T[7], T[2] + T[8]};
+                pts.push_back({A[0], A[1], A[2]}); pts.push_back({B[0], B[1], B[2]}); pts.push_back({Cc[0], Cc[1], Cc[2]});
+                n[0] += T[4] * T[8] - T[5] * T[7]; n[1] += T[5] * T[6] - T[3] * T[8]; n[2] += T[3] * T[7] - T[4] * T[6];
+                const double *E[3][2] = {{A, B}, {B, Cc}, {Cc, A}};
+                for (auto &e : E) {
+                    const double d[3] = {e[1][0] - e[0][0], e[1][1] - e[0][1], e[1][2] - e[0][2]};
+                    const double l2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                    if (l2 > le2) { le2 = l2; le[0] = d[0]; le[1] = d[1]; le[2] = d[2]; }
+                }
+            }
+            double ax[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            const double nl = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (nl > 1e-300 && le2 > 0) {
+                for (int a = 0; a < 3; a++) n[a] /= nl;
+                const double dp = le[0] * n[0] + le[1] * n[1] + le[2] * n[2];
+                double u[3] = {le[0] - dp * n[0], le[1] - dp * n[1], le[2] - dp * n[2]};
+                const double ul = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+                if (ul > 1e-9 * std::sqrt(le2)) {
+                    for (int a = 0; a < 3; a++) u[a] /= ul;
+                    const double w[3] = {n[1] * u[2] - n[2] * u[1], n[2] * u[0] - n[0] * u[2], n[0] * u[1] - n[1] * u[0]};
+                    for (int a = 0; a < 3; a++) { ax[0][a] = n[a]; ax[1][a] = u[a]; ax[2][a] = w[a]; }
+                }
+            }
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, scale = 0;
+            for (const auto &q : pts)
+                for (int k = 0; k < 3; k++) {
+                    const double pr = q[0] * ax[k][0] + q[1] * ax[k][1] + q[2] * ax[k][2];
+                    lo[k] = std::min(lo[k], pr); hi[k] = std::max(hi[k], pr);
+                    scale = std::max(scale, std::fabs(pr));
+                }
+            double *o = &out.leaf_obb[(size_t)15 * b.first];
+            for (int a = 0; a < 3; a++) {
+                o[a] = 0.0;
+                for (int k = 0; k < 3; k++) o[a] += 0.5 * (lo[k] + hi[k]) * ax[k][a];
+            }
+            for (int k = 0; k < 3; k++) {
+                for (int a = 0; a < 3; a++) o[3 + 3 * k + a] = ax[k][a];
+                o[12 + k] = 0.5 * (hi[k] - lo[k]) + 1e-9 * (1.0 + scale);
+            }
         }
         if (max_depth > 3) { err = "mesh too large for the 3-level 32-ary tree (more than ~130k triangles)"; return false; }
     }

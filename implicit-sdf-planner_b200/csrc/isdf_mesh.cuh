@@ -35,6 +35,11 @@ struct DevMesh {
     const WideNode *wnodes; // wnodes[0] is the root of the 32-ary tree
     const double *tris;     // 9 doubles per triangle in leaf order: a, ab, ac
     const double *pnormals; // 21 doubles per triangle: face, edge ab, edge bc, edge ca, vertex a, b, c
+    // oriented box of every 32-ary-tree leaf, 15 doubles at index first_tri: centre, three unit axes (leaf normal first), half
+    // extents. A leaf is a handful of adjacent triangles, i.e. a nearly flat patch: the oriented box is ~1 mm thick where the
+    // axis-aligned one is centimetres, and 1-2 m away from the mesh (the swept-volume range test) that difference decides
+    // whether a search opens ten leaves or a quarter of the mesh. May be null (no extra pruning).
+    const double *leaf_obb;
     // body-frame cell grid over the mesh AABB padded by gpad (filled on the device at isdf_set_shape_mesh time):
     const float *cell_dist;     // signed distance of the cell CENTRE to the mesh
     const uint32_t *cell_seed;  // triangle (leaf order) nearest to the cell centre: a tight initial bound for queries in the cell
@@ -249,8 +254,17 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
             const double ex = fmax(fmax(nd->lo[0][lane] - p.x, p.x - nd->hi[0][lane]), 0.0);
             const double ey = fmax(fmax(nd->lo[1][lane] - p.y, p.y - nd->hi[1][lane]), 0.0);
             const double ez = fmax(fmax(nd->lo[2][lane] - p.z, p.z - nd->hi[2][lane]), 0.0);
-            const double d2 = ex * ex + ey * ey + ez * ez;
-            const bool alive = (ch != WIDE_EMPTY) && (d2 < best);
+            double d2 = ex * ex + ey * ey + ez * ez;
+            bool alive = (ch != WIDE_EMPTY) && (d2 < best);
+            if (alive && ch < 0 && M.leaf_obb) {   // second, tighter lower bound for leaves: distance to the oriented box
+                const double *o = M.leaf_obb + 15 * (size_t)((~ch) >> 3);
+                const d3 r = mk3(p.x - o[0], p.y - o[1], p.z - o[2]);
+                const double e0 = fmax(fabs(r.x * o[3] + r.y * o[4] + r.z * o[5]) - o[12], 0.0);
+                const double e1 = fmax(fabs(r.x * o[6] + r.y * o[7] + r.z * o[8]) - o[13], 0.0);
+                const double e2 = fmax(fabs(r.x * o[9] + r.y * o[10] + r.z * o[11]) - o[14], 0.0);
+                d2 = fmax(d2, e0 * e0 + e1 * e1 + e2 * e2);
+                alive = d2 < best;
+            }
             // ---- leaves: compacted into a shared list, then 8 per pass x 4 triangle slots ------------------------------
             const bool is_leaf = alive && ch < 0;
             const unsigned leafmask = __ballot_sync(0xffffffffu, is_leaf);

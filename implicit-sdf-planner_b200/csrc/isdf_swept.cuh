@@ -105,6 +105,7 @@ struct SvArgs {
     unsigned long long *counter;  // reference-equivalent SDF evaluation count
     int rank, world;
     const double *g_t, *g_s, *g_g;  // tier-T1: given t*, sdf*, g_rel (null = search)
+    unsigned long long *dbg;        // -DISDF_PHASE_TIMING: 8 per point {total, coarse, bracket pass, exact pass, descent, intervals, exact searches, -}
 };
 
 // ---- k_sv_table ---------------------------------------------------------------------------------------------------
@@ -143,6 +144,41 @@ __device__ __forceinline__ double sv_sdf_bounded(const DevShape &S, d3 prel, dou
     return shape_sdf_analytic(S, prel);
 }
 
+// Cell-grid bracket of the mesh SDF at a body-frame point: the SDF is 1-Lipschitz, so every point of a cell lies within
+// ghd of the cell centre's signed distance. Outside the grid only the lower bound gpad is known.
+__device__ __forceinline__ void mesh_bracket(const DevMesh &M, d3 prel, double &lo, double &hi) {
+    lo = -1e300; hi = 1e300;
+    if (M.gdim[0] <= 0) return;
+    const int cell = mesh_cell_index(M, prel);
+    if (cell < 0) { lo = M.gpad; return; }
+    const double dc = (double)__ldg(M.cell_dist + cell);
+    lo = dc - M.ghd; hi = dc + M.ghd;
+}
+
+__device__ __forceinline__ d3 sv_body_point(const SvArgs &A, const TrajView &tr, d3 p, double t) {
+    d3 x, v, a, j;
+    traj_pvaj(tr, t, x, v, a, j);
+    const rot3 R = quat_rot(flat_quat_only(A.cfg.fp, v, a));
+    return rot_applyT(R, p - x);
+}
+
+// Exact mesh SDF for the lanes flagged in `need` (each with its own body-frame point): one warp-cooperative search per
+// flagged lane, in lane order. A lane-per-query search costs ~10x more here because the interesting queries sit 1-2 m from
+// the mesh, where a closest-triangle search prunes badly and 32 private traversals diverge.
+__device__ __forceinline__ double mesh_sdf_each(const DevMesh &M, bool need, d3 prel, double reach, double dflt, int lane, WideStack *stk) {
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    double out = dflt;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const d3 q = mk3(__shfl_sync(0xffffffffu, prel.x, src), __shfl_sync(0xffffffffu, prel.y, src), __shfl_sync(0xffffffffu, prel.z, src));
+        d3 g;
+        const double v = mesh_sdf_grad_warp(M, q, reach, g, lane, stk);
+        if (lane == src) out = v;
+    }
+    return out;
+}
+
 // getSDFAtTimeStamp (swm:550-556)
 template <bool MESH>
 __device__ __forceinline__ double sv_sdf_at(const SvArgs &A, const TrajView &tr, d3 p, double t, double reach) {
@@ -158,8 +194,8 @@ __device__ __forceinline__ d3 shfl3(d3 v, int src) {
 
 // Warp-cooperative getonlyGrad1 at a body-frame point known to every lane.
 template <bool MESH>
-__device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane) {
-    if (MESH) { d3 g = mk3(0, 0, 0); mesh_sdf_grad(S.mesh, tmp, 1e300, g); return g; }   // every lane the same point: uniform control flow
+__device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane, WideStack *stk) {
+    if (MESH) { d3 g = mk3(0, 0, 0); mesh_sdf_grad_warp(S.mesh, tmp, 1e300, g, lane, stk); return g; }
     if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) return unit3(tmp);
     d3 q = tmp;
     if (S.kind == ISDF_SHAPE_BOX) {
@@ -325,6 +361,16 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
     d3 grel = mk3(0, 0, 0);
     unsigned nevals = 0;
     bool found = false;
+#ifdef ISDF_PHASE_TIMING
+    const long long pt_begin = clock64();
+    long long pt_coarse = 0, pt_p1 = 0, pt_p2 = 0, pt_gd = 0, pt_mark = 0;
+    unsigned pt_intervals = 0, pt_exact = 0;
+#define PT_MARK() (pt_mark = clock64())
+#define PT_ADD(acc) ((acc) += clock64() - pt_mark)
+#else
+#define PT_MARK() ((void)0)
+#define PT_ADD(acc) ((void)0)
+#endif
 
     if (A.g_t) {
         sdf_value = A.g_s[pk]; tstar = A.g_t[pk]; grel = mk3(A.g_g[3 * pk], A.g_g[3 * pk + 1], A.g_g[3 * pk + 2]);
@@ -332,21 +378,33 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
     } else {
         // ---- coarse scan: in-range bitmap -------------------------------------------------------------------------
         uint32_t *fl = sflags[warp];
+        PT_MARK();
         for (int base = 0; base < nc; base += 32) {
             const int k = base + lane;
-            bool in = false;
+            bool in = false, undecided = false;
+            d3 prel_k = mk3(0, 0, 0);
             if (k < nc) {
                 const double *o = A.poses + 12 * (size_t)k;
                 const d3 d = mk3(p.x - __ldg(o), p.y - __ldg(o + 1), p.z - __ldg(o + 2));
                 const d3 prel = mk3(__ldg(o + 3) * d.x + __ldg(o + 6) * d.y + __ldg(o + 9) * d.z,
                                     __ldg(o + 4) * d.x + __ldg(o + 7) * d.y + __ldg(o + 10) * d.z,
                                     __ldg(o + 5) * d.x + __ldg(o + 8) * d.y + __ldg(o + 11) * d.z);
-                in = sv_sdf_bounded<MESH>(A.shape, prel, inf) < inf;
+                if (MESH) {   // the cell bracket settles the range test for everything but a thin band around `inf`
+                    double blo, bhi;
+                    mesh_bracket(A.shape.mesh, prel, blo, bhi);
+                    if (bhi < inf) in = true;
+                    else if (blo < inf) { undecided = true; prel_k = prel; }
+                } else in = sv_sdf_bounded<MESH>(A.shape, prel, inf) < inf;
+            }
+            if (MESH) {
+                const double v = mesh_sdf_each(A.shape.mesh, undecided, prel_k, inf, inf, lane, &wstk[MESH ? warp : 0]);
+                if (undecided) in = v < inf;
             }
             const unsigned b = __ballot_sync(0xffffffffu, in);
             if (lane == 0) fl[base >> 5] = b;
         }
         __syncwarp();
+        PT_ADD(pt_coarse);
         nevals += nc;
         const int nwords = (nc + 31) >> 5;
         // last run entry (in-range sample whose predecessor is out of range): its SDF initialises range_mindis (quirk Q2)
@@ -358,7 +416,9 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
             if (starts) last_entry = w * 32 + (31 - __clz(starts));
         }
         if (last_entry >= 0) {
-            double range_mindis = sv_sdf_at<MESH>(A, tr, p, A.times[last_entry], inf);  // same value the coarse pass saw
+            double range_mindis;   // same value the coarse pass saw
+            if (MESH) { d3 g_; range_mindis = mesh_sdf_grad_warp(A.shape.mesh, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, &wstk[MESH ? warp : 0]); }
+            else range_mindis = sv_sdf_at<MESH>(A, tr, p, A.times[last_entry], inf);
             double range_time_seed = 0.0;
             double min_sdf_star = 1e1;
             // walk the closed runs in order
@@ -385,13 +445,49 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                 const double ub = fmin(dur, A.times[kout] + 0.2);
                 // ---- fine scan of [lb, ub) at dt = 0.02 (swm:423-438): t advances by repeated addition ----------------
                 {
+                    // Mesh robots: the reference keeps the FIRST sample attaining the minimum over the interval. A sample
+                    // whose cell lower bound exceeds the smallest cell upper bound of the interval cannot be that sample, so
+                    // pass 1 brackets every sample from the cell grid (no search) and pass 2 runs the exact closest-triangle
+                    // search only on the survivors around the closest approach. Skipped samples compare as +inf: the selected
+                    // sample, its value and the reference's evaluation count are unchanged.
+                    double cut = 1e300;
+                    PT_MARK();
+                    if (MESH) {
+                        double t = lb;
+                        for (int q = 0; q < lane; q++) t += 0.02;
+                        while (__any_sync(0xffffffffu, t < ub)) {
+                            if (t < ub) {
+                                double blo, bhi;
+                                mesh_bracket(A.shape.mesh, sv_body_point(A, tr, p, t), blo, bhi);
+                                cut = fmin(cut, bhi);
+                            }
+                            for (int q = 0; q < 32; q++) t += 0.02;
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) cut = fmin(cut, __shfl_xor_sync(0xffffffffu, cut, o));
+                    }
+                    PT_ADD(pt_p1);
+                    PT_MARK();
                     double t = lb;
                     for (int q = 0; q < lane; q++) t += 0.02;
                     int mi = lane;
                     while (__any_sync(0xffffffffu, t < ub)) {
                         const bool valid = t < ub;
                         double dis = 1e300;
-                        if (valid) dis = sv_sdf_at<MESH>(A, tr, p, t, inf);
+                        if (MESH) {
+                            bool need = false;
+                            d3 prel = mk3(0, 0, 0);
+                            if (valid) {
+                                prel = sv_body_point(A, tr, p, t);
+                                double blo, bhi;
+                                mesh_bracket(A.shape.mesh, prel, blo, bhi);
+                                need = blo <= cut;
+                            }
+#ifdef ISDF_PHASE_TIMING
+                            pt_exact += __popc(__ballot_sync(0xffffffffu, need));
+#endif
+                            dis = mesh_sdf_each(A.shape.mesh, need, prel, inf, 1e300, lane, &wstk[MESH ? warp : 0]);
+                        } else if (valid) dis = sv_sdf_at<MESH>(A, tr, p, t, inf);
                         nevals += __popc(__ballot_sync(0xffffffffu, valid));
                         // warp argmin, ties -> smaller sample index (first occurrence wins under the strict '<')
                         double bd = dis; int bi = mi; double bt = t;
@@ -406,13 +502,19 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                         for (int q = 0; q < 32; q++) t += 0.02;
                         mi += 32;
                     }
+                    PT_ADD(pt_p2);
                 }
+                PT_MARK();
                 // ---- descent inside the interval (swm:730-734) ---------------------------------------------------------
                 const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
                 double sdf_star = 1e1, t_star = 0;
                 if (MESH) sv_gradient_descent_mesh(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane, &wstk[MESH ? warp : 0]);
                 else sv_gradient_descent<MESH>(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
                 if (sdf_star < min_sdf_star) { min_sdf_star = sdf_star; tstar = t_star; found = true; }
+                PT_ADD(pt_gd);
+#ifdef ISDF_PHASE_TIMING
+                pt_intervals++;
+#endif
                 pos = kout;
             }
             if (found) {
@@ -421,11 +523,18 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                 d3 x, v, a, j;
                 traj_pvaj(tr, tstar, x, v, a, j);
                 const rot3 R = quat_rot(flat_quat_only(cfg.fp, v, a));
-                grel = warp_grad<MESH>(A.shape, rot_applyT(R, p - x), lane);
+                grel = warp_grad<MESH>(A.shape, rot_applyT(R, p - x), lane, &wstk[MESH ? warp : 0]);
             }
         }
     }
 
+#ifdef ISDF_PHASE_TIMING
+    if (A.dbg && lane == 0) {
+        unsigned long long *o = A.dbg + 8 * (size_t)pk;
+        o[0] = (unsigned long long)(clock64() - pt_begin); o[1] = pt_coarse; o[2] = pt_p1; o[3] = pt_p2; o[4] = pt_gd;
+        o[5] = pt_intervals; o[6] = pt_exact; o[7] = 0;
+    }
+#endif
     // ---- chain-rule tail (hpp:578-636) ----------------------------------------------------------------------------------
     int piece = -1;
     if (lane == 0) {
@@ -511,7 +620,8 @@ struct SweptState {
     int P = 0;
     DevBuf<double> d_pts, d_tstar, d_sdf, d_grel, d_times, d_poses, d_state, d_partial, d_piece_gdt, d_piece_cost;
     DevBuf<int> d_piece, d_meta;
-    DevBuf<unsigned long long> d_counter;
+    DevBuf<unsigned long long> d_counter, d_dbg;
+    bool dbg_on = false;
 
     cudaError_t set_points(const double *pts, int n, cudaStream_t st) {
         cudaError_t e = cudaSuccess;
@@ -555,6 +665,12 @@ struct SweptState {
         A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
         A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
         A.out = d_out; A.counter = d_counter.p; A.rank = rank; A.world = world; A.g_t = g_t; A.g_s = g_s; A.g_g = g_g;
+        A.dbg = nullptr;
+        if (dbg_on) {
+            if ((e = d_dbg.ensure((size_t)8 * P)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(d_dbg.p, 0, sizeof(unsigned long long) * 8 * P, st)) != cudaSuccess) return e;
+            A.dbg = d_dbg.p;
+        }
         const size_t sm = sizeof(double) * 19 * (size_t)N;
         if (sm > 200 * 1024) return cudaErrorInvalidValue;
         if ((e = cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
@@ -577,7 +693,7 @@ struct SweptState {
     }
     void release() {
         d_pts.release(); d_tstar.release(); d_sdf.release(); d_grel.release(); d_times.release(); d_poses.release(); d_state.release();
-        d_partial.release(); d_piece_gdt.release(); d_piece_cost.release(); d_piece.release(); d_meta.release(); d_counter.release();
+        d_partial.release(); d_piece_gdt.release(); d_piece_cost.release(); d_piece.release(); d_meta.release(); d_counter.release(); d_dbg.release();
     }
 };
 
