@@ -7,12 +7,15 @@
 //   k_sv_table : the coarse time grid t = 0, 0.2, ... (same running sum as the reference's for-loop) and the robot
 //                pose at each coarse time are computed ONCE per evaluation and shared by every point (the reference
 //                recomputes the pose per point per sample);
-//   k_sv_points: one WARP per obstacle point. Lanes split the coarse scan (ballot -> in-range bitmap -> intervals via
+//   k_sv_points: analytic shapes — one WARP per obstacle point. Lanes split the coarse scan (ballot -> in-range bitmap -> intervals via
 //                bit scans), split each fine scan, and run the sign-descent SPECULATIVELY: in one pass the 32 lanes
 //                evaluate f(x), the six finite-difference samples of the gradient and all 18 candidate steps
 //                x -/+ 0.02/2^d, so an outer iteration costs one SDF latency instead of up to 9 + 7 dependent ones.
 //                Accept/reject decisions replay the reference's sequential logic exactly (same comparisons, same
 //                iteration accounting);
+//   k_sv_points_mesh: mesh robots — one CTA (8 warps) per obstacle point; every exact SDF value is a warp-cooperative
+//                closest-triangle search, the scans are pruned with the body-frame cell grid's Lipschitz brackets and
+//                the warps evaluate the descent's step candidates in parallel (details at the kernel);
 //   k_sv_reduce / k_sv_finish: deterministic per-piece reduction (fixed thread->point map, fixed trees) and the
 //                gradT(j<i) prefix of hpp:642-645 as a suffix sum.
 #pragma once
@@ -138,12 +141,6 @@ __global__ void __launch_bounds__(256) k_sv_table(const __grid_constant__ SvArgs
 }
 
 // ---- helpers for k_sv_points ------------------------------------------------------------------------------------
-template <bool MESH>
-__device__ __forceinline__ double sv_sdf_bounded(const DevShape &S, d3 prel, double reach) {
-    if (MESH) { d3 g; return mesh_sdf_grad(S.mesh, prel, reach, g); }
-    return shape_sdf_analytic(S, prel);
-}
-
 // Cell-grid bracket of the mesh SDF at a body-frame point: the SDF is 1-Lipschitz, so every point of a cell lies within
 // ghd of the cell centre's signed distance. Outside the grid only the lower bound gpad is known.
 __device__ __forceinline__ void mesh_bracket(const DevMesh &M, d3 prel, double &lo, double &hi) {
@@ -179,23 +176,17 @@ __device__ __forceinline__ double mesh_sdf_each(const DevMesh &M, bool need, d3 
     return out;
 }
 
-// getSDFAtTimeStamp (swm:550-556)
-template <bool MESH>
-__device__ __forceinline__ double sv_sdf_at(const SvArgs &A, const TrajView &tr, d3 p, double t, double reach) {
-    d3 x, v, a, j;
-    traj_pvaj(tr, t, x, v, a, j);
-    const rot3 R = quat_rot(flat_quat_only(A.cfg.fp, v, a));
-    return sv_sdf_bounded<MESH>(A.shape, rot_applyT(R, p - x), reach);
+// getSDFAtTimeStamp (swm:550-556), analytic shapes
+__device__ __forceinline__ double sv_sdf_at(const SvArgs &A, const TrajView &tr, d3 p, double t) {
+    return shape_sdf_analytic(A.shape, sv_body_point(A, tr, p, t));
 }
 
 __device__ __forceinline__ d3 shfl3(d3 v, int src) {
     return mk3(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src));
 }
 
-// Warp-cooperative getonlyGrad1 at a body-frame point known to every lane.
-template <bool MESH>
-__device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane, WideStack *stk) {
-    if (MESH) { d3 g = mk3(0, 0, 0); mesh_sdf_grad_warp(S.mesh, tmp, 1e300, g, lane, stk); return g; }
+// Warp-cooperative getonlyGrad1 (analytic shapes) at a body-frame point known to every lane.
+__device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane) {
     if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) return unit3(tmp);
     d3 q = tmp;
     if (S.kind == ISDF_SHAPE_BOX) {
@@ -221,47 +212,6 @@ __device__ __forceinline__ d3 warp_grad(const DevShape &S, d3 tmp, int lane, Wid
 
 // gradientDescent (swm:1000-1062), one speculative warp pass per outer iteration.
 // lanes 0..8: x - tau_d (taken when g > 0), lanes 9..17: x + tau_d (g < 0), lane 18: f(x), lanes 19..24: FD samples.
-// Mesh robots: a speculative pass would cost 25 independent BVH searches; instead the descent runs in the reference's
-// sequential order and every SDF evaluation is ONE warp-cooperative search (lane = candidate triangle / child box).
-__device__ void sv_gradient_descent_mesh(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0,
-                                         double &fx, double &x, unsigned &nevals, int lane, WideStack *stk) {
-    const DevMesh &M = A.shape.mesh;
-    const double alpha = 0.02, tol = 1e-5;
-    int iter = 0; bool stop = false;
-    double prev_x = 10000000.0;
-    x = x0;
-    while (iter < 300 && !stop && fabs(x - prev_x) > tol) {
-        d3 xt, v, a, j;
-        traj_pvaj(tr, x, xt, v, a, j);
-        FlatState fs;
-        flat_state(A.cfg.fp, v, a, j, fs);
-        const rot3 R = quat_rot(flat_quat(fs));
-        const d3 tmp = rot_applyT(R, p - xt);
-        d3 g = mk3(0, 0, 0);
-        const double f_here = mesh_sdf_grad_warp(M, tmp, 1e300, g, lane, stk);
-        if (iter == 0) { fx = f_here; nevals++; }
-        const d3 omg = flat_omega(fs);
-        const d3 rv = rot_applyT(R, v), wx = cross3(omg, tmp);
-        const double gd = g.x * -(rv.x + wx.x) + g.y * -(rv.y + wx.y) + g.z * -(rv.z + wx.z);
-        const int sgn = (int)(gd > 0) - (int)(gd < 0);
-        double tau = alpha;
-        prev_x = x;
-        for (int div = 1; div < 10; div++) {
-            iter = iter + 1; nevals++;
-            const double xc = fmax(fmin(x - tau * sgn, t_max), t_min);
-            d3 x2, v2, a2, j2;
-            traj_pvaj(tr, xc, x2, v2, a2, j2);
-            const rot3 R2 = quat_rot(flat_quat_only(A.cfg.fp, v2, a2));
-            d3 g2 = mk3(0, 0, 0);
-            const double fc = mesh_sdf_grad_warp(M, rot_applyT(R2, p - x2), 1e300, g2, lane, stk);
-            if ((fc - fx) < 0) { x = xc; fx = fc; break; }
-            tau = 0.5 * tau;
-            if (div == 9) stop = true;
-        }
-    }
-}
-
-template <bool MESH>
 __device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0,
                                     double &fx, double &x, unsigned &nevals, int lane) {
     const DevShape &S = A.shape;
@@ -269,7 +219,7 @@ __device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, d
     int iter = 0; bool stop = false;
     double prev_x = 10000000.0;
     x = x0;
-    const bool central = !MESH && S.kind != ISDF_SHAPE_BALL && S.kind != ISDF_SHAPE_POINT && S.kind != ISDF_SHAPE_BOX;
+    const bool central = S.kind != ISDF_SHAPE_BALL && S.kind != ISDF_SHAPE_POINT && S.kind != ISDF_SHAPE_BOX;
     while (iter < 300 && !stop && fabs(x - prev_x) > tol) {
         double t = x;
         if (lane < 18) {
@@ -292,17 +242,14 @@ __device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, d
             double c = (ax == 0 ? tmp.x : (ax == 1 ? tmp.y : tmp.z)) - dx;
             if ((lane - 19) & 1) c = c + 2 * dx;
             if (ax == 0) q.x = c; else if (ax == 1) q.y = c; else q.z = c;
-        } else if (!MESH && S.kind == ISDF_SHAPE_BOX && lane >= 19 && lane < 22) {
+        } else if (S.kind == ISDF_SHAPE_BOX && lane >= 19 && lane < 22) {
             if (lane == 19) q.x += 0.01; else if (lane == 20) q.y += 0.01; else q.z += 0.01;
         }
-        double val; d3 gm = mk3(0, 0, 0);
-        if (MESH) val = mesh_sdf_grad(S.mesh, q, 1e300, gm);
-        else val = shape_sdf_analytic(S, q);
+        const double val = shape_sdf_analytic(S, q);
         if (iter == 0) { fx = __shfl_sync(0xffffffffu, val, 18); nevals++; }
         // gradient of the SDF at (x, tmp@lane18)
         d3 g;
-        if (MESH) g = shfl3(gm, 18);
-        else if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) g = shfl3(unit3(tmp), 18);
+        if (S.kind == ISDF_SHAPE_BALL || S.kind == ISDF_SHAPE_POINT) g = shfl3(unit3(tmp), 18);
         else if (S.kind == ISDF_SHAPE_BOX) {
             const double f0 = __shfl_sync(0xffffffffu, val, 18);
             g = mk3((__shfl_sync(0xffffffffu, val, 19) - f0) / 0.01, (__shfl_sync(0xffffffffu, val, 20) - f0) / 0.01,
@@ -335,13 +282,52 @@ __device__ void sv_gradient_descent(const SvArgs &A, const TrajView &tr, d3 p, d
     }
 }
 
-// ---- k_sv_points: one warp per obstacle point -------------------------------------------------------------------------
-template <bool MESH>
+// ---- chain-rule tail of one obstacle point (hpp:578-636): stores t*, sdf*, g_rel and the point's contribution to its piece ----
+__device__ __forceinline__ void sv_point_tail(const SvArgs &A, const double *sC, const TrajView &tr, int pk, d3 p, bool found, double tstar,
+                                              double sdf_value, d3 grel) {
+    const DevCfg &cfg = A.cfg;
+    int piece = -1;
+    A.tstar[pk] = tstar; A.sdf[pk] = sdf_value;
+    A.grel[3 * pk] = grel.x; A.grel[3 * pk + 1] = grel.y; A.grel[3 * pk + 2] = grel.z;
+    double f, df;
+    hinge(cfg.safety - sdf_value, 0.01, f, df);   // mu hard-coded 0.01 (hpp:851)
+    if (found && f > 2.220446049250313e-16) {     // returns costp > DBL_EPSILON (hpp:865)
+        double tl = tstar;
+        const int i = traj_locate(tr, tl);
+        PieceEval pe;
+        piece_eval(sC + 6 * i, sC + 6 * A.N + 6 * i, sC + 12 * A.N + 6 * i, tl, pe);
+        FlatState fs;
+        flat_state(cfg.fp, pe.vel, pe.acc, pe.jer, fs);
+        const quat4 q = flat_quat(fs);
+        const rot3 R = quat_rot(q);
+        const d3 wg = rot_apply(R, grel);
+        const d3 dd = p - pe.pos;
+        double jq[4];
+        quat_pull(q, grel, dd, jq);
+        const d3 gP = mk3(cfg.wp * (df * wg.x), cfg.wp * (df * wg.y), cfg.wp * (df * wg.z));
+        const double gQ[4] = {cfg.wp * (-df * jq[0]), cfg.wp * (-df * jq[1]), cfg.wp * (-df * jq[2]), cfg.wp * (-df * jq[3])};
+        const double pena = cfg.wp * f;
+        d3 gV, gA, gJ;
+        flat_adjoint(cfg.fp, fs, pe.vel, pe.acc, gQ, mk3(0, 0, 0), mk3(0, 0, 0), gV, gA, gJ);
+        double *o = A.partial + (size_t)pk * PARTIAL_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            o[k] = pe.b0[k] * gP.x + pe.b1[k] * gV.x + pe.b2[k] * gA.x + pe.b3[k] * gJ.x;
+            o[6 + k] = pe.b0[k] * gP.y + pe.b1[k] * gV.y + pe.b2[k] * gA.y + pe.b3[k] * gJ.y;
+            o[12 + k] = pe.b0[k] * gP.z + pe.b1[k] * gV.z + pe.b2[k] * gA.z + pe.b3[k] * gJ.z;
+        }
+        o[18] = (-dot3(gP, pe.vel) + -dot3(gV, pe.acc) + -dot3(gA, pe.jer) + -dot3(gJ, pe.sna));
+        o[19] = pena;
+        piece = i;
+    }
+    A.piece[pk] = piece;
+}
+
+// ---- k_sv_points: one warp per obstacle point, analytic shapes ----------------------------------------------------------
 __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant__ SvArgs A) {
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
     __shared__ uint32_t sflags[SV_WARPS][SV_FLAG_WORDS];
-    __shared__ WideStack wstk[MESH ? SV_WARPS : 1];
 #pragma nv_diag_suppress static_var_with_dynamic_init
     __shared__ cuda::barrier<cuda::thread_scope_block> bar;
     stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
@@ -361,16 +347,6 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
     d3 grel = mk3(0, 0, 0);
     unsigned nevals = 0;
     bool found = false;
-#ifdef ISDF_PHASE_TIMING
-    const long long pt_begin = clock64();
-    long long pt_coarse = 0, pt_p1 = 0, pt_p2 = 0, pt_gd = 0, pt_mark = 0;
-    unsigned pt_intervals = 0, pt_exact = 0;
-#define PT_MARK() (pt_mark = clock64())
-#define PT_ADD(acc) ((acc) += clock64() - pt_mark)
-#else
-#define PT_MARK() ((void)0)
-#define PT_ADD(acc) ((void)0)
-#endif
 
     if (A.g_t) {
         sdf_value = A.g_s[pk]; tstar = A.g_t[pk]; grel = mk3(A.g_g[3 * pk], A.g_g[3 * pk + 1], A.g_g[3 * pk + 2]);
@@ -378,33 +354,21 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
     } else {
         // ---- coarse scan: in-range bitmap -------------------------------------------------------------------------
         uint32_t *fl = sflags[warp];
-        PT_MARK();
         for (int base = 0; base < nc; base += 32) {
             const int k = base + lane;
-            bool in = false, undecided = false;
-            d3 prel_k = mk3(0, 0, 0);
+            bool in = false;
             if (k < nc) {
                 const double *o = A.poses + 12 * (size_t)k;
                 const d3 d = mk3(p.x - __ldg(o), p.y - __ldg(o + 1), p.z - __ldg(o + 2));
                 const d3 prel = mk3(__ldg(o + 3) * d.x + __ldg(o + 6) * d.y + __ldg(o + 9) * d.z,
                                     __ldg(o + 4) * d.x + __ldg(o + 7) * d.y + __ldg(o + 10) * d.z,
                                     __ldg(o + 5) * d.x + __ldg(o + 8) * d.y + __ldg(o + 11) * d.z);
-                if (MESH) {   // the cell bracket settles the range test for everything but a thin band around `inf`
-                    double blo, bhi;
-                    mesh_bracket(A.shape.mesh, prel, blo, bhi);
-                    if (bhi < inf) in = true;
-                    else if (blo < inf) { undecided = true; prel_k = prel; }
-                } else in = sv_sdf_bounded<MESH>(A.shape, prel, inf) < inf;
-            }
-            if (MESH) {
-                const double v = mesh_sdf_each(A.shape.mesh, undecided, prel_k, inf, inf, lane, &wstk[MESH ? warp : 0]);
-                if (undecided) in = v < inf;
+                in = shape_sdf_analytic(A.shape, prel) < inf;
             }
             const unsigned b = __ballot_sync(0xffffffffu, in);
             if (lane == 0) fl[base >> 5] = b;
         }
         __syncwarp();
-        PT_ADD(pt_coarse);
         nevals += nc;
         const int nwords = (nc + 31) >> 5;
         // last run entry (in-range sample whose predecessor is out of range): its SDF initialises range_mindis (quirk Q2)
@@ -416,9 +380,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
             if (starts) last_entry = w * 32 + (31 - __clz(starts));
         }
         if (last_entry >= 0) {
-            double range_mindis;   // same value the coarse pass saw
-            if (MESH) { d3 g_; range_mindis = mesh_sdf_grad_warp(A.shape.mesh, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, &wstk[MESH ? warp : 0]); }
-            else range_mindis = sv_sdf_at<MESH>(A, tr, p, A.times[last_entry], inf);
+            double range_mindis = sv_sdf_at(A, tr, p, A.times[last_entry]);   // same value the coarse pass saw
             double range_time_seed = 0.0;
             double min_sdf_star = 1e1;
             // walk the closed runs in order
@@ -445,49 +407,13 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                 const double ub = fmin(dur, A.times[kout] + 0.2);
                 // ---- fine scan of [lb, ub) at dt = 0.02 (swm:423-438): t advances by repeated addition ----------------
                 {
-                    // Mesh robots: the reference keeps the FIRST sample attaining the minimum over the interval. A sample
-                    // whose cell lower bound exceeds the smallest cell upper bound of the interval cannot be that sample, so
-                    // pass 1 brackets every sample from the cell grid (no search) and pass 2 runs the exact closest-triangle
-                    // search only on the survivors around the closest approach. Skipped samples compare as +inf: the selected
-                    // sample, its value and the reference's evaluation count are unchanged.
-                    double cut = 1e300;
-                    PT_MARK();
-                    if (MESH) {
-                        double t = lb;
-                        for (int q = 0; q < lane; q++) t += 0.02;
-                        while (__any_sync(0xffffffffu, t < ub)) {
-                            if (t < ub) {
-                                double blo, bhi;
-                                mesh_bracket(A.shape.mesh, sv_body_point(A, tr, p, t), blo, bhi);
-                                cut = fmin(cut, bhi);
-                            }
-                            for (int q = 0; q < 32; q++) t += 0.02;
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) cut = fmin(cut, __shfl_xor_sync(0xffffffffu, cut, o));
-                    }
-                    PT_ADD(pt_p1);
-                    PT_MARK();
                     double t = lb;
                     for (int q = 0; q < lane; q++) t += 0.02;
                     int mi = lane;
                     while (__any_sync(0xffffffffu, t < ub)) {
                         const bool valid = t < ub;
                         double dis = 1e300;
-                        if (MESH) {
-                            bool need = false;
-                            d3 prel = mk3(0, 0, 0);
-                            if (valid) {
-                                prel = sv_body_point(A, tr, p, t);
-                                double blo, bhi;
-                                mesh_bracket(A.shape.mesh, prel, blo, bhi);
-                                need = blo <= cut;
-                            }
-#ifdef ISDF_PHASE_TIMING
-                            pt_exact += __popc(__ballot_sync(0xffffffffu, need));
-#endif
-                            dis = mesh_sdf_each(A.shape.mesh, need, prel, inf, 1e300, lane, &wstk[MESH ? warp : 0]);
-                        } else if (valid) dis = sv_sdf_at<MESH>(A, tr, p, t, inf);
+                        if (valid) dis = sv_sdf_at(A, tr, p, t);
                         nevals += __popc(__ballot_sync(0xffffffffu, valid));
                         // warp argmin, ties -> smaller sample index (first occurrence wins under the strict '<')
                         double bd = dis; int bi = mi; double bt = t;
@@ -502,19 +428,12 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                         for (int q = 0; q < 32; q++) t += 0.02;
                         mi += 32;
                     }
-                    PT_ADD(pt_p2);
                 }
-                PT_MARK();
                 // ---- descent inside the interval (swm:730-734) ---------------------------------------------------------
                 const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
                 double sdf_star = 1e1, t_star = 0;
-                if (MESH) sv_gradient_descent_mesh(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane, &wstk[MESH ? warp : 0]);
-                else sv_gradient_descent<MESH>(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
+                sv_gradient_descent(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
                 if (sdf_star < min_sdf_star) { min_sdf_star = sdf_star; tstar = t_star; found = true; }
-                PT_ADD(pt_gd);
-#ifdef ISDF_PHASE_TIMING
-                pt_intervals++;
-#endif
                 pos = kout;
             }
             if (found) {
@@ -523,57 +442,322 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
                 d3 x, v, a, j;
                 traj_pvaj(tr, tstar, x, v, a, j);
                 const rot3 R = quat_rot(flat_quat_only(cfg.fp, v, a));
-                grel = warp_grad<MESH>(A.shape, rot_applyT(R, p - x), lane, &wstk[MESH ? warp : 0]);
+                grel = warp_grad(A.shape, rot_applyT(R, p - x), lane);
             }
         }
     }
 
+    if (lane == 0) {
+        if (A.counter && nevals) atomicAdd(A.counter, (unsigned long long)nevals);
+        sv_point_tail(A, sC, tr, pk, p, found, tstar, sdf_value, grel);
+    }
+}
+
+// ---- k_sv_points_mesh: one CTA (SVM_WARPS warps) per obstacle point, mesh robots ----------------------------------------
+// The work per point is extremely uneven (half of the points never come within range; a few need >100 closest-triangle
+// searches in sequence), and with 10^2-10^4 points the kernel is a single wave: its duration is the SLOWEST point, not the
+// sum. So a point gets a whole CTA and the dependent chain is cut three ways:
+//   * coarse / fine scans: SVM_THREADS samples per round; consecutive fine samples go to different warps, so the survivors of
+//     the bracket pass (a contiguous run around the closest approach) are searched by all warps at once;
+//   * sign descent: one outer iteration evaluates the step candidates x -/+ 0.02/2^d, d = 1..8, on the eight warps at once
+//     (each a warp-cooperative search) and then replays the reference's sequential accept/reject logic on the results;
+//   * the SDF value and gradient of an accepted candidate are carried into the next iteration (same point, same function),
+//     which removes the re-evaluation at the new x — guarded by a bit-compare of the body-frame point.
+// Decisions, values and the reference-equivalent evaluation count are those of the sequential algorithm.
+constexpr int SVM_WARPS = 8;
+constexpr int SVM_THREADS = SVM_WARPS * 32;
+
+struct SvmShared {
+    uint32_t flags[SV_FLAG_WORDS];
+    WideStack stk[SVM_WARPS];
+    double red_d[SVM_WARPS], red_t[SVM_WARPS];
+    int red_i[SVM_WARPS];
+    double cand_f[9], cand_x[9], cand_g[9][3], cand_q[9][3];
+    double bc[4];
+};
+
+__device__ __forceinline__ bool same_bits(d3 a, d3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+
+// gradientDescent (swm:1000-1062) for one point, executed by the whole CTA. Returns sdf(x), x and the unit gradient g at the
+// body-frame point q of the final x.
+__device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0, SvmShared &S,
+                                            double &fx, double &x, d3 &g, d3 &gq, unsigned &nevals, int lane, int warp) {
+    const DevMesh &M = A.shape.mesh;
+    WideStack *stk = &S.stk[warp];
+    const double alpha = 0.02, tol = 1e-5;
+    int iter = 0; bool stop = false, have = false;
+    double prev_x = 10000000.0;
+    x = x0;
+    g = mk3(0, 0, 0); gq = mk3(0, 0, 0);
+    double fval = 0.0;
+    while (iter < 300 && !stop && fabs(x - prev_x) > tol) {
+        d3 xt, v, a, j;
+        traj_pvaj(tr, x, xt, v, a, j);
+        FlatState fs;
+        flat_state(A.cfg.fp, v, a, j, fs);
+        const rot3 R = quat_rot(flat_quat(fs));
+        const d3 tmp = rot_applyT(R, p - xt);
+        if (!(have && same_bits(tmp, gq))) {          // CTA-uniform: every thread computed the same tmp
+            if (warp == 0) {
+                d3 g0 = mk3(0, 0, 0);
+                const double f0 = mesh_sdf_grad_warp(M, tmp, 1e300, g0, lane, stk);
+                if (lane == 0) { S.bc[0] = f0; S.bc[1] = g0.x; S.bc[2] = g0.y; S.bc[3] = g0.z; }
+            }
+            __syncthreads();
+            fval = S.bc[0]; g = mk3(S.bc[1], S.bc[2], S.bc[3]); gq = tmp; have = true;
+            __syncthreads();
+        }
+        if (iter == 0) { fx = fval; if (warp == 0) nevals++; }
+        const d3 omg = flat_omega(fs);
+        const d3 rv = rot_applyT(R, v), wx = cross3(omg, tmp);
+        const double gd = g.x * -(rv.x + wx.x) + g.y * -(rv.y + wx.y) + g.z * -(rv.z + wx.z);
+        const int sgn = (int)(gd > 0) - (int)(gd < 0);
+        prev_x = x;
+        bool accepted = false;
+        for (int b0 = 1; b0 < 10 && !accepted; b0 += SVM_WARPS) {
+            const int mydiv = b0 + warp;
+            if (mydiv < 10) {
+                double tau = alpha;
+                for (int q = 1; q < mydiv; q++) tau = 0.5 * tau;
+                const double xc = fmax(fmin(x - tau * sgn, t_max), t_min);
+                const d3 qc = sv_body_point(A, tr, p, xc);
+                d3 g2 = mk3(0, 0, 0);
+                const double fc = mesh_sdf_grad_warp(M, qc, 1e300, g2, lane, stk);
+                if (lane == 0) {
+                    S.cand_f[mydiv - 1] = fc; S.cand_x[mydiv - 1] = xc;
+                    S.cand_g[mydiv - 1][0] = g2.x; S.cand_g[mydiv - 1][1] = g2.y; S.cand_g[mydiv - 1][2] = g2.z;
+                    S.cand_q[mydiv - 1][0] = qc.x; S.cand_q[mydiv - 1][1] = qc.y; S.cand_q[mydiv - 1][2] = qc.z;
+                }
+            }
+            __syncthreads();
+            const int dend = min(b0 + SVM_WARPS, 10);
+            for (int div = b0; div < dend; div++) {      // the reference's sequential loop over the halvings
+                iter = iter + 1;
+                if (warp == 0) nevals++;
+                const double fc = S.cand_f[div - 1];
+                if ((fc - fx) < 0) {
+                    x = S.cand_x[div - 1]; fx = fc; fval = fc;
+                    g = mk3(S.cand_g[div - 1][0], S.cand_g[div - 1][1], S.cand_g[div - 1][2]);
+                    gq = mk3(S.cand_q[div - 1][0], S.cand_q[div - 1][1], S.cand_q[div - 1][2]);
+                    accepted = true;
+                    break;
+                }
+                if (div == 9) stop = true;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_constant__ SvArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    double *sC = smem, *sT = smem + 18 * A.N;
+    __shared__ SvmShared S;
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+    stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
+    const TrajView tr = {sT, sC, A.N};
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pk = A.rank + A.world * blockIdx.x;     // grid = number of points of this rank
+    const DevMesh &M = A.shape.mesh;
+    WideStack *stk = &S.stk[warp];
+    const d3 p = mk3(A.pts[3 * pk], A.pts[3 * pk + 1], A.pts[3 * pk + 2]);
+    const DevCfg &cfg = A.cfg;
+    const double dur = A.state[0];
+    const int nc = A.meta[0];
+    const double inf = 2 * cfg.safety + 0.1;   // safty_hor_inf (swm:383)
+
+    double sdf_value = 1e1, tstar = A.tstar[pk];
+    d3 grel = mk3(0, 0, 0);
+    unsigned nevals = 0;      // per warp; lane 0 of every warp adds its share to the counter
+    bool found = false;
 #ifdef ISDF_PHASE_TIMING
-    if (A.dbg && lane == 0) {
+    const long long pt_begin = clock64();
+    long long pt_coarse = 0, pt_p1 = 0, pt_p2 = 0, pt_gd = 0, pt_mark = 0;
+    unsigned pt_intervals = 0;
+#define PT_MARK() (pt_mark = clock64())
+#define PT_ADD(acc) ((acc) += clock64() - pt_mark)
+#else
+#define PT_MARK() ((void)0)
+#define PT_ADD(acc) ((void)0)
+#endif
+
+    if (A.g_t) {
+        sdf_value = A.g_s[pk]; tstar = A.g_t[pk]; grel = mk3(A.g_g[3 * pk], A.g_g[3 * pk + 1], A.g_g[3 * pk + 2]);
+        found = true;
+    } else {
+        // ---- coarse scan (swm:392-421): in-range bitmap; the cell bracket settles all but a thin band around `inf` ---------
+        PT_MARK();
+        for (int base = 0; base < nc; base += SVM_THREADS) {
+            const int k = base + tid;
+            bool in = false, undecided = false;
+            d3 prel = mk3(0, 0, 0);
+            if (k < nc) {
+                const double *o = A.poses + 12 * (size_t)k;
+                const d3 d = mk3(p.x - __ldg(o), p.y - __ldg(o + 1), p.z - __ldg(o + 2));
+                prel = mk3(__ldg(o + 3) * d.x + __ldg(o + 6) * d.y + __ldg(o + 9) * d.z,
+                           __ldg(o + 4) * d.x + __ldg(o + 7) * d.y + __ldg(o + 10) * d.z,
+                           __ldg(o + 5) * d.x + __ldg(o + 8) * d.y + __ldg(o + 11) * d.z);
+                double blo, bhi;
+                mesh_bracket(M, prel, blo, bhi);
+                if (bhi < inf) in = true;
+                else if (blo < inf) undecided = true;
+            }
+            const double v = mesh_sdf_each(M, undecided, prel, inf, inf, lane, stk);
+            if (undecided) in = v < inf;
+            const unsigned b = __ballot_sync(0xffffffffu, in);
+            const int w = (base >> 5) + warp;
+            if (lane == 0 && w < SV_FLAG_WORDS) S.flags[w] = b;
+        }
+        __syncthreads();
+        PT_ADD(pt_coarse);
+        if (warp == 0) nevals += nc;
+        const uint32_t *fl = S.flags;
+        const int nwords = (nc + 31) >> 5;
+        // last run entry (in-range sample whose predecessor is out of range): its SDF initialises range_mindis (quirk Q2)
+        int last_entry = -1;
+        for (int w = nwords - 1; w >= 0 && last_entry < 0; w--) {
+            const uint32_t cur = fl[w];
+            const uint32_t prevbit = (w > 0) ? (fl[w - 1] >> 31) : 0u;
+            const uint32_t starts = cur & ~((cur << 1) | prevbit);
+            if (starts) last_entry = w * 32 + (31 - __clz(starts));
+        }
+        if (last_entry >= 0) {
+            if (warp == 0) {
+                d3 g_;
+                const double v = mesh_sdf_grad_warp(M, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, stk);
+                if (lane == 0) S.bc[0] = v;
+            }
+            __syncthreads();
+            double range_mindis = S.bc[0];
+            __syncthreads();
+            double range_time_seed = 0.0;
+            double min_sdf_star = 1e1;
+            d3 g_best = mk3(0, 0, 0), q_best = mk3(0, 0, 0);
+            int pos = 0;
+            while (pos < nc) {
+                int kin = -1;
+                for (int w = pos >> 5; w < nwords; w++) {
+                    uint32_t cur = fl[w];
+                    if (w == (pos >> 5)) cur &= ~((1u << (pos & 31)) - 1u);
+                    if (cur) { kin = w * 32 + __ffs(cur) - 1; break; }
+                }
+                if (kin < 0) break;
+                int kout = -1;
+                for (int w = kin >> 5; w < nwords; w++) {
+                    uint32_t cur = ~fl[w];
+                    if (w == (kin >> 5)) cur &= ~((1u << (kin & 31)) - 1u);
+                    if (w == nwords - 1 && (nc & 31)) cur &= (1u << (nc & 31)) - 1u;
+                    if (cur) { kout = w * 32 + __ffs(cur) - 1; break; }
+                }
+                if (kout < 0) break;  // run still open at the end of the scan: dropped (quirk Q2)
+                const double lb = fmax(0.0, A.times[kin] - 0.2);
+                const double ub = fmin(dur, A.times[kout] + 0.2);
+                // ---- fine scan of [lb, ub) at dt = 0.02 (swm:423-438): t advances by repeated addition -----------------
+                // The reference keeps the FIRST sample attaining the minimum over the interval. A sample whose cell lower
+                // bound exceeds the smallest cell upper bound of the interval cannot be that sample: pass 1 brackets every
+                // sample from the cell grid (no search), pass 2 runs the exact search on the survivors only.
+                const int first = lane * SVM_WARPS + warp;      // sample index of this thread in a round of SVM_THREADS
+                PT_MARK();
+                double cut = 1e300;
+                {
+                    double t = lb;
+                    for (int q = 0; q < first; q++) t += 0.02;
+                    while (t < ub) {
+                        double blo, bhi;
+                        mesh_bracket(M, sv_body_point(A, tr, p, t), blo, bhi);
+                        cut = fmin(cut, bhi);
+                        for (int q = 0; q < SVM_THREADS; q++) t += 0.02;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cut = fmin(cut, __shfl_xor_sync(0xffffffffu, cut, o));
+                    if (lane == 0) S.red_d[warp] = cut;
+                    __syncthreads();
+                    cut = S.red_d[0];
+                    for (int w = 1; w < SVM_WARPS; w++) cut = fmin(cut, S.red_d[w]);
+                    __syncthreads();
+                }
+                PT_ADD(pt_p1);
+                PT_MARK();
+                {
+                    double t = lb;
+                    for (int q = 0; q < first; q++) t += 0.02;
+                    int mi = first;
+                    double bd = 1e300, bt = 0.0; int bi = 0x7fffffff;
+                    while (__any_sync(0xffffffffu, t < ub)) {
+                        const bool valid = t < ub;
+                        bool need = false;
+                        d3 prel = mk3(0, 0, 0);
+                        if (valid) {
+                            prel = sv_body_point(A, tr, p, t);
+                            double blo, bhi;
+                            mesh_bracket(M, prel, blo, bhi);
+                            need = blo <= cut;
+                        }
+                        const double dis = mesh_sdf_each(M, need, prel, inf, 1e300, lane, stk);
+                        nevals += __popc(__ballot_sync(0xffffffffu, valid));
+                        if (dis < bd) { bd = dis; bi = mi; bt = t; }      // own samples come in increasing index order
+                        for (int q = 0; q < SVM_THREADS; q++) t += 0.02;
+                        mi += SVM_THREADS;
+                    }
+                    // first occurrence of the minimum: lexicographic (value, sample index) min over the CTA
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        const double otm = __shfl_xor_sync(0xffffffffu, bt, o);
+                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = otm; }
+                    }
+                    if (lane == 0) { S.red_d[warp] = bd; S.red_i[warp] = bi; S.red_t[warp] = bt; }
+                    __syncthreads();
+                    bd = S.red_d[0]; bi = S.red_i[0]; bt = S.red_t[0];
+                    for (int w = 1; w < SVM_WARPS; w++) {
+                        const double od = S.red_d[w]; const int oi = S.red_i[w];
+                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = S.red_t[w]; }
+                    }
+                    __syncthreads();
+                    if (bd < range_mindis) { range_mindis = bd; range_time_seed = bt; }
+                }
+                PT_ADD(pt_p2);
+                PT_MARK();
+                // ---- descent inside the interval (swm:730-734) ---------------------------------------------------------
+                const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
+                double sdf_star = 1e1, t_star = 0;
+                d3 g_s, q_s;
+                svm_descent(A, tr, p, tmin_, tmax_, range_time_seed, S, sdf_star, t_star, g_s, q_s, nevals, lane, warp);
+                if (sdf_star < min_sdf_star) { min_sdf_star = sdf_star; tstar = t_star; found = true; g_best = g_s; q_best = q_s; }
+                PT_ADD(pt_gd);
+#ifdef ISDF_PHASE_TIMING
+                pt_intervals++;
+#endif
+                pos = kout;
+            }
+            if (found) {
+                sdf_value = min_sdf_star;
+                // getGradPrelAtTimeStamp (swm:566-572) at the winning t*: the descent already holds it unless the pose differs
+                const d3 qf = sv_body_point(A, tr, p, tstar);
+                if (same_bits(qf, q_best)) grel = g_best;
+                else {
+                    if (warp == 0) {
+                        d3 g0 = mk3(0, 0, 0);
+                        mesh_sdf_grad_warp(M, qf, 1e300, g0, lane, stk);
+                        if (lane == 0) { S.bc[1] = g0.x; S.bc[2] = g0.y; S.bc[3] = g0.z; }
+                    }
+                    __syncthreads();
+                    grel = mk3(S.bc[1], S.bc[2], S.bc[3]);
+                }
+            }
+        }
+    }
+#ifdef ISDF_PHASE_TIMING
+    if (A.dbg && tid == 0) {
         unsigned long long *o = A.dbg + 8 * (size_t)pk;
         o[0] = (unsigned long long)(clock64() - pt_begin); o[1] = pt_coarse; o[2] = pt_p1; o[3] = pt_p2; o[4] = pt_gd;
-        o[5] = pt_intervals; o[6] = pt_exact; o[7] = 0;
+        o[5] = pt_intervals; o[6] = 0; o[7] = 0;
     }
 #endif
-    // ---- chain-rule tail (hpp:578-636) ----------------------------------------------------------------------------------
-    int piece = -1;
-    if (lane == 0) {
-        A.tstar[pk] = tstar; A.sdf[pk] = sdf_value;
-        A.grel[3 * pk] = grel.x; A.grel[3 * pk + 1] = grel.y; A.grel[3 * pk + 2] = grel.z;
-        if (A.counter && nevals) atomicAdd(A.counter, (unsigned long long)nevals);
-        double f, df;
-        hinge(cfg.safety - sdf_value, 0.01, f, df);   // mu hard-coded 0.01 (hpp:851)
-        if (found && f > 2.220446049250313e-16) {     // returns costp > DBL_EPSILON (hpp:865)
-            double tl = tstar;
-            const int i = traj_locate(tr, tl);
-            PieceEval pe;
-            piece_eval(sC + 6 * i, sC + 6 * A.N + 6 * i, sC + 12 * A.N + 6 * i, tl, pe);
-            FlatState fs;
-            flat_state(cfg.fp, pe.vel, pe.acc, pe.jer, fs);
-            const quat4 q = flat_quat(fs);
-            const rot3 R = quat_rot(q);
-            const d3 wg = rot_apply(R, grel);
-            const d3 dd = p - pe.pos;
-            double jq[4];
-            quat_pull(q, grel, dd, jq);
-            const d3 gP = mk3(cfg.wp * (df * wg.x), cfg.wp * (df * wg.y), cfg.wp * (df * wg.z));
-            const double gQ[4] = {cfg.wp * (-df * jq[0]), cfg.wp * (-df * jq[1]), cfg.wp * (-df * jq[2]), cfg.wp * (-df * jq[3])};
-            const double pena = cfg.wp * f;
-            d3 gV, gA, gJ;
-            flat_adjoint(cfg.fp, fs, pe.vel, pe.acc, gQ, mk3(0, 0, 0), mk3(0, 0, 0), gV, gA, gJ);
-            double *o = A.partial + (size_t)pk * PARTIAL_STRIDE;
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                o[k] = pe.b0[k] * gP.x + pe.b1[k] * gV.x + pe.b2[k] * gA.x + pe.b3[k] * gJ.x;
-                o[6 + k] = pe.b0[k] * gP.y + pe.b1[k] * gV.y + pe.b2[k] * gA.y + pe.b3[k] * gJ.y;
-                o[12 + k] = pe.b0[k] * gP.z + pe.b1[k] * gV.z + pe.b2[k] * gA.z + pe.b3[k] * gJ.z;
-            }
-            o[18] = (-dot3(gP, pe.vel) + -dot3(gV, pe.acc) + -dot3(gA, pe.jer) + -dot3(gJ, pe.sna));
-            o[19] = pena;
-            piece = i;
-        }
-        A.piece[pk] = piece;
-    }
+    if (lane == 0 && A.counter && nevals) atomicAdd(A.counter, (unsigned long long)nevals);
+    if (tid == 0) sv_point_tail(A, sC, tr, pk, p, found, tstar, sdf_value, grel);
 }
 
 // ---- reductions --------------------------------------------------------------------------------------------------
@@ -676,15 +860,15 @@ struct SweptState {
         if ((e = cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
         if (sm > 48 * 1024) {
             cudaFuncSetAttribute(k_sv_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(k_sv_points<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(k_sv_points<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points_mesh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         }
         k_sv_table<<<1, 256, sm, st>>>(A);
         const int Mloc = (P - rank + world - 1) / world;
         const unsigned grid = (unsigned)((Mloc + SV_WARPS - 1) / SV_WARPS);
         if (grid > 0) {
-            if (shape.kind == ISDF_SHAPE_MESH) k_sv_points<true><<<grid, SV_THREADS, sm, st>>>(A);
-            else k_sv_points<false><<<grid, SV_THREADS, sm, st>>>(A);
+            if (shape.kind == ISDF_SHAPE_MESH) k_sv_points_mesh<<<(unsigned)Mloc, SVM_THREADS, sm, st>>>(A);
+            else k_sv_points<<<grid, SV_THREADS, sm, st>>>(A);
         }
         k_sv_reduce<<<N, 256, 0, st>>>(A);
         k_sv_finish<<<1, 32, 0, st>>>(A);
