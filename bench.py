@@ -254,6 +254,46 @@ def lbfgs_cpu(max_iterations=2):
             "evaluations": r["evaluations"], "seconds": dt, "cores": oc.threads_num}
 
 
+# ---- secondary metric: the swept-volume term alone (BASELINE configs[3]), mesh robot = the reference's live default ---------------
+def swept_ours(device, with_cpu, cpu_points=423):
+    import isdf_b200 as I
+    import workloads as W
+    X = 256
+    occ = W.random_map(X, X, X, p=0.02, seed=2, slabs=3)
+    cfg = I.default_config_values()
+    cfg.flags = I.WITH_DYNAMICS
+    T, Cc, wp = W.make_trajectory(64, [0, 0, 0], [X, X, X], seed=11, jitter=0.2)
+    pts = W.gather_obstacle_points(occ, [0, 0, 0], 1.0, wp, cfg.kernel_size / 3.0)
+    V, F = W.rounded_cone_mesh()
+    poly = [0, 0, 0, 120, 0, 0]
+    ev = I.Evaluator(cfg, device=device)
+    ev.set_shape_mesh(V, F, poly)
+    ev.set_points(pts)
+    for _ in range(3):
+        ev.eval_swept(T, Cc)
+    ks, es = [], []
+    for _ in range(10):
+        t0 = time.perf_counter(); ev.eval_swept(T, Cc); es.append(time.perf_counter() - t0)
+        ks.append(ev.stats().last_kernel_ms)
+    st = ev.stats()
+    out = {"config": f"BASELINE configs[3]: 256^3 map, 64-piece trajectory ({T.sum():.0f} s), {len(pts)} obstacle points, 3900-triangle mesh robot; "
+                     "SV-SDF query (coarse 0.2 s scan, fine 0.02 s scan, sign descent) + chain rule per point",
+           "kernel_ms": statistics.median(ks), "e2e_ms": 1e3 * statistics.median(es), "points_per_s": len(pts) / (statistics.median(ks) * 1e-3),
+           "reference_equivalent_sdf_evals": int(st.last_sdf_evals)}
+    ev.close()
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        oc = O.config_from(cfg); oc.threads_num = os.cpu_count() or 1
+        sh = O.Shape.mesh(V, F, poly, wn_mode=O.WN_BH)
+        n = min(len(pts), cpu_points)
+        idx = np.linspace(0, len(pts) - 1, n).astype(int)          # spread over the trajectory: per-point work is very uneven
+        t0 = time.perf_counter(); O.eval_swept(oc, sh, T, Cc, pts[idx], use_omp=True); dt = time.perf_counter() - t0
+        out["cpu"] = {"ms_full_estimate": 1e3 * dt * len(pts) / n, "cores": oc.threads_num, "sample": f"{n} of {len(pts)} points, OpenMP oracle port"}
+        out["speedup_kernel_vs_cpu"] = out["cpu"]["ms_full_estimate"] / out["kernel_ms"]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -431,6 +471,11 @@ def run_ours(args):
                     line["extra"]["lbfgs"]["cpu"] = lbfgs_cpu()
             except Exception as e:   # secondary metric must never take the headline line down
                 line["extra"]["lbfgs"] = {"error": repr(e)}
+        if world == 1 and not args.no_swept:
+            try:
+                line["extra"]["swept"] = swept_ours(local, not args.no_cpu_baseline)
+            except Exception as e:
+                line["extra"]["swept"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, cfg, occ, T, Cc, V, F, budget_s=args.cpu_budget)
             line["extra"]["speedup_kernel_vs_cpu"] = line["value"] / line["cpu_baseline"]["value"]
@@ -452,6 +497,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lbfgs", action="store_true", help="skip the secondary L-BFGS iterations/s measurement")
+    ap.add_argument("--no-swept", action="store_true", help="skip the secondary swept-volume (SV-SDF) measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-pieces", type=int, default=16, help="--impl reference: pieces per step sample (of 64)")
     ap.add_argument("--robot", default="mesh", help="mesh (headline) or an analytic shape name, e.g. SmoothIntersection (diagnostic runs)")
