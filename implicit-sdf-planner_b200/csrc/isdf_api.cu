@@ -4,6 +4,7 @@
 #include "isdf_types.cuh"
 #include "isdf_discrete.cuh"
 #include "isdf_swept.cuh"
+#include "isdf_minco.cuh"
 #include "isdf_host_mesh.cuh"
 #include <cstdio>
 #include <cstring>
@@ -53,6 +54,8 @@ struct isdf_ctx {
     int warp_slots = 148 * 12;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
     DevBuf<unsigned long long> d_counter, d_dbg;
+    DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout;   // batched callback (isdf_minco.cuh)
+    int minco_B = 0, minco_N = 0;
     bool dbg_on = false;
     double *h_stage = nullptr;   // pinned
     size_t h_stage_n = 0;
@@ -140,6 +143,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_split_ticket.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
+    c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -670,6 +674,91 @@ extern "C" int isdf_get_piece_costs(isdf_ctx *c, double *piece_cost, int n) {
     if (set_device(c)) return ISDF_ERR_CUDA;
     CU_TRY(cudaStreamSynchronize(c->stream));
     CU_TRY(cudaMemcpy(piece_cost, c->d_piece_cost.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- batched optimiser callback on the device (MINCO -> time-integral term -> adjoint), SURVEY §8f row 1 ----------------------
+static int callback_batch_launch(isdf_ctx *c, int B, int N0, const double *d_head, const double *d_tail, int bc_stride, double rho,
+                                 const double *d_x, double *d_cost, double *d_grad, cudaStream_t st) {
+    const size_t BN = (size_t)B * N0;
+    const size_t smem = minco_smem_bytes(N0);
+    if (smem > 220 * 1024) return fail(ISDF_ERR_UNSUPPORTED, "pieces per problem too large for the shared-memory banded solver (N0 <= 290)");
+    if (BN * (size_t)(c->cfg.integral_intervs + 1) > 0x7fffffffull) return fail(ISDF_ERR_UNSUPPORTED, "batch too large: B*N0*(K+1) must fit in 31 bits");
+    CU_TRY(c->d_mT.ensure(BN)); CU_TRY(c->d_mC.ensure(18 * BN)); CU_TRY(c->d_mlu.ensure(78 * BN)); CU_TRY(c->d_men.ensure(B));
+    CU_TRY(c->d_mgC.ensure(18 * BN)); CU_TRY(c->d_mgT.ensure(BN)); CU_TRY(c->d_mout.ensure(19 * BN + 1));
+    MincoArgs M;
+    M.B = B; M.N = N0; M.x = d_x; M.head = d_head; M.tail = d_tail; M.bc_stride = bc_stride; M.rho = rho;
+    M.T = c->d_mT.p; M.C = c->d_mC.p; M.lu = c->d_mlu.p; M.energy = c->d_men.p; M.gC_e = c->d_mgC.p; M.gT_e = c->d_mgT.p;
+    M.disc_out = nullptr; M.piece_cost = nullptr; M.cost = d_cost; M.grad = d_grad;
+    CU_TRY(cudaFuncSetAttribute(k_minco_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(k_minco_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_minco_forward<<<B, 32, smem, st>>>(M);
+    int r = launch_discrete(c, (int)BN, M.T, M.C, c->d_mout.p, st);
+    if (r) return r;
+    M.disc_out = c->d_mout.p; M.piece_cost = c->d_piece_cost.p;
+    k_minco_backward<<<B, 32, smem, st>>>(M);
+    c->stats.kernel_launches += 2;
+    c->minco_B = B; c->minco_N = N0;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int callback_batch_check(isdf_ctx *c, int B, int N0) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (B < 1 || N0 < 1) return fail(ISDF_ERR_INVALID, "B < 1 or N0 < 1");
+    if ((long long)B * N0 > 0x7fffffffll) return fail(ISDF_ERR_INVALID, "B*N0 overflows");
+    if (c->world != 1) return fail(ISDF_ERR_STATE, "the batched callback shards by PROBLEM: keep isdf_set_shard(ctx, 0, 1) and give each rank its own problems");
+    return check_eval_state(c, B * N0, true);
+}
+
+extern "C" int isdf_callback_batch_device(isdf_ctx *c, int B, int N0, const double *d_head, const double *d_tail, int per_problem_bc, double rho,
+                                          const double *d_x, double *d_cost, double *d_grad, void *cuda_stream) {
+    int r = callback_batch_check(c, B, N0);
+    if (r) return r;
+    if (!d_head || !d_tail || !d_x || !d_cost || !d_grad) return fail(ISDF_ERR_INVALID, "NULL device pointer");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    return callback_batch_launch(c, B, N0, d_head, d_tail, per_problem_bc ? 9 : 0, rho, d_x, d_cost, d_grad, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int isdf_callback_batch(isdf_ctx *c, int B, int N0, const double *head, const double *tail, int per_problem_bc, double rho,
+                                   const double *x, double *cost, double *grad) {
+    auto poison_all = [&]() { if (cost && B > 0) for (int b = 0; b < B; b++) cost[b] = std::numeric_limits<double>::quiet_NaN(); };
+    int r = callback_batch_check(c, B, N0);
+    if (r) { poison_all(); return r; }
+    if (!head || !tail || !x || !cost || !grad) { poison_all(); return fail(ISDF_ERR_INVALID, "NULL argument"); }
+    auto body = [&]() -> int {
+        if (set_device(c)) return ISDF_ERR_CUDA;
+        const size_t dim = (size_t)N0 + 3 * (size_t)(N0 - 1), nbc = per_problem_bc ? (size_t)9 * B : 9;
+        CU_TRY(c->d_mx.upload(x, dim * B, c->stream));
+        CU_TRY(c->d_mbc.ensure(2 * nbc));
+        CU_TRY(cudaMemcpyAsync(c->d_mbc.p, head, sizeof(double) * nbc, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMemcpyAsync(c->d_mbc.p + nbc, tail, sizeof(double) * nbc, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c->d_mcost.ensure(B)); CU_TRY(c->d_mgrad.ensure(dim * B));
+        CU_TRY(cudaEventRecord(c->ev0, c->stream));
+        int rr = callback_batch_launch(c, B, N0, c->d_mbc.p, c->d_mbc.p + nbc, per_problem_bc ? 9 : 0, rho, c->d_mx.p, c->d_mcost.p, c->d_mgrad.p, c->stream);
+        if (rr) return rr;
+        CU_TRY(cudaEventRecord(c->ev1, c->stream));
+        CU_TRY(cudaMemcpyAsync(cost, c->d_mcost.p, sizeof(double) * B, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(grad, c->d_mgrad.p, sizeof(double) * dim * B, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->stats.last_kernel_ms = ms;
+        return 0;
+    };
+    r = body();
+    if (r) poison_all();
+    return r;
+}
+
+extern "C" int isdf_get_batch_trajectories(isdf_ctx *c, double *T, double *coeffs, double *energy) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (c->minco_B <= 0) return fail(ISDF_ERR_STATE, "no batched callback evaluated yet");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    const size_t BN = (size_t)c->minco_B * c->minco_N;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (T) CU_TRY(cudaMemcpy(T, c->d_mT.p, sizeof(double) * BN, cudaMemcpyDeviceToHost));
+    if (coeffs) CU_TRY(cudaMemcpy(coeffs, c->d_mC.p, sizeof(double) * 18 * BN, cudaMemcpyDeviceToHost));
+    if (energy) CU_TRY(cudaMemcpy(energy, c->d_men.p, sizeof(double) * c->minco_B, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -27,7 +27,7 @@ ABI_SYMBOLS = ["isdf_default_config", "isdf_create", "isdf_destroy", "isdf_last_
                "isdf_set_map_u8", "isdf_set_map_f64", "isdf_points_in_aabb", "isdf_eval_discrete",
                "isdf_eval_discrete_device", "isdf_set_points", "isdf_eval_swept", "isdf_eval_swept_device",
                "isdf_get_swept_results", "isdf_eval_swept_given", "isdf_get_piece_costs",
-               "isdf_gather_obstacle_points"]
+               "isdf_gather_obstacle_points", "isdf_callback_batch", "isdf_callback_batch_device", "isdf_get_batch_trajectories"]
 
 
 class Config(C.Structure):
@@ -92,6 +92,9 @@ def load_library(path=None):
     lib.isdf_get_swept_results.argtypes = [vp, dp, dp, dp]
     lib.isdf_get_piece_costs.argtypes = [vp, dp, C.c_int]
     lib.isdf_gather_obstacle_points.argtypes = [vp, dp, C.c_int, C.c_double, dp, dp, C.c_int, C.POINTER(C.c_int), C.c_int]
+    lib.isdf_callback_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, C.c_double, dp, dp, dp]
+    lib.isdf_callback_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]
+    lib.isdf_get_batch_trajectories.argtypes = [vp, dp, dp, dp]
     lib.isdf_eval_swept_given.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
     for s in ABI_SYMBOLS:
         if s != "isdf_last_error":
@@ -208,6 +211,30 @@ class Evaluator:
         if set_as_points:
             self.n_points = n.value
         return out[:min(n.value, cap)].copy(), n.value
+
+    def callback_batch(self, head, tail, rho, X):
+        """B decision vectors [tau (N0) | xi (3(N0-1))] -> (cost[B], grad[B, 4*N0-3]); head/tail 3x3 (columns p, v, a), shared (3,3)
+        or per problem (B,3,3); passed to the library column-major."""
+        X = _f64(X)
+        B, dim = X.shape
+        N0 = (dim + 3) // 4
+        assert 4 * N0 - 3 == dim
+        head, tail = np.asarray(head, dtype=np.float64), np.asarray(tail, dtype=np.float64)
+        per = int(head.ndim == 3)
+        colmajor = (lambda a: np.ascontiguousarray(np.swapaxes(a, -1, -2)).reshape(-1))
+        h, t = colmajor(head), colmajor(tail)
+        cost, grad = np.zeros(B), np.zeros((B, dim))
+        Xf = np.ascontiguousarray(X).reshape(-1)
+        self._check(self.lib.isdf_callback_batch(self.h, B, N0, _dp(h), _dp(t), per, float(rho), _dp(Xf), _dp(cost), _dp(grad.reshape(-1))))
+        return cost, grad
+
+    def callback_batch_device(self, B, N0, d_head, d_tail, per_problem_bc, rho, d_x, d_cost, d_grad, stream=None):
+        self._check(self.lib.isdf_callback_batch_device(self.h, B, N0, d_head, d_tail, int(per_problem_bc), float(rho), d_x, d_cost, d_grad, stream))
+
+    def batch_trajectories(self, B, N0):
+        T, Cc, en = np.zeros(B * N0), np.zeros(18 * B * N0), np.zeros(B)
+        self._check(self.lib.isdf_get_batch_trajectories(self.h, _dp(T), _dp(Cc), _dp(en)))
+        return T, Cc, en
 
     def piece_costs(self, n):
         out = np.zeros(n)

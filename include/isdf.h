@@ -136,6 +136,25 @@ int isdf_eval_discrete_device(isdf_ctx *ctx, int N, const double *d_T, const dou
  * random restarts is simply a longer coefficient block) the cost of trajectory b is the sum of its N0 entries. */
 int isdf_get_piece_costs(isdf_ctx *ctx, double *piece_cost, int n);
 
+/* ---- batched optimiser callback on the device (MINCO on both sides of the hot loop) -------------------- */
+/* B independent problems (random restarts, BASELINE configs[4]) in one call. Restates TrajOptimizer::costFunctionLmbm
+ * (back_end_optimizer.hpp:358-430) with the time-integral term as the only penalty (use the per-problem host adapter
+ * host/isdf_cost_callback.hpp when the swept-volume term is wanted: obstacle point sets are per trajectory):
+ *   x_b = [tau (N0) | xi (3(N0-1), waypoint-major)] -> forwardT (hpp:214-241) -> MINCO_S3NU::setParameters (minco.hpp:433-513,
+ *   banded LU :99-135) -> getEnergy + partials (:530-582) -> addTimeIntPenaltyParallel over the concatenated B*N0 pieces ->
+ *   propogateGrad (:584-654) -> + rho*sum(T) -> backwardGradT / backwardGradP (hpp:283-330).
+ * head / tail: 3x3 column-major (columns p, v, a), one pair shared by the batch (per_problem_bc = 0) or B pairs (= 1).
+ * x: B x (4*N0-3) row-major; cost: B; grad: B x (4*N0-3). On failure every cost[b] is NaN. N0 <= 290.
+ * Multi-GPU: shard by problem (each rank calls this with its own problems and isdf_set_shard(ctx, 0, 1)); no collective. */
+int isdf_callback_batch(isdf_ctx *ctx, int B, int N0, const double *head, const double *tail, int per_problem_bc, double rho,
+                        const double *x, double *cost, double *grad);
+/* device-resident variant (all pointers on ctx's device, asynchronous on cuda_stream) */
+int isdf_callback_batch_device(isdf_ctx *ctx, int B, int N0, const double *d_head, const double *d_tail, int per_problem_bc,
+                               double rho, const double *d_x, double *d_cost, double *d_grad, void *cuda_stream);
+/* the trajectories of the last batched callback: durations (B*N0), coefficient block (6*B*N0 x 3 column-major, piece b*N0+i),
+ * jerk energies (B); any may be NULL */
+int isdf_get_batch_trajectories(isdf_ctx *ctx, double *T, double *coeffs, double *energy);
+
 /* ---- swept-volume term: addSaftyPenaOnSweptVolumeParallel (hpp:557-649) + getSDFofSweptVolume (swm:710-747) --- */
 /* parallel_points (plan_manager.cpp:246-254): P x 3 row-major world-frame voxel centres; resets lastTstar to 0 */
 int isdf_set_points(isdf_ctx *ctx, const double *pts, int P);

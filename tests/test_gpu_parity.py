@@ -465,6 +465,62 @@ def test_batch_of_trajectories_as_one_concatenated_block():
     ev.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot", ["Ball", "mesh"])
+def test_batched_device_callback_matches_host_callback(robot):
+    """the whole callback (forwardT -> MINCO -> energy -> time-integral term incl. the discrete collision loop ->
+    propogateGrad -> rho*sum(T) -> backwardGradT/P) for B problems in one device call == the per-problem host adapter
+    (host MINCO port pinned against the oracle) driving the same kernels; trajectories bit-identical to the host MINCO."""
+    import host_lib as H
+    cfg, occ, _, _, _ = small_case(N=6, K=16, seed=3)
+    cfg.vmax, cfg.omgmax = 1.2, 0.5
+    B, N0 = 7, 6
+    rho = 20.0
+    rng = np.random.default_rng(9)
+    heads, tails, X = [], [], []
+    for b in range(B):
+        wp = W.random_walk_waypoints(N0, [0, 0, 0], [50, 50, 34], seed=200 + b)
+        h, t = np.zeros((3, 3)), np.zeros((3, 3))
+        h[:, 0], t[:, 0] = wp[0], wp[-1]
+        h[:, 1] = rng.normal(size=3) * 0.3                          # non-zero boundary velocity
+        tau = rng.normal(size=N0) * 0.6 + 0.6                       # both branches of forwardT
+        X.append(np.concatenate([tau, (wp[1:-1] + rng.normal(size=(N0 - 1, 3)) * 0.2).reshape(-1)]))
+        heads.append(h); tails.append(t)
+    X = np.array(X)
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, BMIN, 1.0)
+    if robot == "mesh":
+        V, F = MESHES["rcone"]()
+        ev.set_shape_mesh(V, F, [0, 0, 0, 120, 0, 0])
+    else:
+        ev.set_shape_named(robot)
+    L = H.lib()
+    ref_c, ref_g, ref_co = [], [], []
+    for b in range(B):
+        hh, tt = np.asfortranarray(heads[b]), np.asfortranarray(tails[b])
+        be = L.isdf_host_backend_create(ev.h, N0, hh.ctypes.data_as(H.dp), tt.ctypes.data_as(H.dp), rho, 0, 1)
+        g = np.zeros(X.shape[1])
+        ref_c.append(L.isdf_host_backend_cost(be, X[b].ctypes.data_as(H.dp), g.ctypes.data_as(H.dp), g.size))
+        ref_g.append(g)
+        L.isdf_host_backend_destroy(be)
+        tau = X[b, :N0]
+        Tt = np.where(tau > 0, (0.5 * tau + 1) * tau + 1, 1 / ((0.5 * tau - 1) * tau + 1))
+        ref_co.append(H.minco_forward(heads[b], tails[b], X[b, N0:].reshape(-1, 3).T, Tt)[0])
+    cost, grad = ev.callback_batch(np.array(heads), np.array(tails), rho, X)
+    Tb, Cb, en = ev.batch_trajectories(B, N0)
+    Cm = Cb.reshape(3, 6 * B * N0)
+    for b in range(B):
+        assert np.array_equal(Cm[:, 6 * N0 * b:6 * N0 * (b + 1)].reshape(-1), np.asarray(ref_co[b]).reshape(-1))
+        assert abs(cost[b] - ref_c[b]) <= 1e-13 * abs(ref_c[b]), (b, cost[b], ref_c[b])
+        assert rel_l2(grad[b], ref_g[b]) <= 1e-12, (b, rel_l2(grad[b], ref_g[b]))
+    assert np.all(np.isfinite(cost)) and len(set(np.round(cost, 6))) == B
+    # shared boundary conditions: one head/tail pair for the whole batch
+    cost2, grad2 = ev.callback_batch(heads[0], tails[0], rho, X[:2])
+    assert abs(cost2[0] - ref_c[0]) <= 1e-13 * abs(ref_c[0]) and rel_l2(grad2[0], ref_g[0]) <= 1e-12
+    assert np.isfinite(cost2[1])
+    ev.close()
+
+
 def test_obstacle_gather_matches_reference_semantics():
     """plan_manager.cpp:232-254 + getPointsInAABBOutOfLastOne (pcs:182-216): same set, same (waypoint, address) order as the oracle."""
     cfg, occ, T, Cc, wp = small_case(N=6, K=8, seed=4, noise=0.08)
