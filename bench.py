@@ -320,6 +320,61 @@ def run_reference(args):
     return 0
 
 
+def batch_callback_bench(ev, w, cfg, dev, rank, world, B, barrier, max_over_ranks, reps=3):
+    """B problems per GPU through isdf_callback_batch_device: x -> MINCO -> time-integral term with the discrete collision loop over the
+    concatenated B*N pieces -> adjoint -> grad(x). Problems differ per rank (seeds), nothing is exchanged: weak scaling by construction."""
+    import torch
+    import workloads as W
+    N0, X = w["pieces"], w["map_dim"]
+    dim = 4 * N0 - 3
+    xs, heads, tails = np.zeros((B, dim)), np.zeros((B, 9)), np.zeros((B, 9))
+    for b in range(B):
+        wp = W.random_walk_waypoints(N0, [0, 0, 0], [X, X, X], seed=1000 + rank * B + b)
+        xs[b, :N0] = 1.0                                   # tau = 1 -> T = 2.5 s (inittime)
+        xs[b, N0:] = wp[1:-1].reshape(-1)
+        heads[b, 0:3], tails[b, 0:3] = wp[0], wp[-1]       # column-major 3x3: first column = position
+    d_x, d_h, d_t = (torch.from_numpy(a).to(dev) for a in (xs, heads, tails))
+    d_cost = torch.zeros(B, dtype=torch.float64, device=dev)
+    d_grad = torch.zeros(B, dim, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ev.set_shard(0, 1)
+
+    def step():
+        ev.callback_batch_device(B, N0, d_h.data_ptr(), d_t.data_ptr(), 1, 20.0, d_x.data_ptr(), d_cost.data_ptr(), d_grad.data_ptr(), stream)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); barrier()
+        e0.record(); step(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(max_over_ranks(e0.elapsed_time(e1)))
+    ms = statistics.mean(ts)
+    c = d_cost.cpu().numpy()
+    per_problem = None
+    if world == 1:
+        # the same problems one at a time through the host adapter (host MINCO port + isdf_eval_discrete with host buffers)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import host_lib as H
+        L = H.lib()
+        nb = min(B, 16)
+        g = np.zeros(dim)
+        t0 = time.perf_counter()
+        cs = []
+        for b in range(nb):
+            be = L.isdf_host_backend_create(ev.h, N0, heads[b].ctypes.data_as(H.dp), tails[b].ctypes.data_as(H.dp), 20.0, 0, 1)
+            cs.append(L.isdf_host_backend_cost(be, xs[b].ctypes.data_as(H.dp), g.ctypes.data_as(H.dp), dim))
+            L.isdf_host_backend_destroy(be)
+        dt = time.perf_counter() - t0
+        per_problem = {"callbacks_per_s": nb / dt, "problems": nb, "max_rel_cost_diff_vs_batched": float(np.max(np.abs(np.array(cs) - c[:nb]) / np.abs(c[:nb])))}
+    return {"callbacks_per_s": world * B * 1e3 / ms, "host_adapter_one_at_a_time": per_problem, "ms_per_batch_max_over_ranks": ms, "problems_per_gpu": B, "problems_total": world * B,
+            "scaling": "weak", "finite_costs": bool(np.all(np.isfinite(c))), "mean_cost": float(c.mean()),
+            "what": f"BASELINE configs[4]: {world * B} random-restart problems ({N0} pieces x {w['samples_per_piece']} samples, shared {X}^3 map, mesh robot), "
+                    "decision vector in -> cost and gradient out, MINCO forward/adjoint + time-integral/collision term all on the device; no collective"}
+
+
 def workload_name(w):
     return (f"BASELINE configs[2]: random {w['map_dim']}^3 voxel map (p={w['occupancy']}, wall slabs), {w['pieces']}-piece MINCO traj, "
             f"{w['samples_per_piece']} samples/piece, mesh-SDF robot ({w['mesh']}), discrete collision cost+grad")
@@ -445,6 +500,15 @@ def run_ours(args):
         batch_weak = {"evals_per_s": world * 1e3 / statistics.mean(tb), "ms_per_step_max_over_ranks": statistics.mean(tb), "scaling": "weak",
                       "what": f"{world} different trajectories (seed 11+rank), one per GPU, evaluated concurrently; no collective"}
 
+    # ---- BASELINE configs[4]: batch of random restarts, whole callback on the device, B_local problems per GPU, no collective ----
+    batch_cb = None
+    if not args.no_batch and not args.small:
+        try:
+            batch_cb = batch_callback_bench(ev, w, cfg, dev, rank, world, args.batch_per_gpu, barrier, max_over_ranks)
+        except Exception as e:
+            batch_cb = {"error": repr(e)}
+        ev.set_shard(rank, world)
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         ab = algorithmic_bytes(w)
@@ -463,7 +527,8 @@ def run_ours(args):
                 "extra": {"pairs_per_eval": int(pairs), "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step_warm_l2": statistics.mean(warm),
                           "evals_per_s_warm_l2": 1e3 / statistics.mean(warm), "ms_min": min(times), "ms_max": max(times),
                           "kernel_ms_in_host_call": kernel_ms_alone, "wall_s_timed_loop": wall,
-                          "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:])), "batch_weak": batch_weak}}
+                          "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:])), "batch_weak": batch_weak,
+                          "batch_callback": batch_cb}}
         if world == 1 and not args.no_lbfgs:
             try:
                 line["extra"]["lbfgs"] = lbfgs_ours(local)
@@ -497,6 +562,8 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lbfgs", action="store_true", help="skip the secondary L-BFGS iterations/s measurement")
+    ap.add_argument("--no-batch", action="store_true", help="skip the batched device-callback measurement (configs[4])")
+    ap.add_argument("--batch-per-gpu", type=int, default=128, help="problems per GPU in the batched callback measurement (1024 / 8 GPUs)")
     ap.add_argument("--no-swept", action="store_true", help="skip the secondary swept-volume (SV-SDF) measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-pieces", type=int, default=16, help="--impl reference: pieces per step sample (of 64)")
