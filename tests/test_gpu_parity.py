@@ -309,22 +309,36 @@ def test_swept_end_to_end_parity(name):
     ev.close()
 
 
-@pytest.mark.parametrize("mesh", ["lprism", "rcone"])
-def test_swept_end_to_end_mesh(mesh):
-    cfg, T, Cc, pts = sv_case(seed=7, npts=200)
+@pytest.mark.parametrize("mesh,poly", [("lprism", None), ("rcone", None), ("rcone", [0.1, -0.05, 0.0, 120.0, 20.0, -35.0]), ("ico", None)])
+def test_swept_end_to_end_mesh(mesh, poly):
+    """mesh robots: CTA-per-point kernel (bracket-pruned scans, warp-cooperative searches, parallel step candidates) replays the
+    reference's sequential search: same hit set, t*, SV-SDF values, reference-equivalent evaluation count, cost and gradient."""
+    cfg, T, Cc, pts = sv_case(seed=7, npts=260)
     V, F = MESHES[mesh]()
-    osh = O.Shape.mesh(V, F)
+    osh = O.Shape.mesh(V, F, poly) if poly is not None else O.Shape.mesh(V, F)
     ref = O.eval_swept(O.config_from(cfg), osh, T, Cc, pts)
     ev = I.Evaluator(cfg)
-    ev.set_shape_mesh(V, F)
+    ev.set_shape_mesh(V, F, poly)
     ev.set_points(pts)
     got = ev.eval_swept(T, Cc)
     ts, sd, gr = ev.swept_results()
     hit = ref["sdf"] < 9.99
-    assert np.array_equal(sd < 9.99, hit)
+    assert hit.sum() > 20 and np.array_equal(sd < 9.99, hit)
     dt = np.abs(ts - ref["tstar"])[hit]
     assert (dt <= 8e-5).mean() >= 0.99
+    assert np.allclose(sd[hit], ref["sdf"][hit], rtol=0, atol=1e-6)
     check_eval(got, (ref["cost"], ref["gradC"], ref["gradT"]), tol=1e-6, what=f"T2 mesh {mesh}")
+    assert ev.stats().last_sdf_evals == ref["nsdf"]
+    # second evaluation: lastTstar carried over, identical result (the search does not depend on the previous t*)
+    again = ev.eval_swept(T, Cc)
+    assert again[0] == got[0] and np.array_equal(again[1], got[1]) and np.array_equal(again[2], got[2])
+    # point shards (one rank per GPU) sum to the full evaluation
+    acc = [0.0, np.zeros_like(got[1]), np.zeros_like(got[2])]
+    for r in range(3):
+        ev.set_shard(r, 3)
+        c, gC, gT = ev.eval_swept(T, Cc)
+        acc[0] += c; acc[1] += gC; acc[2] += gT
+    assert abs(acc[0] - got[0]) <= 1e-12 * max(abs(got[0]), 1) and rel_l2(grads(acc[1], acc[2]), grads(got[1], got[2])) < 1e-12
     ev.close()
 
 
