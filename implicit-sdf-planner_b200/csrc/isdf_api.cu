@@ -49,8 +49,9 @@ struct isdf_ctx {
     DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
-    DevBuf<int> d_tickets;       // N piece tickets + 1 pieces_done (+ swept counters)
-    DevBuf<int> d_items, d_item_count, d_split_ticket; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
+    DevBuf<int> d_tickets;       // pieces_done counter of the epilogue kernel
+    DevBuf<double> d_tot; DevBuf<int> d_sample_slot;   // per-sample collision sums handed from the scan kernels to the epilogue
+    DevBuf<int> d_items, d_item_count; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
     int warp_slots = 148 * 12;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
     DevBuf<unsigned long long> d_counter, d_dbg;
@@ -142,7 +143,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
-    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_split_ticket.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
+    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_sample_slot.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
     c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -567,13 +568,15 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     const long long S = (long long)N * (K + 1);
     CU_TRY(c->d_partial.ensure((size_t)S * PARTIAL_STRIDE));
     CU_TRY(c->d_piece_cost.ensure(N));
-    if (c->d_tickets.n < (size_t)N + 1) {
-        CU_TRY(c->d_tickets.ensure((size_t)N + 1));
-        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int) * (N + 1), st));
+    if (c->d_tickets.n < 1) {
+        CU_TRY(c->d_tickets.ensure(1));
+        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int), st));
     }
+    CU_TRY(c->d_tot.ensure((size_t)S * 8));
+    CU_TRY(c->d_sample_slot.ensure((size_t)S));
     DiscArgs A;
     A.cfg = c->dcfg; A.grid = c->grid; A.shape = c->shape; A.N = N; A.T = d_T; A.C = d_C;
-    A.partial = c->d_partial.p; A.piece_ticket = c->d_tickets.p; A.pieces_done = c->d_tickets.p + c->d_tickets.n - 1;
+    A.partial = c->d_partial.p; A.tot = c->d_tot.p; A.sample_slot = c->d_sample_slot.p; A.pieces_done = c->d_tickets.p;
     A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
     A.rank = c->rank; A.world = c->world;
     A.dbg = nullptr;
@@ -588,19 +591,19 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     if (c->d_items.n < 3 * max_items + (size_t)M) { CU_TRY(c->d_items.ensure(3 * max_items + (size_t)M)); c->order_for = -1; }   // a regrown table holds no items yet
     CU_TRY(c->d_item_count.ensure(1));
     CU_TRY(c->d_subsum.ensure((size_t)max_split * ROW_CLASSES * 8));
-    if (c->d_split_ticket.n < (size_t)max_split) {
-        CU_TRY(c->d_split_ticket.ensure((size_t)max_split)); CU_TRY(c->d_split_work.ensure((size_t)max_split));
-        CU_TRY(cudaMemsetAsync(c->d_split_ticket.p, 0, sizeof(int) * max_split, st));
+    if (c->d_split_work.n < (size_t)max_split) {
+        CU_TRY(c->d_split_work.ensure((size_t)max_split));
         CU_TRY(cudaMemsetAsync(c->d_split_work.p, 0, sizeof(unsigned) * max_split, st));
     }
     A.work = c->d_work.p;
     const bool have_items = (c->order_for == sig);
     A.items = have_items ? c->d_items.p : nullptr;
-    A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_ticket = c->d_split_ticket.p; A.split_work = c->d_split_work.p;
+    A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_work = c->d_split_work.p;
     const unsigned grid = (unsigned)(((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS);
     if (c->items_pending) CU_TRY(cudaStreamWaitEvent(st, c->ev_items_done, 0));   // the table this launch reads (or overwrites next)
     if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
     else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
+    k_discrete_epilogue<<<(unsigned)N, EPI_THREADS, 0, st>>>(A);
     // build the next evaluation's work items on the aux stream: overlaps the caller's D2H / all-reduce / host work
     CU_TRY(cudaEventRecord(c->ev_main_done, st));
     CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_main_done, 0));
@@ -608,8 +611,7 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     CU_TRY(cudaEventRecord(c->ev_items_done, c->aux_stream));
     c->items_pending = true;
     c->order_for = sig;
-    c->stats.kernel_launches++;
-    c->stats.kernel_launches++;
+    c->stats.kernel_launches += 3;   // scan kernel, epilogue, work-item builder
     c->stats.evals_discrete++;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -36,7 +36,10 @@ constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than 
 // CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md): the analytic kernel
 // is fastest at 4 (128 regs), the mesh kernel at 3 (168 regs; forcing more spills the cooperative BVH search and is slower)
 constexpr int ANALYTIC_MIN_BLOCKS = 4;
-constexpr int MESH_MIN_BLOCKS = 3;
+#ifndef ISDF_MESH_MIN_BLOCKS
+#define ISDF_MESH_MIN_BLOCKS 4
+#endif
+constexpr int MESH_MIN_BLOCKS = ISDF_MESH_MIN_BLOCKS;
 
 struct DiscArgs {
     DevCfg cfg;
@@ -46,7 +49,8 @@ struct DiscArgs {
     const double *T;       // N
     const double *C;       // 6N x 3 column-major
     double *partial;       // S x PARTIAL_STRIDE
-    int *piece_ticket;     // N  (zero on entry, zero on exit)
+    double *tot;           // S x 8: collision sums of a sample evaluated as ONE work item {costp, gradp(3), grad_quat(4)}
+    int *sample_slot;      // S: -1 = sums in tot, otherwise the split slot whose class sums (subsum) make up the sample
     int *pieces_done;      // 1  (zero on entry, zero on exit)
     double *piece_cost;    // N
     double *out;           // 19N+1: cost | gradC | gradT
@@ -55,8 +59,7 @@ struct DiscArgs {
     const int *items;                  // may be null: 3 ints per work item {local sample m, row class or -1 = all, split slot or -1}
     const int *item_count;             // number of valid items (device)
     double *subsum;                    // split slot x ROW_CLASSES x 8 class sums
-    int *split_ticket;                 // split slot -> arrivals (zero on entry, zero on exit)
-    unsigned *split_work;              // split slot -> work accumulated by the parts
+    unsigned *split_work;              // split slot -> work accumulated by the parts (zero on entry, zeroed by the epilogue)
     unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
     int rank, world;       // this launch evaluates samples s with s % world == rank
 };
@@ -237,51 +240,6 @@ __device__ __forceinline__ void sample_epilogue(const DiscArgs &A, int i, int j,
     st[19] = node * step * pena;
 }
 
-// Called by a full warp after the partials of sample s (piece i) are in HBM: take a ticket; the last warp of the
-// piece sums it in ascending sample order, the last piece sums the costs. Deterministic regardless of scheduling.
-__device__ __forceinline__ void piece_finish(const DiscArgs &A, int i, int lane) {
-    const int K = A.cfg.K, N = A.N;
-    __threadfence();
-    int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(A.piece_ticket + i, 1);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    const int first_s = i * (K + 1), last_s = first_s + K;
-    const int f0 = first_s + ((A.rank - first_s) % A.world + A.world) % A.world;  // first local sample >= first_s
-    const int local_cnt = (f0 > last_s) ? 0 : ((last_s - f0) / A.world + 1);
-    if (ticket != local_cnt - 1) return;
-    __threadfence();
-    if (lane < PARTIAL_STRIDE) {
-        double sum = 0.0;
-        int ss = f0;
-        // 8 independent loads in flight per step; the additions stay in ascending-sample order
-        for (; ss + 7 * A.world <= last_s; ss += 8 * A.world) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = __ldcg(A.partial + (size_t)(ss + u * A.world) * PARTIAL_STRIDE + lane);
-#pragma unroll
-            for (int u = 0; u < 8; u++) sum += v[u];
-        }
-        for (; ss <= last_s; ss += A.world) sum += __ldcg(A.partial + (size_t)ss * PARTIAL_STRIDE + lane);
-        if (lane < 18) { const int ax = lane / 6, k = lane - 6 * ax; A.out[1 + (size_t)ax * 6 * N + 6 * i + k] = sum; }
-        else if (lane == 18) A.out[1 + 18 * N + i] = sum;
-        else A.piece_cost[i] = sum;
-    }
-    if (lane == 0) A.piece_ticket[i] = 0;
-    __threadfence();
-    int done = 0;
-    if (lane == 0) done = atomicAdd(A.pieces_done, 1);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != N - 1) return;
-    __threadfence();
-    // cost = sum over pieces in ascending order: lanes fetch, every lane adds in the same order
-    double c = 0.0;
-    for (int base = 0; base < N; base += 32) {
-        const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
-        for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
-    }
-    if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; }
-}
-
 // ============================================================================================================================
 // Work item of this warp: {global sample, first class, one-past-last class, split slot}. Returns false when there is none.
 struct Item { int s, c0, c1, hslot; };
@@ -303,41 +261,92 @@ __device__ __forceinline__ bool fetch_item(const DiscArgs &A, Item &it) {
     return true;
 }
 
-// Shared tail of both kernels. Whole-sample item: `tot` already holds the class sums added in class order. Split item:
-// publish this class's sums; the LAST part to arrive adds the ROW_CLASSES class sums in the same order and finishes.
-__device__ __forceinline__ void sample_finish(const DiscArgs &A, const Item &it, int i, int j, double Ti, double tot[8], unsigned npairs,
-                                              double *stage, long long t_begin, unsigned work) {
+// Shared tail of both kernels: publish the sample's (or this row class's) collision sums. The per-sample chain rule and the
+// per-piece reduction run afterwards in k_discrete_epilogue with one THREAD per sample — inside these kernels that scalar chain
+// (~10k cycles of dependent FP64) would occupy a whole warp with 31 idle lanes.
+__device__ __forceinline__ void sample_finish(const DiscArgs &A, const Item &it, double tot[8], unsigned npairs, long long t_begin, unsigned work) {
     const int lane = threadIdx.x & 31;
     const int s = it.s;
     if (lane == 0 && A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
     if (it.hslot >= 0) {
         double *sub = A.subsum + ((size_t)it.hslot * ROW_CLASSES + it.c0) * 8;
         if (lane < 8) sub[lane] = tot[lane];
-        if (lane == 0) atomicAdd(A.split_work + it.hslot, work);
-        __threadfence();
-        int t = 0;
-        if (lane == 0) t = atomicAdd(A.split_ticket + it.hslot, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t != ROW_CLASSES - 1) return;
-        __threadfence();
-        const double *all = A.subsum + (size_t)it.hslot * ROW_CLASSES * 8;
-#pragma unroll
-        for (int v = 0; v < 8; v++) { double a = 0.0; for (int c = 0; c < ROW_CLASSES; c++) a += __ldcg(all + c * 8 + v); tot[v] = a; }
-        work = __ldcg(A.split_work + it.hslot);
-        if (lane == 0) { A.split_ticket[it.hslot] = 0; A.split_work[it.hslot] = 0; }
+        if (lane == 0) { atomicAdd(A.split_work + it.hslot, work); A.sample_slot[s] = it.hslot; }   // every part writes the same slot
+    } else {
+        if (lane < 8) A.tot[(size_t)s * 8 + lane] = tot[lane];
+        if (lane == 0) { A.sample_slot[s] = -1; if (A.work) A.work[s] = work; }
     }
-    if (lane == 0) {
-        sample_epilogue(A, i, j, Ti, tot[0], mk3(tot[1], tot[2], tot[3]), tot[4], tot[5], tot[6], tot[7], stage);
-        if (A.work) A.work[s] = work;       // cost estimate for the next evaluation's longest-first order
-    }
-    __syncwarp();
-    if (lane < PARTIAL_STRIDE) A.partial[(size_t)s * PARTIAL_STRIDE + lane] = stage[lane];
 #ifdef ISDF_PHASE_TIMING
     if (A.dbg && lane == 0) A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin);
 #else
     if (A.dbg && lane == 0) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = work; }
 #endif
-    piece_finish(A, i, lane);
+}
+
+// One CTA per piece, one thread per pose sample of the piece: hpp:505-551 (dynamic penalties, flatness adjoint, chain rule onto the
+// piece's 6x3 coefficients and its duration), then the deterministic per-piece reduction — 20 threads, one per output component,
+// add the samples' partials in ascending sample order — and, in the last CTA to finish, the total cost in ascending piece order.
+constexpr int EPI_THREADS = 288;
+__global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_constant__ DiscArgs A) {
+    const int K = A.cfg.K, N = A.N, i = blockIdx.x;
+    const int first_s = i * (K + 1), last_s = first_s + K;
+    const int f0 = first_s + ((A.rank - first_s) % A.world + A.world) % A.world;  // first local sample >= first_s
+    const int local_cnt = (f0 > last_s) ? 0 : ((last_s - f0) / A.world + 1);
+    const double Ti = __ldg(A.T + i);
+    for (int idx = threadIdx.x; idx < local_cnt; idx += EPI_THREADS) {
+        const int s = f0 + idx * A.world;
+        const int j = s - first_s;
+        double tot[8];
+        const int slot = A.sample_slot[s];
+        if (slot < 0) {
+#pragma unroll
+            for (int v = 0; v < 8; v++) tot[v] = __ldcg(A.tot + (size_t)s * 8 + v);
+        } else {   // split sample: class sums added in class order — the same additions a whole-sample item performs
+            const double *all = A.subsum + (size_t)slot * ROW_CLASSES * 8;
+#pragma unroll
+            for (int v = 0; v < 8; v++) { double a = 0.0; for (int c = 0; c < ROW_CLASSES; c++) a += __ldcg(all + c * 8 + v); tot[v] = a; }
+            if (A.work) A.work[s] = A.split_work[slot];
+            A.split_work[slot] = 0;
+        }
+        double st[PARTIAL_STRIDE];
+        sample_epilogue(A, i, j, Ti, tot[0], mk3(tot[1], tot[2], tot[3]), tot[4], tot[5], tot[6], tot[7], st);
+#pragma unroll
+        for (int v = 0; v < PARTIAL_STRIDE; v++) A.partial[(size_t)s * PARTIAL_STRIDE + v] = st[v];
+    }
+    __syncthreads();
+    if (threadIdx.x < PARTIAL_STRIDE) {
+        const int comp = threadIdx.x;
+        double sum = 0.0;
+        int ss = f0;
+        // 8 independent loads in flight per step; the additions stay in ascending-sample order
+        for (; ss + 7 * A.world <= last_s; ss += 8 * A.world) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = A.partial[(size_t)(ss + u * A.world) * PARTIAL_STRIDE + comp];
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum += v[u];
+        }
+        for (; ss <= last_s; ss += A.world) sum += A.partial[(size_t)ss * PARTIAL_STRIDE + comp];
+        if (comp < 18) { const int ax = comp / 6, k = comp - 6 * ax; A.out[1 + (size_t)ax * 6 * N + 6 * i + k] = sum; }
+        else if (comp == 18) A.out[1 + 18 * N + i] = sum;
+        else A.piece_cost[i] = sum;
+    }
+    if (threadIdx.x >= 32) return;
+    // warp 0: last piece to finish adds the piece costs in ascending order
+    const int lane = threadIdx.x;
+    __threadfence();
+    __syncwarp();
+    int done = 0;
+    if (lane == 0) done = atomicAdd(A.pieces_done, 1);
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != N - 1) return;
+    __threadfence();
+    double c = 0.0;
+    for (int base = 0; base < N; base += 32) {
+        const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
+        for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
+    }
+    if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; }
 }
 
 // ============================================================================================================================
@@ -346,7 +355,6 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
     __shared__ uint32_t qA[DISC_WARPS][QCAP];
     __shared__ uint32_t qB[DISC_WARPS][QCAP];
     __shared__ double qBs[DISC_WARPS][QCAP];
-    __shared__ double stage[DISC_WARPS][PARTIAL_STRIDE];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -434,13 +442,12 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
         tot[0] = warp_sum(acc.c); tot[1] = warp_sum(acc.gx); tot[2] = warp_sum(acc.gy); tot[3] = warp_sum(acc.gz);
         tot[4] = warp_sum(acc.q0); tot[5] = warp_sum(acc.q1); tot[6] = warp_sum(acc.q2); tot[7] = warp_sum(acc.q3);
     }
-    sample_finish(A, it, i, j, Ti, tot, npairs, stage[warp], t_begin, npairs);
+    sample_finish(A, it, tot, npairs, t_begin, npairs);
 }
 
 // ============================================================================================================================
 // mesh shapes
 __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
-    __shared__ double stage[DISC_WARPS][PARTIAL_STRIDE];
     __shared__ WideStack wstack[DISC_WARPS];
     __shared__ double cacc[DISC_WARPS][ROW_CLASSES][8];   // per-warp class accumulators
 
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
         (void)t_pose;
     }
 #endif
-    sample_finish(A, it, i, j, Ti, tot, npairs, stage[warp], t_begin, 64u * nquery + npairs);
+    sample_finish(A, it, tot, npairs, t_begin, 64u * nquery + npairs);
 }
 
 
