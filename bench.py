@@ -138,15 +138,19 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+def ncu_capture(key="k_discrete_dram_bytes_per_launch"):
+    """a figure of the dominant kernel from the committed ncu --set full capture (profiles/roofline_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_discrete_dram_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
+
+
+def ncu_traffic():
+    return ncu_capture("k_discrete_dram_bytes_per_launch")
 
 
 # ---- CPU arm: the reference's algorithm (oracle port, OpenMP `parallel for schedule(dynamic)` + `critical`) -----------------
@@ -412,10 +416,40 @@ def run_ours(args):
     d_out = torch.zeros(19 * N + 1, dtype=torch.float64, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
+    ref_nccl = None
+    if world > 1:                                         # untimed cross-check for the fused exchange: same shards, NCCL sum
+        ev.eval_discrete_device(N, d_T.data_ptr(), d_C.data_ptr(), d_out.data_ptr(), stream)
+        allreduce_partials(d_out)
+        torch.cuda.synchronize()
+        ref_nccl = d_out.cpu().numpy().copy()
+    # multi-GPU reduction: fused into the evaluation through NVLink peer memory (isdf_peer_*); NCCL all-reduce if that cannot be set up
+    collective = "none"
+    if world > 1:
+        import torch.distributed as dist
+        collective = "nccl"
+        if args.collective == "peer":
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, ev.peer_export(world, 19 * N + 1))
+                ev.peer_connect(world, rank, handles, fuse=True)
+                okf = torch.ones(1, device=dev)
+            except Exception as e:
+                okf = torch.zeros(1, device=dev)
+                if rank == 0:
+                    print(f"bench: peer-memory exchange unavailable ({e}); using NCCL", file=sys.stderr)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if okf.item() == 1:
+                collective = "peer"
+            else:
+                try:
+                    ev.peer_disconnect()
+                except Exception:
+                    pass
+            dist.barrier()
 
     def step_device():
-        ev.eval_discrete_device(N, d_T.data_ptr(), d_C.data_ptr(), d_out.data_ptr(), stream)
-        if world > 1:
+        ev.eval_discrete_device(N, d_T.data_ptr(), d_C.data_ptr(), d_out.data_ptr(), stream)   # collective == "peer": includes the exchange
+        if collective == "nccl":
             allreduce_partials(d_out)
 
     sampler = ClockSampler(local) if rank == 0 else None   # nvidia-smi needs ~0.5 s to start: begin before the warm-up
@@ -466,7 +500,7 @@ def run_ours(args):
         torch.cuda.synchronize(); barrier()
         t0 = time.perf_counter()
         c, gC, gT = ev.eval_discrete(T, Cc)               # isdf_eval_discrete: pinned staging, H2D, kernel, D2H, sync
-        if world > 1:
+        if collective == "nccl":
             h_part[0] = c; h_part[1:1 + 18 * N] = torch.from_numpy(gC); h_part[1 + 18 * N:] = torch.from_numpy(gT)
             d_tmp = h_part.to(dev, non_blocking=True)
             allreduce_partials(d_tmp)
@@ -516,18 +550,22 @@ def run_ours(args):
         line = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(w), **w, "l2": "flushed (512 MiB write) between timed steps",
-                           "parallelism": f"sample-interleaved shards x{world} + 1 NCCL all-reduce of {19 * N + 1} doubles" if world > 1 else "1 GPU"},
+                           "parallelism": (f"sample-interleaved shards x{world} + " + (f"rank-ordered sum of {19 * N + 1} doubles over NVLink peer memory, fused into the epilogue kernel"
+                                                                                      if collective == "peer" else f"1 NCCL all-reduce of {19 * N + 1} doubles")) if world > 1 else "1 GPU"},
                 "clocks": clocks,
                 "e2e": {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * 19 * N, "d2h_bytes_per_step": 8 * (19 * N + 1) + 8,
                         "ms_per_step": ms_e2e, "api": "isdf_eval_discrete (host buffers)"},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                             "peak_source": peak_src, "kernel": "k_discrete<MESH>", "algorithmic_bytes_per_launch": ab // world,
+                             "peak_source": peak_src, "kernel": "k_discrete_mesh", "algorithmic_bytes_per_launch": ab // world,
+                             "fp64_pipe_active_pct_ncu": ncu_capture("fp64_pipe_active_pct"), "issue_slots_busy_pct_ncu": ncu_capture("issue_slots_busy_pct"),
                              "note": "window bytes counted at 1 B/voxel per sample (SURVEY §8d); the kernel is FP64/latency bound, see DESIGN.md"},
                 "extra": {"pairs_per_eval": int(pairs), "pairs_per_s": pairs / (ms * 1e-3), "ms_per_step_warm_l2": statistics.mean(warm),
                           "evals_per_s_warm_l2": 1e3 / statistics.mean(warm), "ms_min": min(times), "ms_max": max(times),
                           "kernel_ms_in_host_call": kernel_ms_alone, "wall_s_timed_loop": wall,
                           "cost": float(result[0]), "grad_norm": float(np.linalg.norm(result[1:])), "batch_weak": batch_weak,
+                          "collective": collective,
+                          "collective_vs_nccl_rel_l2": (float(np.linalg.norm(result - ref_nccl) / np.linalg.norm(ref_nccl)) if ref_nccl is not None else None),
                           "batch_callback": batch_cb}}
         if world == 1 and not args.no_lbfgs:
             try:
@@ -546,9 +584,15 @@ def run_ours(args):
             line["extra"]["speedup_kernel_vs_cpu"] = line["value"] / line["cpu_baseline"]["value"]
             line["extra"]["speedup_e2e_vs_cpu"] = line["e2e"]["value"] / line["cpu_baseline"]["value"]
         print(json.dumps(line))
-    ev.close()
     if world > 1:
         import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        if collective == "peer":
+            ev.peer_status()
+            ev.peer_disconnect()
+    ev.close()
+    if world > 1:
         dist.destroy_process_group()
     return 0
 
@@ -562,6 +606,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="tiny workload for plumbing checks (not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lbfgs", action="store_true", help="skip the secondary L-BFGS iterations/s measurement")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N > 1: reduction of the sharded evaluation")
     ap.add_argument("--no-batch", action="store_true", help="skip the batched device-callback measurement (configs[4])")
     ap.add_argument("--batch-per-gpu", type=int, default=128, help="problems per GPU in the batched callback measurement (1024 / 8 GPUs)")
     ap.add_argument("--no-swept", action="store_true", help="skip the secondary swept-volume (SV-SDF) measurement")

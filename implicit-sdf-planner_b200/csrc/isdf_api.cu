@@ -64,6 +64,13 @@ struct isdf_ctx {
     SweptState sv;
     // shard
     int rank = 0, world = 1;
+    // peer-memory reduction (isdf_peer.cuh)
+    void *peer_buf = nullptr;            // own exchange buffer (cudaMalloc, exported through CUDA IPC)
+    void *peer_open[PEER_MAX] = {};      // peers' buffers opened here (null for self / unused)
+    PeerArgs peer = {};                  // world == 0: not connected
+    bool peer_fused = false;             // sharded *_device evaluations finish with the exchange
+    int peer_world_alloc = 0, peer_cap = 0;
+    DevBuf<int> d_peer_status;
     isdf_stats stats;
 };
 
@@ -144,6 +151,9 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_sample_slot.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
+    for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
+    if (c->peer_buf) cudaFree(c->peer_buf);
+    c->d_peer_status.release();
     c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -579,6 +589,12 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     A.partial = c->d_partial.p; A.tot = c->d_tot.p; A.sample_slot = c->d_sample_slot.p; A.pieces_done = c->d_tickets.p;
     A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
     A.rank = c->rank; A.world = c->world;
+    A.peer = PeerArgs{};
+    if (c->peer_fused && c->peer.world > 1 && c->world > 1) {   // an unsharded call (isdf_set_shard(ctx, 0, 1)) stays local
+        if (c->peer.world != c->world || c->peer.rank != c->rank) return fail(ISDF_ERR_STATE, "peer group does not match isdf_set_shard");
+        if (19 * N + 1 > c->peer.cap) return fail(ISDF_ERR_INVALID, "peer exchange buffer too small for this N (isdf_peer_export max_doubles)");
+        A.peer = c->peer; A.peer.epoch = ++c->peer.epoch;
+    }
     A.dbg = nullptr;
     if (c->dbg_on) { CU_TRY(c->d_dbg.ensure((size_t)3 * S)); CU_TRY(cudaMemsetAsync(c->d_dbg.p, 0, sizeof(unsigned long long) * 3 * S, st)); A.dbg = c->d_dbg.p; }
     const long long M = (S - c->rank + c->world - 1) / c->world;
@@ -764,6 +780,85 @@ extern "C" int isdf_get_batch_trajectories(isdf_ctx *c, double *T, double *coeff
     return 0;
 }
 
+// ---- multi-GPU: rank-ordered sum of the sharded evaluation through NVLink peer memory (isdf_peer.cuh) ------------------------------
+static size_t peer_bytes(int world, int cap) { return sizeof(unsigned long long) * 2 * PEER_MAX + sizeof(double) * 2 * (size_t)world * cap; }
+
+extern "C" int isdf_peer_export(isdf_ctx *c, int world, int max_doubles, unsigned char *handle64) {
+    if (!c || !handle64 || world < 2 || world > PEER_MAX || max_doubles < 1) return fail(ISDF_ERR_INVALID, "bad argument (2 <= world <= 16)");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    if (c->peer.world) return fail(ISDF_ERR_STATE, "already connected: isdf_peer_disconnect first");
+    if (c->peer_buf) { cudaFree(c->peer_buf); c->peer_buf = nullptr; }
+    CU_TRY(cudaMalloc(&c->peer_buf, peer_bytes(world, max_doubles)));
+    CU_TRY(cudaMemset(c->peer_buf, 0, peer_bytes(world, max_doubles)));
+    CU_TRY(c->d_peer_status.ensure(1));
+    CU_TRY(cudaMemset(c->d_peer_status.p, 0, sizeof(int)));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, c->peer_buf));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &h, 64);
+    c->peer_world_alloc = world; c->peer_cap = max_doubles;
+    return 0;
+}
+
+extern "C" int isdf_peer_connect(isdf_ctx *c, int world, int rank, const unsigned char *handles, int fuse_into_eval) {
+    if (!c || !handles || rank < 0 || rank >= world) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (!c->peer_buf || world != c->peer_world_alloc) return fail(ISDF_ERR_STATE, "isdf_peer_export with the same world first");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    PeerArgs P = {};
+    P.world = world; P.rank = rank; P.cap = c->peer_cap; P.epoch = 0; P.status = c->d_peer_status.p;
+    for (int p = 0; p < world; p++) {
+        void *base = c->peer_buf;
+        if (p != rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + (size_t)64 * p, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int q = 0; q < p; q++) if (c->peer_open[q]) { cudaIpcCloseMemHandle(c->peer_open[q]); c->peer_open[q] = nullptr; }
+                return fail(ISDF_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+            c->peer_open[p] = base;
+        }
+        P.flags[p] = (unsigned long long *)base;
+        P.slots[p] = (double *)((char *)base + sizeof(unsigned long long) * 2 * PEER_MAX);
+    }
+    c->peer = P;
+    c->peer_fused = fuse_into_eval != 0;
+    return 0;
+}
+
+extern "C" int isdf_peer_allreduce_device(isdf_ctx *c, double *d_vec, int n, void *cuda_stream) {
+    if (!c || !d_vec || n < 1) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (c->peer.world < 2) return fail(ISDF_ERR_STATE, "not connected (isdf_peer_connect)");
+    if (n > c->peer.cap) return fail(ISDF_ERR_INVALID, "vector longer than the exchange buffer");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    PeerArgs P = c->peer;
+    P.epoch = ++c->peer.epoch;
+    k_peer_allreduce<<<1, 512, 0, (cudaStream_t)cuda_stream>>>(P, d_vec, n);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int isdf_peer_status(isdf_ctx *c) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (!c->d_peer_status.p) return 0;
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    int st = 0;
+    CU_TRY(cudaMemcpy(&st, c->d_peer_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) return fail(ISDF_ERR_CUDA, "peer exchange timed out: a rank did not reach the same evaluation");
+    return 0;
+}
+
+extern "C" int isdf_peer_disconnect(isdf_ctx *c) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    cudaDeviceSynchronize();
+    for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) { cudaIpcCloseMemHandle(c->peer_open[p]); c->peer_open[p] = nullptr; }
+    if (c->peer_buf) { cudaFree(c->peer_buf); c->peer_buf = nullptr; }
+    c->peer = PeerArgs{}; c->peer_fused = false; c->peer_world_alloc = 0; c->peer_cap = 0;
+    return 0;
+}
+
 // ---- swept volume -------------------------------------------------------------------------------------------
 extern "C" int isdf_set_points(isdf_ctx *c, const double *pts, int P) {
     if (!c || P < 0 || (P > 0 && !pts)) return fail(ISDF_ERR_INVALID, "bad argument");
@@ -780,6 +875,15 @@ static int swept_common(isdf_ctx *c, int N, const double *d_T, const double *d_C
     c->stats.kernel_launches += launches;
     c->stats.evals_swept++;
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? ISDF_ERR_INVALID : ISDF_ERR_CUDA, std::string("swept: ") + cudaGetErrorString(e));
+    if (c->peer_fused && c->peer.world > 1 && c->world > 1) {   // an unsharded call (isdf_set_shard(ctx, 0, 1)) stays local
+        if (c->peer.world != c->world || c->peer.rank != c->rank) return fail(ISDF_ERR_STATE, "peer group does not match isdf_set_shard");
+        if (19 * N + 1 > c->peer.cap) return fail(ISDF_ERR_INVALID, "peer exchange buffer too small for this N (isdf_peer_export max_doubles)");
+        PeerArgs P = c->peer;
+        P.epoch = ++c->peer.epoch;
+        k_peer_allreduce<<<1, 512, 0, st>>>(P, d_out, 19 * N + 1);
+        c->stats.kernel_launches++;
+        CU_TRY(cudaGetLastError());
+    }
     return 0;
 }
 

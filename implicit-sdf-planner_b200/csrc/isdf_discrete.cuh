@@ -25,6 +25,7 @@
 //     in ascending sample order — independent of scheduling, so results are bit-reproducible run to run.
 #pragma once
 #include "isdf_types.cuh"
+#include "isdf_peer.cuh"
 
 namespace isdf {
 
@@ -62,6 +63,7 @@ struct DiscArgs {
     unsigned *split_work;              // split slot -> work accumulated by the parts (zero on entry, zeroed by the epilogue)
     unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
     int rank, world;       // this launch evaluates samples s with s % world == rank
+    PeerArgs peer;         // peer.world > 1: the epilogue's last CTA also sums `out` over the ranks through peer memory (isdf_peer.cuh)
 };
 
 struct PairAcc { double c, gx, gy, gz, q0, q1, q2, q3; };
@@ -331,22 +333,28 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
         else if (comp == 18) A.out[1 + 18 * N + i] = sum;
         else A.piece_cost[i] = sum;
     }
-    if (threadIdx.x >= 32) return;
-    // warp 0: last piece to finish adds the piece costs in ascending order
-    const int lane = threadIdx.x;
+    // last CTA to finish: total cost = piece costs added in ascending order, then (multi-GPU) the exchange over peer memory
+    __shared__ int s_last;
     __threadfence();
-    __syncwarp();
-    int done = 0;
-    if (lane == 0) done = atomicAdd(A.pieces_done, 1);
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != N - 1) return;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(A.pieces_done, 1) == N - 1);
+    __syncthreads();
+    if (!s_last) return;
     __threadfence();
-    double c = 0.0;
-    for (int base = 0; base < N; base += 32) {
-        const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
-        for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double c = 0.0;
+        for (int base = 0; base < N; base += 32) {
+            const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
+            for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
+        }
+        if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; }
     }
-    if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; }
+    if (A.peer.world > 1) {
+        __threadfence();
+        __syncthreads();
+        peer_allreduce_block(A.peer, A.out, 19 * N + 1);
+    }
 }
 
 // ============================================================================================================================

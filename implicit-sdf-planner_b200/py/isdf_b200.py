@@ -27,7 +27,8 @@ ABI_SYMBOLS = ["isdf_default_config", "isdf_create", "isdf_destroy", "isdf_last_
                "isdf_set_map_u8", "isdf_set_map_f64", "isdf_points_in_aabb", "isdf_eval_discrete",
                "isdf_eval_discrete_device", "isdf_set_points", "isdf_eval_swept", "isdf_eval_swept_device",
                "isdf_get_swept_results", "isdf_eval_swept_given", "isdf_get_piece_costs",
-               "isdf_gather_obstacle_points", "isdf_callback_batch", "isdf_callback_batch_device", "isdf_get_batch_trajectories"]
+               "isdf_gather_obstacle_points", "isdf_callback_batch", "isdf_callback_batch_device", "isdf_get_batch_trajectories",
+               "isdf_peer_export", "isdf_peer_connect", "isdf_peer_allreduce_device", "isdf_peer_status", "isdf_peer_disconnect"]
 
 
 class Config(C.Structure):
@@ -95,6 +96,11 @@ def load_library(path=None):
     lib.isdf_callback_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, C.c_double, dp, dp, dp]
     lib.isdf_callback_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]
     lib.isdf_get_batch_trajectories.argtypes = [vp, dp, dp, dp]
+    lib.isdf_peer_export.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    lib.isdf_peer_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    lib.isdf_peer_allreduce_device.argtypes = [vp, vp, C.c_int, vp]
+    lib.isdf_peer_status.argtypes = [vp]
+    lib.isdf_peer_disconnect.argtypes = [vp]
     lib.isdf_eval_swept_given.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
     for s in ABI_SYMBOLS:
         if s != "isdf_last_error":
@@ -235,6 +241,26 @@ class Evaluator:
         T, Cc, en = np.zeros(B * N0), np.zeros(18 * B * N0), np.zeros(B)
         self._check(self.lib.isdf_get_batch_trajectories(self.h, _dp(T), _dp(Cc), _dp(en)))
         return T, Cc, en
+
+    # ---- multi-GPU reduction over peer memory (see include/isdf.h) ----
+    def peer_export(self, world, max_doubles):
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.isdf_peer_export(self.h, world, max_doubles, buf))
+        return bytes(buf.raw)
+
+    def peer_connect(self, world, rank, handles, fuse=True):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._check(self.lib.isdf_peer_connect(self.h, world, rank, blob, int(fuse)))
+
+    def peer_allreduce_device(self, d_vec, n, stream=None):
+        self._check(self.lib.isdf_peer_allreduce_device(self.h, d_vec, n, stream))
+
+    def peer_status(self):
+        self._check(self.lib.isdf_peer_status(self.h))
+
+    def peer_disconnect(self):
+        self._check(self.lib.isdf_peer_disconnect(self.h))
 
     def piece_costs(self, n):
         out = np.zeros(n)

@@ -155,6 +155,20 @@ int isdf_callback_batch_device(isdf_ctx *ctx, int B, int N0, const double *d_hea
  * jerk energies (B); any may be NULL */
 int isdf_get_batch_trajectories(isdf_ctx *ctx, double *T, double *coeffs, double *energy);
 
+/* ---- multi-GPU reduction through NVLink / NVSwitch peer memory (optional; ncclAllReduce over the same 19N+1 doubles is the
+ * library alternative). One process per GPU. Sequence on every rank:
+ *   isdf_set_shard(ctx, rank, world); isdf_peer_export(ctx, world, max_doubles, h) -> all-gather the 64-byte handles ->
+ *   isdf_peer_connect(ctx, world, rank, handles, fuse) -> barrier -> evaluations ... -> barrier -> isdf_peer_disconnect(ctx).
+ * With fuse != 0 every sharded isdf_eval_discrete* / isdf_eval_swept* call ends with the exchange inside the evaluation's last
+ * kernel (discrete: the same CTA that finishes the rank's vector pushes it to the peers), so `d_out` / the accumulated host
+ * results are the ALL-RANK sums, added in rank order: bit-identical on every rank. All ranks must issue the same sequence of
+ * evaluations. A rank that never arrives makes the others time out (~2 s) and isdf_peer_status() report it; nothing hangs. */
+int isdf_peer_export(isdf_ctx *ctx, int world, int max_doubles, unsigned char *handle64);
+int isdf_peer_connect(isdf_ctx *ctx, int world, int rank, const unsigned char *handles /* world x 64 */, int fuse_into_eval);
+int isdf_peer_allreduce_device(isdf_ctx *ctx, double *d_vec, int n, void *cuda_stream);   /* stand-alone, in place */
+int isdf_peer_status(isdf_ctx *ctx);
+int isdf_peer_disconnect(isdf_ctx *ctx);
+
 /* ---- swept-volume term: addSaftyPenaOnSweptVolumeParallel (hpp:557-649) + getSDFofSweptVolume (swm:710-747) --- */
 /* parallel_points (plan_manager.cpp:246-254): P x 3 row-major world-frame voxel centres; resets lastTstar to 0 */
 int isdf_set_points(isdf_ctx *ctx, const double *pts, int P);

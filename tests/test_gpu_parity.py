@@ -553,3 +553,17 @@ def test_obstacle_gather_matches_reference_semantics():
     ref = O.eval_swept(O.config_from(cfg), O.Shape.named("Torus"), T, Cc, pts)
     check_eval(got, (ref["cost"], ref["gradC"], ref["gradT"]), what="gather->swept")
     ev.close()
+
+
+def test_multi_gpu_peer_memory_reduction():
+    """isdf_peer_*: the sharded evaluation's sum over ranks through NVLink peer memory, fused into the epilogue kernel — needs >= 2
+    GPUs in the box (skipped on the single-GPU test box; run with `gpurun --gpus 2`). See tests/multi_gpu_peer.py."""
+    import subprocess, sys, torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 8)), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(here, "multi_gpu_peer.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "PEER OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
