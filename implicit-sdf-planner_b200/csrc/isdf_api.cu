@@ -5,6 +5,8 @@
 #include "isdf_discrete.cuh"
 #include "isdf_swept.cuh"
 #include "isdf_minco.cuh"
+#include "isdf_frontend.cuh"
+#include <queue>
 #include "isdf_host_mesh.cuh"
 #include <cstdio>
 #include <cstring>
@@ -64,6 +66,12 @@ struct isdf_ctx {
     SweptState sv;
     // shard
     int rank = 0, world = 1;
+    // front end attitude kernels (isdf_frontend.cuh)
+    DevBuf<double> d_fe_rot; DevBuf<uint8_t> d_fe_kernels, d_fe_order, d_fe_ok; DevBuf<uint32_t> d_fe_masks, d_fe_out;
+    DevBuf<int> d_fe_ind; DevBuf<double> d_fe_father, d_fe_child;
+    bool fe_ready = false;
+    int fe_xk = 0, fe_yk = 0, fe_ks = 0;
+    double fe_max_roll = 0, fe_max_pitch = 0, fe_ang_res = 0, fe_margin = 0;
     // peer-memory reduction (isdf_peer.cuh)
     void *peer_buf = nullptr;            // own exchange buffer (cudaMalloc, exported through CUDA IPC)
     void *peer_open[PEER_MAX] = {};      // peers' buffers opened here (null for self / unused)
@@ -154,6 +162,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
+    c->d_fe_rot.release(); c->d_fe_kernels.release(); c->d_fe_order.release(); c->d_fe_ok.release(); c->d_fe_masks.release(); c->d_fe_out.release(); c->d_fe_ind.release(); c->d_fe_father.release(); c->d_fe_child.release();
     c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -205,7 +214,7 @@ extern "C" int isdf_set_shape_analytic(isdf_ctx *c, int kind, const double *para
     c->shape.kind = kind;
     for (int i = 0; i < nparams; i++) c->shape.par[i] = params[i];
     shape_common(c, rot, trans);
-    c->have_shape = true;
+    c->have_shape = true; c->fe_ready = false;
     c->order_for = -1;   // work items of another shape class may carry split slots
     return 0;
 }
@@ -308,7 +317,7 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
         }
     }
     c->shape.mesh = m;
-    c->have_shape = true;
+    c->have_shape = true; c->fe_ready = false;
     c->order_for = -1;
     return 0;
 }
@@ -856,6 +865,184 @@ extern "C" int isdf_peer_disconnect(isdf_ctx *c) {
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) { cudaIpcCloseMemHandle(c->peer_open[p]); c->peer_open[p] = nullptr; }
     if (c->peer_buf) { cudaFree(c->peer_buf); c->peer_buf = nullptr; }
     c->peer = PeerArgs{}; c->peer_fused = false; c->peer_world_alloc = 0; c->peer_cap = 0;
+    return 0;
+}
+
+// ---- front end: attitude-kernel feasibility (isdf_frontend.cuh), SURVEY §8f row 4 ------------------------------------------------
+// Eigen::AngleAxisd(rotx, UnitX) * Eigen::AngleAxisd(roty, UnitY) -> Matrix3d (Shape.hpp:431): quaternion product, toRotationMatrix
+static void attitude_rotation(double rotx, double roty, double R[9]) {
+    const double sa = std::sin(0.5 * rotx), sb = std::sin(0.5 * roty);
+    const double aw = std::cos(0.5 * rotx), ax = sa * 1.0, ay = sa * 0.0, az = sa * 0.0;
+    const double bw = std::cos(0.5 * roty), bx = sb * 0.0, by = sb * 1.0, bz = sb * 0.0;
+    const double w = aw * bw - ax * bx - ay * by - az * bz;
+    const double x = aw * bx + ax * bw + ay * bz - az * by;
+    const double y = aw * by + ay * bw + az * bx - ax * bz;
+    const double z = aw * bz + az * bw + ax * by - ay * bx;
+    const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1.0 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1.0 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.0 - (txx + tyy);
+}
+
+static FrontArgs front_args(isdf_ctx *c) {
+    FrontArgs A = {};
+    A.grid = c->grid; A.shape = c->shape;
+    for (int i = 0; i < 9; i++) A.rot[i] = c->shape.rot[i];
+    for (int i = 0; i < 3; i++) A.trans[i] = c->shape.trans[i];
+    if (c->shape.kind != ISDF_SHAPE_MESH) {   // the kernel applies ((pos - trans) * Rotate) * R_obj itself and evaluates the bare body
+        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int i = 0; i < 9; i++) A.shape.rot[i] = I[i];
+        for (int i = 0; i < 3; i++) A.shape.trans[i] = 0.0;
+    }
+    A.ks = c->fe_ks; A.xk = c->fe_xk; A.yk = c->fe_yk; A.natt = c->fe_xk * c->fe_yk;
+    A.res = c->cfg.occupancy_resolution; A.margin = c->fe_margin;
+    A.att_rot = c->d_fe_rot.p; A.kernels = c->d_fe_kernels.p; A.offset_masks = c->d_fe_masks.p; A.order = c->d_fe_order.p;
+    A.max_roll = c->fe_max_roll; A.max_pitch = c->fe_max_pitch; A.ang_res = c->fe_ang_res;
+    return A;
+}
+
+extern "C" int isdf_frontend_build_kernels(isdf_ctx *c, const isdf_kernel_config *kc, int *xkernel_size, int *ykernel_size) {
+    if (!c || !kc) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (!c->have_shape) return fail(ISDF_ERR_STATE, "shape not set");
+    if (!(kc->kernel_ang_res > 0) || kc->kernel_max_roll < 0 || kc->kernel_max_pitch < 0) return fail(ISDF_ERR_INVALID, "bad attitude grid");
+    const int ks = c->cfg.kernel_size;
+    if (ks < 1 || (ks & 1) == 0) return fail(ISDF_ERR_INVALID, "kernel_size must be odd (Shape.hpp:258)");
+    if (ks > 33) return fail(ISDF_ERR_UNSUPPORTED, "kernel_size > 33");
+    const int xk = (int)std::floor(2 * kc->kernel_max_roll / kc->kernel_ang_res) + 1, yk = (int)std::floor(2 * kc->kernel_max_pitch / kc->kernel_ang_res) + 1;   // swm:135-136
+    if (xk * yk > FE_MAX_ATT) return fail(ISDF_ERR_UNSUPPORTED, "more than 128 attitudes");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    const int natt = xk * yk, n3 = ks * ks * ks;
+    std::vector<double> rot((size_t)9 * natt, 0.0);
+    {
+        int i = 0;
+        for (double roll = -kc->kernel_max_roll; roll <= kc->kernel_max_roll && i < xk; roll += kc->kernel_ang_res, i++) {   // Shape.hpp:424-427
+            int j = 0;
+            for (double pitch = -kc->kernel_max_pitch; pitch <= kc->kernel_max_pitch && j < yk; pitch += kc->kernel_ang_res, j++)
+                attitude_rotation(roll * M_PI / 180.0, pitch * M_PI / 180.0, &rot[(size_t)9 * (i * yk + j)]);
+        }
+    }
+    // visiting order of visit_kernels_by_distance for every start attitude: level pose, then the BFS sequence without it
+    std::vector<uint8_t> order((size_t)natt * natt, 0xff);
+    const int zi = (xk - 1) / 2, zj = (yk - 1) / 2;
+    for (int sx = 0; sx < xk; sx++)
+        for (int sy = 0; sy < yk; sy++) {
+            uint8_t *o = &order[(size_t)(sx * yk + sy) * natt];
+            int n = 0;
+            o[n++] = (uint8_t)(zi * yk + zj);
+            std::vector<uint8_t> vis((size_t)natt, 0);
+            std::queue<std::pair<int, int>> q;
+            q.push({sx, sy}); vis[sx * yk + sy] = 1;
+            const int dirs[4][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}};
+            int deep = 0;
+            while (!q.empty()) {
+                deep++;
+                const int x = q.front().first, y = q.front().second;
+                q.pop();
+                if (x != zi || y != zj) o[n++] = (uint8_t)(x * yk + y);
+                for (auto &d : dirs) {
+                    const int nx = x + d[0], ny = y + d[1];
+                    if (nx < 0 || nx >= xk || ny < 0 || ny >= yk || vis[nx * yk + ny]) continue;
+                    vis[nx * yk + ny] = 1;
+                    q.push({nx, ny});
+                }
+                if (deep > 800) break;   // maxdeepth (swm:852)
+            }
+        }
+    CU_TRY(c->d_fe_rot.upload(rot.data(), rot.size(), c->stream));
+    CU_TRY(c->d_fe_order.upload(order.data(), order.size(), c->stream));
+    CU_TRY(c->d_fe_kernels.ensure((size_t)natt * n3));
+    CU_TRY(c->d_fe_masks.ensure((size_t)4 * n3));
+    c->fe_xk = xk; c->fe_yk = yk; c->fe_ks = ks;
+    c->fe_max_roll = kc->kernel_max_roll; c->fe_max_pitch = kc->kernel_max_pitch; c->fe_ang_res = kc->kernel_ang_res;
+    c->fe_margin = std::max(kc->front_end_safeh, c->cfg.occupancy_resolution / 2);   // Shape.hpp:423
+    FrontArgs A = front_args(c);
+    const long long nt = (long long)natt * n3;
+    k_frontend_kernels<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(A);
+    k_frontend_offset_masks<<<(unsigned)((n3 + 255) / 256), 256, 0, c->stream>>>(A);
+    c->stats.kernel_launches += 2;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->fe_ready = true;
+    if (xkernel_size) *xkernel_size = xk;
+    if (ykernel_size) *ykernel_size = yk;
+    return 0;
+}
+
+extern "C" int isdf_frontend_get_kernels(isdf_ctx *c, uint8_t *out, int n) {
+    if (!c || !out) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (!c->fe_ready) return fail(ISDF_ERR_STATE, "isdf_frontend_build_kernels first (and again after changing the shape)");
+    const size_t want = (size_t)c->fe_xk * c->fe_yk * c->fe_ks * c->fe_ks * c->fe_ks;
+    if ((size_t)n != want) return fail(ISDF_ERR_INVALID, "n must be xkernel_size * ykernel_size * kernel_size^3");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    CU_TRY(cudaMemcpy(out, c->d_fe_kernels.p, want, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int frontend_state(isdf_ctx *c) {
+    if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
+    if (!c->fe_ready) return fail(ISDF_ERR_STATE, "isdf_frontend_build_kernels first (and again after changing the shape)");
+    if (!c->have_map) return fail(ISDF_ERR_STATE, "map not set");
+    return 0;
+}
+
+extern "C" int isdf_frontend_feasibility_device(isdf_ctx *c, uint32_t *d_masks, void *cuda_stream) {
+    int r = frontend_state(c);
+    if (r) return r;
+    if (!d_masks) return fail(ISDF_ERR_INVALID, "NULL device pointer");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    FrontArgs A = front_args(c);
+    A.out = d_masks;
+    const size_t smem = sizeof(uint32_t) * 4 * (size_t)A.ks * A.ks * A.ks;
+    CU_TRY(cudaFuncSetAttribute(k_frontend_feasibility, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nvox = (long long)c->grid.X * c->grid.Y * c->grid.Z;
+    const unsigned grid = (unsigned)std::min<long long>((nvox + 255) / 256, 148ll * 64);
+    k_frontend_feasibility<<<grid, 256, smem, (cudaStream_t)cuda_stream>>>(A);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int isdf_frontend_feasibility(isdf_ctx *c, uint32_t *masks) {
+    int r = frontend_state(c);
+    if (r) return r;
+    if (!masks) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    const size_t nvox = (size_t)c->grid.X * c->grid.Y * c->grid.Z;
+    CU_TRY(c->d_fe_out.ensure(4 * nvox));
+    CU_TRY(cudaEventRecord(c->ev0, c->stream));
+    r = isdf_frontend_feasibility_device(c, c->d_fe_out.p, c->stream);
+    if (r) return r;
+    CU_TRY(cudaEventRecord(c->ev1, c->stream));
+    CU_TRY(cudaMemcpyAsync(masks, c->d_fe_out.p, sizeof(uint32_t) * 4 * nvox, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.last_kernel_ms = ms;
+    return 0;
+}
+
+extern "C" int isdf_frontend_check_batch(isdf_ctx *c, int n, const int32_t *ind, const double *father_roll_pitch, double *child_roll_pitch, uint8_t *ok) {
+    int r = frontend_state(c);
+    if (r) return r;
+    if (n < 0 || (n > 0 && (!ind || !father_roll_pitch || !child_roll_pitch || !ok))) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (n == 0) return 0;
+    for (int q = 0; q < n; q++)
+        if (ind[3 * q] < 0 || ind[3 * q] >= c->grid.X || ind[3 * q + 1] < 0 || ind[3 * q + 1] >= c->grid.Y || ind[3 * q + 2] < 0 || ind[3 * q + 2] >= c->grid.Z)
+            return fail(ISDF_ERR_INVALID, "voxel index outside the map");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    CU_TRY(c->d_fe_ind.upload(ind, (size_t)3 * n, c->stream));
+    CU_TRY(c->d_fe_father.upload(father_roll_pitch, (size_t)2 * n, c->stream));
+    CU_TRY(c->d_fe_child.ensure((size_t)2 * n)); CU_TRY(c->d_fe_ok.ensure(n)); CU_TRY(c->d_fe_out.ensure((size_t)4 * n));
+    FrontArgs A = front_args(c);
+    A.out = c->d_fe_out.p; A.nq = n; A.q_ind = c->d_fe_ind.p; A.q_father = c->d_fe_father.p; A.q_child = c->d_fe_child.p; A.q_ok = c->d_fe_ok.p;
+    const size_t smem = sizeof(uint32_t) * 4 * (size_t)A.ks * A.ks * A.ks;
+    CU_TRY(cudaFuncSetAttribute(k_frontend_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_frontend_check<<<(unsigned)((n + 255) / 256), 256, smem, c->stream>>>(A);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(child_roll_pitch, c->d_fe_child.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(ok, c->d_fe_ok.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -1,4 +1,5 @@
-// Fused discrete collision cost/gradient kernels: ONE launch per optimiser step.
+// Discrete collision cost/gradient kernels: a scan kernel (warp per pose sample) and an epilogue kernel (thread per sample,
+// CTA per piece) per optimiser step.
 //
 // Reference semantics: addTimeIntPenaltyParallel (back_end_optimizer.hpp:432-554) with grad_cost_p (hpp:766-824)
 // wired into the sample loop exactly as hpp:619-626 wires its swept-volume sibling; PCSmapManager::getPointsInAABB
@@ -18,11 +19,12 @@
 //     difference SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87). Evaluating those only for active voxels is exact
 //     because an inactive voxel contributes nothing (hpp:809-821);
 //   * k_discrete_mesh — voxels that survive the exact culls (body-frame box, inflated mesh AABB, per-cell distance lower
-//     bound) are answered by WARP-COOPERATIVE nearest-triangle searches (32-ary tree, lane = child / triangle slot),
-//     seeded with the cell's nearest triangle;
-//   * sample epilogue (penalties, flatness adjoint, beta-basis outer products), then a deterministic two-level
-//     reduction: per-sample partials in HBM, and the LAST warp to finish a piece (ticket counter) sums that piece
-//     in ascending sample order — independent of scheduling, so results are bit-reproducible run to run.
+//     bound) are answered by WARP-COOPERATIVE nearest-triangle queries: the cell's exact candidate list near the surface,
+//     elsewhere the 32-ary tree (lane = child / triangle slot) seeded with the cell's nearest triangle;
+//   * k_discrete_epilogue — the per-sample chain rule (penalties, flatness adjoint, beta-basis outer products) as one THREAD
+//     per sample, then a deterministic reduction inside the piece's CTA: 20 threads add the partials in ascending sample
+//     order; the last CTA adds the piece costs in ascending order and (several GPUs) runs the peer-memory exchange —
+//     independent of scheduling, so results are bit-reproducible run to run and identical on every rank.
 #pragma once
 #include "isdf_types.cuh"
 #include "isdf_peer.cuh"
@@ -35,7 +37,7 @@ constexpr int QCAP = 64;
 constexpr int ROW_CLASSES = 8;          // a pose window's rows are summed in 8 interleaved classes (canonical order)
 constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than this (work units: 64 per mesh query + 1 per culled pair)
 // CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md): the analytic kernel
-// is fastest at 4 (128 regs), the mesh kernel at 3 (168 regs; forcing more spills the cooperative BVH search and is slower)
+// is fastest at 4 (128 regs); so is the mesh kernel since the per-sample epilogue left it (3/4/5 -> 0.475/0.453/0.463 ms)
 constexpr int ANALYTIC_MIN_BLOCKS = 4;
 #ifndef ISDF_MESH_MIN_BLOCKS
 #define ISDF_MESH_MIN_BLOCKS 4

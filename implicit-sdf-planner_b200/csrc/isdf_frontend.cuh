@@ -1,0 +1,167 @@
+// Front end: attitude-kernel collision checks for the whole map at once.
+//
+// Reference (per A* node expansion, serial): the robot is rasterised into one kernel_size^3 occupancy kernel per
+// (roll, pitch) attitude (Shape.hpp:405-461); kernelConv<true> (sw_manager.hpp:821-846) ANDs the kernel's byte rows with the
+// inflated, byte-packed map (PCSmap_manager.h:46-78) at the voxel; visit_kernels_by_distance (sw_manager.hpp:852-913) tries the
+// level attitude and then a BFS over the attitude grid until a kernel fits; checkKernelValue (:914-941) maps that back to angles.
+//
+// B200 mapping: the question "which attitudes fit at voxel v" is answered for EVERY voxel in one pass, as a 128-bit mask per
+// voxel, so the graph search itself does O(1) lookups. The convolution is turned inside out: instead of testing up to 121 kernels
+// x 169 rows per voxel, each kernel offset (a,b,c) carries the SET OF ATTITUDES whose kernel occupies it (a 128-bit mask,
+// kernel_size^3 x 16 B = 35 KB in shared memory); a voxel ORs the masks of the OCCUPIED voxels of its window — found with the same
+// bit-row reads as the discrete collision kernel — and the attitudes left unset are collision-free. Work per voxel is
+// proportional to the obstacles near it, not to the number of attitudes; integer/bit arithmetic only, so parity with the
+// reference's byte AND is exact (cells outside the map are free, like the reference's inflation margin).
+//   k_frontend_kernels      one thread per (attitude, a, b, c): SDF at the rotated body point <= margin
+//   k_frontend_offset_masks one thread per (a, b, c): the 128-bit attitude set of that offset
+//   k_frontend_feasibility  one thread per voxel (z fastest): window scan + mask OR -> collision-free attitude mask
+//   k_frontend_check        one thread per query: same mask, then the reference's visiting order (level pose, BFS from the father)
+#pragma once
+#include "isdf_types.cuh"
+
+namespace isdf {
+
+constexpr int FE_MAX_ATT = 128;
+
+struct FrontArgs {
+    DevGrid grid;
+    DevShape shape;          // analytic shapes: rot = I, trans = 0 (the pre-transform is applied explicitly, see k_frontend_kernels)
+    double rot[9], trans[3]; // the shape's real pre-transform
+    int ks, natt, xk, yk;
+    double res, margin;
+    const double *att_rot;   // natt x 9 row-major: Rx(roll) * Ry(pitch), built on the host exactly like Eigen does
+    uint8_t *kernels;        // natt x ks^3 booleans, address a*ks*ks + b*ks + c
+    uint32_t *offset_masks;  // ks^3 x 4
+    uint32_t *out;           // X*Y*Z x 4 (feasibility) — or n x 4 for the batched check
+    // batched check
+    int nq;
+    const int *q_ind;        // nq x 3
+    const double *q_father;  // nq x 2 (roll, pitch) degrees
+    double *q_child;         // nq x 2
+    uint8_t *q_ok;           // nq
+    const uint8_t *order;    // natt x natt: visiting order of visit_kernels_by_distance for every start attitude (0xff = end)
+    double max_roll, max_pitch, ang_res;
+};
+
+__global__ void k_frontend_kernels(const __grid_constant__ FrontArgs A) {
+    const int n3 = A.ks * A.ks * A.ks;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)A.natt * n3) return;
+    const int att = (int)(t / n3), v = (int)(t - (long long)att * n3);
+    const int a = v / (A.ks * A.ks), b = (v / A.ks) % A.ks, c = v % A.ks;
+    const int side = (int)(0.5 * (A.ks - 1));
+    const d3 pos = mk3(A.res * a - side * A.res, A.res * b - side * A.res, A.res * c - side * A.res);
+    const double *R = A.att_rot + 9 * att;
+    double sdf;
+    if (A.shape.kind == ISDF_SHAPE_BALL || A.shape.kind == ISDF_SHAPE_POINT) sdf = shape_sdf_analytic(A.shape, pos);     // ignore R_obj
+    else if (A.shape.kind == ISDF_SHAPE_MESH) {
+        const d3 q = mk3(pos.x * R[0] + pos.y * R[3] + pos.z * R[6], pos.x * R[1] + pos.y * R[4] + pos.z * R[7], pos.x * R[2] + pos.y * R[5] + pos.z * R[8]);
+        d3 g;
+        sdf = mesh_sdf_grad(A.shape.mesh, q, 1e300, g);                                                               // pos * R_obj
+    } else {
+        const double x = pos.x - A.trans[0], y = pos.y - A.trans[1], z = pos.z - A.trans[2];                           // ((pos - trans) * Rotate) * R_obj
+        const d3 p1 = mk3(x * A.rot[0] + y * A.rot[3] + z * A.rot[6], x * A.rot[1] + y * A.rot[4] + z * A.rot[7], x * A.rot[2] + y * A.rot[5] + z * A.rot[8]);
+        const d3 q = mk3(p1.x * R[0] + p1.y * R[3] + p1.z * R[6], p1.x * R[1] + p1.y * R[4] + p1.z * R[7], p1.x * R[2] + p1.y * R[5] + p1.z * R[8]);
+        sdf = shape_sdf_analytic(A.shape, q);   // A.shape carries identity rot / zero trans: only the body is evaluated
+    }
+    A.kernels[t] = (sdf <= A.margin) ? 1 : 0;
+}
+
+__global__ void k_frontend_offset_masks(const __grid_constant__ FrontArgs A) {
+    const int n3 = A.ks * A.ks * A.ks;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n3) return;
+    uint32_t m[4] = {0, 0, 0, 0};
+    for (int att = 0; att < A.natt; att++)
+        if (A.kernels[(size_t)att * n3 + v]) m[att >> 5] |= 1u << (att & 31);
+    for (int k = 0; k < 4; k++) A.offset_masks[4 * v + k] = m[k];
+}
+
+// attitudes whose kernel collides with the map when centred on voxel (ix, iy, iz); sm = offset masks in shared memory
+__device__ __forceinline__ void frontend_colliding(const FrontArgs &A, const uint32_t *sm, int ix, int iy, int iz, uint32_t m[4]) {
+    const DevGrid &G = A.grid;
+    const int ks = A.ks, side = (ks - 1) / 2;
+    const uint32_t full[4] = {A.natt >= 32 ? 0xffffffffu : ((1u << A.natt) - 1u),
+                              A.natt >= 64 ? 0xffffffffu : (A.natt > 32 ? ((1u << (A.natt - 32)) - 1u) : 0u),
+                              A.natt >= 96 ? 0xffffffffu : (A.natt > 64 ? ((1u << (A.natt - 64)) - 1u) : 0u),
+                              A.natt >= 128 ? 0xffffffffu : (A.natt > 96 ? ((1u << (A.natt - 96)) - 1u) : 0u)};
+    m[0] = m[1] = m[2] = m[3] = 0u;
+    const int z0 = iz - side;                            // window z range [z0, z0 + ks)
+    const int w0 = (z0 >= 0) ? (z0 >> 5) : -1;           // word holding z0 (floor division for z0 >= -32)
+    const int sh = z0 - 32 * w0;                         // 0..31
+    const unsigned long long wmask = (ks >= 64) ? ~0ull : ((1ull << ks) - 1ull);
+    for (int a = 0; a < ks; a++) {
+        const int x = ix + a - side;
+        if (x < 0 || x >= G.X) continue;
+        for (int b = 0; b < ks; b++) {
+            const int y = iy + b - side;
+            if (y < 0 || y >= G.Y) continue;
+            const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+            const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
+            const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
+            unsigned long long bits = ((((unsigned long long)hi << 32) | lo) >> sh) & wmask;   // bit c = voxel z0 + c (words past Z are zero)
+            const uint32_t *mrow = sm + 4 * (size_t)((a * ks + b) * ks);
+            while (bits) {
+                const int c = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                m[0] |= mrow[4 * c]; m[1] |= mrow[4 * c + 1]; m[2] |= mrow[4 * c + 2]; m[3] |= mrow[4 * c + 3];
+            }
+        }
+        if (m[0] == full[0] && m[1] == full[1] && m[2] == full[2] && m[3] == full[3]) return;   // nothing fits any more
+    }
+}
+
+__device__ __forceinline__ void frontend_stage_masks(const FrontArgs &A, uint32_t *sm) {
+    const int n = 4 * A.ks * A.ks * A.ks;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) sm[k] = A.offset_masks[k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_frontend_feasibility(const __grid_constant__ FrontArgs A) {
+    extern __shared__ uint32_t fe_sm[];
+    frontend_stage_masks(A, fe_sm);
+    const DevGrid &G = A.grid;
+    const long long nvox = (long long)G.X * G.Y * G.Z;
+    const uint32_t valid[4] = {A.natt >= 32 ? 0xffffffffu : ((1u << A.natt) - 1u),
+                               A.natt >= 64 ? 0xffffffffu : (A.natt > 32 ? ((1u << (A.natt - 32)) - 1u) : 0u),
+                               A.natt >= 96 ? 0xffffffffu : (A.natt > 64 ? ((1u << (A.natt - 64)) - 1u) : 0u),
+                               A.natt >= 128 ? 0xffffffffu : (A.natt > 96 ? ((1u << (A.natt - 96)) - 1u) : 0u)};
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+        const int iz = (int)(v % G.Z), iy = (int)((v / G.Z) % G.Y), ix = (int)(v / ((long long)G.Z * G.Y));
+        uint32_t m[4];
+        frontend_colliding(A, fe_sm, ix, iy, iz, m);
+        uint4 o = make_uint4(~m[0] & valid[0], ~m[1] & valid[1], ~m[2] & valid[2], ~m[3] & valid[3]);
+        reinterpret_cast<uint4 *>(A.out)[v] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_frontend_check(const __grid_constant__ FrontArgs A) {
+    extern __shared__ uint32_t fe_sm[];
+    frontend_stage_masks(A, fe_sm);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= A.nq) return;
+    const int ix = A.q_ind[3 * q], iy = A.q_ind[3 * q + 1], iz = A.q_ind[3 * q + 2];
+    const double fr = A.q_father[2 * q], fp = A.q_father[2 * q + 1];
+    uint32_t m[4];
+    frontend_colliding(A, fe_sm, ix, iy, iz, m);
+    for (int k = 0; k < 4; k++) A.out[4 * (size_t)q + k] = ~m[k];
+    const int fi = (int)((fr + A.max_roll) / A.ang_res), fj = (int)((fp + A.max_pitch) / A.ang_res);   // checkKernelValue (swm:917-918)
+    double cr = fr, cp = fp;
+    uint8_t ok = 0;
+    if (fi >= 0 && fi < A.xk && fj >= 0 && fj < A.yk) {
+        const uint8_t *ord = A.order + (size_t)(fi * A.yk + fj) * A.natt;
+        for (int k = 0; k < A.natt; k++) {
+            const int att = ord[k];
+            if (att == 0xff) break;
+            if (!((m[att >> 5] >> (att & 31)) & 1u)) {
+                const int ri = att / A.yk, rj = att - ri * A.yk;
+                cr = fr + (ri - fi) * A.ang_res; cp = fp + (rj - fj) * A.ang_res;
+                ok = 1;
+                break;
+            }
+        }
+    }
+    A.q_child[2 * q] = cr; A.q_child[2 * q + 1] = cp; A.q_ok[q] = ok;
+}
+
+}  // namespace isdf

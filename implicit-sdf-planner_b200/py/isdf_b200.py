@@ -28,7 +28,13 @@ ABI_SYMBOLS = ["isdf_default_config", "isdf_create", "isdf_destroy", "isdf_last_
                "isdf_eval_discrete_device", "isdf_set_points", "isdf_eval_swept", "isdf_eval_swept_device",
                "isdf_get_swept_results", "isdf_eval_swept_given", "isdf_get_piece_costs",
                "isdf_gather_obstacle_points", "isdf_callback_batch", "isdf_callback_batch_device", "isdf_get_batch_trajectories",
-               "isdf_peer_export", "isdf_peer_connect", "isdf_peer_allreduce_device", "isdf_peer_status", "isdf_peer_disconnect"]
+               "isdf_frontend_build_kernels", "isdf_frontend_get_kernels", "isdf_frontend_feasibility", "isdf_frontend_feasibility_device",
+               "isdf_frontend_check_batch", "isdf_peer_export", "isdf_peer_connect", "isdf_peer_allreduce_device", "isdf_peer_status", "isdf_peer_disconnect"]
+
+
+class KernelConfig(C.Structure):
+    """isdf_kernel_config"""
+    _fields_ = [(n, C.c_double) for n in ["kernel_max_roll", "kernel_max_pitch", "kernel_ang_res", "front_end_safeh"]]
 
 
 class Config(C.Structure):
@@ -96,6 +102,11 @@ def load_library(path=None):
     lib.isdf_callback_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, C.c_double, dp, dp, dp]
     lib.isdf_callback_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]
     lib.isdf_get_batch_trajectories.argtypes = [vp, dp, dp, dp]
+    lib.isdf_frontend_build_kernels.argtypes = [vp, C.POINTER(KernelConfig), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.isdf_frontend_get_kernels.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int]
+    lib.isdf_frontend_feasibility.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.isdf_frontend_feasibility_device.argtypes = [vp, vp, vp]
+    lib.isdf_frontend_check_batch.argtypes = [vp, C.c_int, ip, dp, dp, C.POINTER(C.c_uint8)]
     lib.isdf_peer_export.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     lib.isdf_peer_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
     lib.isdf_peer_allreduce_device.argtypes = [vp, vp, C.c_int, vp]
@@ -241,6 +252,37 @@ class Evaluator:
         T, Cc, en = np.zeros(B * N0), np.zeros(18 * B * N0), np.zeros(B)
         self._check(self.lib.isdf_get_batch_trajectories(self.h, _dp(T), _dp(Cc), _dp(en)))
         return T, Cc, en
+
+    # ---- front end: attitude kernels (see include/isdf.h) ----
+    def frontend_build_kernels(self, max_roll=45.0, max_pitch=45.0, ang_res=9.0, front_end_safeh=0.0):
+        kc = KernelConfig(max_roll, max_pitch, ang_res, front_end_safeh)
+        xk, yk = C.c_int(0), C.c_int(0)
+        self._check(self.lib.isdf_frontend_build_kernels(self.h, C.byref(kc), C.byref(xk), C.byref(yk)))
+        self.fe_dims = (xk.value, yk.value)
+        return self.fe_dims
+
+    def frontend_kernels(self, ks):
+        xk, yk = self.fe_dims
+        out = np.zeros(xk * yk * ks ** 3, dtype=np.uint8)
+        self._check(self.lib.isdf_frontend_get_kernels(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)), out.size))
+        return out.reshape(xk * yk, ks, ks, ks)
+
+    def frontend_feasibility(self, X, Y, Z):
+        out = np.zeros((X * Y * Z, 4), dtype=np.uint32)
+        self._check(self.lib.isdf_frontend_feasibility(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def frontend_feasibility_device(self, d_masks, stream=None):
+        self._check(self.lib.isdf_frontend_feasibility_device(self.h, d_masks, stream))
+
+    def frontend_check_batch(self, ind, father):
+        ind = np.ascontiguousarray(ind, dtype=np.int32).reshape(-1, 3)
+        father = _f64(father).reshape(-1, 2)
+        n = ind.shape[0]
+        child, ok = np.zeros((n, 2)), np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.isdf_frontend_check_batch(self.h, n, ind.ctypes.data_as(C.POINTER(C.c_int32)), _dp(father.reshape(-1)), _dp(child.reshape(-1)),
+                                                       ok.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return child, ok.astype(bool)
 
     # ---- multi-GPU reduction over peer memory (see include/isdf.h) ----
     def peer_export(self, world, max_doubles):

@@ -72,6 +72,12 @@ typedef enum isdf_query {
     ISDF_QUERY_SDF_GRAD = 2   /* getSDFwithGrad1(pos_rel, grad) */
 } isdf_query;
 
+/* attitude grid of the front end's collision kernels (config yaml: kernel_max_roll / kernel_max_pitch / kernel_ang_res, degrees;
+ * front_end_safeh); kernel_size and occupancy_resolution come from isdf_config */
+typedef struct isdf_kernel_config {
+    double kernel_max_roll, kernel_max_pitch, kernel_ang_res, front_end_safeh;
+} isdf_kernel_config;
+
 typedef struct isdf_stats {
     int64_t kernel_launches;   /* kernels of this library launched since isdf_create */
     int64_t evals_discrete;    /* isdf_eval_discrete* calls */
@@ -168,6 +174,25 @@ int isdf_peer_connect(isdf_ctx *ctx, int world, int rank, const unsigned char *h
 int isdf_peer_allreduce_device(isdf_ctx *ctx, double *d_vec, int n, void *cuda_stream);   /* stand-alone, in place */
 int isdf_peer_status(isdf_ctx *ctx);
 int isdf_peer_disconnect(isdf_ctx *ctx);
+
+/* ---- front end: attitude-kernel collision checks -------------------------------------------------------- */
+/* BasicShape::initShape's kernel branch (Shape.hpp:405-461): one kernel_size^3 occupancy kernel of the robot per (roll, pitch)
+ * attitude, voxel set when getonlySDF(pos, Rx(roll)*Ry(pitch)) <= max(front_end_safeh, occupancy_resolution/2). Returns the
+ * attitude grid size (sw_manager.hpp:135-136); at most 128 attitudes, kernel_size odd and <= 33. Call again after changing
+ * the shape. */
+int isdf_frontend_build_kernels(isdf_ctx *ctx, const isdf_kernel_config *kc, int *xkernel_size, int *ykernel_size);
+/* the kernels as booleans, [attitude i*ykernel_size+j][a*ks*ks + b*ks + c] (Shape.hpp:453), n = xk*yk*ks^3 bytes */
+int isdf_frontend_get_kernels(isdf_ctx *ctx, uint8_t *out, int n);
+/* kernelConv<true> (sw_manager.hpp:821-846) for EVERY voxel and EVERY attitude: masks[4*voxel .. 4*voxel+3] is a 128-bit set,
+ * bit i*ykernel_size+j = 1 when attitude (i,j) is collision-free with the robot centred on that voxel (voxel = ix*Y*Z+iy*Z+iz).
+ * Cells outside the map count as free, like the reference's inflated map kernel (PCSmap_manager.h:46-78). */
+int isdf_frontend_feasibility(isdf_ctx *ctx, uint32_t *masks /* X*Y*Z*4, host */);
+int isdf_frontend_feasibility_device(isdf_ctx *ctx, uint32_t *d_masks, void *cuda_stream);
+/* checkKernelValue (sw_manager.hpp:914-941) for n queries: voxel index (n x 3), father (roll, pitch) in degrees (n x 2) ->
+ * child (roll, pitch) = the first collision-free attitude in visit_kernels_by_distance's order (level pose, then BFS from the
+ * father's attitude, sw_manager.hpp:852-913); ok[q] = 0 when no attitude fits (child = father). */
+int isdf_frontend_check_batch(isdf_ctx *ctx, int n, const int32_t *ind, const double *father_roll_pitch,
+                              double *child_roll_pitch, uint8_t *ok);
 
 /* ---- swept-volume term: addSaftyPenaOnSweptVolumeParallel (hpp:557-649) + getSDFofSweptVolume (swm:710-747) --- */
 /* parallel_points (plan_manager.cpp:246-254): P x 3 row-major world-frame voxel centres; resets lastTstar to 0 */

@@ -4,6 +4,7 @@
 // `use_omp` selects the reference's `parallel for schedule(dynamic)` + `critical` structure).
 #include "oracle_planner.hpp"
 #include "oracle_minco.hpp"
+#include "oracle_frontend.hpp"
 #include <cstdio>
 
 using namespace orc;
@@ -191,6 +192,40 @@ int orc_minco_backward(int N, const double *headPVA, const double *tailPVA, cons
     m.set_parameters(inPs, T);
     m.propagate_grad(gradC, gradT, gradP_out, gradT_out);
     return 0;
+}
+
+// ---- front end: attitude kernels (oracle_frontend.hpp) --------------------------------------------------------------------
+void *orc_frontend_create(void *shape, double max_roll, double max_pitch, double ang_res, double front_end_safeh, double res, int ks,
+                          const uint8_t *occ, int X, int Y, int Z, int *xk, int *yk) {
+    FrontEnd *f = new FrontEnd();
+    KernelCfg c; c.max_roll = max_roll; c.max_pitch = max_pitch; c.ang_res = ang_res; c.front_end_safeh = front_end_safeh; c.res = res; c.ks = ks;
+    f->build_kernels(((OrcShape *)shape)->s, c);
+    if (occ) f->build_map_kernel(occ, X, Y, Z);
+    if (xk) *xk = f->xk;
+    if (yk) *yk = f->yk;
+    return f;
+}
+void orc_frontend_destroy(void *h) { delete (FrontEnd *)h; }
+void orc_frontend_kernels(void *h, uint8_t *out) { FrontEnd *f = (FrontEnd *)h; std::copy(f->kernels.begin(), f->kernels.end(), out); }
+// masks: n x 4 uint32, bit (i*yk + j) set = attitude (i, j) is collision-free at voxel ind
+void orc_frontend_feasibility(void *h, int n, const int *ind, uint32_t *masks) {
+    FrontEnd *f = (FrontEnd *)h;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int q = 0; q < n; q++) {
+        uint32_t m[4] = {0, 0, 0, 0};
+        for (int i = 0; i < f->xk; i++)
+            for (int j = 0; j < f->yk; j++)
+                if (f->conv(i, j, ind + 3 * q)) { const int b = i * f->yk + j; m[b >> 5] |= 1u << (b & 31); }
+        for (int k = 0; k < 4; k++) masks[4 * (size_t)q + k] = m[k];
+    }
+}
+void orc_frontend_check(void *h, int n, const int *ind, const double *father, double *child, uint8_t *ok) {
+    FrontEnd *f = (FrontEnd *)h;
+    for (int q = 0; q < n; q++) {
+        double cr = father[2 * q], cp = father[2 * q + 1];
+        ok[q] = f->check(father[2 * q], father[2 * q + 1], cr, cp, ind + 3 * q) ? 1 : 0;
+        child[2 * q] = cr; child[2 * q + 1] = cp;
+    }
 }
 
 int orc_omp_max_threads() {

@@ -60,6 +60,14 @@ def lib():
         L.orc_gather_obstacle_points.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, dp, C.c_double, dp, C.c_int, C.c_double, dp, dp, C.c_int]
         L.orc_minco_forward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         L.orc_minco_backward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
+        u8p, ip, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+        L.orc_frontend_create.restype = C.c_void_p
+        L.orc_frontend_create.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, u8p, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_frontend_destroy.argtypes = [C.c_void_p]
+        L.orc_frontend_kernels.argtypes = [C.c_void_p, u8p]
+        L.orc_frontend_feasibility.argtypes = [C.c_void_p, C.c_int, ip, u32p]
+        L.orc_frontend_check.argtypes = [C.c_void_p, C.c_int, ip, dp, dp, u8p]
         _lib = L
     return _lib
 
@@ -130,6 +138,45 @@ class Shape:
     def __del__(self):
         try:
             lib().orc_shape_destroy(self.h)
+        except Exception:
+            pass
+
+
+class FrontEnd:
+    """oracle_frontend.hpp: the reference's attitude kernels, byte-packed map kernel, kernelConv<true>, BFS over attitudes."""
+
+    def __init__(self, shape, occ, ks=13, res=1.0, max_roll=45.0, max_pitch=45.0, ang_res=9.0, front_end_safeh=0.0):
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        X, Y, Z = occ.shape
+        xk, yk = C.c_int(0), C.c_int(0)
+        self.shape = shape
+        self.h = lib().orc_frontend_create(shape.h, max_roll, max_pitch, ang_res, front_end_safeh, res, ks, occ.ctypes.data_as(C.POINTER(C.c_uint8)), X, Y, Z,
+                                           C.byref(xk), C.byref(yk))
+        self.xk, self.yk, self.ks = xk.value, yk.value, ks
+
+    def kernels(self):
+        out = np.zeros(self.xk * self.yk * self.ks ** 3, dtype=np.uint8)
+        lib().orc_frontend_kernels(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out.reshape(self.xk * self.yk, self.ks, self.ks, self.ks)
+
+    def feasibility(self, ind):
+        ind = np.ascontiguousarray(ind, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros((ind.shape[0], 4), dtype=np.uint32)
+        lib().orc_frontend_feasibility(self.h, ind.shape[0], ind.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return out
+
+    def check(self, ind, father):
+        ind = np.ascontiguousarray(ind, dtype=np.int32).reshape(-1, 3)
+        father = f64(father).reshape(-1, 2)
+        n = ind.shape[0]
+        child, ok = np.zeros((n, 2)), np.zeros(n, dtype=np.uint8)
+        lib().orc_frontend_check(self.h, n, ind.ctypes.data_as(C.POINTER(C.c_int32)), _p(father.reshape(-1)), _p(child.reshape(-1)),
+                                 ok.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return child, ok.astype(bool)
+
+    def __del__(self):
+        try:
+            lib().orc_frontend_destroy(self.h)
         except Exception:
             pass
 

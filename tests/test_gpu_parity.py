@@ -567,3 +567,69 @@ def test_multi_gpu_peer_memory_reduction():
            "--master-port", "29517", os.path.join(here, "multi_gpu_peer.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "PEER OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+# ---- front end: attitude kernels -------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot,ks", [("CappedCone", 13), ("TwistBox", 13), ("Torus", 9), ("Ball", 5), ("CSG", 13), ("Box", 13), ("mesh", 13), ("tilted", 13)])
+def test_frontend_kernels_and_feasibility_bit_exact(robot, ks):
+    """robot occupancy kernels per attitude (Shape.hpp:405-461), kernelConv<true> for every voxel x every attitude
+    (sw_manager.hpp:821-846), checkKernelValue's first fit in BFS order (:852-941): all integer / boolean -> exact equality."""
+    cfg, _, _, _, _ = small_case(N=2, K=4, seed=3, kernel_size=ks)
+    X, Y, Z = 40, 36, 28
+    occ = W.three_slit_map(X, Y, Z, noise=0.003, seed=5)
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, [0, 0, 0], cfg.occupancy_resolution)
+    if robot == "mesh":
+        V, F = MESHES["rcone"]()
+        poly = [0.1, 0.0, -0.1, 120.0, 10.0, 0.0]
+        ev.set_shape_mesh(V, F, poly); osh = O.Shape.mesh(V, F, poly)
+    elif robot == "Box":
+        ev.set_shape_analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.9, 0.4]); osh = O.Shape.analytic(I.SHAPE_KINDS["BOX"], [1.5, 0.9, 0.4])
+    elif robot == "tilted":
+        R, t = tilted()
+        ev.set_shape_named("RoundedCone", R, t); osh = O.Shape.named("RoundedCone", R, t)
+    else:
+        ev.set_shape_named(robot); osh = O.Shape.named(robot)
+    safeh = 0.8 if robot in ("Torus", "mesh") else 0.0
+    assert ev.frontend_build_kernels(45.0, 45.0, 9.0, safeh) == (11, 11)
+    fe = O.FrontEnd(osh, occ, ks=ks, res=cfg.occupancy_resolution, front_end_safeh=safeh)
+    K = ev.frontend_kernels(ks)
+    assert np.array_equal(K, fe.kernels()), f"{robot}: {(K != fe.kernels()).sum()} kernel voxels differ"
+    assert 0 < K[60].sum() < ks ** 3
+    masks = ev.frontend_feasibility(X, Y, Z)
+    ix, iy, iz = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    ind = np.stack([ix, iy, iz], -1).reshape(-1, 3)
+    ref = fe.feasibility(ind)
+    assert np.array_equal(masks, ref), f"{robot}: {(masks != ref).any(axis=1).sum()} voxels differ"
+    nfit = np.array([bin(int(w)).count("1") for w in masks.reshape(-1)]).reshape(-1, 4).sum(axis=1)
+    assert (nfit == 0).any() and (nfit > 0).any()
+    rng = np.random.default_rng(3)
+    n = 3000
+    q = ind[rng.integers(0, len(ind), n)]
+    father = np.stack([rng.integers(-5, 6, n) * 9.0, rng.integers(-5, 6, n) * 9.0], 1)
+    father[:50] += rng.uniform(0, 8.9, (50, 2)) * (father[:50] < 36)           # off-grid fathers truncate like the reference's int cast
+    child, ok = ev.frontend_check_batch(q, father)
+    rchild, rok = fe.check(q, father)
+    assert np.array_equal(ok, rok) and np.array_equal(child, rchild)
+    ev.close()
+
+
+def test_frontend_state_errors():
+    cfg, occ, _, _, _ = small_case(N=2, K=4, seed=3)
+    ev = I.Evaluator(cfg)
+    with pytest.raises(RuntimeError):
+        ev.frontend_build_kernels()                        # no shape
+    ev.set_shape_named("Torus")
+    ev.frontend_build_kernels()
+    with pytest.raises(RuntimeError):
+        ev.frontend_feasibility(4, 4, 4)                   # no map
+    ev.set_map_u8(occ, BMIN, 1.0)
+    ev.set_shape_named("Ball")
+    with pytest.raises(RuntimeError):
+        ev.frontend_feasibility(*occ.shape)                # kernels are stale after a shape change
+    with pytest.raises(RuntimeError):
+        ev.frontend_build_kernels(45.0, 45.0, 1.0)         # 91 x 91 attitudes > 128
+    ev.frontend_build_kernels()
+    with pytest.raises(RuntimeError):
+        ev.frontend_check_batch([[0, 0, occ.shape[2]]], [[0.0, 0.0]])   # voxel outside the map
+    ev.close()
