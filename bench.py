@@ -379,6 +379,50 @@ def batch_callback_bench(ev, w, cfg, dev, rank, world, B, barrier, max_over_rank
                     "decision vector in -> cost and gradient out, MINCO forward/adjoint + time-integral/collision term all on the device; no collective"}
 
 
+def frontend_bench(ev, w, occ, V, F, dev, with_cpu, reps=3):
+    """SURVEY 8f row 4 on the bench map: which of the 121 (roll, pitch) attitudes of the mesh robot fit at EVERY voxel (128-bit mask per voxel)."""
+    import torch
+    X = w["map_dim"]
+    t0 = time.perf_counter()
+    xk, yk = ev.frontend_build_kernels(45.0, 45.0, 9.0, 0.0)          # config_CappedCone.yaml:62-64
+    t_build = time.perf_counter() - t0
+    nvox = X ** 3
+    d_masks = torch.empty(nvox * 4, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ev.frontend_feasibility_device(d_masks.data_ptr(), stream)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ev.frontend_feasibility_device(d_masks.data_ptr(), stream); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    fit = int((d_masks.view(-1, 4) != 0).any(dim=1).sum().item())
+    peak, peak_src = measured_peak_hbm()
+    nbytes = nvox * 16 + nvox // 8
+    out = {"what": f"attitude-kernel feasibility of all {X}^3 voxels x {xk * yk} attitudes (kernel {w['kernel_size']}^3, mesh robot): kernelConv<true> of "
+                   "sw_manager.hpp:821-846 for every voxel, 128-bit mask out",
+           "ms": ms, "voxels_per_s": nvox / (ms * 1e-3), "voxel_attitude_checks_per_s": nvox * xk * yk / (ms * 1e-3), "kernel_build_s": t_build,
+           "voxels_with_a_fitting_attitude": fit,
+           "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
+                        "note": "16 B mask written + 1 bit occupancy read per voxel; the window reads hit L1/L2"}}
+    del d_masks
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        sub = np.ascontiguousarray(occ[:96, :96, :96])
+        fe = O.FrontEnd(O.Shape.mesh(V, F, w["poly_params"], wn_mode=O.WN_BH), sub, ks=w["kernel_size"])
+        rng = np.random.default_rng(0)
+        n = 200000
+        ind = rng.integers(0, 96, (n, 3))
+        t0 = time.perf_counter(); fe.feasibility(ind); dt = time.perf_counter() - t0
+        out["cpu"] = {"voxels_per_s": n / dt, "cores": os.cpu_count(), "sample": f"{n} random voxels of a 96^3 corner of the same map, oracle byte-kernel port, OpenMP"}
+        out["speedup_vs_cpu"] = out["voxels_per_s"] / out["cpu"]["voxels_per_s"]
+    return out
+
+
 def workload_name(w):
     return (f"BASELINE configs[2]: random {w['map_dim']}^3 voxel map (p={w['occupancy']}, wall slabs), {w['pieces']}-piece MINCO traj, "
             f"{w['samples_per_piece']} samples/piece, mesh-SDF robot ({w['mesh']}), discrete collision cost+grad")
@@ -574,6 +618,11 @@ def run_ours(args):
                     line["extra"]["lbfgs"]["cpu"] = lbfgs_cpu()
             except Exception as e:   # secondary metric must never take the headline line down
                 line["extra"]["lbfgs"] = {"error": repr(e)}
+        if world == 1 and not args.no_frontend and args.robot == "mesh" and not args.small:
+            try:
+                line["extra"]["frontend"] = frontend_bench(ev, w, occ, V, F, dev, not args.no_cpu_baseline)
+            except Exception as e:
+                line["extra"]["frontend"] = {"error": repr(e)}
         if world == 1 and not args.no_swept:
             try:
                 line["extra"]["swept"] = swept_ours(local, not args.no_cpu_baseline)
@@ -609,6 +658,7 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N > 1: reduction of the sharded evaluation")
     ap.add_argument("--no-batch", action="store_true", help="skip the batched device-callback measurement (configs[4])")
     ap.add_argument("--batch-per-gpu", type=int, default=128, help="problems per GPU in the batched callback measurement (1024 / 8 GPUs)")
+    ap.add_argument("--no-frontend", action="store_true", help="skip the front-end attitude-kernel feasibility measurement")
     ap.add_argument("--no-swept", action="store_true", help="skip the secondary swept-volume (SV-SDF) measurement")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-pieces", type=int, default=16, help="--impl reference: pieces per step sample (of 64)")
