@@ -908,7 +908,7 @@ extern "C" int isdf_frontend_build_kernels(isdf_ctx *c, const isdf_kernel_config
     if (!(kc->kernel_ang_res > 0) || kc->kernel_max_roll < 0 || kc->kernel_max_pitch < 0) return fail(ISDF_ERR_INVALID, "bad attitude grid");
     const int ks = c->cfg.kernel_size;
     if (ks < 1 || (ks & 1) == 0) return fail(ISDF_ERR_INVALID, "kernel_size must be odd (Shape.hpp:258)");
-    if (ks > 33) return fail(ISDF_ERR_UNSUPPORTED, "kernel_size > 33");
+    if (ks > 29) return fail(ISDF_ERR_UNSUPPORTED, "kernel_size > 29");
     const int xk = (int)std::floor(2 * kc->kernel_max_roll / kc->kernel_ang_res) + 1, yk = (int)std::floor(2 * kc->kernel_max_pitch / kc->kernel_ang_res) + 1;   // swm:135-136
     if (xk * yk > FE_MAX_ATT) return fail(ISDF_ERR_UNSUPPORTED, "more than 128 attitudes");
     if (set_device(c)) return ISDF_ERR_CUDA;
@@ -995,8 +995,8 @@ extern "C" int isdf_frontend_feasibility_device(isdf_ctx *c, uint32_t *d_masks, 
     A.out = d_masks;
     const size_t smem = sizeof(uint32_t) * 4 * (size_t)A.ks * A.ks * A.ks;
     CU_TRY(cudaFuncSetAttribute(k_frontend_feasibility, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long nvox = (long long)c->grid.X * c->grid.Y * c->grid.Z;
-    const unsigned grid = (unsigned)std::min<long long>((nvox + 255) / 256, 148ll * 64);
+    const long long nrun = (long long)c->grid.X * c->grid.Y * ((c->grid.Z + FE_ZRUN - 1) / FE_ZRUN);
+    const unsigned grid = (unsigned)std::min<long long>((nrun + 255) / 256, 148ll * 64);
     k_frontend_feasibility<<<grid, 256, smem, (cudaStream_t)cuda_stream>>>(A);
     c->stats.kernel_launches++;
     CU_TRY(cudaGetLastError());

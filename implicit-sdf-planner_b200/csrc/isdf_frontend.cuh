@@ -14,7 +14,7 @@
 // reference's byte AND is exact (cells outside the map are free, like the reference's inflation margin).
 //   k_frontend_kernels      one thread per (attitude, a, b, c): SDF at the rotated body point <= margin
 //   k_frontend_offset_masks one thread per (a, b, c): the 128-bit attitude set of that offset
-//   k_frontend_feasibility  one thread per voxel (z fastest): window scan + mask OR -> collision-free attitude mask
+//   k_frontend_feasibility  one thread per run of 4 voxels along z: window scan + mask OR -> collision-free attitude masks
 //   k_frontend_check        one thread per query: same mask, then the reference's visiting order (level pose, BFS from the father)
 #pragma once
 #include "isdf_types.cuh"
@@ -117,26 +117,69 @@ __device__ __forceinline__ void frontend_stage_masks(const FrontArgs &A, uint32_
     __syncthreads();
 }
 
+// One thread per run of FE_ZRUN voxels along z: the run's window rows are read once (ks + FE_ZRUN - 1 bits), every occupied map
+// voxel found in a row is applied to each of the run's voxels it overlaps (offset c = bit - j), one 128-bit shared-memory load
+// and four ORs per (occupied voxel, run voxel) pair.
+constexpr int FE_ZRUN = 4;
 __global__ void __launch_bounds__(256) k_frontend_feasibility(const __grid_constant__ FrontArgs A) {
-    extern __shared__ uint32_t fe_sm[];
+    extern __shared__ __align__(16) uint32_t fe_sm[];
     frontend_stage_masks(A, fe_sm);
+    const uint4 *sm4 = reinterpret_cast<const uint4 *>(fe_sm);
     const DevGrid &G = A.grid;
-    const long long nvox = (long long)G.X * G.Y * G.Z;
-    const uint32_t valid[4] = {A.natt >= 32 ? 0xffffffffu : ((1u << A.natt) - 1u),
-                               A.natt >= 64 ? 0xffffffffu : (A.natt > 32 ? ((1u << (A.natt - 32)) - 1u) : 0u),
-                               A.natt >= 96 ? 0xffffffffu : (A.natt > 64 ? ((1u << (A.natt - 64)) - 1u) : 0u),
-                               A.natt >= 128 ? 0xffffffffu : (A.natt > 96 ? ((1u << (A.natt - 96)) - 1u) : 0u)};
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
-        const int iz = (int)(v % G.Z), iy = (int)((v / G.Z) % G.Y), ix = (int)(v / ((long long)G.Z * G.Y));
-        uint32_t m[4];
-        frontend_colliding(A, fe_sm, ix, iy, iz, m);
-        uint4 o = make_uint4(~m[0] & valid[0], ~m[1] & valid[1], ~m[2] & valid[2], ~m[3] & valid[3]);
-        reinterpret_cast<uint4 *>(A.out)[v] = o;
+    const int ks = A.ks, side = (ks - 1) / 2;
+    const int zruns = (G.Z + FE_ZRUN - 1) / FE_ZRUN;
+    const long long nrun = (long long)G.X * G.Y * zruns;
+    const uint4 valid = make_uint4(A.natt >= 32 ? 0xffffffffu : ((1u << A.natt) - 1u),
+                                   A.natt >= 64 ? 0xffffffffu : (A.natt > 32 ? ((1u << (A.natt - 32)) - 1u) : 0u),
+                                   A.natt >= 96 ? 0xffffffffu : (A.natt > 64 ? ((1u << (A.natt - 64)) - 1u) : 0u),
+                                   A.natt >= 128 ? 0xffffffffu : (A.natt > 96 ? ((1u << (A.natt - 96)) - 1u) : 0u));
+    const int wbits = ks + FE_ZRUN - 1;                                  // <= 32 (ks <= 29)
+    const unsigned long long wmask = (1ull << wbits) - 1ull;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < nrun; r += (long long)gridDim.x * blockDim.x) {
+        const int zr = (int)(r % zruns), iy = (int)((r / zruns) % G.Y), ix = (int)(r / ((long long)zruns * G.Y));
+        const int iz0 = zr * FE_ZRUN;
+        uint4 m[FE_ZRUN];
+#pragma unroll
+        for (int j = 0; j < FE_ZRUN; j++) m[j] = make_uint4(0u, 0u, 0u, 0u);
+        const int z0 = iz0 - side;                                       // bit p of a row window = voxel z0 + p
+        const int w0 = (z0 >= 0) ? (z0 >> 5) : -1;
+        const int sh = z0 - 32 * w0;
+        bool done = false;
+        for (int a = 0; a < ks && !done; a++) {
+            const int x = ix + a - side;
+            if (x < 0 || x >= G.X) continue;
+            for (int b = 0; b < ks; b++) {
+                const int y = iy + b - side;
+                if (y < 0 || y >= G.Y) continue;
+                const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+                const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
+                const uint32_t hi = (sh + wbits > 32 && w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
+                unsigned bits = (unsigned)(((((unsigned long long)hi << 32) | lo) >> sh) & wmask);
+                const uint4 *mrow = sm4 + (size_t)((a * ks + b) * ks);
+                while (bits) {
+                    const int p = __ffs((int)bits) - 1;
+                    bits &= bits - 1;
+#pragma unroll
+                    for (int j = 0; j < FE_ZRUN; j++) {
+                        const int c = p - j;
+                        if (c >= 0 && c < ks) { const uint4 t = mrow[c]; m[j].x |= t.x; m[j].y |= t.y; m[j].z |= t.z; m[j].w |= t.w; }
+                    }
+                }
+            }
+            done = true;                                                   // every attitude of every run voxel collides already?
+#pragma unroll
+            for (int j = 0; j < FE_ZRUN; j++)
+                done = done && ((m[j].x & valid.x) == valid.x) && ((m[j].y & valid.y) == valid.y) && ((m[j].z & valid.z) == valid.z) && ((m[j].w & valid.w) == valid.w);
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(A.out) + ((size_t)ix * G.Y + iy) * G.Z + iz0;
+#pragma unroll
+        for (int j = 0; j < FE_ZRUN; j++)
+            if (iz0 + j < G.Z) o[j] = make_uint4(~m[j].x & valid.x, ~m[j].y & valid.y, ~m[j].z & valid.z, ~m[j].w & valid.w);
     }
 }
 
 __global__ void __launch_bounds__(256) k_frontend_check(const __grid_constant__ FrontArgs A) {
-    extern __shared__ uint32_t fe_sm[];
+    extern __shared__ __align__(16) uint32_t fe_sm[];
     frontend_stage_masks(A, fe_sm);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= A.nq) return;

@@ -178,7 +178,7 @@ int isdf_peer_disconnect(isdf_ctx *ctx);
 /* ---- front end: attitude-kernel collision checks -------------------------------------------------------- */
 /* BasicShape::initShape's kernel branch (Shape.hpp:405-461): one kernel_size^3 occupancy kernel of the robot per (roll, pitch)
  * attitude, voxel set when getonlySDF(pos, Rx(roll)*Ry(pitch)) <= max(front_end_safeh, occupancy_resolution/2). Returns the
- * attitude grid size (sw_manager.hpp:135-136); at most 128 attitudes, kernel_size odd and <= 33. Call again after changing
+ * attitude grid size (sw_manager.hpp:135-136); at most 128 attitudes, kernel_size odd and <= 29. Call again after changing
  * the shape. */
 int isdf_frontend_build_kernels(isdf_ctx *ctx, const isdf_kernel_config *kc, int *xkernel_size, int *ykernel_size);
 /* the kernels as booleans, [attitude i*ykernel_size+j][a*ks*ks + b*ks + c] (Shape.hpp:453), n = xk*yk*ks^3 bytes */
