@@ -3,7 +3,7 @@
 # usage (GPU box): bash profiles/tools/sanitize.sh [tag]
 tag=${1:-r01}
 mkdir -p gpurun_out
-SEL='swept_end_to_end_mesh and lprism or batched_device_callback or swept_golden or discrete_golden or discrete_parity_mesh and box or shards_sum_to_full and 3'
+SEL='swept_end_to_end_mesh and lprism or batched_device_callback or swept_golden or discrete_golden or discrete_parity_mesh and box or shards_sum_to_full and 3 or frontend_kernels and TwistBox or frontend_state'
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --target-processes all --error-exitcode 86 \
       python -m pytest tests -m gpu -q -x --timeout 800 -k "$SEL" > gpurun_out/sanitize_${tag}_${tool}.log 2>&1
