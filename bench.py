@@ -292,8 +292,12 @@ def swept_ours(device, with_cpu, cpu_points=423):
         sh = O.Shape.mesh(V, F, poly, wn_mode=O.WN_BH)
         n = min(len(pts), cpu_points)
         idx = np.linspace(0, len(pts) - 1, n).astype(int)          # spread over the trajectory: per-point work is very uneven
-        t0 = time.perf_counter(); O.eval_swept(oc, sh, T, Cc, pts[idx], use_omp=True); dt = time.perf_counter() - t0
-        out["cpu"] = {"ms_full_estimate": 1e3 * dt * len(pts) / n, "cores": oc.threads_num, "sample": f"{n} of {len(pts)} points, OpenMP oracle port"}
+        O.eval_swept(oc, sh, T, Cc, pts[idx[:32]], use_omp=True)      # wake the OpenMP pool
+        dts = []
+        for _ in range(2):
+            t0 = time.perf_counter(); O.eval_swept(oc, sh, T, Cc, pts[idx], use_omp=True); dts.append(time.perf_counter() - t0)
+        dt = min(dts)                                                 # the faster run: the CPU arm gets the benefit of the doubt
+        out["cpu"] = {"ms_full_estimate": 1e3 * dt * len(pts) / n, "cores": oc.threads_num, "sample": f"{n} of {len(pts)} points, OpenMP oracle port, best of 2"}
         out["speedup_kernel_vs_cpu"] = out["cpu"]["ms_full_estimate"] / out["kernel_ms"]
     return out
 
@@ -417,8 +421,12 @@ def frontend_bench(ev, w, occ, V, F, dev, with_cpu, reps=3):
         rng = np.random.default_rng(0)
         n = 200000
         ind = rng.integers(0, 96, (n, 3))
-        t0 = time.perf_counter(); fe.feasibility(ind); dt = time.perf_counter() - t0
-        out["cpu"] = {"voxels_per_s": n / dt, "cores": os.cpu_count(), "sample": f"{n} random voxels of a 96^3 corner of the same map, oracle byte-kernel port, OpenMP"}
+        fe.feasibility(ind[:2000])                                    # wake the OpenMP pool
+        dts = []
+        for _ in range(2):
+            t0 = time.perf_counter(); fe.feasibility(ind); dts.append(time.perf_counter() - t0)
+        dt = min(dts)
+        out["cpu"] = {"voxels_per_s": n / dt, "cores": os.cpu_count(), "sample": f"{n} random voxels of a 96^3 corner of the same map, oracle byte-kernel port, OpenMP, best of 2"}
         out["speedup_vs_cpu"] = out["voxels_per_s"] / out["cpu"]["voxels_per_s"]
     return out
 
