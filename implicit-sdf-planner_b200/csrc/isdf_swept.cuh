@@ -13,7 +13,7 @@
 //                x -/+ 0.02/2^d, so an outer iteration costs one SDF latency instead of up to 9 + 7 dependent ones.
 //                Accept/reject decisions replay the reference's sequential logic exactly (same comparisons, same
 //                iteration accounting);
-//   k_sv_points_mesh: mesh robots — one CTA (8 warps) per obstacle point; every exact SDF value is a warp-cooperative
+//   k_sv_points_cta<MESH>: one CTA (8 warps) per obstacle point; mesh robots: every exact SDF value is a warp-cooperative
 //                closest-triangle search, the scans are pruned with the body-frame cell grid's Lipschitz brackets and
 //                the warps evaluate the descent's step candidates in parallel (details at the kernel);
 //   k_sv_reduce / k_sv_finish: deterministic per-piece reduction (fixed thread->point map, fixed trees) and the
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
     }
 }
 
-// ---- k_sv_points_mesh: one CTA (SVM_WARPS warps) per obstacle point, mesh robots ----------------------------------------
+// ---- k_sv_points_cta: one CTA (SVM_WARPS warps) per obstacle point (designed for mesh robots) ----------------------------------------
 // The work per point is extremely uneven (half of the points never come within range; a few need >100 closest-triangle
 // searches in sequence), and with 10^2-10^4 points the kernel is a single wave: its duration is the SLOWEST point, not the
 // sum. So a point gets a whole CTA and the dependent chain is cut three ways:
@@ -464,6 +464,10 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
 //   * the SDF value and gradient of an accepted candidate are carried into the next iteration (same point, same function),
 //     which removes the re-evaluation at the new x — guarded by a bit-compare of the body-frame point.
 // Decisions, values and the reference-equivalent evaluation count are those of the sequential algorithm.
+#ifndef ISDF_SV_ANALYTIC_CTA
+#define ISDF_SV_ANALYTIC_CTA 1
+#endif
+constexpr bool SV_ANALYTIC_CTA = ISDF_SV_ANALYTIC_CTA != 0;   // analytic shapes: CTA per point (k_sv_points_cta<false>) or warp per point (k_sv_points)
 constexpr int SVM_WARPS = 8;
 constexpr int SVM_THREADS = SVM_WARPS * 32;
 
@@ -549,7 +553,10 @@ __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr,
     }
 }
 
-__global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_constant__ SvArgs A) {
+// MESH = false: analytic shapes through the same CTA-per-point structure — the scans are 256 samples wide and exact (an analytic
+// SDF is cheap, no bracket pass), the sign descent is the lane-speculative sv_gradient_descent on warp 0.
+template <bool MESH>
+__global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta(const __grid_constant__ SvArgs A) {
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
     __shared__ SvmShared S;
@@ -598,13 +605,17 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_con
                 prel = mk3(__ldg(o + 3) * d.x + __ldg(o + 6) * d.y + __ldg(o + 9) * d.z,
                            __ldg(o + 4) * d.x + __ldg(o + 7) * d.y + __ldg(o + 10) * d.z,
                            __ldg(o + 5) * d.x + __ldg(o + 8) * d.y + __ldg(o + 11) * d.z);
-                double blo, bhi;
-                mesh_bracket(M, prel, blo, bhi);
-                if (bhi < inf) in = true;
-                else if (blo < inf) undecided = true;
+                if (MESH) {
+                    double blo, bhi;
+                    mesh_bracket(M, prel, blo, bhi);
+                    if (bhi < inf) in = true;
+                    else if (blo < inf) undecided = true;
+                } else in = shape_sdf_analytic(A.shape, prel) < inf;
             }
-            const double v = mesh_sdf_each(M, undecided, prel, inf, inf, lane, stk);
-            if (undecided) in = v < inf;
+            if (MESH) {
+                const double v = mesh_sdf_each(M, undecided, prel, inf, inf, lane, stk);
+                if (undecided) in = v < inf;
+            }
             const unsigned b = __ballot_sync(0xffffffffu, in);
             const int w = (base >> 5) + warp;
             if (lane == 0 && w < SV_FLAG_WORDS) S.flags[w] = b;
@@ -623,14 +634,17 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_con
             if (starts) last_entry = w * 32 + (31 - __clz(starts));
         }
         if (last_entry >= 0) {
-            if (warp == 0) {
-                d3 g_;
-                const double v = mesh_sdf_grad_warp(M, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, stk);
-                if (lane == 0) S.bc[0] = v;
-            }
-            __syncthreads();
-            double range_mindis = S.bc[0];
-            __syncthreads();
+            double range_mindis;
+            if (MESH) {
+                if (warp == 0) {
+                    d3 g_;
+                    const double v = mesh_sdf_grad_warp(M, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, stk);
+                    if (lane == 0) S.bc[0] = v;
+                }
+                __syncthreads();
+                range_mindis = S.bc[0];
+                __syncthreads();
+            } else range_mindis = sv_sdf_at(A, tr, p, A.times[last_entry]);
             double range_time_seed = 0.0;
             double min_sdf_star = 1e1;
             d3 g_best = mk3(0, 0, 0), q_best = mk3(0, 0, 0);
@@ -660,7 +674,7 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_con
                 const int first = lane * SVM_WARPS + warp;      // sample index of this thread in a round of SVM_THREADS
                 PT_MARK();
                 double cut = 1e300;
-                {
+                if (MESH) {
                     double t = lb;
                     for (int q = 0; q < first; q++) t += 0.02;
                     while (t < ub) {
@@ -686,15 +700,18 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_con
                     double bd = 1e300, bt = 0.0; int bi = 0x7fffffff;
                     while (__any_sync(0xffffffffu, t < ub)) {
                         const bool valid = t < ub;
-                        bool need = false;
-                        d3 prel = mk3(0, 0, 0);
-                        if (valid) {
-                            prel = sv_body_point(A, tr, p, t);
-                            double blo, bhi;
-                            mesh_bracket(M, prel, blo, bhi);
-                            need = blo <= cut;
-                        }
-                        const double dis = mesh_sdf_each(M, need, prel, inf, 1e300, lane, stk);
+                        double dis = 1e300;
+                        if (MESH) {
+                            bool need = false;
+                            d3 prel = mk3(0, 0, 0);
+                            if (valid) {
+                                prel = sv_body_point(A, tr, p, t);
+                                double blo, bhi;
+                                mesh_bracket(M, prel, blo, bhi);
+                                need = blo <= cut;
+                            }
+                            dis = mesh_sdf_each(M, need, prel, inf, 1e300, lane, stk);
+                        } else if (valid) dis = sv_sdf_at(A, tr, p, t);
                         nevals += __popc(__ballot_sync(0xffffffffu, valid));
                         if (dis < bd) { bd = dis; bi = mi; bt = t; }      // own samples come in increasing index order
                         for (int q = 0; q < SVM_THREADS; q++) t += 0.02;
@@ -723,8 +740,17 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_con
                 // ---- descent inside the interval (swm:730-734) ---------------------------------------------------------
                 const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
                 double sdf_star = 1e1, t_star = 0;
-                d3 g_s, q_s;
-                svm_descent(A, tr, p, tmin_, tmax_, range_time_seed, S, sdf_star, t_star, g_s, q_s, nevals, lane, warp);
+                d3 g_s = mk3(0, 0, 0), q_s = mk3(1e300, 1e300, 1e300);
+                if (MESH) svm_descent(A, tr, p, tmin_, tmax_, range_time_seed, S, sdf_star, t_star, g_s, q_s, nevals, lane, warp);
+                else {
+                    if (warp == 0) {
+                        sv_gradient_descent(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
+                        if (lane == 0) { S.bc[0] = sdf_star; S.bc[1] = t_star; }
+                    }
+                    __syncthreads();
+                    sdf_star = S.bc[0]; t_star = S.bc[1];
+                    __syncthreads();
+                }
                 if (sdf_star < min_sdf_star) { min_sdf_star = sdf_star; tstar = t_star; found = true; g_best = g_s; q_best = q_s; }
                 PT_ADD(pt_gd);
 #ifdef ISDF_PHASE_TIMING
@@ -736,11 +762,12 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_mesh(const __grid_con
                 sdf_value = min_sdf_star;
                 // getGradPrelAtTimeStamp (swm:566-572) at the winning t*: the descent already holds it unless the pose differs
                 const d3 qf = sv_body_point(A, tr, p, tstar);
-                if (same_bits(qf, q_best)) grel = g_best;
+                if (MESH && same_bits(qf, q_best)) grel = g_best;
                 else {
                     if (warp == 0) {
                         d3 g0 = mk3(0, 0, 0);
-                        mesh_sdf_grad_warp(M, qf, 1e300, g0, lane, stk);
+                        if (MESH) mesh_sdf_grad_warp(M, qf, 1e300, g0, lane, stk);
+                        else g0 = warp_grad(A.shape, qf, lane);
                         if (lane == 0) { S.bc[1] = g0.x; S.bc[2] = g0.y; S.bc[3] = g0.z; }
                     }
                     __syncthreads();
@@ -860,14 +887,16 @@ struct SweptState {
         if ((e = cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
         if (sm > 48 * 1024) {
             cudaFuncSetAttribute(k_sv_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            cudaFuncSetAttribute(k_sv_points_mesh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             cudaFuncSetAttribute(k_sv_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         }
         k_sv_table<<<1, 256, sm, st>>>(A);
         const int Mloc = (P - rank + world - 1) / world;
         const unsigned grid = (unsigned)((Mloc + SV_WARPS - 1) / SV_WARPS);
         if (grid > 0) {
-            if (shape.kind == ISDF_SHAPE_MESH) k_sv_points_mesh<<<(unsigned)Mloc, SVM_THREADS, sm, st>>>(A);
+            if (shape.kind == ISDF_SHAPE_MESH) k_sv_points_cta<true><<<(unsigned)Mloc, SVM_THREADS, sm, st>>>(A);
+            else if (SV_ANALYTIC_CTA) k_sv_points_cta<false><<<(unsigned)Mloc, SVM_THREADS, sm, st>>>(A);
             else k_sv_points<<<grid, SV_THREADS, sm, st>>>(A);
         }
         k_sv_reduce<<<N, 256, 0, st>>>(A);
