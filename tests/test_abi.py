@@ -76,3 +76,29 @@ def test_argument_validation_without_gpu_calls():
     h = C.c_void_p()
     assert lib.isdf_create(C.byref(bad), 0, C.byref(h)) == -1
     assert b"config" in lib.isdf_last_error()
+
+
+def test_header_is_plain_c99():
+    src = '#include "isdf.h"\nint main(void) { isdf_config c; isdf_kernel_config k = {45, 45, 9, 0}; (void)c; (void)k; return 0; }\n'
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert C.sizeof(I.KernelConfig) == 32
+
+
+def test_new_entry_points_validate_arguments_without_gpu_calls():
+    import numpy as np
+    lib = I.load_library()
+    cost = np.zeros(3)
+    x, g, bc = np.zeros(3 * 13), np.zeros(3 * 13), np.zeros(9)
+    dp = C.POINTER(C.c_double)
+    r = lib.isdf_callback_batch(None, 3, 4, bc.ctypes.data_as(dp), bc.ctypes.data_as(dp), 0, 20.0, x.ctypes.data_as(dp), cost.ctypes.data_as(dp), g.ctypes.data_as(dp))
+    assert r == -1 and np.all(np.isnan(cost))            # every cost poisoned: either optimiser driver stops
+    assert lib.isdf_frontend_build_kernels(None, None, None, None) == -1
+    assert lib.isdf_frontend_feasibility(None, None) == -1
+    assert lib.isdf_frontend_check_batch(None, 0, None, None, None, None) == -1
+    assert lib.isdf_peer_export(None, 2, 10, None) == -1
+    assert lib.isdf_peer_connect(None, 2, 0, None, 1) == -1
+    assert lib.isdf_peer_allreduce_device(None, None, 0, None) == -1
+    assert lib.isdf_peer_status(None) == -1 and lib.isdf_peer_disconnect(None) == -1
+    assert lib.isdf_get_batch_trajectories(None, None, None, None) == -1
