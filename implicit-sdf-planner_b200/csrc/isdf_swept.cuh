@@ -468,7 +468,10 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
 #define ISDF_SV_ANALYTIC_CTA 1
 #endif
 constexpr bool SV_ANALYTIC_CTA = ISDF_SV_ANALYTIC_CTA != 0;   // analytic shapes: CTA per point (k_sv_points_cta<false>) or warp per point (k_sv_points)
-constexpr int SVM_WARPS = 8;
+#ifndef ISDF_SVM_WARPS
+#define ISDF_SVM_WARPS 8
+#endif
+constexpr int SVM_WARPS = ISDF_SVM_WARPS;   // A/B on B200 (profiles/r01_tuning.md)
 constexpr int SVM_THREADS = SVM_WARPS * 32;
 
 struct SvmShared {
