@@ -455,12 +455,13 @@ def frontend_bench(ev, w, occ, V, F, dev, with_cpu, reps=3):
         rng = np.random.default_rng(0)
         n = 200000
         ind = rng.integers(0, 96, (n, 3))
+        O.lib().orc_set_num_threads(usable_cores())                   # the front-end loop uses OpenMP's default team
         fe.feasibility(ind[:2000])                                    # wake the OpenMP pool
         dts = []
         for _ in range(2):
             t0 = time.perf_counter(); fe.feasibility(ind); dts.append(time.perf_counter() - t0)
         dt = min(dts)
-        out["cpu"] = {"voxels_per_s": n / dt, "cores": os.cpu_count(), "sample": f"{n} random voxels of a 96^3 corner of the same map, oracle byte-kernel port, OpenMP, best of 2"}
+        out["cpu"] = {"voxels_per_s": n / dt, "cores": usable_cores(), "sample": f"{n} random voxels of a 96^3 corner of the same map, oracle byte-kernel port, OpenMP, best of 2"}
         out["speedup_vs_cpu"] = out["voxels_per_s"] / out["cpu"]["voxels_per_s"]
     return out
 

@@ -228,6 +228,14 @@ void orc_frontend_check(void *h, int n, const int *ind, const double *father, do
     }
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_omp_max_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();
