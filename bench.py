@@ -400,6 +400,7 @@ def batch_callback_bench(ev, w, cfg, dev, rank, world, B, barrier, max_over_rank
         # the same problems one at a time through the host adapter (host MINCO port + isdf_eval_discrete with host buffers)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import host_lib as H
+        from ctypes import c_int as C_int
         L = H.lib()
         nb = min(B, 16)
         g = np.zeros(dim)
@@ -411,7 +412,26 @@ def batch_callback_bench(ev, w, cfg, dev, rank, world, B, barrier, max_over_rank
             L.isdf_host_backend_destroy(be)
         dt = time.perf_counter() - t0
         per_problem = {"callbacks_per_s": nb / dt, "problems": nb, "max_rel_cost_diff_vs_batched": float(np.max(np.abs(np.array(cs) - c[:nb]) / np.abs(c[:nb])))}
-    return {"callbacks_per_s": world * B * 1e3 / ms, "host_adapter_one_at_a_time": per_problem, "ms_per_batch_max_over_ranks": ms, "problems_per_gpu": B, "problems_total": world * B,
+    lockstep = None
+    if world == 1:
+        # B restarts under the lock-step batched L-BFGS driver (host/isdf_lbfgs.hpp): every round = one batched device callback
+        try:
+            nb = min(B, 32)
+            Xl = np.ascontiguousarray(xs[:nb]).copy().reshape(-1)
+            fl, rl = np.zeros(nb), np.zeros(nb, dtype=np.int32)
+            itl, evl, stl = np.zeros(nb, dtype=np.int32), np.zeros(nb, dtype=np.int32), C_int()
+            ipt = H.C.POINTER(H.C.c_int)
+            t0 = time.perf_counter()
+            rounds = L.isdf_host_lbfgs_batch_backend(ev.h, nb, N0, np.ascontiguousarray(heads[:nb]).ctypes.data_as(H.dp), np.ascontiguousarray(tails[:nb]).ctypes.data_as(H.dp),
+                                                     20.0, Xl.ctypes.data_as(H.dp), fl.ctypes.data_as(H.dp), rl.ctypes.data_as(ipt), 16, 10, 1e-6, 0.0, 12,
+                                                     itl.ctypes.data_as(ipt), evl.ctypes.data_as(ipt), H.C.byref(stl))
+            dt = time.perf_counter() - t0
+            lockstep = {"problems": nb, "rounds": int(rounds), "iterations_total": int(itl.sum()), "evaluations_total": int(evl.sum()), "seconds": dt,
+                        "iters_per_s": float(itl.sum() / dt), "callback_evals_per_s": float(evl.sum() / dt), "status": int(stl.value),
+                        "mean_cost_start": float(c[:nb].mean()), "mean_cost_end": float(fl.mean()), "max_iterations": 12}
+        except Exception as e:
+            lockstep = {"error": repr(e)}
+    return {"callbacks_per_s": world * B * 1e3 / ms, "host_adapter_one_at_a_time": per_problem, "lockstep_lbfgs": lockstep, "ms_per_batch_max_over_ranks": ms, "problems_per_gpu": B, "problems_total": world * B,
             "scaling": "weak", "finite_costs": bool(np.all(np.isfinite(c))), "mean_cost": float(c.mean()),
             "what": f"BASELINE configs[4]: {world * B} random-restart problems ({N0} pieces x {w['samples_per_piece']} samples, shared {X}^3 map, mesh robot), "
                     "decision vector in -> cost and gradient out, MINCO forward/adjoint + time-integral/collision term all on the device; no collective"}

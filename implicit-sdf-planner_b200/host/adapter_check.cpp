@@ -4,6 +4,7 @@
 #include "isdf_cost_callback.hpp"
 #include "isdf_lbfgs.hpp"
 #include <cstring>
+#include <vector>
 
 using namespace isdf_host;
 
@@ -57,6 +58,39 @@ int isdf_host_lbfgs_generic(int n, double *x, double *f, lbfgs_eval_raw_t eval, 
 int isdf_host_lbfgs_backend(void *be, double *x, int n, double *f, int mem_size, int past, double delta, double g_epsilon, int max_iterations,
                             int *iterations, int *evaluations) {
     return isdf_host_lbfgs_generic(n, x, f, &BackEnd::costFunctionLbfgs, be, mem_size, past, delta, g_epsilon, max_iterations, iterations, evaluations);
+}
+
+// lock-step batched driver on any batched callback (CPU tests: identical to the sequential driver instance by instance) ...
+int isdf_host_lbfgs_batch_generic(int B, int n, double *x, double *f, int *ret, lbfgs_eval_batch_t eval, void *instance, int mem_size, int past,
+                                  double delta, double g_epsilon, int max_iterations, int *iterations, int *evaluations) {
+    LbfgsParams pr; pr.mem_size = mem_size; pr.past = past; pr.delta = delta; pr.g_epsilon = g_epsilon; pr.max_iterations = max_iterations;
+    pr.min_step = 1.0e-32;
+    if (B < 1 || n < 1 || mem_size < 1) return -1;
+    std::vector<LbfgsStats> st(B);
+    const int rounds = lbfgs_optimize_batch(B, n, x, f, ret, eval, instance, pr, st.data());
+    for (int b = 0; b < B; b++) { if (iterations) iterations[b] = st[b].iterations; if (evaluations) evaluations[b] = st[b].evaluations; }
+    return rounds;
+}
+// ... and on the device callback for B random-restart problems (isdf_callback_batch: MINCO + time-integral/collision term + adjoint)
+struct BatchBackEnd { isdf_ctx *ctx; int N0; const double *heads, *tails; double rho; std::vector<double> h, t; int status; };
+static void batch_backend_eval(void *inst, int nb, const int *ids, const double *x, double *f, double *g) {
+    BatchBackEnd &b = *static_cast<BatchBackEnd *>(inst);
+    b.h.resize((size_t)9 * nb); b.t.resize((size_t)9 * nb);
+    for (int q = 0; q < nb; q++) {
+        std::memcpy(&b.h[(size_t)9 * q], b.heads + (size_t)9 * ids[q], sizeof(double) * 9);
+        std::memcpy(&b.t[(size_t)9 * q], b.tails + (size_t)9 * ids[q], sizeof(double) * 9);
+    }
+    const int r = isdf_callback_batch(b.ctx, nb, b.N0, b.h.data(), b.t.data(), 1, b.rho, x, f, g);   // on failure every f is NaN: the instances stop
+    if (r != ISDF_OK) b.status = r;
+}
+int isdf_host_lbfgs_batch_backend(isdf_ctx *ctx, int B, int N0, const double *heads, const double *tails, double rho, double *x, double *f, int *ret,
+                                  int mem_size, int past, double delta, double g_epsilon, int max_iterations, int *iterations, int *evaluations,
+                                  int *status) {
+    BatchBackEnd be{ctx, N0, heads, tails, rho, {}, {}, 0};
+    const int rounds = isdf_host_lbfgs_batch_generic(B, 4 * N0 - 3, x, f, ret, &batch_backend_eval, &be, mem_size, past, delta, g_epsilon, max_iterations,
+                                                     iterations, evaluations);
+    if (status) *status = be.status;
+    return rounds;
 }
 
 }  // extern "C"

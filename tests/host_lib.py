@@ -30,6 +30,10 @@ def lib():
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.isdf_host_lbfgs_backend.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        ip = C.POINTER(C.c_int)
+        L.isdf_host_lbfgs_batch_generic.argtypes = [C.c_int, C.c_int, dp, dp, ip, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, ip, ip]
+        L.isdf_host_lbfgs_batch_backend.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, ip, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                                    ip, ip, ip]
         _lib = L
     return _lib
 
@@ -54,6 +58,31 @@ def lbfgs_minimize(fun, x0, mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_
     r = lib().isdf_host_lbfgs_generic(n, _p(x), C.byref(fx), C.cast(cfn, C.c_void_p), None, mem_size, past, delta, g_epsilon, max_iterations,
                                       C.byref(it), C.byref(ev))
     return dict(ret=r, x=x, f=fx.value, iterations=it.value, evaluations=ev.value)
+
+
+EVAL_BATCH_T = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_int), dp, dp, dp)   # lbfgs_eval_batch_t
+
+
+def lbfgs_minimize_batch(fun, X0, mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_iterations=0):
+    """fun(id, x) -> (f, grad) per instance; B instances advanced in lock step by the product's batched driver."""
+    X = f(X0).copy()
+    B, n = X.shape
+
+    def cb(_inst, nb, ids, xp, fp, gp):
+        xs = np.ctypeslib.as_array(xp, shape=(nb, n))
+        fs = np.ctypeslib.as_array(fp, shape=(nb,))
+        gs = np.ctypeslib.as_array(gp, shape=(nb, n))
+        for q in range(nb):
+            fv, gv = fun(ids[q], xs[q].copy())
+            fs[q] = fv; gs[q] = gv
+    cfn = EVAL_BATCH_T(cb)
+    fx, ret, it, ev = np.zeros(B), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    ip = C.POINTER(C.c_int)
+    Xf = X.reshape(-1)
+    rounds = lib().isdf_host_lbfgs_batch_generic(B, n, _p(Xf), _p(fx), ret.ctypes.data_as(ip), C.cast(cfn, C.c_void_p), None, mem_size, past,
+                                                 delta, g_epsilon, max_iterations, it.ctypes.data_as(ip), ev.ctypes.data_as(ip))
+    X = Xf.reshape(B, n)
+    return dict(rounds=rounds, ret=ret, x=X, f=fx, iterations=it, evaluations=ev)
 
 
 def _p(a):

@@ -58,3 +58,48 @@ def test_lbfgs_driver_known_answers():
     assert H.lbfgs_minimize(rosen, np.zeros(2), mem_size=0)["ret"] == -1022    # LBFGSERR_INVALID_MEMSIZE
     # NaN cost aborts with LBFGSERR_INVALID_FUNCVAL: what the C ABI's NaN-on-error relies on
     assert H.lbfgs_minimize(lambda x: (float("nan"), x), np.ones(2))["ret"] == -1012
+
+
+def test_batched_lbfgs_driver_equals_sequential_instances():
+    """lbfgs_optimize_batch: B instances in lock step, each bit-identical (iterates, value, iteration / evaluation counts, return
+    code) to the sequential driver run alone — including instances that finish early, hit the direction-reset re-evaluation,
+    fail in the line search, or start at a stationary point."""
+    def rosen(x):
+        f = np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2)
+        g = np.zeros_like(x)
+        g[:-1] = -400 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+        g[1:] += 200 * (x[1:] - x[:-1] ** 2)
+        return f, g
+    A = np.diag([1.0, 10.0, 100.0, 3.0])
+
+    def quad(x):
+        return 0.5 * x @ A @ x, A @ x
+
+    def hinge(x):       # smoothed-L1 like kink: piecewise cubic / linear, exercises long line searches
+        f, g = 0.0, np.zeros_like(x)
+        for i, v in enumerate(x):
+            a = abs(v)
+            if a > 0.1:
+                f += a - 0.05; g[i] = np.sign(v)
+            else:
+                f += (0.1 - a / 2) * (a / 0.1) ** 3
+                g[i] = np.sign(v) * ((a / 0.1) ** 2 * (-a / 0.2 + 3 * (0.1 - a / 2) / 0.1))
+        return f, g
+    funs = [rosen, quad, hinge, rosen, quad, lambda x: (float("nan"), x), quad]
+    rng = np.random.default_rng(4)
+    X0 = rng.normal(size=(len(funs), 4))
+    X0[6] = 0.0                                                      # stationary start: converges without a line search
+    X0[3] = [-1.2, 1.0, -0.5, 0.8]
+    kw = dict(mem_size=6, past=3, delta=1e-9, g_epsilon=1e-7, max_iterations=200)
+    rb = H.lbfgs_minimize_batch(lambda i, x: funs[i](x), X0, **kw)
+    assert rb["rounds"] >= max(rb["evaluations"])
+    kinds = set()
+    for b, fn in enumerate(funs):
+        rs = H.lbfgs_minimize(fn, X0[b], **kw)
+        assert rs["ret"] == rb["ret"][b], (b, rs["ret"], rb["ret"][b])
+        assert rs["iterations"] == rb["iterations"][b] and rs["evaluations"] == rb["evaluations"][b], b
+        assert np.array_equal(rs["x"], rb["x"][b]), b
+        if np.isfinite(rs["f"]):
+            assert rs["f"] == rb["f"][b], b
+        kinds.add(int(rs["ret"]))
+    assert len(kinds) >= 3 and min(rb["iterations"]) == 0 and max(rb["iterations"]) > 10
