@@ -102,3 +102,18 @@ def test_new_entry_points_validate_arguments_without_gpu_calls():
     assert lib.isdf_peer_allreduce_device(None, None, 0, None) == -1
     assert lib.isdf_peer_status(None) == -1 and lib.isdf_peer_disconnect(None) == -1
     assert lib.isdf_get_batch_trajectories(None, None, None, None) == -1
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/minimal.c: a C99 program against include/isdf.h + libisdf_b200.so only (no torch, no C++ runtime on its side)."""
+    import torch
+    exe = str(tmp_path / "minimal")
+    libdir = os.path.dirname(I.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "minimal.c"), "-o", exe, I.LIB_PATH, f"-Wl,-rpath,{libdir}", "-lm"], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    run = subprocess.run([exe], capture_output=True, timeout=120)
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and b"cost" in run.stdout, (run.stdout, run.stderr)
+    else:
+        assert run.returncode == 3 and b"isdf_create: -3" in run.stderr      # ISDF_ERR_CUDA, never a silent CPU path
