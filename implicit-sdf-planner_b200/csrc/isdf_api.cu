@@ -50,16 +50,19 @@ struct isdf_ctx {
     DevShape shape;
     DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt;
     // evaluation scratch
-    DevBuf<double> d_T, d_C, d_out, d_partial, d_piece_cost;
+    DevBuf<double> d_T, d_C, d_out, d_piece_cost;
     DevBuf<int> d_tickets;       // pieces_done counter of the epilogue kernel
     DevBuf<double> d_tot; DevBuf<int> d_sample_slot;   // per-sample collision sums handed from the scan kernels to the epilogue
     DevBuf<int> d_items, d_item_count; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
-    int warp_slots = 148 * 12;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
+    int warp_slots = 148 * 16;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
+    int sm_count = 148, mesh_blocks = 4, analytic_blocks = 4;   // persistent grids: one CTA per resident slot
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
     DevBuf<unsigned long long> d_counter, d_dbg;
     DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout;   // batched callback (isdf_minco.cuh)
     int minco_B = 0, minco_N = 0;
     bool dbg_on = false;
+    bool no_items = false;       // diagnostics: always launch in natural order, never split (isdf_dbg_schedule)
+    int warp_slots_override = 0; // diagnostics: pretend the device has this many resident warps (forces splitting)
     double *h_stage = nullptr;   // pinned
     size_t h_stage_n = 0;
     // swept volume
@@ -103,7 +106,9 @@ extern "C" int isdf_default_config(isdf_config *cfg) {
     cfg->weight_v = 1000.0; cfg->weight_p = 4000.0; cfg->weight_omg = 1000.0; cfg->weight_theta = 1000.0;
     cfg->smoothing_eps = 1.0e-2; cfg->safety_hor = 0.866; cfg->occupancy_resolution = 1.0;
     cfg->kernel_size = 13; cfg->integral_intervs = 64; cfg->threads_num = 30;
-    cfg->flags = ISDF_WITH_DYNAMICS | ISDF_WITH_COLLISION;
+    // the LIVE reference callback (hpp:358-430): collision through the swept-volume term only; grad_cost_p is dead code there, so the
+    // discrete collision term is opt-in (flags |= ISDF_WITH_COLLISION) — a default BackEnd must not penalise collision twice
+    cfg->flags = ISDF_WITH_DYNAMICS;
     return 0;
 }
 
@@ -117,15 +122,20 @@ extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
     if (device < 0 || device >= ndev) return fail(ISDF_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
     CU_TRY(cudaSetDevice(device));
     // fail loudly if the sm_100a image cannot run here
-    cudaFuncAttributes fa;
-    CU_TRY(cudaFuncGetAttributes(&fa, (const void *)k_discrete_analytic));
+    int nb_mesh = 0, nb_analytic = 0;
+    CU_TRY(discrete_resident_blocks(&nb_mesh, &nb_analytic));
+    // pose-window offsets are packed 10 bits per axis (isdf_discrete.cuh); the inclusive index range of a window is at most
+    // kernel_size + 2 voxels when the map resolution equals occupancy_resolution (isdf_set_map checks the resolution)
+    if (cfg->kernel_size + 2 > WINDOW_AXIS_MAX) return fail(ISDF_ERR_UNSUPPORTED, "kernel_size too large (pose windows are limited to 1023 voxels per axis)");
     isdf_ctx *c = new isdf_ctx();
     c->device = device; c->cfg = *cfg;
     {
-        cudaDeviceProp prop; int nb = 0;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_discrete_mesh, DISC_THREADS, 0) == cudaSuccess && nb > 0)
-            c->warp_slots = prop.multiProcessorCount * nb * DISC_WARPS;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && nb_mesh > 0 && nb_analytic > 0) {
+            c->sm_count = prop.multiProcessorCount;
+            c->mesh_blocks = nb_mesh; c->analytic_blocks = nb_analytic;
+            c->warp_slots = prop.multiProcessorCount * nb_mesh * DISC_WARPS;
+        }
     }
     std::memset(&c->stats, 0, sizeof(c->stats));
     std::memset(&c->grid, 0, sizeof(c->grid));
@@ -157,7 +167,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
-    c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_partial.release(); c->d_piece_cost.release();
+    c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_sample_slot.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
@@ -585,24 +595,25 @@ extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints,
 static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *d_C, double *d_out, cudaStream_t st) {
     const int K = c->cfg.integral_intervs;
     const long long S = (long long)N * (K + 1);
-    CU_TRY(c->d_partial.ensure((size_t)S * PARTIAL_STRIDE));
+    if (S > 0x7fffffffll) return fail(ISDF_ERR_UNSUPPORTED, "N * (integral_intervs + 1) must fit in 31 bits");
     CU_TRY(c->d_piece_cost.ensure(N));
-    if (c->d_tickets.n < 1) {
-        CU_TRY(c->d_tickets.ensure(1));
-        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, sizeof(int), st));
+    if (c->d_tickets.n < 2) {   // [0] pieces_done of the epilogue, [1] work-item cursor of the persistent scan warps
+        CU_TRY(c->d_tickets.ensure(2));
+        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, 2 * sizeof(int), st));
     }
     CU_TRY(c->d_tot.ensure((size_t)S * 8));
     CU_TRY(c->d_sample_slot.ensure((size_t)S));
     DiscArgs A;
     A.cfg = c->dcfg; A.grid = c->grid; A.shape = c->shape; A.N = N; A.T = d_T; A.C = d_C;
-    A.partial = c->d_partial.p; A.tot = c->d_tot.p; A.sample_slot = c->d_sample_slot.p; A.pieces_done = c->d_tickets.p;
+    A.tot = c->d_tot.p; A.sample_slot = c->d_sample_slot.p; A.pieces_done = c->d_tickets.p; A.item_cursor = c->d_tickets.p + 1;
     A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
     A.rank = c->rank; A.world = c->world;
     A.peer = PeerArgs{};
-    if (c->peer_fused && c->peer.world > 1 && c->world > 1) {   // an unsharded call (isdf_set_shard(ctx, 0, 1)) stays local
+    const bool fused = c->peer_fused && c->peer.world > 1 && c->world > 1;   // an unsharded call (isdf_set_shard(ctx, 0, 1)) stays local
+    if (fused) {
         if (c->peer.world != c->world || c->peer.rank != c->rank) return fail(ISDF_ERR_STATE, "peer group does not match isdf_set_shard");
         if (19 * N + 1 > c->peer.cap) return fail(ISDF_ERR_INVALID, "peer exchange buffer too small for this N (isdf_peer_export max_doubles)");
-        A.peer = c->peer; A.peer.epoch = ++c->peer.epoch;
+        A.peer = c->peer; A.peer.epoch = c->peer.epoch + 1;   // committed below, once the exchange kernel is really enqueued
     }
     A.dbg = nullptr;
     if (c->dbg_on) { CU_TRY(c->d_dbg.ensure((size_t)3 * S)); CU_TRY(cudaMemsetAsync(c->d_dbg.p, 0, sizeof(unsigned long long) * 3 * S, st)); A.dbg = c->d_dbg.p; }
@@ -610,35 +621,38 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
     // longest-first order from the previous evaluation of the same problem shape (first evaluation: natural order)
     const long long sig = ((long long)N << 20) ^ ((long long)c->rank << 10) ^ c->world ^ ((long long)K << 40);
-    const int max_split = (c->shape.kind == ISDF_SHAPE_MESH) ? (int)(M / 4 + 1) : 0;   // only mesh samples have a heavy tail worth splitting
+    const bool mesh = (c->shape.kind == ISDF_SHAPE_MESH);
+    const int max_split = mesh ? (int)std::min<long long>(M / 4 + 1, MAX_SPLIT_SLOTS) : 0;   // only mesh samples have a heavy tail worth splitting
     const size_t max_items = (size_t)M + (size_t)(ROW_CLASSES - 1) * max_split;
     CU_TRY(c->d_work.ensure((size_t)S));
     if (c->d_items.n < 3 * max_items + (size_t)M) { CU_TRY(c->d_items.ensure(3 * max_items + (size_t)M)); c->order_for = -1; }   // a regrown table holds no items yet
     CU_TRY(c->d_item_count.ensure(1));
-    CU_TRY(c->d_subsum.ensure((size_t)max_split * ROW_CLASSES * 8));
-    if (c->d_split_work.n < (size_t)max_split) {
-        CU_TRY(c->d_split_work.ensure((size_t)max_split));
-        CU_TRY(cudaMemsetAsync(c->d_split_work.p, 0, sizeof(unsigned) * max_split, st));
+    CU_TRY(c->d_subsum.ensure((size_t)std::max(max_split, 1) * ROW_CLASSES * 8));
+    if (c->d_split_work.n < (size_t)std::max(max_split, 1)) {
+        CU_TRY(c->d_split_work.ensure((size_t)std::max(max_split, 1)));
+        CU_TRY(cudaMemsetAsync(c->d_split_work.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
     }
     A.work = c->d_work.p;
-    const bool have_items = (c->order_for == sig);
+    const bool have_items = (c->order_for == sig) && !c->no_items;
     A.items = have_items ? c->d_items.p : nullptr;
     A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_work = c->d_split_work.p;
-    const unsigned grid = (unsigned)(((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS);
+    // persistent grid: one CTA per resident slot (or fewer when there are fewer items than warps)
+    const long long want = ((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS;
+    const long long resident = (long long)c->sm_count * (mesh ? c->mesh_blocks : c->analytic_blocks);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min(want, resident));
     if (c->items_pending) CU_TRY(cudaStreamWaitEvent(st, c->ev_items_done, 0));   // the table this launch reads (or overwrites next)
-    if (c->shape.kind == ISDF_SHAPE_MESH) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
-    else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
-    k_discrete_epilogue<<<(unsigned)N, EPI_THREADS, 0, st>>>(A);
+    CU_TRY(discrete_launch_scan(A, mesh, grid, st));
+    CU_TRY(discrete_launch_epilogue(A, st));
+    if (fused) c->peer.epoch = A.peer.epoch;
     // build the next evaluation's work items on the aux stream: overlaps the caller's D2H / all-reduce / host work
     CU_TRY(cudaEventRecord(c->ev_main_done, st));
     CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_main_done, 0));
-    k_build_items<<<1, 1024, 0, c->aux_stream>>>(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots, c->d_items.p, c->d_item_count.p);
+    CU_TRY(discrete_launch_build_items(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots_override > 0 ? c->warp_slots_override : c->warp_slots, c->d_items.p, c->d_item_count.p, c->aux_stream));
     CU_TRY(cudaEventRecord(c->ev_items_done, c->aux_stream));
     c->items_pending = true;
     c->order_for = sig;
     c->stats.kernel_launches += 3;   // scan kernel, epilogue, work-item builder
     c->stats.evals_discrete++;
-    CU_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -1149,6 +1163,43 @@ extern "C" int isdf_get_swept_results(isdf_ctx *c, double *tstar, double *sdf, d
 
 // ---- internal diagnostics (not part of include/isdf.h) ------------------------------------------------------------
 extern "C" int isdf_dbg_enable(isdf_ctx *c, int on) { if (!c) return -1; c->dbg_on = on != 0; c->sv.dbg_on = on != 0; return 0; }
+// scheduling diagnostics: natural_order != 0 -> every launch in natural sample order, nothing split (the state of a context's FIRST
+// evaluation); warp_slots > 0 -> build the work items as if the device had that many resident warps (small values force heavy
+// samples to be split, so tests can compare split parts against the oracle on one GPU); 0 restores the device's own figure.
+extern "C" int isdf_dbg_schedule(isdf_ctx *c, int natural_order, int warp_slots) {
+    if (!c) return -1;
+    c->no_items = natural_order != 0; c->warp_slots_override = warp_slots > 0 ? warp_slots : 0; c->order_for = -1;
+    return 0;
+}
+// number of work items / split samples of the table built by the last discrete evaluation
+extern "C" int isdf_dbg_item_stats(isdf_ctx *c, int *item_count, int *split_parts) {
+    if (!c || !item_count || !split_parts || !c->d_item_count.p) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -3;
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->aux_stream);
+    int n = 0;
+    if (cudaMemcpy(&n, c->d_item_count.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    std::vector<int> it((size_t)3 * std::max(n, 1));
+    if (n > 0 && cudaMemcpy(it.data(), c->d_items.p, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    int parts = 0;
+    for (int k = 0; k < n; k++) if (it[3 * k + 2] >= 0) parts++;
+    *item_count = n; *split_parts = parts;
+    return 0;
+}
+// the device flatness map and its adjoint as compiled into the epilogue kernel: vaj n x 9 (vel, acc, jer), grads n x 10
+// (quat_grad 4, omg_grad 3, vel_grad 3) -> out n x 16 (quat 4, omg 3, total grads wrt vel, acc, jer)
+extern "C" int isdf_dbg_flatness(isdf_ctx *c, int n, const double *vaj, const double *grads, double *out) {
+    if (!c || n < 1 || !vaj || !grads || !out) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -3;
+    DevBuf<double> dv, dg, dout;
+    cudaError_t e = dv.upload(vaj, (size_t)9 * n, c->stream);
+    if (e == cudaSuccess) e = dg.upload(grads, (size_t)10 * n, c->stream);
+    if (e == cudaSuccess) e = dout.ensure((size_t)16 * n);
+    if (e == cudaSuccess) e = discrete_launch_dbg_flatness(c->dcfg.fp, n, dv.p, dg.p, dout.p, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout.p, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dv.release(); dg.release(); dout.release();
+    return e == cudaSuccess ? 0 : -3;
+}
 extern "C" int isdf_dbg_swept_stats(isdf_ctx *c, unsigned long long *out, long long n) {
     if (!c || !out || (size_t)n > c->sv.d_dbg.n) return -1;
     cudaStreamSynchronize(c->stream);

@@ -1,30 +1,39 @@
-// Discrete collision cost/gradient kernels: a scan kernel (warp per pose sample) and an epilogue kernel (thread per sample,
-// CTA per piece) per optimiser step.
+// Discrete collision cost/gradient kernels: a scan kernel (persistent warps drawing pose-sample work items) and an epilogue kernel
+// (thread per sample, CTA per piece) per optimiser step.
 //
 // Reference semantics: addTimeIntPenaltyParallel (back_end_optimizer.hpp:432-554) with grad_cost_p (hpp:766-824)
 // wired into the sample loop exactly as hpp:619-626 wires its swept-volume sibling; PCSmapManager::getPointsInAABB
 // (PCSmap_manager.h:148-170); getSDFWithGradWhenRobotAtState (sw_manager.hpp:537-541).
 //
 // Mapping (B200-first, not the reference's OpenMP-over-samples + critical section):
-//   * the pose window is read from the BIT-packed occupancy: lane = (x,y) row, one or two 32-bit loads + funnel
-//     shift give the row's z-run; a warp prefix sum over popcounts enumerates only the occupied voxels
-//     (the reference tests every voxel and heap-allocates a vector per sample, hpp:787);
-//   * work items, longest first: the per-sample work measured in the previous evaluation (an optimiser moves the
-//     trajectory only a little between steps) sorts the samples, and a sample that grazes an obstacle (dozens of mesh
-//     queries) is split into ROW_CLASSES items — window rows r with r % ROW_CLASSES == c — taken by different warps.
-//     The per-sample sum is ALWAYS formed class by class in the same order, whether one warp walks all classes or
-//     eight warps take one each, so the split never changes a bit of the result;
+//   * the pose window is read from the BIT-packed occupancy: lane = (x,y) row, one or two 32-bit loads + funnel shift give the
+//     row's z-run; only the occupied voxels are enumerated, in the reference's (x, y, z) order per row, and compacted through a
+//     per-warp shared-memory queue so that every cull pass runs on 32 live voxels (the reference tests every voxel and
+//     heap-allocates a vector per sample, hpp:787);
+//   * PERSISTENT warps draw work items (longest first) from one device counter: a warp that finishes a light sample takes the
+//     next item at once instead of idling until its CTA's slowest warp is done;
+//   * work items: the per-sample work measured in the previous evaluation (an optimiser moves the trajectory only a little
+//     between steps) sorts the samples, and a sample that grazes an obstacle (dozens of mesh queries) is split into 2..32 items,
+//     each a contiguous range of the 32 interleaved ROW CLASSES (window row r belongs to class r % 32). The per-sample sum is
+//     ALWAYS formed class by class in the same order, whether one warp walks all classes or 32 warps take one each, so the split
+//     never changes a bit of the result;
 //   * k_discrete_analytic — two warp-level compaction queues keep lanes dense: queue A = voxels inside the body-frame
 //     cull box, queue B = voxels whose hinge is active (sdf < safety_hor) and therefore need the 6 extra finite-
 //     difference SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87). Evaluating those only for active voxels is exact
 //     because an inactive voxel contributes nothing (hpp:809-821);
 //   * k_discrete_mesh — voxels that survive the exact culls (body-frame box, inflated mesh AABB, per-cell distance lower
-//     bound) are answered by WARP-COOPERATIVE nearest-triangle queries: the cell's exact candidate list near the surface,
-//     elsewhere the 32-ary tree (lane = child / triangle slot) seeded with the cell's nearest triangle;
+//     bound) are answered by WARP-COOPERATIVE nearest-triangle searches (the cell's exact candidate list near the surface, 64
+//     candidates per pass with a division-free closest-point test; elsewhere the 32-ary tree seeded with the cell's nearest
+//     triangle); sign, gradient, hinge and pose chain rule of the answered voxels are DEFERRED and evaluated one voxel per lane;
+//     the warp-uniform pose (position, rotation, quaternion) lives in shared memory, not in 16 x 2 registers of every lane;
 //   * k_discrete_epilogue — the per-sample chain rule (penalties, flatness adjoint, beta-basis outer products) as one THREAD
-//     per sample, then a deterministic reduction inside the piece's CTA: 20 threads add the partials in ascending sample
-//     order; the last CTA adds the piece costs in ascending order and (several GPUs) runs the peer-memory exchange —
-//     independent of scheduling, so results are bit-reproducible run to run and identical on every rank.
+//     per sample, then a deterministic reduction inside the piece's CTA from shared memory: 20 threads add the partials in
+//     ascending sample order; the last CTA adds the piece costs in ascending order and (several GPUs) runs the peer-memory
+//     exchange — independent of scheduling, so results are bit-reproducible run to run and identical on every rank.
+//
+// This header is included by two translation units: isdf_api.cu (argument block, host-side constants, the device helpers the
+// service kernels share) and isdf_discrete_tu.cu, which defines ISDF_DISCRETE_TU and is the only one that instantiates the
+// kernels — compiled WITH FMA contraction, while the swept-volume TU keeps -fmad=false for its sequential decision replay.
 #pragma once
 #include "isdf_types.cuh"
 #include "isdf_peer.cuh"
@@ -34,15 +43,17 @@ namespace isdf {
 constexpr int DISC_WARPS = 4;
 constexpr int DISC_THREADS = DISC_WARPS * 32;
 constexpr int QCAP = 64;
-constexpr int ROW_CLASSES = 8;          // a pose window's rows are summed in 8 interleaved classes (canonical order)
+constexpr int ROW_CLASSES = 32;         // a pose window's rows are summed in 32 interleaved classes (canonical order): row r -> class r % 32
 constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than this (work units: 64 per mesh query + 1 per culled pair)
-// CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md): the analytic kernel
-// is fastest at 4 (128 regs); so is the mesh kernel since the per-sample epilogue left it (3/4/5 -> 0.475/0.453/0.463 ms)
+constexpr int MAX_SPLIT_SLOTS = 8192;   // split samples per launch (2 KB of class sums each)
+constexpr int WINDOW_AXIS_MAX = 1023;   // voxels per window axis: window offsets are packed 10 bits per axis
+// CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md, r02_tuning.md)
 constexpr int ANALYTIC_MIN_BLOCKS = 4;
 #ifndef ISDF_MESH_MIN_BLOCKS
 #define ISDF_MESH_MIN_BLOCKS 4
 #endif
 constexpr int MESH_MIN_BLOCKS = ISDF_MESH_MIN_BLOCKS;
+constexpr int EPI_THREADS = 288;
 
 struct DiscArgs {
     DevCfg cfg;
@@ -51,16 +62,16 @@ struct DiscArgs {
     int N;
     const double *T;       // N
     const double *C;       // 6N x 3 column-major
-    double *partial;       // S x PARTIAL_STRIDE
     double *tot;           // S x 8: collision sums of a sample evaluated as ONE work item {costp, gradp(3), grad_quat(4)}
     int *sample_slot;      // S: -1 = sums in tot, otherwise the split slot whose class sums (subsum) make up the sample
     int *pieces_done;      // 1  (zero on entry, zero on exit)
     double *piece_cost;    // N
     double *out;           // 19N+1: cost | gradC | gradT
     unsigned long long *pair_counter;  // may be null
-    unsigned long long *dbg;           // may be null: per sample {cycles, pairs, queries}
-    const int *items;                  // may be null: 3 ints per work item {local sample m, row class or -1 = all, split slot or -1}
+    unsigned long long *dbg;           // may be null: per sample {cycles, pairs, work}
+    const int *items;                  // may be null: 3 ints per work item {local sample m, -1 = all classes or c0 | c1 << 8, split slot or -1}
     const int *item_count;             // number of valid items (device)
+    int *item_cursor;                  // persistent warps draw items from this counter (zero on entry; the epilogue zeroes it again)
     double *subsum;                    // split slot x ROW_CLASSES x 8 class sums
     unsigned *split_work;              // split slot -> work accumulated by the parts (zero on entry, zeroed by the epilogue)
     unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
@@ -109,29 +120,31 @@ __device__ __forceinline__ d3 voxel_centre(const DevGrid &G, int ix, int iy, int
     return mk3((ix + 0.5) * G.res + G.bmin[0], (iy + 0.5) * G.res + G.bmin[1], (iz + 0.5) * G.res + G.bmin[2]);
 }
 
+// one window row's z-run [zs, zs + nzc) as a bit mask (bit k = voxel zs + k)
+__device__ __forceinline__ uint32_t row_bits(const DevGrid &G, int ix, int iy, int zs, uint32_t zmask) {
+    const uint32_t *row = G.bits + ((size_t)ix * G.Y + iy) * G.Zw;
+    const int wz = zs >> 5, sh = zs & 31;
+    const uint32_t lo = __ldg(row + wz);
+    const uint32_t hi = (sh != 0 && wz + 1 < G.Zw) ? __ldg(row + wz + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh) & zmask;
+}
+
 // Enumerate the occupied voxels of a window, 32 at a time, in the reference's order (x, then y, then z ascending).
-// visit(valid, ix, iy, iz) is called by the whole warp; lanes without a voxel pass valid = false.
-// cls >= 0: only the rows of that class are visited (row r = cls + ROW_CLASSES * k); cls < 0: every row.
-// visit additionally receives the row index r (row class = r % ROW_CLASSES).
+// visit(valid, ix, iy, iz, r) is called by the whole warp; lanes without a voxel pass valid = false. (analytic kernel)
 template <class Visit>
-__device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, int lane, int cls, Visit &&visit) {
+__device__ __forceinline__ void scan_window(const DevGrid &G, const Window &W, int lane, Visit &&visit) {
     const int ny = W.iy1 - W.iy0 + 1;
     const int nrows = (W.ix1 - W.ix0 + 1) * ny;
     for (int zs = W.iz0; zs <= W.iz1; zs += 32) {
         const int nzc = min(32, W.iz1 - zs + 1);
         const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
-        const int wz = zs >> 5, sh = zs & 31;
-        const int rstep = cls < 0 ? 1 : ROW_CLASSES, rfirst = cls < 0 ? 0 : cls;
-        for (int rb = 0; rfirst + rstep * rb < nrows; rb += 32) {
-            const int r = rfirst + rstep * (rb + lane);
+        for (int rb = 0; rb < nrows; rb += 32) {
+            const int r = rb + lane;
             uint32_t bits = 0;
             int rx = 0, ry = 0;
             if (r < nrows) {
                 rx = r / ny; ry = r - rx * ny;
-                const uint32_t *row = G.bits + ((size_t)(W.ix0 + rx) * G.Y + (W.iy0 + ry)) * G.Zw;
-                const uint32_t lo = __ldg(row + wz);
-                const uint32_t hi = (sh != 0 && wz + 1 < G.Zw) ? __ldg(row + wz + 1) : 0u;
-                bits = __funnelshift_r(lo, hi, sh) & zmask;
+                bits = row_bits(G, W.ix0 + rx, W.iy0 + ry, zs, zmask);
             }
             const int cnt = __popc(bits);
             int incl = cnt;
@@ -245,18 +258,23 @@ __device__ __forceinline__ void sample_epilogue(const DiscArgs &A, int i, int j,
 }
 
 // ============================================================================================================================
-// Work item of this warp: {global sample, first class, one-past-last class, split slot}. Returns false when there is none.
+// Work item of a warp: {global sample, first class, one-past-last class, split slot}.
 struct Item { int s, c0, c1, hslot; };
-__device__ __forceinline__ bool fetch_item(const DiscArgs &A, Item &it) {
+
+// Persistent-warp scheduler: the warp's next work item, or false when the table is exhausted. Which warp takes which item
+// never touches the arithmetic, so results stay bit-reproducible.
+__device__ __forceinline__ bool next_item(const DiscArgs &A, Item &it, int lane) {
     const int K = A.cfg.K;
     const int S = A.N * (K + 1);
     const int M = (S - A.rank + A.world - 1) / A.world;   // local samples; local m -> global s = rank + world * m
-    const int slot = blockIdx.x * DISC_WARPS + (threadIdx.x >> 5);
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(A.item_cursor, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
     if (A.items) {
         if (slot >= __ldg(A.item_count)) return false;
         const int m = __ldg(A.items + 3 * slot), part = __ldg(A.items + 3 * slot + 1);
         it.s = A.rank + A.world * m;
-        it.c0 = part < 0 ? 0 : part; it.c1 = part < 0 ? ROW_CLASSES : part + 1;
+        it.c0 = part < 0 ? 0 : (part & 0xff); it.c1 = part < 0 ? ROW_CLASSES : (part >> 8);
         it.hslot = __ldg(A.items + 3 * slot + 2);
         return true;
     }
@@ -265,75 +283,77 @@ __device__ __forceinline__ bool fetch_item(const DiscArgs &A, Item &it) {
     return true;
 }
 
-// Shared tail of both kernels: publish the sample's (or this row class's) collision sums. The per-sample chain rule and the
-// per-piece reduction run afterwards in k_discrete_epilogue with one THREAD per sample — inside these kernels that scalar chain
-// (~10k cycles of dependent FP64) would occupy a whole warp with 31 idle lanes.
-__device__ __forceinline__ void sample_finish(const DiscArgs &A, const Item &it, double tot[8], unsigned npairs, long long t_begin, unsigned work) {
+// Shared tail of both scan kernels for an item that covers the WHOLE sample: lanes 0..7 hold the eight collision sums.
+// The per-sample chain rule and the per-piece reduction run afterwards in k_discrete_epilogue with one THREAD per sample.
+__device__ __forceinline__ void sample_finish_whole(const DiscArgs &A, const Item &it, double mine, unsigned npairs, long long t_begin, unsigned work) {
     const int lane = threadIdx.x & 31;
     const int s = it.s;
-    if (lane == 0 && A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
-    if (it.hslot >= 0) {
-        double *sub = A.subsum + ((size_t)it.hslot * ROW_CLASSES + it.c0) * 8;
-        if (lane < 8) sub[lane] = tot[lane];
-        if (lane == 0) { atomicAdd(A.split_work + it.hslot, work); A.sample_slot[s] = it.hslot; }   // every part writes the same slot
-    } else {
-        if (lane < 8) A.tot[(size_t)s * 8 + lane] = tot[lane];
-        if (lane == 0) { A.sample_slot[s] = -1; if (A.work) A.work[s] = work; }
+    if (lane < 8) A.tot[(size_t)s * 8 + lane] = mine;
+    if (lane == 0) {
+        if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
+        A.sample_slot[s] = -1;
+        if (A.work) A.work[s] = work;
+        if (A.dbg) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = work; }
     }
-#ifdef ISDF_PHASE_TIMING
-    if (A.dbg && lane == 0) A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin);
-#else
-    if (A.dbg && lane == 0) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = work; }
-#endif
 }
 
+#ifdef ISDF_DISCRETE_TU
+// ============================================================================================================================
 // One CTA per piece, one thread per pose sample of the piece: hpp:505-551 (dynamic penalties, flatness adjoint, chain rule onto the
-// piece's 6x3 coefficients and its duration), then the deterministic per-piece reduction — 20 threads, one per output component,
-// add the samples' partials in ascending sample order — and, in the last CTA to finish, the total cost in ascending piece order.
-constexpr int EPI_THREADS = 288;
+// piece's 6x3 coefficients and its duration), then the deterministic per-piece reduction — the samples' 20 partials are staged in
+// shared memory and 20 threads, one per output component, add them in ascending sample order — and, in the last CTA to finish,
+// the total cost in ascending piece order.
 __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_constant__ DiscArgs A) {
+    __shared__ double sp[PARTIAL_STRIDE][EPI_THREADS + 1];   // component-major, padded: conflict-free writes, <= 2-way reads
     const int K = A.cfg.K, N = A.N, i = blockIdx.x;
     const int first_s = i * (K + 1), last_s = first_s + K;
     const int f0 = first_s + ((A.rank - first_s) % A.world + A.world) % A.world;  // first local sample >= first_s
     const int local_cnt = (f0 > last_s) ? 0 : ((last_s - f0) / A.world + 1);
     const double Ti = __ldg(A.T + i);
-    for (int idx = threadIdx.x; idx < local_cnt; idx += EPI_THREADS) {
-        const int s = f0 + idx * A.world;
-        const int j = s - first_s;
-        double tot[8];
-        const int slot = A.sample_slot[s];
-        if (slot < 0) {
+    double run = 0.0;   // threads 0..19: running sum of output component threadIdx.x
+    for (int chunk = 0; chunk < local_cnt; chunk += EPI_THREADS) {
+        const int idx = chunk + threadIdx.x;
+        if (idx < local_cnt) {
+            const int s = f0 + idx * A.world;
+            const int j = s - first_s;
+            double tot[8];
+            const int slot = A.sample_slot[s];
+            if (slot < 0) {
 #pragma unroll
-            for (int v = 0; v < 8; v++) tot[v] = __ldcg(A.tot + (size_t)s * 8 + v);
-        } else {   // split sample: class sums added in class order — the same additions a whole-sample item performs
-            const double *all = A.subsum + (size_t)slot * ROW_CLASSES * 8;
+                for (int v = 0; v < 8; v++) tot[v] = __ldcg(A.tot + (size_t)s * 8 + v);
+            } else {   // split sample: class sums added in class order — the same additions a whole-sample item performs
+                const double *all = A.subsum + (size_t)slot * ROW_CLASSES * 8;
 #pragma unroll
-            for (int v = 0; v < 8; v++) { double a = 0.0; for (int c = 0; c < ROW_CLASSES; c++) a += __ldcg(all + c * 8 + v); tot[v] = a; }
-            if (A.work) A.work[s] = A.split_work[slot];
-            A.split_work[slot] = 0;
+                for (int v = 0; v < 8; v++) { double a = 0.0; for (int c = 0; c < ROW_CLASSES; c++) a += __ldcg(all + c * 8 + v); tot[v] = a; }
+                if (A.work) A.work[s] = A.split_work[slot];
+                A.split_work[slot] = 0;
+            }
+            double st[PARTIAL_STRIDE];
+            sample_epilogue(A, i, j, Ti, tot[0], mk3(tot[1], tot[2], tot[3]), tot[4], tot[5], tot[6], tot[7], st);
+#pragma unroll
+            for (int v = 0; v < PARTIAL_STRIDE; v++) sp[v][threadIdx.x] = st[v];
         }
-        double st[PARTIAL_STRIDE];
-        sample_epilogue(A, i, j, Ti, tot[0], mk3(tot[1], tot[2], tot[3]), tot[4], tot[5], tot[6], tot[7], st);
+        __syncthreads();
+        if (threadIdx.x < PARTIAL_STRIDE) {
+            const int n = min(EPI_THREADS, local_cnt - chunk);
+            const double *row = sp[threadIdx.x];
+            int k = 0;
+            for (; k + 8 <= n; k += 8) {   // 8 loads in flight per step; the additions stay in ascending-sample order
+                double v[8];
 #pragma unroll
-        for (int v = 0; v < PARTIAL_STRIDE; v++) A.partial[(size_t)s * PARTIAL_STRIDE + v] = st[v];
+                for (int u = 0; u < 8; u++) v[u] = row[k + u];
+#pragma unroll
+                for (int u = 0; u < 8; u++) run += v[u];
+            }
+            for (; k < n; k++) run += row[k];
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x < PARTIAL_STRIDE) {
         const int comp = threadIdx.x;
-        double sum = 0.0;
-        int ss = f0;
-        // 8 independent loads in flight per step; the additions stay in ascending-sample order
-        for (; ss + 7 * A.world <= last_s; ss += 8 * A.world) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = A.partial[(size_t)(ss + u * A.world) * PARTIAL_STRIDE + comp];
-#pragma unroll
-            for (int u = 0; u < 8; u++) sum += v[u];
-        }
-        for (; ss <= last_s; ss += A.world) sum += A.partial[(size_t)ss * PARTIAL_STRIDE + comp];
-        if (comp < 18) { const int ax = comp / 6, k = comp - 6 * ax; A.out[1 + (size_t)ax * 6 * N + 6 * i + k] = sum; }
-        else if (comp == 18) A.out[1 + 18 * N + i] = sum;
-        else A.piece_cost[i] = sum;
+        if (comp < 18) { const int ax = comp / 6, k = comp - 6 * ax; A.out[1 + (size_t)ax * 6 * N + 6 * i + k] = run; }
+        else if (comp == 18) A.out[1 + 18 * N + i] = run;
+        else A.piece_cost[i] = run;
     }
     // last CTA to finish: total cost = piece costs added in ascending order, then (multi-GPU) the exchange over peer memory
     __shared__ int s_last;
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
             const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
             for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
         }
-        if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; }
+        if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; *A.item_cursor = 0; }
     }
     if (A.peer.world > 1) {
         __threadfence();
@@ -371,191 +391,301 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
     const DevCfg &cfg = A.cfg;
     const int K = cfg.K;
     Item it;
-    if (!fetch_item(A, it)) return;
-    const int s = it.s;
-    const int i = s / (K + 1), j = s - i * (K + 1);
-    const double Ti = __ldg(A.T + i);
-    const double step = Ti * (1.0 / K);
-    const long long t_begin = A.dbg ? clock64() : 0;
+    while (next_item(A, it, lane)) {
+        const int s = it.s;
+        const int i = s / (K + 1), j = s - i * (K + 1);
+        const double Ti = __ldg(A.T + i);
+        const double step = Ti * (1.0 / K);
+        const long long t_begin = A.dbg ? clock64() : 0;
 
-    d3 pos; quat4 q; rot3 R;
-    sample_pose(A, i, j, step, pos, q, R);
+        d3 pos; quat4 q; rot3 R;
+        sample_pose(A, i, j, step, pos, q, R);
 
-    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned npairs = 0;
+        double mine = 0.0;
+        unsigned npairs = 0;
 
-    if (cfg.flags & ISDF_WITH_COLLISION) {
-        const DevGrid &G = A.grid;
-        const double h = cfg.half_bd;
-        const Window W = window_of(G, pos, h);
-        PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};
-        int nA = 0, nB = 0;  // queue fill (warp-uniform)
+        if (cfg.flags & ISDF_WITH_COLLISION) {
+            const DevGrid &G = A.grid;
+            const double h = cfg.half_bd;
+            const Window W = window_of(G, pos, h);
+            PairAcc acc = {0, 0, 0, 0, 0, 0, 0, 0};
+            int nA = 0, nB = 0;  // queue fill (warp-uniform)
 
-        auto entry_centre = [&](uint32_t e) { return voxel_centre(G, W.ix0 + (int)(e & 0xffu), W.iy0 + (int)((e >> 8) & 0xffu), (int)(e >> 16)); };
-        // queue B consumer: finite-difference gradient + accumulation for `cnt` active voxels
-        auto drain_B = [&](int cnt) {
-            if (lane < cnt) {
-                const double sdf = qBs[warp][lane];
-                const d3 d = entry_centre(qB[warp][lane]) - pos;
-                const d3 prel = rot_applyT(R, d);
-                const d3 g = shape_grad_analytic(A.shape, prel, sdf);
-                pair_accumulate(cfg, R, q, d, sdf, g, acc);
-            }
-            __syncwarp();
-            const int rest = nB - cnt;
-            uint32_t e2 = 0; double s2 = 0;
-            if (lane < rest) { e2 = qB[warp][cnt + lane]; s2 = qBs[warp][cnt + lane]; }
-            __syncwarp();
-            if (lane < rest) { qB[warp][lane] = e2; qBs[warp][lane] = s2; }
-            __syncwarp();
-            nB = rest;
-        };
-        // queue A consumer: SDF for `cnt` voxels inside the cull box
-        auto drain_A = [&](int cnt) {
-            bool active = false; uint32_t e = 0; double sdf = 0.0;
-            if (lane < cnt) {
-                e = qA[warp][lane];
-                const d3 prel = rot_applyT(R, entry_centre(e) - pos);
-                sdf = shape_sdf_analytic(A.shape, prel);
-                active = (cfg.safety - sdf) > 0.0;
-            }
-            __syncwarp();
-            const int rest = nA - cnt;
-            uint32_t e2 = 0;
-            if (lane < rest) e2 = qA[warp][cnt + lane];
-            __syncwarp();
-            if (lane < rest) qA[warp][lane] = e2;
-            nA = rest;
-            const unsigned bal = __ballot_sync(0xffffffffu, active);
-            if (active) { const int p = nB + __popc(bal & lt_mask); qB[warp][p] = e; qBs[warp][p] = sdf; }
-            nB += __popc(bal);
-            __syncwarp();
-            if (nB >= 32) drain_B(32);
-        };
+            auto entry_centre = [&](uint32_t e) { return voxel_centre(G, W.ix0 + (int)(e & 0x3ffu), W.iy0 + (int)((e >> 10) & 0x3ffu), W.iz0 + (int)(e >> 20)); };
+            // queue B consumer: finite-difference gradient + accumulation for `cnt` active voxels
+            auto drain_B = [&](int cnt) {
+                if (lane < cnt) {
+                    const double sdf = qBs[warp][lane];
+                    const d3 d = entry_centre(qB[warp][lane]) - pos;
+                    const d3 prel = rot_applyT(R, d);
+                    const d3 g = shape_grad_analytic(A.shape, prel, sdf);
+                    pair_accumulate(cfg, R, q, d, sdf, g, acc);
+                }
+                __syncwarp();
+                const int rest = nB - cnt;
+                uint32_t e2 = 0; double s2 = 0;
+                if (lane < rest) { e2 = qB[warp][cnt + lane]; s2 = qBs[warp][cnt + lane]; }
+                __syncwarp();
+                if (lane < rest) { qB[warp][lane] = e2; qBs[warp][lane] = s2; }
+                __syncwarp();
+                nB = rest;
+            };
+            // queue A consumer: SDF for `cnt` voxels inside the cull box
+            auto drain_A = [&](int cnt) {
+                bool active = false; uint32_t e = 0; double sdf = 0.0;
+                if (lane < cnt) {
+                    e = qA[warp][lane];
+                    const d3 prel = rot_applyT(R, entry_centre(e) - pos);
+                    sdf = shape_sdf_analytic(A.shape, prel);
+                    active = (cfg.safety - sdf) > 0.0;
+                }
+                __syncwarp();
+                const int rest = nA - cnt;
+                uint32_t e2 = 0;
+                if (lane < rest) e2 = qA[warp][cnt + lane];
+                __syncwarp();
+                if (lane < rest) qA[warp][lane] = e2;
+                nA = rest;
+                const unsigned bal = __ballot_sync(0xffffffffu, active);
+                if (active) { const int p = nB + __popc(bal & lt_mask); qB[warp][p] = e; qBs[warp][p] = sdf; }
+                nB += __popc(bal);
+                __syncwarp();
+                if (nB >= 32) drain_B(32);
+            };
 
-        scan_window(G, W, lane, -1, [&](bool valid, int vx, int vy, int vz, int) {
-            bool pass = false;
-            if (valid) {
-                const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
-                pass = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            npairs += __popc(bal);
-            if (pass) qA[warp][nA + __popc(bal & lt_mask)] = (uint32_t)(vx - W.ix0) | ((uint32_t)(vy - W.iy0) << 8) | ((uint32_t)vz << 16);
-            nA += __popc(bal);
-            __syncwarp();
-            if (nA >= 32) drain_A(32);
-        });
-        if (nA > 0) drain_A(nA);
-        if (nB > 0) drain_B(nB);
-        // xor butterfly: fixed order (analytic samples are never split: their work is near-uniform)
-        tot[0] = warp_sum(acc.c); tot[1] = warp_sum(acc.gx); tot[2] = warp_sum(acc.gy); tot[3] = warp_sum(acc.gz);
-        tot[4] = warp_sum(acc.q0); tot[5] = warp_sum(acc.q1); tot[6] = warp_sum(acc.q2); tot[7] = warp_sum(acc.q3);
+            scan_window(G, W, lane, [&](bool valid, int vx, int vy, int vz, int) {
+                bool pass = false;
+                if (valid) {
+                    const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
+                    pass = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                npairs += __popc(bal);
+                if (pass) qA[warp][nA + __popc(bal & lt_mask)] = (uint32_t)(vx - W.ix0) | ((uint32_t)(vy - W.iy0) << 10) | ((uint32_t)(vz - W.iz0) << 20);
+                nA += __popc(bal);
+                __syncwarp();
+                if (nA >= 32) drain_A(32);
+            });
+            if (nA > 0) drain_A(nA);
+            if (nB > 0) drain_B(nB);
+            // xor butterfly: fixed order (analytic samples are never split: their work is near-uniform)
+            const double t0 = warp_sum(acc.c), t1 = warp_sum(acc.gx), t2 = warp_sum(acc.gy), t3 = warp_sum(acc.gz);
+            const double t4 = warp_sum(acc.q0), t5 = warp_sum(acc.q1), t6 = warp_sum(acc.q2), t7 = warp_sum(acc.q3);
+            mine = lane == 0 ? t0 : lane == 1 ? t1 : lane == 2 ? t2 : lane == 3 ? t3 : lane == 4 ? t4 : lane == 5 ? t5 : lane == 6 ? t6 : t7;
+        }
+        sample_finish_whole(A, it, mine, npairs, t_begin, npairs);
+        __syncwarp();
     }
-    sample_finish(A, it, tot, npairs, t_begin, npairs);
 }
 
 // ============================================================================================================================
 // mesh shapes
+struct QRes { double ex, ey, ez, d2; int tri, feat; uint32_t code; int cls; };   // an answered voxel awaiting its deferred tail
+struct MeshWarpSmem {
+    double pose[16];                     // warp-uniform pose: pos 0..2, R rows 3..11, q (w, x, y, z) 12..15
+    double cacc[ROW_CLASSES][8];         // class accumulators
+    double vals[32][8];                  // deferred tails: one voxel's eight contributions per lane
+    QRes qr[32];
+    uint32_t vq[64];                     // ring of occupied-voxel codes (dx | dy << 10 | dz << 20, relative to the window origin)
+    WideStack stk;
+};
+
+__device__ __forceinline__ d3 smem_pos(const double *ps) { return mk3(ps[0], ps[1], ps[2]); }
+__device__ __forceinline__ rot3 smem_rot(const double *ps) {
+    rot3 R; R.r0 = mk3(ps[3], ps[4], ps[5]); R.r1 = mk3(ps[6], ps[7], ps[8]); R.r2 = mk3(ps[9], ps[10], ps[11]); return R;
+}
+
 __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
-    __shared__ WideStack wstack[DISC_WARPS];
-    __shared__ double cacc[DISC_WARPS][ROW_CLASSES][8];   // per-warp class accumulators
+    __shared__ MeshWarpSmem wsm[DISC_WARPS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const DevCfg &cfg = A.cfg;
     const DevMesh &Mh = A.shape.mesh;
+    const DevGrid &G = A.grid;
     const int K = cfg.K;
+    MeshWarpSmem &sm = wsm[warp];
+    const double h = cfg.half_bd, sf = cfg.safety;
     Item it;
-    if (!fetch_item(A, it)) return;
-    const int s = it.s;
-    const int i = s / (K + 1), j = s - i * (K + 1);
-    const double Ti = __ldg(A.T + i);
-    const double step = Ti * (1.0 / K);
-    const long long t_begin = A.dbg ? clock64() : 0;
-#ifdef ISDF_PHASE_TIMING
-    long long t_query = 0, t_pose = 0;
-#endif
-
-    d3 pos; quat4 q; rot3 R;
-    sample_pose(A, i, j, step, pos, q, R);
-#ifdef ISDF_PHASE_TIMING
-    t_pose = clock64() - t_begin;
-#endif
-
-    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned npairs = 0, nquery = 0;
-
-    if (cfg.flags & ISDF_WITH_COLLISION) {
-        const DevGrid &G = A.grid;
-        const double h = cfg.half_bd, sf = cfg.safety;
-        const Window W = window_of(G, pos, h);
+    while (next_item(A, it, lane)) {
+        const int s = it.s;
+        const int i = s / (K + 1), j = s - i * (K + 1);
+        const long long t_begin = A.dbg ? clock64() : 0;
+        unsigned npairs = 0, nquery = 0;
         const bool whole = (it.c1 - it.c0) == ROW_CLASSES;
-        if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) cacc[warp][c][lane] = 0.0;
-        __syncwarp();
-        // whole sample: one pass over all rows, contributions filed by row class; split part: only this class's rows.
-        // Either way a class sum adds the same terms in the same (row, z) order.
-        scan_window(G, W, lane, whole ? -1 : it.c0, [&](bool valid, int vx, int vy, int vz, int vr) {
-            bool pass = false, box = false;
-            int cell = -1;
-            if (valid) {
-                const d3 prel = rot_applyT(R, voxel_centre(G, vx, vy, vz) - pos);
-                box = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
-                // exact skips: outside the mesh AABB inflated by safety_hor, or in a cell whose every point is >= safety_hor away
-                pass = box && !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
-                                prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf) && !mesh_far(Mh, prel, sf, cell);
-            }
-            npairs += __popc(__ballot_sync(0xffffffffu, box));
-            unsigned bal = __ballot_sync(0xffffffffu, pass);
-#ifdef ISDF_PHASE_TIMING
-            const long long tq0 = clock64();
-#endif
-            while (bal) {   // one surviving voxel at a time, in voxel order
-                const int sl = __ffs(bal) - 1;
-                bal &= bal - 1;
-                nquery++;
-                const int ox = __shfl_sync(0xffffffffu, vx, sl), oy = __shfl_sync(0xffffffffu, vy, sl), oz = __shfl_sync(0xffffffffu, vz, sl);
-                const int cls = __shfl_sync(0xffffffffu, vr, sl) % ROW_CLASSES;
-                const int qcell = __shfl_sync(0xffffffffu, cell, sl);
-                const d3 d = voxel_centre(G, ox, oy, oz) - pos;
-                d3 g = mk3(0, 0, 0);
-                const double sdf = mesh_sdf_grad_warp(Mh, rot_applyT(R, d), sf, g, lane, &wstack[warp], qcell);
-                PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};   // identical on every lane
-                pair_accumulate(cfg, R, q, d, sdf, g, one);
-                if (lane < 8 && one.c > 0.0) {
-                    const double v = lane == 0 ? one.c : lane == 1 ? one.gx : lane == 2 ? one.gy : lane == 3 ? one.gz :
-                                     lane == 4 ? one.q0 : lane == 5 ? one.q1 : lane == 6 ? one.q2 : one.q3;
-                    cacc[warp][cls][lane] += v;
+
+        if (cfg.flags & ISDF_WITH_COLLISION) {
+            Window W;
+            {   // pose -> shared memory (every lane computes the same values; lane 0 publishes them)
+                const double Ti = __ldg(A.T + i);
+                d3 pos; quat4 q; rot3 R;
+                sample_pose(A, i, j, Ti * (1.0 / K), pos, q, R);
+                W = window_of(G, pos, h);
+                if (lane == 0) {
+                    double *ps = sm.pose;
+                    ps[0] = pos.x; ps[1] = pos.y; ps[2] = pos.z;
+                    ps[3] = R.r0.x; ps[4] = R.r0.y; ps[5] = R.r0.z; ps[6] = R.r1.x; ps[7] = R.r1.y; ps[8] = R.r1.z;
+                    ps[9] = R.r2.x; ps[10] = R.r2.y; ps[11] = R.r2.z;
+                    ps[12] = q.w; ps[13] = q.x; ps[14] = q.y; ps[15] = q.z;
                 }
             }
-#ifdef ISDF_PHASE_TIMING
-            t_query += clock64() - tq0;
-#endif
-        });
+            for (int k = lane; k < ROW_CLASSES * 8; k += 32) (&sm.cacc[0][0])[k] = 0.0;
+            __syncwarp();
+            const int ny = W.iy1 - W.iy0 + 1;
+            const int nrows = (W.ix1 - W.ix0 + 1) * ny;
+            int nq = 0, head = 0, nres = 0;   // voxel ring fill / head, answered voxels awaiting their tail (warp-uniform)
+
+            // deferred tails: sign, gradient, hinge, chain rule onto (position, quaternion) — one answered voxel per lane; the
+            // contributions are then added to the class accumulators in voxel order by lanes 0..7 (one per component)
+            auto flush_tails = [&]() __attribute__((always_inline)) {
+                __syncwarp();
+                bool active = false;
+                if (lane < nres) {
+                    const QRes r = sm.qr[lane];
+                    d3 g = mk3(0, 0, 0);
+                    const double sdf = mesh_finish(Mh, mk3(r.ex, r.ey, r.ez), r.d2, r.tri, r.feat, g);
+                    const double *ps = sm.pose;
+                    const d3 d = voxel_centre(G, W.ix0 + (int)(r.code & 0x3ffu), W.iy0 + (int)((r.code >> 10) & 0x3ffu), W.iz0 + (int)(r.code >> 20)) - smem_pos(ps);
+                    quat4 q; q.w = ps[12]; q.x = ps[13]; q.y = ps[14]; q.z = ps[15];
+                    PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};
+                    pair_accumulate(cfg, smem_rot(ps), q, d, sdf, g, one);
+                    active = one.c > 0.0;
+                    double *v = sm.vals[lane];
+                    v[0] = one.c; v[1] = one.gx; v[2] = one.gy; v[3] = one.gz; v[4] = one.q0; v[5] = one.q1; v[6] = one.q2; v[7] = one.q3;
+                }
+                unsigned act = __ballot_sync(0xffffffffu, active);
+                __syncwarp();
+                if (lane < 8) {
+                    while (act) {
+                        const int k = __ffs(act) - 1;
+                        act &= act - 1;
+                        sm.cacc[sm.qr[k].cls][lane] += sm.vals[k][lane];
+                    }
+                }
+                __syncwarp();
+                nres = 0;
+            };
+
+            // cull + search for the n oldest voxels of the ring (n <= 32)
+            auto process = [&](int n) __attribute__((always_inline)) {
+                bool pass = false, box = false;
+                int cell = -1;
+                uint32_t code = 0;
+                d3 prel = mk3(0, 0, 0);
+                if (lane < n) {
+                    code = sm.vq[(head + lane) & 63];
+                    const double *ps = sm.pose;
+                    const d3 d = voxel_centre(G, W.ix0 + (int)(code & 0x3ffu), W.iy0 + (int)((code >> 10) & 0x3ffu), W.iz0 + (int)(code >> 20)) - smem_pos(ps);
+                    prel = rot_applyT(smem_rot(ps), d);
+                    box = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
+                    // exact skips: outside the mesh AABB inflated by safety_hor, or in a cell whose every point is >= safety_hor away
+                    pass = box && !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
+                                    prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf) && !mesh_far(Mh, prel, sf, cell);
+                }
+                head = (head + n) & 63; nq -= n;
+                npairs += __popc(__ballot_sync(0xffffffffu, box));
+                unsigned bal = __ballot_sync(0xffffffffu, pass);
+                while (bal) {   // one surviving voxel at a time, in voxel order
+                    const int sl = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    nquery++;
+                    const d3 p = mk3(__shfl_sync(0xffffffffu, prel.x, sl), __shfl_sync(0xffffffffu, prel.y, sl), __shfl_sync(0xffffffffu, prel.z, sl));
+                    const int qcell = __shfl_sync(0xffffffffu, cell, sl);
+                    const uint32_t qcode = __shfl_sync(0xffffffffu, code, sl);
+                    double d2; d3 c = mk3(0, 0, 0); int tri, feat;
+                    if (mesh_search_warp(Mh, p, sf, lane, &sm.stk, qcell, d2, c, tri, feat)) {
+                        if (lane == 0) {
+                            QRes r;
+                            r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.d2 = d2; r.tri = tri; r.feat = feat; r.code = qcode;
+                            r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu)) % ROW_CLASSES);
+                            sm.qr[nres] = r;
+                        }
+                        if (++nres == 32) flush_tails();
+                    }
+                }
+            };
+
+            // Producer loop (one cull/search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
+            // are appended to the ring, and whenever 32 voxels are queued — or the window is exhausted — they are processed.
+            //   whole sample: a batch is 32 consecutive rows = 32 different classes; the lanes emit their rows' voxels round-robin
+            //                 (lowest z first), which keeps every CLASS's voxels in (row, z) order;
+            //   split part  : rows of the classes [c0, c1) only, emitted row by row so that a class's rows stay in ascending order.
+            const int w = it.c1 - it.c0;
+            const int nk = whole ? nrows : ((nrows + ROW_CLASSES - 1) / ROW_CLASSES) * w;   // row slots to visit per z-chunk
+            int zs = W.iz0, kb = -32;
+            uint32_t bits = 0, rowcode = 0;
+            unsigned pending = 0;
+            bool finished = false;
+            while (!finished || nq > 0) {
+                if (!finished) {
+                    if (pending == 0u) {   // next batch of rows
+                        kb += 32;
+                        if (kb >= nk) { kb = 0; zs += 32; }
+                        if (zs > W.iz1) finished = true;
+                        else {
+                            const int nzc = min(32, W.iz1 - zs + 1);
+                            const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
+                            const int k = kb + lane;
+                            const int r = whole ? k : (k / w) * ROW_CLASSES + it.c0 + (k % w);
+                            bits = 0;
+                            if (k < nk && r < nrows) {
+                                const int rx = r / ny, ry = r - rx * ny;
+                                bits = row_bits(G, W.ix0 + rx, W.iy0 + ry, zs, zmask);
+                                rowcode = (uint32_t)rx | ((uint32_t)ry << 10) | ((uint32_t)(zs - W.iz0) << 20);
+                            }
+                            pending = __ballot_sync(0xffffffffu, bits != 0u);
+                        }
+                    } else if (whole) {    // one round: every lane that still has voxels emits its lowest one
+                        if (bits != 0u) {
+                            const int z = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            sm.vq[(head + nq + __popc(pending & lt_mask)) & 63] = rowcode + ((uint32_t)z << 20);
+                        }
+                        nq += __popc(pending);
+                        pending = __ballot_sync(0xffffffffu, bits != 0u);
+                    } else {               // one row: lane z emits voxel z of the row
+                        const int src = __ffs(pending) - 1;
+                        pending &= pending - 1;
+                        const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
+                        const uint32_t rc = __shfl_sync(0xffffffffu, rowcode, src);
+                        if ((b >> lane) & 1u) sm.vq[(head + nq + __popc(b & lt_mask)) & 63] = rc + ((uint32_t)lane << 20);
+                        nq += __popc(b);
+                    }
+                    __syncwarp();
+                }
+                if (nq >= 32 || (finished && nq > 0)) process(min(nq, 32));
+            }
+            if (nres > 0) flush_tails();
+            __syncwarp();
+            // sample (or part) total: class sums added in class order
+            if (whole) {
+                double mine = 0.0;
+                if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) mine += sm.cacc[c][lane];
+                sample_finish_whole(A, it, mine, npairs, t_begin, 64u * nquery + npairs);
+            } else {
+                double *sub = A.subsum + (size_t)it.hslot * ROW_CLASSES * 8;
+                if (lane < 8) for (int c = it.c0; c < it.c1; c++) sub[c * 8 + lane] = sm.cacc[c][lane];
+                if (lane == 0) {
+                    if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
+                    atomicAdd(A.split_work + it.hslot, 64u * nquery + npairs);
+                    A.sample_slot[s] = it.hslot;   // every part writes the same slot
+                }
+            }
+        } else {
+            sample_finish_whole(A, it, 0.0, 0u, t_begin, 0u);
+        }
         __syncwarp();
-        // sample (or part) total: class sums added in class order
-        double mine = 0.0;
-        if (lane < 8) for (int c = it.c0; c < it.c1; c++) mine += cacc[warp][c][lane];
-#pragma unroll
-        for (int v = 0; v < 8; v++) tot[v] = __shfl_sync(0xffffffffu, mine, v);
     }
-#ifdef ISDF_PHASE_TIMING
-    if (A.dbg && lane == 0 && it.hslot < 0) {   // whole samples only: {total set later, pose+scan cycles, query cycles} and counts in the upper bits
-        const long long t_scan_end = clock64() - t_begin;
-        A.dbg[3 * (size_t)s + 1] = ((unsigned long long)nquery << 40) | (unsigned long long)(t_scan_end - t_query);
-        A.dbg[3 * (size_t)s + 2] = ((unsigned long long)npairs << 40) | (unsigned long long)t_query;
-        (void)t_pose;
-    }
-#endif
-    sample_finish(A, it, tot, npairs, t_begin, 64u * nquery + npairs);
 }
 
 
-// Work items for the next evaluation: bucket sort by reported work, descending. A sample is split into ROW_CLASSES items
-// (work/ROW_CLASSES each) only when it alone would outlast the launch's balanced share: work > 0.7 * total / warp_slots —
-// with one GPU almost nothing is split (splitting costs redundant pose + sparse row scans), with the samples sharded
-// over 8 GPUs the same trajectory has 8x less work per GPU and its heavy samples are spread over 8 warps each. Placement inside a bucket uses
-// shared-memory atomics: the order only decides WHICH warp takes WHICH item, never the arithmetic, so results stay
-// bit-reproducible. One CTA, ~10 us, off the critical path of the evaluation that produced `work`.
+// Work items for the next evaluation: bucket sort by reported work, descending. A sample is split into f = 2..32 items (each a
+// contiguous range of 32/f row classes, work/f each) only when it alone would outlast the launch's balanced share:
+// work > thr = 0.7 * total / warp_slots, f = the power of two that brings a part down to ~thr. With one GPU almost nothing is
+// split (splitting costs redundant pose work and sparse row scans); with the samples sharded over 8 GPUs the same trajectory has
+// 8x less work per GPU and its heavy samples are spread over up to 32 warps each. Placement inside a bucket uses shared-memory
+// atomics: the order only decides WHICH warp takes WHICH item, never the arithmetic, so results stay bit-reproducible.
+// One CTA, ~10 us, off the critical path of the evaluation that produced `work`.
 constexpr int ORDER_BUCKETS = 1024;
 __device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 3, (unsigned)ORDER_BUCKETS - 1u); }
 __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots,
@@ -564,7 +694,8 @@ __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int 
     __shared__ int cursor[ORDER_BUCKETS];
     __shared__ int nsplit;
     __shared__ unsigned long long total_work;
-    __shared__ unsigned split_work;
+    __shared__ unsigned split_thr;
+    int *scratch = items + 3 * ((size_t)M + (size_t)(ROW_CLASSES - 1) * max_split);   // behind the item table: per sample (slot << 6) | f, or -1
     hist[threadIdx.x] = 0; cursor[threadIdx.x] = 0;
     if (threadIdx.x == 0) { nsplit = 0; total_work = 0ull; }
     __syncthreads();
@@ -587,20 +718,27 @@ __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int 
         for (; b >= 0; b--) { if (cum + cursor[b] > max_split) break; cum += cursor[b]; }
         if (b >= 0) thr = max(thr, (unsigned)(b + 1) << 3);   // buckets above b fit into the split slots
         if (b == ORDER_BUCKETS - 1) thr = 0xffffffffu;        // even the top bucket alone overflows: no splitting
-        split_work = thr;
+        split_thr = thr;
     }
     __syncthreads();
     cursor[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned SPLIT_WORK = split_work;
-    // pass 1: decide splits (first come first served up to max_split), histogram the item keys
+    const unsigned THR = split_thr;
+    // pass 1: decide splits (first come first served up to max_split) and their factor, histogram the item keys
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         const unsigned w = work[rank + world * m];
-        int hs = -1;
-        if (w >= SPLIT_WORK) { hs = atomicAdd(&nsplit, 1); if (hs >= max_split) hs = -1; }
-        if (hs >= 0) atomicAdd(&hist[order_bucket(w / ROW_CLASSES)], ROW_CLASSES);
-        else atomicAdd(&hist[order_bucket(w)], 1);
-        items[3 * (size_t)(M + (ROW_CLASSES - 1) * max_split) + m] = hs;   // scratch behind the item table
+        int code = -1;
+        if (w >= THR) {
+            const int hs = atomicAdd(&nsplit, 1);
+            if (hs < max_split) {
+                int f = 2;
+                while (f < ROW_CLASSES && (unsigned long long)THR * (unsigned)f < (unsigned long long)w) f <<= 1;
+                code = (hs << 6) | f;
+                atomicAdd(&hist[order_bucket(w / (unsigned)f)], f);
+            }
+        }
+        if (code < 0) atomicAdd(&hist[order_bucket(w)], 1);
+        scratch[m] = code;
     }
     __syncthreads();
     if (threadIdx.x < 32) {   // exclusive scan over buckets in DESCENDING bucket order
@@ -616,15 +754,27 @@ __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int 
     __syncthreads();
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         const unsigned w = work[rank + world * m];
-        const int hs = items[3 * (size_t)(M + (ROW_CLASSES - 1) * max_split) + m];
-        if (hs >= 0) {
-            const int pos = atomicAdd(&cursor[order_bucket(w / ROW_CLASSES)], ROW_CLASSES);
-            for (int c = 0; c < ROW_CLASSES; c++) { items[3 * (pos + c)] = m; items[3 * (pos + c) + 1] = c; items[3 * (pos + c) + 2] = hs; }
+        const int code = scratch[m];
+        if (code >= 0) {
+            const int hs = code >> 6, f = code & 63, cw = ROW_CLASSES / f;
+            const int pos = atomicAdd(&cursor[order_bucket(w / (unsigned)f)], f);
+            for (int p = 0; p < f; p++) { items[3 * (pos + p)] = m; items[3 * (pos + p) + 1] = (p * cw) | ((p * cw + cw) << 8); items[3 * (pos + p) + 2] = hs; }
         } else {
             const int pos = atomicAdd(&cursor[order_bucket(w)], 1);
             items[3 * pos] = m; items[3 * pos + 1] = -1; items[3 * pos + 2] = -1;
         }
     }
 }
+#endif  // ISDF_DISCRETE_TU
+
+// ---- launch interface of the discrete translation unit (isdf_discrete_tu.cu) ------------------------------------------------------
+cudaError_t discrete_launch_scan(const DiscArgs &A, bool mesh, unsigned grid, cudaStream_t st);
+cudaError_t discrete_launch_epilogue(const DiscArgs &A, cudaStream_t st);
+cudaError_t discrete_launch_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots, int *items,
+                                        int *item_count, cudaStream_t st);
+// resident CTAs per SM of the scan kernels (occupancy API); also the "can this image run here" probe of isdf_create
+cudaError_t discrete_resident_blocks(int *mesh_blocks, int *analytic_blocks);
+// diagnostics: the device flatness map / adjoint exactly as the epilogue compiles it (tests pin it to the reference's flatness.hpp)
+cudaError_t discrete_launch_dbg_flatness(const FlatParams &fp, int n, const double *vaj, const double *grads, double *out, cudaStream_t st);
 
 }  // namespace isdf

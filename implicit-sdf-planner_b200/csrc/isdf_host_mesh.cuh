@@ -136,11 +136,19 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
     detail::build_rec(bn, order, 0, nF, tv, cen);
     // leaf-ordered triangle + pseudonormal arrays
     out.ntris = nF;
-    out.tris.resize((size_t)9 * nF); out.pnormals.resize((size_t)21 * nF);
+    out.tris.assign((size_t)TRI_STRIDE * nF, 0.0); out.pnormals.resize((size_t)21 * nF);
     for (int pos = 0; pos < nF; pos++) {
         const int t = order[pos];
-        double *T = &out.tris[(size_t)9 * pos];
+        double *T = &out.tris[(size_t)TRI_STRIDE * pos];
         for (int a = 0; a < 3; a++) { T[a] = tv[t][a]; T[3 + a] = tv[t][3 + a] - tv[t][a]; T[6 + a] = tv[t][6 + a] - tv[t][a]; }
+        {   // Gram entries and the reciprocal denominators of the division-free closest-point test (isdf_mesh.cuh, TRI_STRIDE)
+            const double abab = T[3] * T[3] + T[4] * T[4] + T[5] * T[5], abac = T[3] * T[6] + T[4] * T[7] + T[5] * T[8],
+                         acac = T[6] * T[6] + T[7] * T[7] + T[8] * T[8];
+            const double bcbc = (abab - abac) + (acac - abac), det = abab * acac - abac * abac;
+            T[9] = abab; T[10] = abac; T[11] = acac;
+            T[12] = abab > 0.0 ? 1.0 / abab : 0.0; T[13] = acac > 0.0 ? 1.0 / acac : 0.0; T[14] = bcbc > 0.0 ? 1.0 / bcbc : 0.0;
+            T[15] = det > 0.0 ? 1.0 / det : 0.0;
+        }
         double *Pn = &out.pnormals[(size_t)21 * pos];
         for (int a = 0; a < 3; a++) Pn[a] = fn[t][a];
         for (int k = 0; k < 3; k++) {  // edges ab, bc, ca
@@ -222,7 +230,7 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
             double n[3] = {0, 0, 0}, le[3] = {0, 0, 0}, le2 = -1.0;
             std::vector<std::array<double, 3>> pts;
             for (int t = b.first; t < b.first + b.count; t++) {
-                const double *T = &out.tris[(size_t)9 * t];
+                const double *T = &out.tris[(size_t)TRI_STRIDE * t];
                 const double A[3] = {T[0], T[1], T[2]}, B[3] = {T[0] + T[3], T[1] + T[4], T[2] + T[5]}, Cc[3] = {T[0] + T[6], T[1] + T[7], T[2] + T[8]};
                 pts.push_back({A[0], A[1], A[2]}); pts.push_back({B[0], B[1], B[2]}); pts.push_back({Cc[0], Cc[1], Cc[2]});
                 n[0] += T[4] * T[8] - T[5] * T[7]; n[1] += T[5] * T[6] - T[3] * T[8]; n[2] += T[3] * T[7] - T[4] * T[6];

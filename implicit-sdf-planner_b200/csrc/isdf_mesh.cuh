@@ -33,7 +33,7 @@ struct WideNode {           // 1664 bytes
 struct DevMesh {
     const BvhNode *nodes;   // nodes[0] is the root (a single-leaf mesh still gets one node with right = left)
     const WideNode *wnodes; // wnodes[0] is the root of the 32-ary tree
-    const double *tris;     // 9 doubles per triangle in leaf order: a, ab, ac
+    const double *tris;     // TRI_STRIDE doubles per triangle in leaf order: a, ab, ac, Gram entries, reciprocal denominators
     const double *pnormals; // 21 doubles per triangle: face, edge ab, edge bc, edge ca, vertex a, b, c
     // oriented box of every 32-ary-tree leaf, 15 doubles at index first_tri: centre, three unit axes (leaf normal first), half
     // extents. A leaf is a handful of adjacent triangles, i.e. a nearly flat patch: the oriented box is ~1 mm thick where the
@@ -58,6 +58,14 @@ struct DevMesh {
     double sign_radius;     // a point with no triangle within this distance shares its cell centre's sign (0 = unusable)
     double blo[3], bhi[3];  // mesh AABB
 };
+
+// Triangle record, TRI_STRIDE doubles (128 B = four 32-byte sectors, 32-byte aligned), in leaf order:
+//   [0..2] a   [3..5] ab = b-a   [6..8] ac = c-a   [9] ab.ab  [10] ab.ac  [11] ac.ac
+//   [12] 1/ab.ab  [13] 1/ac.ac  [14] 1/|bc|^2  [15] 1/(ab.ab ac.ac - (ab.ac)^2)      (0 where the denominator is 0)
+// The Gram entries turn four of the six dot products of the closest-point test into subtractions, and every quotient of the
+// test has a per-triangle constant denominator (d1-d3 = ab.ab, d2-d6 = ac.ac, (d4-d3)+(d5-d6) = |bc|^2, va+vb+vc = Gram
+// determinant), so the division-free form tri_closest_rec_fast needs no FP64 division at all.
+constexpr int TRI_STRIDE = 16;
 
 ISDF_HD double box_dist2(const double *b, d3 p) {
     const double ex = fmax(fmax(b[0] - p.x, p.x - b[3]), 0.0);
@@ -92,6 +100,47 @@ ISDF_HD d3 tri_closest(d3 p, d3 a, d3 ab, d3 ac, int &feat) {
     return mk3(a.x + (s * ab.x + t * ac.x), a.y + (s * ab.y + t * ac.y), a.z + (s * ab.z + t * ac.z));
 }
 
+// Same classification on a TRI_STRIDE record with the precomputed Gram entries / reciprocals: ~45 FP64 operations, no division.
+// Differs from tri_closest by rounding only (1e-16 relative); used where no sequential decision replays the oracle bit for bit
+// (the discrete path; ISDF_FAST_TRI), tri_closest stays in the swept-volume search.
+ISDF_HD d3 tri_closest_rec_fast(d3 p, const double *T, int &feat) {
+#ifdef __CUDA_ARCH__
+    const double2 *T2 = reinterpret_cast<const double2 *>(T);
+    const double2 r0 = __ldg(T2), r1 = __ldg(T2 + 1), r2 = __ldg(T2 + 2), r3 = __ldg(T2 + 3), r4 = __ldg(T2 + 4), r5 = __ldg(T2 + 5),
+                  r6 = __ldg(T2 + 6), r7 = __ldg(T2 + 7);
+    const d3 a = mk3(r0.x, r0.y, r1.x), ab = mk3(r1.y, r2.x, r2.y), ac = mk3(r3.x, r3.y, r4.x);
+    const double abab = r4.y, abac = r5.x, acac = r5.y, i_ab = r6.x, i_ac = r6.y, i_bc = r7.x, i_det = r7.y;
+#else
+    const d3 a = mk3(T[0], T[1], T[2]), ab = mk3(T[3], T[4], T[5]), ac = mk3(T[6], T[7], T[8]);
+    const double abab = T[9], abac = T[10], acac = T[11], i_ab = T[12], i_ac = T[13], i_bc = T[14], i_det = T[15];
+#endif
+    const d3 ap = p - a;
+    const double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    const double d3_ = d1 - abab, d4 = d2 - abac, d5 = d1 - abac, d6 = d2 - acac;
+    const double vc = d1 * d4 - d3_ * d2, vb = d5 * d2 - d1 * d6, va = d3_ * d6 - d5 * d4;
+    const double e43 = d4 - d3_, e56 = d5 - d6;
+    const double tab = d1 * i_ab, tac = d2 * i_ac, tbc = e43 * i_bc;
+    double s = vb * i_det, t = vc * i_det;
+    int f = 0;
+    if (va <= 0.0 && e43 >= 0.0 && e56 >= 0.0) { s = 1.0 - tbc; t = tbc; f = 2; }
+    if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { s = 0.0; t = tac; f = 3; }
+    if (d6 >= 0.0 && d5 <= d6) { s = 0.0; t = 1.0; f = 6; }
+    if (vc <= 0.0 && d1 >= 0.0 && d3_ <= 0.0) { s = tab; t = 0.0; f = 1; }
+    if (d3_ >= 0.0 && d4 <= d3_) { s = 1.0; t = 0.0; f = 5; }
+    if (d1 <= 0.0 && d2 <= 0.0) { s = 0.0; t = 0.0; f = 4; }
+    feat = f;
+    return mk3(a.x + (s * ab.x + t * ac.x), a.y + (s * ab.y + t * ac.y), a.z + (s * ab.z + t * ac.z));
+}
+
+// closest point of triangle record T (TRI_STRIDE doubles) to p
+ISDF_HD d3 tri_closest_rec(d3 p, const double *T, int &feat) {
+#ifdef ISDF_FAST_TRI
+    return tri_closest_rec_fast(p, T, feat);
+#else
+    return tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), feat);
+#endif
+}
+
 // Exact nearest triangle within sqrt(bound2). Returns squared distance (bound2 if none found; tri = -1).
 // "while-while" traversal: every lane first descends through internal nodes until it holds a leaf, then all lanes of the
 // warp test their leaves together — the long triangle test is not serialised against other lanes' box tests.
@@ -123,9 +172,9 @@ __host__ __device__ inline double mesh_closest(const DevMesh &M, d3 p, double bo
             const int code = ~cur;
             const int first = code >> 2, cnt = (code & 3) + 1;
             for (int t = first; t < first + cnt; t++) {
-                const double *T = M.tris + 9 * (size_t)t;
+                const double *T = M.tris + TRI_STRIDE * (size_t)t;
                 int f;
-                const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+                const d3 q = tri_closest_rec(p, T, f);
                 const d3 e = p - q;
                 const double dd = dot3(e, e);
                 if (dd < best) { best = dd; cbest = q; tri = t; feat = f; }
@@ -167,9 +216,9 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
         double bd = 1e300;
         for (int k = 0; k < cnt; k++) {
             const int t = (int)M.cand[off + k];
-            const double *T = M.tris + 9 * (size_t)t;
+            const double *T = M.tris + TRI_STRIDE * (size_t)t;
             int f;
-            const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+            const d3 q = tri_closest_rec(p, T, f);
             const d3 e = p - q;
             const double dd = dot3(e, e);
             if (dd < bd) { bd = dd; c = q; tri = t; feat = f; }
@@ -186,8 +235,8 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
     double seed_d2 = 1e300;
     if (cell >= 0) {
         const int st = (int)M.cell_seed[cell];
-        const double *T = M.tris + 9 * (size_t)st;
-        const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), feat);
+        const double *T = M.tris + TRI_STRIDE * (size_t)st;
+        const d3 q = tri_closest_rec(p, T, feat);
         const d3 e = p - q;
         seed_d2 = dot3(e, e); c = q; tri = st;
     }
@@ -238,9 +287,9 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
     tri = -1; feat = 0;
     const unsigned lt_mask = (1u << lane) - 1u;
     if (seed >= 0) {   // every lane evaluates the seed triangle (uniform): a tight bound before the first node is opened
-        const double *T = M.tris + 9 * (size_t)seed;
+        const double *T = M.tris + TRI_STRIDE * (size_t)seed;
         int f;
-        const d3 q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+        const d3 q = tri_closest_rec(p, T, f);
         const d3 e = p - q;
         const double dd = dot3(e, e);
         if (dd < best) { best = dd; cbest = q; tri = seed; feat = f; }
@@ -278,9 +327,9 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
                     const int code = ~stk->leaf[idx];
                     const int first = code >> 3, cnt = (code & 7) + 1;
                     for (int k = slot; k < cnt; k += 4) {   // leaves of up to 8 triangles: slots take triangle k and k+4
-                        const double *T = M.tris + 9 * (size_t)(first + k);
+                        const double *T = M.tris + TRI_STRIDE * (size_t)(first + k);
                         int ff;
-                        const d3 qq = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ff);
+                        const d3 qq = tri_closest_rec(p, T, ff);
                         const d3 e = p - qq;
                         const double d = dot3(e, e);
                         if (d < dd) { dd = d; q = qq; f = ff; t = first + k; }
@@ -354,9 +403,9 @@ __device__ __forceinline__ void wide_range(const DevMesh &M, d3 c, double R2, in
                 const int first = code >> 3, cnt = (code & 7) + 1;
                 if (slot < cnt) {
                     t = first + slot;
-                    const double *T = M.tris + 9 * (size_t)t;
+                    const double *T = M.tris + TRI_STRIDE * (size_t)t;
                     int ff;
-                    const d3 q = tri_closest(c, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ff);
+                    const d3 q = tri_closest_rec(c, T, ff);
                     const d3 e = c - q;
                     hit = dot3(e, e) <= R2;
                 }
@@ -378,68 +427,90 @@ __device__ __forceinline__ void wide_range(const DevMesh &M, d3 c, double R2, in
     }
 }
 
-// Warp-cooperative nearest triangle from a cell's candidate list: lanes test 32 candidates per pass, REDUX arg-min.
+// arg-min step shared by the cooperative searches: every lane offers (dd, q, t, f); if the warp's smallest dd beats `best` the
+// winner's values are broadcast. 32-bit order-preserving key (float rounded down) + one REDUX; exact tie-break among equal keys.
+__device__ __forceinline__ void warp_argmin_update(double dd, d3 q, int t, int f, double &best, d3 &cbest, int &tri, int &feat) {
+    const bool candd = dd < best;
+    const unsigned key = candd ? __float_as_uint(__double2float_rd(dd)) : 0xffffffffu;
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+    if (kmin != 0xffffffffu) {
+        unsigned tied = __ballot_sync(0xffffffffu, candd && key == kmin);
+        int win = __ffs(tied) - 1;
+        double wd = __shfl_sync(0xffffffffu, dd, win);
+        tied &= tied - 1;
+        while (tied) {   // rare: several lanes within one float ulp
+            const int o = __ffs(tied) - 1;
+            tied &= tied - 1;
+            const double od = __shfl_sync(0xffffffffu, dd, o);
+            if (od < wd) { wd = od; win = o; }
+        }
+        best = wd;
+        cbest = mk3(__shfl_sync(0xffffffffu, q.x, win), __shfl_sync(0xffffffffu, q.y, win), __shfl_sync(0xffffffffu, q.z, win));
+        tri = __shfl_sync(0xffffffffu, t, win);
+        feat = __shfl_sync(0xffffffffu, f, win);
+    }
+}
+
+// Warp-cooperative nearest triangle from a cell's candidate list: lanes test 32 candidates per pass (64 — two independent
+// closest-point chains per lane — while more than 32 remain), REDUX arg-min.
 __device__ __forceinline__ double list_closest(const DevMesh &M, d3 p, int cell, d3 &cbest, int &tri, int &feat, int lane) {
     const uint32_t off = M.cell_off[cell];
     const int cnt = (int)M.cell_cnt[cell];
     double best = 1e300;
     tri = -1; feat = 0;
-    for (int base = 0; base < cnt; base += 32) {
+    int base = 0;
+#ifdef ISDF_FAST_TRI
+    for (; base + 32 < cnt; base += 64) {   // two candidates per lane: the second chain hides the first one's latency
+        const int k1 = base + 32 + lane;
+        const int t0 = (int)__ldg(M.cand + off + base + lane);
+        const int t1 = (k1 < cnt) ? (int)__ldg(M.cand + off + k1) : t0;
+        int f0, f1;
+        const d3 q0 = tri_closest_rec(p, M.tris + TRI_STRIDE * (size_t)t0, f0);
+        const d3 q1 = tri_closest_rec(p, M.tris + TRI_STRIDE * (size_t)t1, f1);
+        const d3 e0 = p - q0, e1 = p - q1;
+        const double dd0 = dot3(e0, e0), dd1 = dot3(e1, e1);
+        const bool second = dd1 < dd0;
+        warp_argmin_update(second ? dd1 : dd0, second ? q1 : q0, second ? t1 : t0, second ? f1 : f0, best, cbest, tri, feat);
+    }
+#endif
+    for (; base < cnt; base += 32) {
         double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0, t = -1;
         if (base + lane < cnt) {
             t = (int)__ldg(M.cand + off + base + lane);
-            const double *T = M.tris + 9 * (size_t)t;
-            q = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), f);
+            const double *T = M.tris + TRI_STRIDE * (size_t)t;
+            q = tri_closest_rec(p, T, f);
             const d3 e = p - q;
             dd = dot3(e, e);
         }
-        const bool candd = dd < best;
-        const unsigned key = candd ? __float_as_uint(__double2float_rd(dd)) : 0xffffffffu;
-        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-        if (kmin != 0xffffffffu) {
-            unsigned tied = __ballot_sync(0xffffffffu, candd && key == kmin);
-            int win = __ffs(tied) - 1;
-            double wd = __shfl_sync(0xffffffffu, dd, win);
-            tied &= tied - 1;
-            while (tied) {
-                const int o = __ffs(tied) - 1;
-                tied &= tied - 1;
-                const double od = __shfl_sync(0xffffffffu, dd, o);
-                if (od < wd) { wd = od; win = o; }
-            }
-            best = wd;
-            cbest = mk3(__shfl_sync(0xffffffffu, q.x, win), __shfl_sync(0xffffffffu, q.y, win), __shfl_sync(0xffffffffu, q.z, win));
-            tri = __shfl_sync(0xffffffffu, t, win);
-            feat = __shfl_sync(0xffffffffu, f, win);
-        }
+        warp_argmin_update(dd, q, t, f, best, cbest, tri, feat);
     }
     return best;
 }
 
-// Warp-cooperative getSDFwithGrad1 for the mesh shape — same contract as mesh_sdf_grad, all lanes get the same answer.
-// known_cell: cell index already looked up by the caller (and known not to be "far"), or -2 to look it up here.
-__device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk, int known_cell = -2) {
-    d3 c = mk3(0, 0, 0);
-    int tri, feat, cell = known_cell;
-    double d2;
+// Search half of getSDFwithGrad1 for the mesh shape, warp-cooperative: closest triangle of p (cell = p's cell index, or -1
+// outside the grid; the caller has already ruled out "far"). Returns false when nothing lies within `reach` and p is outside
+// (sdf >= reach: the caller's hinge / range test is inactive); otherwise (d2, c, tri, feat), identical on every lane.
+__device__ __forceinline__ bool mesh_search_warp(const DevMesh &M, d3 p, double reach, int lane, WideStack *stk, int cell,
+                                                 double &d2, d3 &c, int &tri, int &feat) {
     const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
-    if (known_cell == -2) {
-        const bool far = mesh_far(M, p, reach, cell);
-        if (bounded && far) return reach;
-    }
     const int seed = (cell >= 0) ? (int)M.cell_seed[cell] : -1;
     if (cell >= 0 && M.cell_cnt && M.cell_cnt[cell] != 0) {
         d2 = list_closest(M, p, cell, c, tri, feat, lane);       // exact: the list holds every possible closest triangle
     } else if (bounded) {
         d2 = wide_closest(M, p, reach * reach, seed, c, tri, feat, lane, stk);
         if (tri < 0) {
-            if (!mesh_cell_inside(M, cell)) return reach;
+            if (!mesh_cell_inside(M, cell)) return false;
             d2 = wide_closest(M, p, 1e300, seed, c, tri, feat, lane, stk);
         }
     } else {
         d2 = wide_closest(M, p, 1e300, seed, c, tri, feat, lane, stk);
     }
-    const d3 e = p - c;
+    return true;
+}
+
+// Sign + gradient half (Shape.cpp:139-151): e = p - closest point; sdf = s * dist, grad = normalise(s * e), s = ±1 from the
+// angle-weighted pseudonormal of the closest feature.
+__device__ __forceinline__ double mesh_finish(const DevMesh &M, d3 e, double d2, int tri, int feat, d3 &g) {
     const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
     double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
     if (side == 0.0) {
@@ -449,6 +520,21 @@ __device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, dou
     const double s = (side < 0.0) ? -1.0 : 1.0;
     g = unit3(s * e);
     return s * sqrt(d2);
+}
+
+// Warp-cooperative getSDFwithGrad1 for the mesh shape — same contract as mesh_sdf_grad, all lanes get the same answer.
+// known_cell: cell index already looked up by the caller (and known not to be "far"), or -2 to look it up here.
+__device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk, int known_cell = -2) {
+    d3 c = mk3(0, 0, 0);
+    int tri, feat, cell = known_cell;
+    double d2;
+    if (known_cell == -2) {
+        const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+        const bool far = mesh_far(M, p, reach, cell);
+        if (bounded && far) return reach;
+    }
+    if (!mesh_search_warp(M, p, reach, lane, stk, cell, d2, c, tri, feat)) return reach;
+    return mesh_finish(M, p - c, d2, tri, feat, g);
 }
 
 }  // namespace isdf

@@ -46,25 +46,30 @@ __device__ __forceinline__ void peer_allreduce_block(const PeerArgs &P, double *
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < P.world) st_release_sys(P.flags[threadIdx.x] + par * PEER_MAX + P.rank, P.epoch);
+    int timed_out = 0;
     if ((int)threadIdx.x < P.world) {
         const unsigned long long *f = P.flags[P.rank] + par * PEER_MAX + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) != P.epoch) {
-            if (clock64() - t0 > 4000000000ll) { *P.status = 1; break; }   // ~2 s: a peer never arrived — fail loudly, do not hang
+            if (clock64() - t0 > 4000000000ll) { *P.status = 1; timed_out = 1; break; }   // ~2 s: a peer never arrived — fail loudly, do not hang
             __nanosleep(64);
         }
     }
-    __syncthreads();
+    // a time-out must never hand partial sums to the optimiser: the whole vector (cost first) becomes NaN, which is the header's
+    // contract for a failed evaluation; the host entry points additionally read *P.status and return ISDF_ERR_CUDA
+    const bool failed = __syncthreads_or(timed_out) != 0;
     const double *mine = P.slots[P.rank] + (size_t)par * P.world * P.cap;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         double s = 0.0;
         for (int p = 0; p < P.world; p++) s += __ldcv(mine + (size_t)p * P.cap + k);
-        vec[k] = s;
+        vec[k] = failed ? __longlong_as_double(0x7ff8000000000000ll) : s;
     }
 }
 
+#ifndef ISDF_DISCRETE_TU   // instantiated once, in isdf_api.cu
 __global__ void __launch_bounds__(512) k_peer_allreduce(const __grid_constant__ PeerArgs P, double *vec, int n) {
     peer_allreduce_block(P, vec, n);
 }
+#endif
 
 }  // namespace isdf

@@ -41,7 +41,7 @@ __device__ __forceinline__ d3 shape_pre(const DevShape &S, d3 p) {
 }
 
 // getonlySDF for the analytic kinds (mesh handled by the caller). p_in is the body-frame query point.
-__device__ double shape_sdf_analytic(const DevShape &S, d3 p_in) {
+static __device__ double shape_sdf_analytic(const DevShape &S, d3 p_in) {
     if (S.kind == ISDF_SHAPE_BALL) return len3(p_in) - S.par[0];   // Shape.hpp:616-619
     if (S.kind == ISDF_SHAPE_POINT) return len3(p_in);             // Shape.hpp:647-650
     const d3 p = shape_pre(S, p_in);

@@ -62,7 +62,7 @@ def default_config_values():
     c.vmax, c.omgmax, c.thetamax = 10, 10, 100.0
     c.weight_v, c.weight_p, c.weight_omg, c.weight_theta = 1000.0, 4000.0, 1000.0, 1000.0
     c.smoothing_eps, c.safety_hor, c.occupancy_resolution = 1e-2, 0.866, 1.0
-    c.kernel_size, c.integral_intervs, c.threads_num, c.flags = 13, 64, 30, WITH_DYNAMICS | WITH_COLLISION
+    c.kernel_size, c.integral_intervs, c.threads_num, c.flags = 13, 64, 30, WITH_DYNAMICS   # discrete collision term: opt-in
     return c
 
 
@@ -353,3 +353,31 @@ class Evaluator:
         s = Stats()
         self._check(self.lib.isdf_get_stats(self.h, C.byref(s)))
         return s
+
+    # ---- diagnostics (isdf_dbg_*: exported by the library, not part of include/isdf.h) ----
+    def dbg_schedule(self, natural_order=False, warp_slots=0):
+        """natural_order: every launch as a context's first one (no work items, nothing split); warp_slots > 0: build the work items as
+        if the device had that many resident warps (small values force heavy samples to be split)."""
+        vp = C.c_void_p
+        self.lib.isdf_dbg_schedule.argtypes = [vp, C.c_int, C.c_int]
+        if self.lib.isdf_dbg_schedule(self.h, int(natural_order), int(warp_slots)) != 0:
+            raise IsdfError(-1, "isdf_dbg_schedule failed")
+
+    def dbg_item_stats(self):
+        n, parts = C.c_int(0), C.c_int(0)
+        self.lib.isdf_dbg_item_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        if self.lib.isdf_dbg_item_stats(self.h, C.byref(n), C.byref(parts)) != 0:
+            raise IsdfError(-1, "isdf_dbg_item_stats failed")
+        return n.value, parts.value
+
+    def dbg_flatness(self, v, a, j, quat_grad, omg_grad, vel_grad):
+        """device flatness map + adjoint as compiled into the epilogue kernel -> (quat, omg, gV, gA, gJ)"""
+        vaj = np.ascontiguousarray(np.concatenate([_f64(v).reshape(-1, 3), _f64(a).reshape(-1, 3), _f64(j).reshape(-1, 3)], axis=1))
+        gr = np.ascontiguousarray(np.concatenate([_f64(quat_grad).reshape(-1, 4), _f64(omg_grad).reshape(-1, 3), _f64(vel_grad).reshape(-1, 3)], axis=1))
+        n = vaj.shape[0]
+        out = np.zeros((n, 16))
+        dp = C.POINTER(C.c_double)
+        self.lib.isdf_dbg_flatness.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+        if self.lib.isdf_dbg_flatness(self.h, n, _dp(vaj), _dp(gr), _dp(out)) != 0:
+            raise IsdfError(-1, "isdf_dbg_flatness failed")
+        return out[:, 0:4], out[:, 4:7], out[:, 7:10], out[:, 10:13], out[:, 13:16]

@@ -88,7 +88,7 @@ typedef struct isdf_stats {
 } isdf_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------------------- */
-/* values of plan_manager/config/config_CappedCone.yaml; flags = DYNAMICS|COLLISION */
+/* values of plan_manager/config/config_CappedCone.yaml; flags = DYNAMICS (the live reference callback; add ISDF_WITH_COLLISION for the discrete grad_cost_p term) */
 int isdf_default_config(isdf_config *cfg);
 /* replaces TrajOptimizer::setParam (hpp:667-722) + SweptVolumeManager ctor (swm:135-150). device = CUDA ordinal. */
 int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out);

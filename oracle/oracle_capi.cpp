@@ -108,6 +108,16 @@ void orc_flat_backward(const orc_config *c, const double *v, const double *a, co
     for (int i = 0; i < 4; i++) { out12[3 * i] = o[i]->x; out12[3 * i + 1] = o[i]->y; out12[3 * i + 2] = o[i]->z; }
 }
 
+// batched twins (n inputs, contiguous rows) for the reference-pin tests against oracle/_ref/libref_flat.so
+void orc_flat_forward_batch(const orc_config *c, int n, const double *v, const double *a, const double *j, double *quat, double *omg) {
+    for (int i = 0; i < n; i++) orc_flat_forward(c, v + 3 * i, a + 3 * i, j + 3 * i, quat + 4 * i, omg + 3 * i);
+}
+void orc_flat_backward_batch(const orc_config *c, int n, const double *v, const double *a, const double *j, const double *pos_grad,
+                             const double *vel_grad, const double *quat_grad, const double *omg_grad, double *out12) {
+    for (int i = 0; i < n; i++)
+        orc_flat_backward(c, v + 3 * i, a + 3 * i, j + 3 * i, pos_grad + 3 * i, vel_grad + 3 * i, quat_grad + 4 * i, omg_grad + 3 * i, out12 + 12 * i);
+}
+
 // Discrete path. occ: X*Y*Z bytes, z fastest. Accumulates nothing: outputs are overwritten.
 int orc_eval_discrete(const orc_config *c, const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res,
                       void *shape, int N, const double *T, const double *C, double *cost, double *gradC, double *gradT,

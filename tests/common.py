@@ -16,8 +16,7 @@ def small_case(N=4, K=16, seed=3, noise=0.03, flags=None, kernel_size=13):
     cfg = I.default_config_values()
     cfg.integral_intervs = K
     cfg.kernel_size = kernel_size
-    if flags is not None:
-        cfg.flags = flags
+    cfg.flags = flags if flags is not None else (I.WITH_DYNAMICS | I.WITH_COLLISION)   # the library default is dynamics only
     occ = W.three_slit_map(64, 64, 64, noise=noise, seed=seed)
     T, Cc, wp = W.make_trajectory(N, [0, 0, 0], [50, 50, 34], seed=seed, jitter=0.3)
     return cfg, occ, T, Cc, wp

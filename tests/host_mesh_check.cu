@@ -40,7 +40,7 @@ int main(int argc, char **argv) {
             // 2. the leaf's axis-aligned and oriented boxes contain its vertices
             const double *o = &hm.leaf_obb[(size_t)15 * first];
             for (int t = first; t < first + cnt; t++) {
-                const double *T = &hm.tris[(size_t)9 * t];
+                const double *T = &hm.tris[(size_t)TRI_STRIDE * t];
                 const d3 vs[3] = {mk3(T[0], T[1], T[2]), mk3(T[0] + T[3], T[1] + T[4], T[2] + T[5]), mk3(T[0] + T[6], T[1] + T[7], T[2] + T[8])};
                 for (const d3 &v : vs) {
                     if (obb_dist2(o, v) != 0.0) { printf("vertex outside its leaf's oriented box (tri %d)\n", t); return 1; }
@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
         const d3 p = mk3(0.5 * (M.blo[0] + M.bhi[0]) + scale * U(rng), 0.5 * (M.blo[1] + M.bhi[1]) + scale * U(rng), 0.5 * (M.blo[2] + M.bhi[2]) + scale * U(rng));
         double brute = 1e300;
         for (int t = 0; t < hm.ntris; t++) {
-            const double *T = &hm.tris[(size_t)9 * t];
+            const double *T = &hm.tris[(size_t)TRI_STRIDE * t];
             int ft; const d3 c = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ft);
             const d3 e = p - c; brute = fmin(brute, dot3(e, e));
         }
@@ -76,7 +76,7 @@ int main(int argc, char **argv) {
                 const int code = ~ch, first = code >> 3, cnt = (code & 7) + 1;
                 double exact = 1e300;
                 for (int t = first; t < first + cnt; t++) {
-                    const double *T = &hm.tris[(size_t)9 * t];
+                    const double *T = &hm.tris[(size_t)TRI_STRIDE * t];
                     int ft; const d3 c = tri_closest(p, mk3(T[0], T[1], T[2]), mk3(T[3], T[4], T[5]), mk3(T[6], T[7], T[8]), ft);
                     const d3 e = p - c; exact = fmin(exact, dot3(e, e));
                 }

@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_FWN = os.path.join(ORACLE_DIR, "_ref", "libref_fwn.so")
+REF_FLAT = os.path.join(ORACLE_DIR, "_ref", "libref_flat.so")
 
 WN_EXACT, WN_BH, WN_RAW = 0, 1, 2
 
@@ -17,7 +18,7 @@ def build(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".hpp", ".cpp"))]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/src/utils/include/igl") and not os.path.exists(REF_FWN):
+    if os.path.isdir("/root/reference/src/utils/include/igl") and not (os.path.exists(REF_FWN) and os.path.exists(REF_FLAT)):
         subprocess.call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -50,6 +51,8 @@ def lib():
         L.orc_mesh_query.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp, dp, dp]
         L.orc_flat_forward.argtypes = [C.POINTER(OrcConfig), dp, dp, dp, dp, dp]
         L.orc_flat_backward.argtypes = [C.POINTER(OrcConfig), dp, dp, dp, dp, dp, dp, dp, dp]
+        L.orc_flat_forward_batch.argtypes = [C.POINTER(OrcConfig), C.c_int, dp, dp, dp, dp, dp]
+        L.orc_flat_backward_batch.argtypes = [C.POINTER(OrcConfig), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         L.orc_eval_discrete.argtypes = [C.POINTER(OrcConfig), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, dp, C.c_double,
                                         C.c_void_p, C.c_int, dp, dp, dp, dp, dp, C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int]
         L.orc_eval_swept.argtypes = [C.POINTER(OrcConfig), C.c_void_p, C.c_int, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp,
@@ -192,6 +195,58 @@ def flat_backward(cfg, v, a, j, pos_grad, vel_grad, quat_grad, omg_grad):
     lib().orc_flat_backward(C.byref(cfg), _p(f64(v)), _p(f64(a)), _p(f64(j)), _p(f64(pos_grad)), _p(f64(vel_grad)), _p(f64(quat_grad)),
                             _p(f64(omg_grad)), _p(out))
     return out.reshape(4, 3)
+
+
+def flat_forward_batch(cfg, v, a, j):
+    v, a, j = f64(v).reshape(-1, 3), f64(a).reshape(-1, 3), f64(j).reshape(-1, 3)
+    n = v.shape[0]
+    q, o = np.zeros((n, 4)), np.zeros((n, 3))
+    lib().orc_flat_forward_batch(C.byref(cfg), n, _p(v), _p(a), _p(j), _p(q), _p(o))
+    return q, o
+
+
+def flat_backward_batch(cfg, v, a, j, pos_grad, vel_grad, quat_grad, omg_grad):
+    v, a, j = f64(v).reshape(-1, 3), f64(a).reshape(-1, 3), f64(j).reshape(-1, 3)
+    n = v.shape[0]
+    out = np.zeros((n, 12))
+    lib().orc_flat_backward_batch(C.byref(cfg), n, _p(v), _p(a), _p(j), _p(f64(pos_grad).reshape(-1, 3)), _p(f64(vel_grad).reshape(-1, 3)),
+                                  _p(f64(quat_grad).reshape(-1, 4)), _p(f64(omg_grad).reshape(-1, 3)), _p(out))
+    return out
+
+
+class RefFlat:
+    """oracle/_ref/libref_flat.so: the reference's own utils/flatness.hpp (optimizated_forward x2, backwardthreadsafe) compiled
+    unmodified against the element-access-only Eigen stand-in — kind "reference"."""
+
+    def __init__(self, cfg):
+        self.L = C.CDLL(REF_FLAT)
+        self.L.ref_flat_forward_quat.argtypes = [dp, C.c_int, dp, dp, dp, dp]
+        self.L.ref_flat_forward_quat_omg.argtypes = [dp, C.c_int, dp, dp, dp, dp, dp]
+        self.L.ref_flat_backward.argtypes = [dp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
+        self.par = np.array([cfg.vehicle_mass, cfg.grav_acc, cfg.horiz_drag, cfg.vert_drag, cfg.paras_drag, cfg.speed_eps], dtype=np.float64)
+
+    def forward_quat(self, v, a, j):
+        v, a, j = f64(v).reshape(-1, 3), f64(a).reshape(-1, 3), f64(j).reshape(-1, 3)
+        q = np.zeros((v.shape[0], 4))
+        self.L.ref_flat_forward_quat(_p(self.par), v.shape[0], _p(v), _p(a), _p(j), _p(q))
+        return q
+
+    def forward(self, v, a, j):
+        v, a, j = f64(v).reshape(-1, 3), f64(a).reshape(-1, 3), f64(j).reshape(-1, 3)
+        q, o = np.zeros((v.shape[0], 4)), np.zeros((v.shape[0], 3))
+        self.L.ref_flat_forward_quat_omg(_p(self.par), v.shape[0], _p(v), _p(a), _p(j), _p(q), _p(o))
+        return q, o
+
+    def backward(self, v, a, j, pos_grad, vel_grad, quat_grad, omg_grad):
+        v, a, j = f64(v).reshape(-1, 3), f64(a).reshape(-1, 3), f64(j).reshape(-1, 3)
+        out = np.zeros((v.shape[0], 12))
+        self.L.ref_flat_backward(_p(self.par), v.shape[0], _p(v), _p(a), _p(j), _p(f64(pos_grad).reshape(-1, 3)), _p(f64(vel_grad).reshape(-1, 3)),
+                                 _p(f64(quat_grad).reshape(-1, 4)), _p(f64(omg_grad).reshape(-1, 3)), _p(out))
+        return out
+
+
+def ref_flat_available():
+    return os.path.exists(REF_FLAT)
 
 
 def eval_discrete(cfg, occ, bmin, res, shape, T, coeffs, use_omp=False, rank=0, world=1):

@@ -247,6 +247,7 @@ def test_discrete_golden_fixture():
     z = np.load(os.path.join(G, "discrete.npz"))
     occ = np.unpackbits(z["occ_bits"])[:np.prod(z["occ_shape"])].reshape(z["occ_shape"]).astype(np.uint8)
     cfg = I.default_config_values()
+    cfg.flags = I.WITH_DYNAMICS | I.WITH_COLLISION
     cfg.integral_intervs = int(z["K"])
     s = np.load(os.path.join(G, "shapes.npz"))
     ev = I.Evaluator(cfg)
