@@ -22,6 +22,7 @@ __global__ void k_mesh_cells(const __grid_constant__ DevMesh M, int nx, int ny, 
 
 __global__ void k_mesh_cell_lists(const __grid_constant__ DevMesh M, long long ncell, double hd, double list_reach, uint16_t *cnt,
                                   const uint32_t *off, uint32_t *cand);
+__global__ void k_mesh_cell_pack(long long ncell, const float *dist, const uint32_t *seed, const uint32_t *off, const uint16_t *cnt, uint4 *rec);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -48,11 +49,11 @@ struct isdf_ctx {
     // shape
     bool have_shape = false;
     DevShape shape;
-    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt;
+    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt; DevBuf<uint4> d_cell_rec;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_piece_cost;
     DevBuf<int> d_tickets;       // pieces_done counter of the epilogue kernel
-    DevBuf<double> d_tot; DevBuf<int> d_sample_slot;   // per-sample collision sums handed from the scan kernels to the epilogue
+    DevBuf<double> d_tot; DevBuf<unsigned> d_split_done;   // per-sample collision sums handed from the scan kernels to the epilogue
     DevBuf<int> d_items, d_item_count; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
     int warp_slots = 148 * 16;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
     int sm_count = 148, mesh_blocks = 4, analytic_blocks = 4;   // persistent grids: one CTA per resident slot
@@ -166,9 +167,9 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
-    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release();
+    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release(); c->d_cell_rec.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_piece_cost.release();
-    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_sample_slot.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
+    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_split_done.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
@@ -326,10 +327,23 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
             m.cell_off = c->d_cell_off.p; m.cell_cnt = c->d_cell_cnt.p; m.cand = c->d_cand.p;
         }
     }
+    // fused 16-byte cell records for the discrete scan kernel's cull stage
+    CU_TRY(c->d_cell_rec.ensure(ncell));
+    k_mesh_cell_pack<<<(unsigned)((ncell + 255) / 256), 256, 0, c->stream>>>((long long)ncell, m.cell_dist, m.cell_seed, m.cell_off, m.cell_cnt, c->d_cell_rec.p);
+    c->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    m.cell_rec = c->d_cell_rec.p;
     c->shape.mesh = m;
     c->have_shape = true; c->fe_ready = false;
     c->order_for = -1;
     return 0;
+}
+
+__global__ void k_mesh_cell_pack(long long ncell, const float *dist, const uint32_t *seed, const uint32_t *off, const uint16_t *cnt, uint4 *rec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell) return;
+    rec[i] = make_uint4(__float_as_uint(dist[i]), seed[i], (off && cnt) ? off[i] : 0u, (off && cnt) ? (uint32_t)cnt[i] : 0u);
 }
 
 // signed distance + nearest triangle at every cell centre of the body-frame grid (one thread per cell)
@@ -602,10 +616,9 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
         CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, 2 * sizeof(int), st));
     }
     CU_TRY(c->d_tot.ensure((size_t)S * 8));
-    CU_TRY(c->d_sample_slot.ensure((size_t)S));
     DiscArgs A;
     A.cfg = c->dcfg; A.grid = c->grid; A.shape = c->shape; A.N = N; A.T = d_T; A.C = d_C;
-    A.tot = c->d_tot.p; A.sample_slot = c->d_sample_slot.p; A.pieces_done = c->d_tickets.p; A.item_cursor = c->d_tickets.p + 1;
+    A.tot = c->d_tot.p; A.pieces_done = c->d_tickets.p; A.item_cursor = c->d_tickets.p + 1;
     A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
     A.rank = c->rank; A.world = c->world;
     A.peer = PeerArgs{};
@@ -632,10 +645,14 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
         CU_TRY(c->d_split_work.ensure((size_t)std::max(max_split, 1)));
         CU_TRY(cudaMemsetAsync(c->d_split_work.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
     }
+    if (c->d_split_done.n < (size_t)std::max(max_split, 1)) {
+        CU_TRY(c->d_split_done.ensure((size_t)std::max(max_split, 1)));
+        CU_TRY(cudaMemsetAsync(c->d_split_done.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
+    }
     A.work = c->d_work.p;
     const bool have_items = (c->order_for == sig) && !c->no_items;
     A.items = have_items ? c->d_items.p : nullptr;
-    A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_work = c->d_split_work.p;
+    A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_work = c->d_split_work.p; A.split_done = c->d_split_done.p;
     // persistent grid: one CTA per resident slot (or fewer when there are fewer items than warps)
     const long long want = ((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS;
     const long long resident = (long long)c->sm_count * (mesh ? c->mesh_blocks : c->analytic_blocks);

@@ -63,7 +63,6 @@ struct DiscArgs {
     const double *T;       // N
     const double *C;       // 6N x 3 column-major
     double *tot;           // S x 8: collision sums of a sample evaluated as ONE work item {costp, gradp(3), grad_quat(4)}
-    int *sample_slot;      // S: -1 = sums in tot, otherwise the split slot whose class sums (subsum) make up the sample
     int *pieces_done;      // 1  (zero on entry, zero on exit)
     double *piece_cost;    // N
     double *out;           // 19N+1: cost | gradC | gradT
@@ -73,7 +72,8 @@ struct DiscArgs {
     const int *item_count;             // number of valid items (device)
     int *item_cursor;                  // persistent warps draw items from this counter (zero on entry; the epilogue zeroes it again)
     double *subsum;                    // split slot x ROW_CLASSES x 8 class sums
-    unsigned *split_work;              // split slot -> work accumulated by the parts (zero on entry, zeroed by the epilogue)
+    unsigned *split_work;              // split slot -> work accumulated by the parts (zero on entry, zeroed by the sample's last part)
+    unsigned *split_done;              // split slot -> parts finished (zero on entry, zeroed by the sample's last part)
     unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
     int rank, world;       // this launch evaluates samples s with s % world == rank
     PeerArgs peer;         // peer.world > 1: the epilogue's last CTA also sums `out` over the ranks through peer memory (isdf_peer.cuh)
@@ -291,7 +291,6 @@ __device__ __forceinline__ void sample_finish_whole(const DiscArgs &A, const Ite
     if (lane < 8) A.tot[(size_t)s * 8 + lane] = mine;
     if (lane == 0) {
         if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
-        A.sample_slot[s] = -1;
         if (A.work) A.work[s] = work;
         if (A.dbg) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = work; }
     }
@@ -316,17 +315,11 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
         if (idx < local_cnt) {
             const int s = f0 + idx * A.world;
             const int j = s - first_s;
-            double tot[8];
-            const int slot = A.sample_slot[s];
-            if (slot < 0) {
-#pragma unroll
-                for (int v = 0; v < 8; v++) tot[v] = __ldcg(A.tot + (size_t)s * 8 + v);
-            } else {   // split sample: class sums added in class order — the same additions a whole-sample item performs
-                const double *all = A.subsum + (size_t)slot * ROW_CLASSES * 8;
-#pragma unroll
-                for (int v = 0; v < 8; v++) { double a = 0.0; for (int c = 0; c < ROW_CLASSES; c++) a += __ldcg(all + c * 8 + v); tot[v] = a; }
-                if (A.work) A.work[s] = A.split_work[slot];
-                A.split_work[slot] = 0;
+            double tot[8];   // the sample's collision sums (a split sample's row was finished by its last part, in class order)
+            {
+                const double2 *tp = reinterpret_cast<const double2 *>(A.tot + (size_t)s * 8);
+                const double2 t0 = __ldcg(tp), t1 = __ldcg(tp + 1), t2 = __ldcg(tp + 2), t3 = __ldcg(tp + 3);
+                tot[0] = t0.x; tot[1] = t0.y; tot[2] = t1.x; tot[3] = t1.y; tot[4] = t2.x; tot[5] = t2.y; tot[6] = t3.x; tot[7] = t3.y;
             }
             double st[PARTIAL_STRIDE];
             sample_epilogue(A, i, j, Ti, tot[0], mk3(tot[1], tot[2], tot[3]), tot[4], tot[5], tot[6], tot[7], st);
@@ -481,11 +474,13 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
 // ============================================================================================================================
 // mesh shapes
 struct QRes { double ex, ey, ez, d2; int tri, feat; uint32_t code; int cls; };   // an answered voxel awaiting its deferred tail
+struct Survivor { double px, py, pz; uint32_t off, cnt, seed, code; };   // a voxel that passed the exact culls: body-frame point, its cell's list (cnt bit 31: cell centre inside), seed triangle (0xffffffff: none)
 struct MeshWarpSmem {
     double pose[16];                     // warp-uniform pose: pos 0..2, R rows 3..11, q (w, x, y, z) 12..15
     double cacc[ROW_CLASSES][8];         // class accumulators
     double vals[32][8];                  // deferred tails: one voxel's eight contributions per lane
     QRes qr[32];
+    Survivor sv[32];                     // culled voxels awaiting their search
     uint32_t vq[64];                     // ring of occupied-voxel codes (dx | dy << 10 | dz << 20, relative to the window origin)
     WideStack stk;
 };
@@ -493,6 +488,12 @@ struct MeshWarpSmem {
 __device__ __forceinline__ d3 smem_pos(const double *ps) { return mk3(ps[0], ps[1], ps[2]); }
 __device__ __forceinline__ rot3 smem_rot(const double *ps) {
     rot3 R; R.r0 = mk3(ps[3], ps[4], ps[5]); R.r1 = mk3(ps[6], ps[7], ps[8]); R.r2 = mk3(ps[9], ps[10], ps[11]); return R;
+}
+// r / ny for 0 <= r < 2^20, 1 <= ny <= 1023 without an integer division: float estimate + one correction step
+__device__ __forceinline__ void row_split(int r, int ny, float inv_ny, int &rx, int &ry) {
+    rx = (int)(((float)r + 0.5f) * inv_ny);
+    ry = r - rx * ny;
+    if (ry < 0) { rx--; ry += ny; } else if (ry >= ny) { rx++; ry -= ny; }
 }
 
 __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
@@ -533,6 +534,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
             __syncwarp();
             const int ny = W.iy1 - W.iy0 + 1;
             const int nrows = (W.ix1 - W.ix0 + 1) * ny;
+            const float inv_ny = 1.0f / (float)ny;
             int nq = 0, head = 0, nres = 0;   // voxel ring fill / head, answered voxels awaiting their tail (warp-uniform)
 
             // deferred tails: sign, gradient, hinge, chain rule onto (position, quaternion) — one answered voxel per lane; the
@@ -566,12 +568,13 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 nres = 0;
             };
 
-            // cull + search for the n oldest voxels of the ring (n <= 32)
-            auto process = [&](int n) __attribute__((always_inline)) {
+            int nsv = 0;   // queued survivors (warp-uniform)
+            // cull stage for the n oldest voxels of the ring (n <= 32): survivors are appended to the survivor queue
+            auto cull = [&](int n) __attribute__((always_inline)) {
                 bool pass = false, box = false;
-                int cell = -1;
                 uint32_t code = 0;
                 d3 prel = mk3(0, 0, 0);
+                uint4 rec = make_uint4(0u, 0xffffffffu, 0u, 0u);   // {dist bits, seed, off, cnt}; seed 0xffffffff = outside the cell grid
                 if (lane < n) {
                     code = sm.vq[(head + lane) & 63];
                     const double *ps = sm.pose;
@@ -580,35 +583,70 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                     box = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
                     // exact skips: outside the mesh AABB inflated by safety_hor, or in a cell whose every point is >= safety_hor away
                     pass = box && !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
-                                    prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf) && !mesh_far(Mh, prel, sf, cell);
+                                    prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf);
+                    if (pass) {
+                        const int cx = (int)floor((prel.x - Mh.glo[0]) * Mh.inv_gcell), cy = (int)floor((prel.y - Mh.glo[1]) * Mh.inv_gcell),
+                                  cz = (int)floor((prel.z - Mh.glo[2]) * Mh.inv_gcell);
+                        if (cx < 0 || cy < 0 || cz < 0 || cx >= Mh.gdim[0] || cy >= Mh.gdim[1] || cz >= Mh.gdim[2]) pass = !(sf <= Mh.gpad);   // outside the grid: >= gpad away
+                        else {
+                            rec = __ldg(Mh.cell_rec + ((size_t)(cx * Mh.gdim[1] + cy) * Mh.gdim[2] + cz));
+                            pass = !((double)__uint_as_float(rec.x) - Mh.ghd >= sf);
+                        }
+                    }
                 }
                 head = (head + n) & 63; nq -= n;
                 npairs += __popc(__ballot_sync(0xffffffffu, box));
-                unsigned bal = __ballot_sync(0xffffffffu, pass);
-                while (bal) {   // one surviving voxel at a time, in voxel order
-                    const int sl = __ffs(bal) - 1;
-                    bal &= bal - 1;
-                    nquery++;
-                    const d3 p = mk3(__shfl_sync(0xffffffffu, prel.x, sl), __shfl_sync(0xffffffffu, prel.y, sl), __shfl_sync(0xffffffffu, prel.z, sl));
-                    const int qcell = __shfl_sync(0xffffffffu, cell, sl);
-                    const uint32_t qcode = __shfl_sync(0xffffffffu, code, sl);
-                    double d2; d3 c = mk3(0, 0, 0); int tri, feat;
-                    if (mesh_search_warp(Mh, p, sf, lane, &sm.stk, qcell, d2, c, tri, feat)) {
-                        if (lane == 0) {
-                            QRes r;
-                            r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.d2 = d2; r.tri = tri; r.feat = feat; r.code = qcode;
-                            r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu)) % ROW_CLASSES);
-                            sm.qr[nres] = r;
-                        }
-                        if (++nres == 32) flush_tails();
-                    }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    Survivor &v = sm.sv[nsv + __popc(bal & lt_mask)];
+                    v.px = prel.x; v.py = prel.y; v.pz = prel.z; v.off = rec.z; v.seed = rec.y; v.code = code;
+                    v.cnt = rec.w | ((rec.y != 0xffffffffu && __uint_as_float(rec.x) < 0.0f) ? 0x80000000u : 0u);
                 }
+                nsv += __popc(bal);
+                __syncwarp();
+            };
+            // search stage for every queued survivor, in voxel order, software-pipelined ACROSS queries: while query k runs, the
+            // first 32 candidate ids of query k+2 are being loaded and the triangle records of query k+1's first pass are
+            // prefetched into L1 — the id -> record -> arithmetic chain of a query starts with its operands already close
+            auto search_all = [&](bool final) __attribute__((always_inline)) {
+                nquery += nsv;
+                auto first_ids = [&](int k) -> int {
+                    if (k >= nsv) return -1;
+                    const uint32_t cnt = sm.sv[k].cnt & 0x7fffffffu;
+                    return (lane < (int)cnt) ? (int)__ldg(Mh.cand + sm.sv[k].off + lane) : -1;
+                };
+                int ids0 = first_ids(0), ids1 = first_ids(1);
+                int k = 0;
+                do {
+                    if (k < nsv) {
+                        const int ids2 = first_ids(k + 2);
+                        const Survivor &v = sm.sv[k];
+                        const d3 p = mk3(v.px, v.py, v.pz);
+                        const uint32_t cnt_in = v.cnt, qcode = v.code;
+                        double d2; d3 c = mk3(0, 0, 0); int tri, feat;
+                        if (mesh_search_rec(Mh, p, sf, lane, &sm.stk, (int)(cnt_in & 0x7fffffffu), v.off, ids0, (int)v.seed, (cnt_in >> 31) != 0u, d2, c, tri, feat)) {
+                            if (lane == 0) {
+                                QRes r;
+                                r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.d2 = d2; r.tri = tri; r.feat = feat; r.code = qcode;
+                                r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu)) % ROW_CLASSES);
+                                sm.qr[nres] = r;
+                            }
+                            nres++;
+                        }
+                        ids0 = ids1; ids1 = ids2;
+                    }
+                    k++;
+                    if (nres == 32 || (final && k >= nsv && nres > 0)) flush_tails();   // the only call site
+                } while (k < nsv);
+                __syncwarp();
+                nsv = 0;
             };
 
-            // Producer loop (one cull/search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
+            // Producer loop (one cull and one search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
             // are appended to the ring, and whenever 32 voxels are queued — or the window is exhausted — they are processed.
-            //   whole sample: a batch is 32 consecutive rows = 32 different classes; the lanes emit their rows' voxels round-robin
-            //                 (lowest z first), which keeps every CLASS's voxels in (row, z) order;
+            //   whole sample: a batch is 32 consecutive rows = 32 different classes, so any emission order keeps every CLASS's
+            //                 voxels in (row, z) order: the batch is emitted at once (row-major) when it fits into the ring,
+            //                 otherwise round-robin, one voxel per lane and round (dense walls);
             //   split part  : rows of the classes [c0, c1) only, emitted row by row so that a class's rows stay in ascending order.
             const int w = it.c1 - it.c0;
             const int nk = whole ? nrows : ((nrows + ROW_CLASSES - 1) / ROW_CLASSES) * w;   // row slots to visit per z-chunk
@@ -616,7 +654,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
             uint32_t bits = 0, rowcode = 0;
             unsigned pending = 0;
             bool finished = false;
-            while (!finished || nq > 0) {
+            for (;;) {
                 if (!finished) {
                     if (pending == 0u) {   // next batch of rows
                         kb += 32;
@@ -629,11 +667,29 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                             const int r = whole ? k : (k / w) * ROW_CLASSES + it.c0 + (k % w);
                             bits = 0;
                             if (k < nk && r < nrows) {
-                                const int rx = r / ny, ry = r - rx * ny;
+                                int rx, ry;
+                                row_split(r, ny, inv_ny, rx, ry);
                                 bits = row_bits(G, W.ix0 + rx, W.iy0 + ry, zs, zmask);
                                 rowcode = (uint32_t)rx | ((uint32_t)ry << 10) | ((uint32_t)(zs - W.iz0) << 20);
                             }
                             pending = __ballot_sync(0xffffffffu, bits != 0u);
+                            if (whole && pending != 0u) {
+                                int incl = __popc(bits);
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                                if (nq + total <= 64) {   // the whole batch fits: emit it at once
+                                    int pos = head + nq + incl - __popc(bits);
+                                    while (bits != 0u) {
+                                        const int z = __ffs(bits) - 1;
+                                        bits &= bits - 1;
+                                        sm.vq[pos & 63] = rowcode + ((uint32_t)z << 20);
+                                        pos++;
+                                    }
+                                    nq += total;
+                                    pending = 0u;
+                                }
+                            }
                         }
                     } else if (whole) {    // one round: every lane that still has voxels emits its lowest one
                         if (bits != 0u) {
@@ -653,9 +709,14 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                     }
                     __syncwarp();
                 }
-                if (nq >= 32 || (finished && nq > 0)) process(min(nq, 32));
+                if (nq >= 32 || (finished && nq > 0)) cull(min(nq, 32));
+                // single call site; the final round runs even without survivors when answered voxels still await their tail
+                const bool last_round = finished && nq == 0;
+                if (nsv > 0 || (last_round && nres > 0)) {
+                    search_all(last_round);
+                }
+                if (last_round) break;
             }
-            if (nres > 0) flush_tails();
             __syncwarp();
             // sample (or part) total: class sums added in class order
             if (whole) {
@@ -663,12 +724,28 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) mine += sm.cacc[c][lane];
                 sample_finish_whole(A, it, mine, npairs, t_begin, 64u * nquery + npairs);
             } else {
+                // split part: publish this part's class sums; the LAST part of the sample to arrive (one ticket per split slot) adds
+                // all 32 class sums in class order — the same additions a whole-sample item performs — so that the epilogue sees
+                // one finished row per sample whether or not it was split
                 double *sub = A.subsum + (size_t)it.hslot * ROW_CLASSES * 8;
-                if (lane < 8) for (int c = it.c0; c < it.c1; c++) sub[c * 8 + lane] = sm.cacc[c][lane];
+                if (lane < 8) for (int c = it.c0; c < it.c1; c++) __stcg(sub + c * 8 + lane, sm.cacc[c][lane]);
+                __threadfence();
+                __syncwarp();
+                unsigned mywork = 64u * nquery + npairs, prev = 0;
                 if (lane == 0) {
                     if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
-                    atomicAdd(A.split_work + it.hslot, 64u * nquery + npairs);
-                    A.sample_slot[s] = it.hslot;   // every part writes the same slot
+                    atomicAdd(A.split_work + it.hslot, mywork);
+                    prev = atomicAdd(A.split_done + it.hslot, 1u);
+                }
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                if ((int)prev == ROW_CLASSES / w - 1) {   // last of the f = 32 / w parts
+                    __threadfence();
+                    double mine = 0.0;
+                    if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) mine += __ldcg(sub + c * 8 + lane);
+                    unsigned total_work = 0;
+                    if (lane == 0) { total_work = atomicExch(A.split_work + it.hslot, 0u); A.split_done[it.hslot] = 0u; }
+                    total_work = __shfl_sync(0xffffffffu, total_work, 0);
+                    sample_finish_whole(A, it, mine, 0u, t_begin, total_work);
                 }
             }
         } else {
@@ -687,46 +764,81 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
 // atomics: the order only decides WHICH warp takes WHICH item, never the arithmetic, so results stay bit-reproducible.
 // One CTA, ~10 us, off the critical path of the evaluation that produced `work`.
 constexpr int ORDER_BUCKETS = 1024;
+constexpr int ITEMS_CACHE = 24;   // samples per thread whose work value is kept in registers (M <= 24576: any single trajectory)
 __device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 3, (unsigned)ORDER_BUCKETS - 1u); }
+
+// inclusive scan of one int per thread over the 1024-thread block (warp scans + a scan of the 32 warp totals)
+__device__ __forceinline__ int block_scan_inclusive_1024(int v, int *warp_tot) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) warp_tot[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int r = v + (wid > 0 ? warp_tot[wid - 1] : 0);
+    __syncthreads();
+    return r;
+}
+
+template <bool CACHED>
 __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots,
                                                       int *items, int *item_count) {
     __shared__ int hist[ORDER_BUCKETS];
     __shared__ int cursor[ORDER_BUCKETS];
-    __shared__ int nsplit;
+    __shared__ int warp_tot[32];
+    __shared__ int nsplit, first_over;
     __shared__ unsigned long long total_work;
-    __shared__ unsigned split_thr;
     int *scratch = items + 3 * ((size_t)M + (size_t)(ROW_CLASSES - 1) * max_split);   // behind the item table: per sample (slot << 6) | f, or -1
-    hist[threadIdx.x] = 0; cursor[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { nsplit = 0; total_work = 0ull; }
+    const int tid = threadIdx.x;
+    unsigned wv[CACHED ? ITEMS_CACHE : 1];
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; wv[u] = (m < M) ? __ldcg(work + rank + (size_t)world * m) : 0u; }
+    }
+    auto work_of = [&](int u, int m) -> unsigned { return CACHED ? wv[u] : __ldcg(work + rank + (size_t)world * m); };
+    hist[tid] = 0; cursor[tid] = 0;
+    if (tid == 0) { nsplit = 0; total_work = 0ull; first_over = ORDER_BUCKETS; }
     __syncthreads();
-    {
+    {   // per-sample work histogram (cursor[]) and total work
         unsigned long long mine = 0ull;
-        for (int m = threadIdx.x; m < M; m += blockDim.x) {
-            const unsigned w = work[rank + world * m];
-            mine += w;
-            atomicAdd(&cursor[order_bucket(w)], 1);          // cursor[] doubles as the per-sample work histogram here
+        if (CACHED) {
+#pragma unroll
+            for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; if (m < M) { mine += wv[u]; atomicAdd(&cursor[order_bucket(wv[u])], 1); } }
+        } else {
+            for (int m = tid; m < M; m += 1024) { const unsigned w = work_of(0, m); mine += w; atomicAdd(&cursor[order_bucket(w)], 1); }
         }
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&total_work, mine);
+        if ((tid & 31) == 0) atomicAdd(&total_work, mine);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // balanced-share threshold, raised if needed so that only the max_split HEAVIEST samples qualify
+    // balanced-share threshold, raised if needed so that only the max_split HEAVIEST samples qualify: walking the buckets from the
+    // top, b = the first bucket whose samples no longer fit into the split slots (thread t looks at bucket 1023 - t)
+    {
+        const int cum = block_scan_inclusive_1024(cursor[ORDER_BUCKETS - 1 - tid], warp_tot);
+        if (cum > max_split) atomicMin(&first_over, tid);
+    }
+    __syncthreads();
+    unsigned THR;
+    {
         const unsigned long long t = (total_work * 7ull) / (10ull * (unsigned long long)max(warp_slots, 1));
-        unsigned thr = (unsigned)min(max(t, (unsigned long long)SPLIT_WORK_MIN), 0xffffffffull);
-        int cum = 0, b = ORDER_BUCKETS - 1;
-        for (; b >= 0; b--) { if (cum + cursor[b] > max_split) break; cum += cursor[b]; }
-        if (b >= 0) thr = max(thr, (unsigned)(b + 1) << 3);   // buckets above b fit into the split slots
-        if (b == ORDER_BUCKETS - 1) thr = 0xffffffffu;        // even the top bucket alone overflows: no splitting
-        split_thr = thr;
+        THR = (unsigned)min(max(t, (unsigned long long)SPLIT_WORK_MIN), 0xffffffffull);
+        if (first_over < ORDER_BUCKETS) {
+            const int b = ORDER_BUCKETS - 1 - first_over;
+            THR = max(THR, (unsigned)(b + 1) << 3);           // buckets above b fit into the split slots
+            if (b == ORDER_BUCKETS - 1) THR = 0xffffffffu;     // even the top bucket alone overflows: no splitting
+        }
     }
     __syncthreads();
-    cursor[threadIdx.x] = 0;
+    cursor[tid] = 0;
     __syncthreads();
-    const unsigned THR = split_thr;
     // pass 1: decide splits (first come first served up to max_split) and their factor, histogram the item keys
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        const unsigned w = work[rank + world * m];
+    auto decide = [&](int m, unsigned w) {
         int code = -1;
         if (w >= THR) {
             const int hs = atomicAdd(&nsplit, 1);
@@ -739,21 +851,22 @@ __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int 
         }
         if (code < 0) atomicAdd(&hist[order_bucket(w)], 1);
         scratch[m] = code;
+    };
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; if (m < M) decide(m, wv[u]); }
+    } else {
+        for (int m = tid; m < M; m += 1024) decide(m, work_of(0, m));
     }
     __syncthreads();
-    if (threadIdx.x < 32) {   // exclusive scan over buckets in DESCENDING bucket order
-        const int lane = threadIdx.x;
-        int local = 0;
-        for (int k = 0; k < 32; k++) local += hist[ORDER_BUCKETS - 1 - (lane * 32 + k)];
-        int incl = local;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        int run = incl - local;
-        for (int k = 0; k < 32; k++) { const int b = ORDER_BUCKETS - 1 - (lane * 32 + k); cursor[b] = run; run += hist[b]; }
-        if (lane == 31) *item_count = run;
+    {   // exclusive scan over buckets in DESCENDING bucket order
+        const int b = ORDER_BUCKETS - 1 - tid;
+        const int incl = block_scan_inclusive_1024(hist[b], warp_tot);
+        cursor[b] = incl - hist[b];
+        if (tid == ORDER_BUCKETS - 1) *item_count = incl;
     }
     __syncthreads();
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        const unsigned w = work[rank + world * m];
+    auto place = [&](int m, unsigned w) {
         const int code = scratch[m];
         if (code >= 0) {
             const int hs = code >> 6, f = code & 63, cw = ROW_CLASSES / f;
@@ -763,6 +876,12 @@ __global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int 
             const int pos = atomicAdd(&cursor[order_bucket(w)], 1);
             items[3 * pos] = m; items[3 * pos + 1] = -1; items[3 * pos + 2] = -1;
         }
+    };
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; if (m < M) place(m, wv[u]); }
+    } else {
+        for (int m = tid; m < M; m += 1024) place(m, work_of(0, m));
     }
 }
 #endif  // ISDF_DISCRETE_TU

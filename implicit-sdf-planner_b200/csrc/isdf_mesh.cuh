@@ -49,6 +49,11 @@ struct DevMesh {
     const uint32_t *cell_off;   // offset into cand
     const uint16_t *cell_cnt;   // number of candidates (0 = no list)
     const uint32_t *cand;       // triangle indices (leaf order)
+    // the same four per-cell values fused into one 16-byte record {float bits of cell_dist, cell_seed, cell_off, cell_cnt}: the
+    // discrete scan kernel's cull stage fetches it with ONE 128-bit load and hands offset / count / seed to the search, instead
+    // of three dependent loads per query (packed by k_mesh_cell_pack at isdf_set_shape_mesh time; may be null)
+    const uint4 *cell_rec;
+    double inv_gcell;           // 1 / gcell
     int ntris;
     int gdim[3];
     double glo[3];
@@ -451,41 +456,46 @@ __device__ __forceinline__ void warp_argmin_update(double dd, d3 q, int t, int f
     }
 }
 
-// Warp-cooperative nearest triangle from a cell's candidate list: lanes test 32 candidates per pass (64 — two independent
-// closest-point chains per lane — while more than 32 remain), REDUX arg-min.
+// Warp-cooperative nearest triangle from a cell's candidate list: lanes test 32 candidates per pass, REDUX arg-min.
+// (Two candidates per lane and pass — a second independent chain — was measured slower: profiles/r02_tuning.md.)
+__device__ __forceinline__ double list_closest_range(const DevMesh &M, d3 p, uint32_t off, int cnt, d3 &cbest, int &tri, int &feat, int lane);
+__device__ __forceinline__ double list_closest_pre(const DevMesh &M, d3 p, uint32_t off, int cnt, int first_id, d3 &cbest, int &tri, int &feat, int lane);
 __device__ __forceinline__ double list_closest(const DevMesh &M, d3 p, int cell, d3 &cbest, int &tri, int &feat, int lane) {
-    const uint32_t off = M.cell_off[cell];
-    const int cnt = (int)M.cell_cnt[cell];
+    return list_closest_range(M, p, M.cell_off[cell], (int)M.cell_cnt[cell], cbest, tri, feat, lane);
+}
+__device__ __forceinline__ double list_closest_range(const DevMesh &M, d3 p, uint32_t off, int cnt, d3 &cbest, int &tri, int &feat, int lane) {
+    return list_closest_pre(M, p, off, cnt, (lane < cnt) ? (int)__ldg(M.cand + off + lane) : -1, cbest, tri, feat, lane);
+}
+// first_id: this lane's candidate of the FIRST pass (cand[off + lane], -1 beyond the list) — the caller may have loaded it long
+// before (software pipelining across queries); the ids of every following pass are requested one pass ahead.
+__device__ __forceinline__ double list_closest_pre(const DevMesh &M, d3 p, uint32_t off, int cnt, int first_id, d3 &cbest, int &tri, int &feat, int lane) {
     double best = 1e300;
     tri = -1; feat = 0;
-    int base = 0;
-#ifdef ISDF_FAST_TRI
-    for (; base + 32 < cnt; base += 64) {   // two candidates per lane: the second chain hides the first one's latency
-        const int k1 = base + 32 + lane;
-        const int t0 = (int)__ldg(M.cand + off + base + lane);
-        const int t1 = (k1 < cnt) ? (int)__ldg(M.cand + off + k1) : t0;
-        int f0, f1;
-        const d3 q0 = tri_closest_rec(p, M.tris + TRI_STRIDE * (size_t)t0, f0);
-        const d3 q1 = tri_closest_rec(p, M.tris + TRI_STRIDE * (size_t)t1, f1);
-        const d3 e0 = p - q0, e1 = p - q1;
-        const double dd0 = dot3(e0, e0), dd1 = dot3(e1, e1);
-        const bool second = dd1 < dd0;
-        warp_argmin_update(second ? dd1 : dd0, second ? q1 : q0, second ? t1 : t0, second ? f1 : f0, best, cbest, tri, feat);
-    }
-#endif
-    for (; base < cnt; base += 32) {
-        double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0, t = -1;
-        if (base + lane < cnt) {
-            t = (int)__ldg(M.cand + off + base + lane);
+    int t = first_id;
+    for (int base = 0; base < cnt; base += 32) {
+        const int nb = base + 32 + lane;
+        const int t_next = (nb < cnt) ? (int)__ldg(M.cand + off + nb) : -1;   // ids of the next pass, in flight during this one
+        double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0;
+        if (t >= 0) {
             const double *T = M.tris + TRI_STRIDE * (size_t)t;
             q = tri_closest_rec(p, T, f);
             const d3 e = p - q;
             dd = dot3(e, e);
         }
         warp_argmin_update(dd, q, t, f, best, cbest, tri, feat);
+        t = t_next;
     }
     return best;
 }
+
+#ifdef ISDF_OUTLINE_TREE_SEARCH
+// Out-of-line copy of the tree search for the discrete scan kernel, where candidate lists answer almost every query: the kernel's
+// hot loop then stays small (instruction cache) — the call's spills are paid only on the rare tree path.
+static __device__ __noinline__ double wide_closest_outlined(const DevMesh &M, d3 p, double bound2, int seed, d3 &cbest, int &tri, int &feat,
+                                                            int lane, WideStack *stk) {
+    return wide_closest(M, p, bound2, seed, cbest, tri, feat, lane, stk);
+}
+#endif
 
 // Search half of getSDFwithGrad1 for the mesh shape, warp-cooperative: closest triangle of p (cell = p's cell index, or -1
 // outside the grid; the caller has already ruled out "far"). Returns false when nothing lies within `reach` and p is outside
@@ -506,6 +516,28 @@ __device__ __forceinline__ bool mesh_search_warp(const DevMesh &M, d3 p, double 
         d2 = wide_closest(M, p, 1e300, seed, c, tri, feat, lane, stk);
     }
     return true;
+}
+
+// The same search with the cell's record already fetched (DevMesh::cell_rec): cnt / off = candidate list (cnt 0: none), seed =
+// nearest triangle of the cell centre (-1 outside the grid), inside = the cell centre is inside the mesh.
+__device__ __forceinline__ bool mesh_search_rec(const DevMesh &M, d3 p, double reach, int lane, WideStack *stk, int cnt, uint32_t off,
+                                                int first_id, int seed, bool inside, double &d2, d3 &c, int &tri, int &feat) {
+    if (cnt != 0) {
+        d2 = list_closest_pre(M, p, off, cnt, first_id, c, tri, feat, lane);
+        return true;
+    }
+    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+    double bound2 = bounded ? reach * reach : 1e300;
+    for (;;) {   // one inlined copy of the tree search: first within `reach`, then (deep inside only) unbounded
+#ifdef ISDF_OUTLINE_TREE_SEARCH
+        d2 = wide_closest_outlined(M, p, bound2, seed, c, tri, feat, lane, stk);
+#else
+        d2 = wide_closest(M, p, bound2, seed, c, tri, feat, lane, stk);
+#endif
+        if (tri >= 0 || bound2 >= 1e299) return true;
+        if (!inside) return false;
+        bound2 = 1e300;
+    }
 }
 
 // Sign + gradient half (Shape.cpp:139-151): e = p - closest point; sdf = s * dist, grad = normalise(s * e), s = ±1 from the

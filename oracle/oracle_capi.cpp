@@ -6,6 +6,7 @@
 #include "oracle_minco.hpp"
 #include "oracle_frontend.hpp"
 #include <cstdio>
+#include <dlfcn.h>
 
 using namespace orc;
 
@@ -63,6 +64,23 @@ void *orc_shape_create_mesh(const double *V, int nV, const int *F, int nF, const
     o->s.kind = SK_MESH;
     o->s.mesh = &o->mesh;
     return o;
+}
+// WN_REF: attach oracle/_ref/libref_fwn.so (the reference's own FastWindingNumberForSoups.h, compiled from /root/reference by
+// `make ref`) to a mesh shape and switch its sign to the reference-faithful s = 1 - 2 w_FWN (Shape.cpp:110-111). Returns 0 on success.
+int orc_shape_attach_ref_fwn(void *h, const char *libpath) {
+    OrcShape *o = (OrcShape *)h;
+    if (!o || o->s.kind != SK_MESH) return -1;
+    void *dl = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return -2;
+    auto create = (void *(*)(const double *, int, const int *, int, int))dlsym(dl, "ref_fwn_create");
+    auto query = (void (*)(void *, const double *, int, double, double *))dlsym(dl, "ref_fwn_query");
+    if (!create || !query) return -3;
+    std::vector<double> V(3 * o->mesh.V.size());
+    for (size_t i = 0; i < o->mesh.V.size(); i++) { V[3 * i] = o->mesh.V[i].x; V[3 * i + 1] = o->mesh.V[i].y; V[3 * i + 2] = o->mesh.V[i].z; }
+    o->mesh.ref_fwn = create(V.data(), (int)o->mesh.V.size(), o->mesh.F.data(), o->mesh.ntri(), 2);   // order 2 (Shape.cpp:86)
+    o->mesh.ref_fwn_query = query;
+    o->mesh.wn_mode = WN_REF;
+    return o->mesh.ref_fwn ? 0 : -4;
 }
 void orc_shape_destroy(void *h) { delete (OrcShape *)h; }
 int orc_shape_kind(void *h) { return ((OrcShape *)h)->s.kind; }

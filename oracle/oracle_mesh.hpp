@@ -9,7 +9,8 @@
 //     *exact* winding number (sum of van Oosterom–Strackee solid angles / 4π) thresholded at 0.5 => s = ±1.
 //     Modes: WN_EXACT (brute force), WN_BH (own FP64 dipole Barnes–Hut tree, thresholded — used for large CPU
 //     baseline runs; validated against WN_EXACT), WN_RAW (s = 1 - 2 w_exact, unthresholded; for comparisons
-//     with the compiled reference FWN header in oracle/_ref).
+//     with the compiled reference FWN header in oracle/_ref), WN_REF (s = 1 - 2 w with w from the reference-compiled FWN
+//     header itself: the reference-faithful SDF value, used to MEASURE what the ±1 policy deviates by).
 #pragma once
 #include "oracle_math.hpp"
 #include <numeric>
@@ -50,12 +51,17 @@ inline double solid_angle(const V3 &q, const V3 &a, const V3 &b, const V3 &c) {
     return 2.0 * std::atan2(num, den);
 }
 
-enum WindingMode { WN_EXACT = 0, WN_BH = 1, WN_RAW = 2 };
+enum WindingMode { WN_EXACT = 0, WN_BH = 1, WN_RAW = 2, WN_REF = 3 };
 
 struct Mesh {
     std::vector<V3> V;
     std::vector<int> F;  // 3 per triangle
     int wn_mode = WN_EXACT;
+    // WN_REF ("reference-faithful" sign): w comes from the REFERENCE-COMPILED igl/FastWindingNumberForSoups.h (oracle/_ref/libref_fwn.so,
+    // attached at run time by oracle_capi.cpp — the oracle itself never contains reference code) and s = 1 - 2 w is NOT thresholded,
+    // exactly as Shape.cpp:110-111 / :131-132 / :144-145 do: FP32, order 2, accuracy scale 2.0.
+    void *ref_fwn = nullptr;
+    void (*ref_fwn_query)(void *, const double *, int, double, double *) = nullptr;
 
     // ---- distance BVH -------------------------------------------------------------------------
     struct Node { V3 lo, hi; int left, right, tri; };  // leaf: tri >= 0
@@ -215,6 +221,12 @@ struct Mesh {
     // s = 1 - 2 w  (Shape.cpp:111) under the oracle's sign policy
     double sign(const V3 &q) const {
         if (wn_mode == WN_RAW) return 1.0 - 2.0 * winding_exact(q);
+        if (wn_mode == WN_REF) {
+            const double p[3] = {q.x, q.y, q.z};
+            double w = 0.0;
+            ref_fwn_query(ref_fwn, p, 1, 2.0, &w);
+            return 1.0 - 2.0 * w;
+        }
         const double w = (wn_mode == WN_BH) ? winding_bh(q) : winding_exact(q);
         return (w > 0.5) ? -1.0 : 1.0;
     }

@@ -10,8 +10,13 @@ rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-cub = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.check_output(["nvdisasm", "-g", "-c", cub]).decode()
+dis = ""   # the library holds one cubin per translation unit: take the one that defines the kernel
+for f in sorted(os.listdir(tmp)):
+    if f.endswith(".cubin"):
+        d = subprocess.check_output(["nvdisasm", "-g", "-c", os.path.join(tmp, f)]).decode()
+        if re.search(r"\.text\.\S*" + re.escape(kern), d):
+            dis = d
+            break
 addr2line, cur, infn = {}, None, False
 for ln in dis.splitlines():
     m = re.match(r"\s*\.text\.(\S+):", ln)

@@ -11,7 +11,7 @@ LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_FWN = os.path.join(ORACLE_DIR, "_ref", "libref_fwn.so")
 REF_FLAT = os.path.join(ORACLE_DIR, "_ref", "libref_flat.so")
 
-WN_EXACT, WN_BH, WN_RAW = 0, 1, 2
+WN_EXACT, WN_BH, WN_RAW, WN_REF = 0, 1, 2, 3
 
 
 def build(force=False):
@@ -45,6 +45,7 @@ def lib():
         L.orc_shape_create_mesh.restype = C.c_void_p
         L.orc_shape_create_mesh.argtypes = [dp, C.c_int, C.POINTER(C.c_int32), C.c_int, dp, C.c_int]
         L.orc_shape_destroy.argtypes = [C.c_void_p]
+        L.orc_shape_attach_ref_fwn.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_shape_kind.argtypes = [C.c_void_p]
         L.orc_shape_params.argtypes = [C.c_void_p, dp]
         L.orc_shape_query.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, C.c_int]
@@ -114,7 +115,12 @@ class Shape:
         V = f64(V).reshape(-1, 3)
         F = np.ascontiguousarray(F, dtype=np.int32).reshape(-1, 3)
         pp = f64(poly_params).reshape(6) if poly_params is not None else None
-        return Shape(lib().orc_shape_create_mesh(_p(V), V.shape[0], F.ctypes.data_as(C.POINTER(C.c_int32)), F.shape[0], _p(pp), wn_mode))
+        sh = Shape(lib().orc_shape_create_mesh(_p(V), V.shape[0], F.ctypes.data_as(C.POINTER(C.c_int32)), F.shape[0], _p(pp),
+                                               WN_EXACT if wn_mode == WN_REF else wn_mode))
+        if wn_mode == WN_REF:   # reference-faithful sign: s = 1 - 2 w with w from the reference-compiled FWN header (oracle/_ref)
+            r = lib().orc_shape_attach_ref_fwn(sh.h, REF_FWN.encode())
+            assert r == 0, f"cannot attach {REF_FWN} (rc {r}); build it with `make -C oracle ref` where /root/reference exists"
+        return sh
 
     def kind(self):
         return lib().orc_shape_kind(self.h)
