@@ -650,7 +650,10 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
         CU_TRY(cudaMemsetAsync(c->d_split_done.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
     }
     A.work = c->d_work.p;
-    const bool have_items = (c->order_for == sig) && !c->no_items;
+    // a launch with far more samples than resident warps (batched callbacks: millions) balances itself through the persistent warps'
+    // dynamic item counter: sorting / splitting would only cost a long single-CTA pass over the work array
+    const bool want_items = !c->no_items && M <= 1024ll * ITEMS_CACHE * 4;
+    const bool have_items = (c->order_for == sig) && want_items;
     A.items = have_items ? c->d_items.p : nullptr;
     A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_work = c->d_split_work.p; A.split_done = c->d_split_done.p;
     // persistent grid: one CTA per resident slot (or fewer when there are fewer items than warps)
@@ -662,13 +665,16 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     CU_TRY(discrete_launch_epilogue(A, st));
     if (fused) c->peer.epoch = A.peer.epoch;
     // build the next evaluation's work items on the aux stream: overlaps the caller's D2H / all-reduce / host work
-    CU_TRY(cudaEventRecord(c->ev_main_done, st));
-    CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_main_done, 0));
-    CU_TRY(discrete_launch_build_items(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots_override > 0 ? c->warp_slots_override : c->warp_slots, c->d_items.p, c->d_item_count.p, c->aux_stream));
-    CU_TRY(cudaEventRecord(c->ev_items_done, c->aux_stream));
-    c->items_pending = true;
-    c->order_for = sig;
-    c->stats.kernel_launches += 3;   // scan kernel, epilogue, work-item builder
+    if (want_items) {
+        CU_TRY(cudaEventRecord(c->ev_main_done, st));
+        CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_main_done, 0));
+        CU_TRY(discrete_launch_build_items(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots_override > 0 ? c->warp_slots_override : c->warp_slots, c->d_items.p, c->d_item_count.p, c->aux_stream));
+        CU_TRY(cudaEventRecord(c->ev_items_done, c->aux_stream));
+        c->items_pending = true;
+        c->order_for = sig;
+        c->stats.kernel_launches++;   // work-item builder
+    }
+    c->stats.kernel_launches += 2;   // scan kernel, epilogue
     c->stats.evals_discrete++;
     return 0;
 }
@@ -1181,8 +1187,9 @@ extern "C" int isdf_get_swept_results(isdf_ctx *c, double *tstar, double *sdf, d
 // ---- internal diagnostics (not part of include/isdf.h) ------------------------------------------------------------
 extern "C" int isdf_dbg_enable(isdf_ctx *c, int on) { if (!c) return -1; c->dbg_on = on != 0; c->sv.dbg_on = on != 0; return 0; }
 // scheduling diagnostics: natural_order != 0 -> every launch in natural sample order, nothing split (the state of a context's FIRST
-// evaluation); warp_slots > 0 -> build the work items as if the device had that many resident warps (small values force heavy
-// samples to be split, so tests can compare split parts against the oracle on one GPU); 0 restores the device's own figure.
+// evaluation); warp_slots > 0 -> build the work items as if the device had that many resident warps (huge values shrink the
+// balanced share per warp and force every non-trivial sample to be split, so tests can compare split parts against the oracle on one
+// GPU); 0 restores the device's own figure.
 extern "C" int isdf_dbg_schedule(isdf_ctx *c, int natural_order, int warp_slots) {
     if (!c) return -1;
     c->no_items = natural_order != 0; c->warp_slots_override = warp_slots > 0 ? warp_slots : 0; c->order_for = -1;

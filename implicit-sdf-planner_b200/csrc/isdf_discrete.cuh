@@ -54,6 +54,7 @@ constexpr int ANALYTIC_MIN_BLOCKS = 4;
 #endif
 constexpr int MESH_MIN_BLOCKS = ISDF_MESH_MIN_BLOCKS;
 constexpr int EPI_THREADS = 288;
+constexpr int ITEMS_CACHE = 24;   // k_build_items: samples per thread whose work value is kept in registers (M <= 24576: any single trajectory)
 
 struct DiscArgs {
     DevCfg cfg;
@@ -764,7 +765,6 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
 // atomics: the order only decides WHICH warp takes WHICH item, never the arithmetic, so results stay bit-reproducible.
 // One CTA, ~10 us, off the critical path of the evaluation that produced `work`.
 constexpr int ORDER_BUCKETS = 1024;
-constexpr int ITEMS_CACHE = 24;   // samples per thread whose work value is kept in registers (M <= 24576: any single trajectory)
 __device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 3, (unsigned)ORDER_BUCKETS - 1u); }
 
 // inclusive scan of one int per thread over the 1024-thread block (warp scans + a scan of the 32 warp totals)

@@ -3,6 +3,8 @@
 #include "isdf_shape_adapter.hpp"
 #include "isdf_cost_callback.hpp"
 #include "isdf_lbfgs.hpp"
+#include "isdf_obj.hpp"
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -42,6 +44,16 @@ void isdf_host_backend_last(void *be, double *cost_pos, double *cost_other, doub
 }
 void isdf_host_backend_destroy(void *be) { delete (BackEnd *)be; }
 void isdf_host_tau_maps(const double *tau, int n, double *T, double *tau_back) { BackEnd::forwardT(tau, T, n); BackEnd::backwardT(T, tau_back, n); }
+// OBJ reader (read_triangle_mesh counterpart): returns 0 and the counts; copies up to capV vertices / capF faces when the buffers are given
+int isdf_host_read_obj(const char *path, double *V, int capV, int32_t *F, int capF, int *nV, int *nF) {
+    std::vector<double> v; std::vector<int32_t> f; std::string err;
+    if (!read_obj(path, v, f, err)) return -1;
+    *nV = (int)(v.size() / 3); *nF = (int)(f.size() / 3);
+    if (V) std::memcpy(V, v.data(), sizeof(double) * 3 * (size_t)std::min(*nV, capV));
+    if (F) std::memcpy(F, f.data(), sizeof(int32_t) * 3 * (size_t)std::min(*nF, capF));
+    return 0;
+}
+int isdf_host_set_shape_obj(isdf_ctx *ctx, const char *path, const double *poly_params6) { return set_shape_obj(ctx, path, poly_params6); }
 double isdf_host_shape_sdf_grad(isdf_ctx *ctx, const double *p, double *grad) { DeviceShape s(ctx); return s.getSDFwithGrad1(p, grad); }
 
 // L-BFGS on any raw callback (known-answer tests, CPU baseline with the oracle as the callback) ...

@@ -357,7 +357,7 @@ class Evaluator:
     # ---- diagnostics (isdf_dbg_*: exported by the library, not part of include/isdf.h) ----
     def dbg_schedule(self, natural_order=False, warp_slots=0):
         """natural_order: every launch as a context's first one (no work items, nothing split); warp_slots > 0: build the work items as
-        if the device had that many resident warps (small values force heavy samples to be split)."""
+        if the device had that many resident warps (huge values force every non-trivial sample to be split)."""
         vp = C.c_void_p
         self.lib.isdf_dbg_schedule.argtypes = [vp, C.c_int, C.c_int]
         if self.lib.isdf_dbg_schedule(self.h, int(natural_order), int(warp_slots)) != 0:

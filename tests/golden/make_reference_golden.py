@@ -1,6 +1,10 @@
 """Golden vectors computed by REFERENCE-COMPILED code (oracle/_ref/*.so built from /root/reference by `make -C oracle ref`).
 Run in the build container (where /root/reference exists):  python tests/golden/make_reference_golden.py
-  flat_reference.npz — inputs and outputs of the reference's utils/flatness.hpp (optimizated_forward, backwardthreadsafe)."""
+  flat_reference.npz — inputs and outputs of the reference's utils/flatness.hpp (optimizated_forward, backwardthreadsafe);
+  ref_meshes.npz     — the robot meshes the reference ships and loads down its mesh Generalshape path (src/plan_manager/shapes/
+                       {Lthick,drone,kuang,box,RoundedCone,mybox}.obj; INPUT data, read with the product's OBJ reader), the
+                       poly_params of the config that names them, seeded query points, and the winding numbers the
+                       reference-compiled igl/FastWindingNumberForSoups.h returns for them (order 2, accuracy scale 2.0: Shape.cpp:86,110)."""
 import os
 import sys
 import numpy as np
@@ -14,8 +18,34 @@ import oracle_lib as O         # noqa: E402
 from test_reference_pins import flat_inputs   # noqa: E402
 
 
+REF_SHAPES = "/root/reference/src/plan_manager/shapes"
+# mesh -> poly_params: config_L.yaml:8-10 (Lthick), config_CappedCone.yaml:8-10 (RoundedCone), config_box.yaml:8-11 (mybox); drone / kuang /
+# box are named by no shipped config (sw_manager.hpp:255-275 sends any unknown name down the mesh path): CappedCone's parameters
+MESHES = {"Lthick": [0, 0, 0, 0, 0, 0], "RoundedCone": [0, 0, 0, 120, 0, 0], "mybox": [0, 0, 0, 0, 0, 0],
+          "drone": [0, 0, 0, 120, 0, 0], "kuang": [0, 0, 0, 120, 0, 0], "box": [0, 0, 0, 120, 0, 0]}
+
+
+def ref_meshes():
+    import host_lib as H
+    import workloads as W
+    out = {}
+    for name, pp in MESHES.items():
+        V, F = H.read_obj(os.path.join(REF_SHAPES, name + ".obj"))
+        R, t = W.rotation_from_poly_params(pp)
+        Vt = V @ R.T + t                                            # Shape.cpp:38-50
+        lo, hi = Vt.min(0) - 1.0, Vt.max(0) + 1.0
+        rng = np.random.default_rng(abs(hash(name)) % 1000 + 5 if False else sum(map(ord, name)))
+        q = lo + (hi - lo) * rng.random((600, 3))
+        w = O.RefFwn(Vt, F, order=2).query(q, 2.0)
+        out[name + "_V"], out[name + "_F"], out[name + "_pp"], out[name + "_q"], out[name + "_w"] = V, F, np.array(pp, float), q, w
+        print(name, V.shape, F.shape, "w range", w.min(), w.max())
+    np.savez_compressed(os.path.join(HERE, "ref_meshes.npz"), names=np.array(list(MESHES)), **out)
+    print("ref_meshes.npz written")
+
+
 def main():
     O.build()
+    ref_meshes()
     cfg = O.config_from(I.default_config_values())
     ref = O.RefFlat(cfg)
     v, a, j, pg, vg, qg, og = flat_inputs(256, seed=123)

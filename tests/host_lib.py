@@ -31,6 +31,8 @@ def lib():
         L.isdf_host_lbfgs_backend.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                               C.POINTER(C.c_int), C.POINTER(C.c_int)]
         ip = C.POINTER(C.c_int)
+        L.isdf_host_read_obj.argtypes = [C.c_char_p, dp, C.c_int, C.POINTER(C.c_int32), C.c_int, ip, ip]
+        L.isdf_host_set_shape_obj.argtypes = [C.c_void_p, C.c_char_p, dp]
         L.isdf_host_lbfgs_batch_generic.argtypes = [C.c_int, C.c_int, dp, dp, ip, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, ip, ip]
         L.isdf_host_lbfgs_batch_backend.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, C.c_double, dp, dp, ip, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                                     ip, ip, ip]
@@ -117,3 +119,14 @@ def tau_maps(tau):
     T, back = np.zeros_like(tau), np.zeros_like(tau)
     lib().isdf_host_tau_maps(_p(tau), tau.size, _p(T), _p(back))
     return T, back
+
+
+def read_obj(path):
+    """host/isdf_obj.hpp read_obj through its test hook -> (V [n,3] float64, F [m,3] int32)"""
+    L = lib()
+    nv, nf = C.c_int(0), C.c_int(0)
+    if L.isdf_host_read_obj(path.encode(), None, 0, None, 0, C.byref(nv), C.byref(nf)) != 0:
+        raise RuntimeError(f"read_obj failed for {path}")
+    V, F = np.zeros((nv.value, 3)), np.zeros((nf.value, 3), dtype=np.int32)
+    L.isdf_host_read_obj(path.encode(), V.ctypes.data_as(dp), nv.value, F.ctypes.data_as(C.POINTER(C.c_int32)), nf.value, C.byref(nv), C.byref(nf))
+    return V, F

@@ -52,3 +52,58 @@ def test_flatness_oracle_equals_committed_reference_outputs():
     q, o = O.flat_forward_batch(cfg, z["v"], z["a"], z["j"])
     b = O.flat_backward_batch(cfg, z["v"], z["a"], z["j"], z["pg"], z["vg"], z["qg"], z["og"])
     assert relerr(q, z["quat"]) <= 1e-15 and relerr(o, z["omg"]) <= 1e-12 and relerr(b, z["back"]) <= 1e-12
+
+
+# ---- the robot meshes the reference ships (src/plan_manager/shapes/*.obj), committed as INPUT fixtures with reference-computed winding numbers
+def ref_mesh_cases():
+    z = np.load(os.path.join(G, "ref_meshes.npz"))
+    return z, [str(n) for n in z["names"]]
+
+
+@pytest.mark.parametrize("name", ["Lthick", "RoundedCone", "mybox", "drone", "kuang", "box"])
+def test_reference_meshes_oracle_sign_and_distance(name):
+    """oracle on the reference's own robot meshes: inside/outside == the reference-compiled FWN's (rounded), exact winding within the FWN's
+    approximation error, BVH distance == brute force; and the reference-faithful mode s = 1 - 2 w_FWN differs from ±1 by ~1e-3."""
+    z, _ = ref_mesh_cases()
+    V, F, pp, q, w_ref = z[name + "_V"], z[name + "_F"], z[name + "_pp"], z[name + "_q"], z[name + "_w"]
+    sh = O.Shape.mesh(V, F, pp)
+    r = sh.mesh_query(q)
+    assert np.array_equal(r["d2"], r["d2_brute"])
+    keep = np.sqrt(r["d2"]) > 1e-3
+    assert np.abs(r["w_exact"] - np.round(r["w_exact"])).max() < 1e-9          # closed, consistently oriented (what the product requires)
+    assert np.abs(w_ref - r["w_exact"])[keep].max() < 5e-3
+    sdf, _ = sh.query(q)
+    assert np.array_equal(sdf[keep] < 0, w_ref[keep] > 0.5)
+    if O.ref_fwn_available():
+        sdf_ref, g_ref = O.Shape.mesh(V, F, pp, wn_mode=O.WN_REF).query(q)
+        assert np.allclose(sdf_ref, (1 - 2 * w_ref) * np.sqrt(r["d2"]), rtol=1e-12, atol=1e-15)   # WN_REF mode = Shape.cpp:110-113 with the fixture's w
+        dev = np.abs(sdf_ref - sdf)[keep] / np.abs(sdf)[keep]
+        assert 1e-7 < dev.max() < 1e-2                                            # the FP32 order-2 tree's error reaches the SDF VALUE ...
+        _, g = sh.query(q)
+        assert np.abs(g_ref - g)[keep].max() < 1e-12                               # ... but not the (normalised) gradient
+
+
+def test_obj_reader_matches_fixture_on_reference_files():
+    """host/isdf_obj.hpp (read_triangle_mesh counterpart, Shape.cpp:36) on the reference's OBJ files — only where /root/reference exists"""
+    import host_lib as H
+    d = "/root/reference/src/plan_manager/shapes"
+    if not os.path.isdir(d):
+        pytest.skip("reference tree absent")
+    z, names = ref_mesh_cases()
+    for name in names:
+        V, F = H.read_obj(os.path.join(d, name + ".obj"))
+        assert np.array_equal(V, z[name + "_V"]) and np.array_equal(F, z[name + "_F"])
+    # independent numpy parse of one file
+    rows = [ln.split() for ln in open(os.path.join(d, "RoundedCone.obj")) if ln[:2] in ("v ", "f ")]
+    Vn = np.array([[float(x) for x in r[1:4]] for r in rows if r[0] == "v"])
+    Fn = np.array([[int(x.split("/")[0]) - 1 for x in r[1:4]] for r in rows if r[0] == "f"], dtype=np.int32)
+    assert np.array_equal(Vn, z["RoundedCone_V"]) and np.array_equal(Fn, z["RoundedCone_F"])
+
+
+def test_obj_reader_forms(tmp_path):
+    """index forms i, i/t, i/t/n, i//n, negative (relative) indices, polygon fans, comments"""
+    import host_lib as H
+    p = tmp_path / "t.obj"
+    p.write_text("# c\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0 1.0\nvn 0 0 1\nvt 0 0\nf 1/1/1 2/1/1 3/1/1 4/1/1\nv 0 0 1\nf -1 1//1 2\nf 1/1 3/1 5/1\n")
+    V, F = H.read_obj(str(p))
+    assert V.shape == (5, 3) and np.array_equal(F, [[0, 1, 2], [0, 2, 3], [4, 0, 1], [0, 2, 4]])
