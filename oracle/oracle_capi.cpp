@@ -146,7 +146,8 @@ int orc_eval_discrete(const orc_config *c, const uint8_t *occ, int X, int Y, int
     G.bmax = V3(bmin[0] + X * res, bmin[1] + Y * res, bmin[2] + Z * res);
     Traj tr; tr.N = N; tr.T = T; tr.C = C;
     EvalOut out;
-    eval_discrete(P, occ ? &G : nullptr, shape ? &((OrcShape *)shape)->s : nullptr, tr, out, use_omp != 0, rank, world > 0 ? world : 1);
+    // use_omp: 0 serial (THE ORACLE), 1 the reference's loop structure, 2 the "fair CPU" arm (per-thread accumulators + exact culls)
+    eval_discrete(P, occ ? &G : nullptr, shape ? &((OrcShape *)shape)->s : nullptr, tr, out, use_omp != 0, rank, world > 0 ? world : 1, use_omp == 2);
     *cost = out.cost;
     std::memcpy(gradC, out.gradC.data(), sizeof(double) * 18 * N);
     std::memcpy(gradT, out.gradT.data(), sizeof(double) * N);

@@ -144,6 +144,27 @@ struct Mesh {
         }
         return best;
     }
+    // same search started from bound2 instead of infinity: tri = -1 when no triangle lies within sqrt(bound2) (the "fair CPU" arm)
+    double closest_within(const V3 &p, double bound2, V3 &c, int &tri) const {
+        double best = bound2; tri = -1;
+        if (nodes.empty()) return best;
+        int stack[128]; int sp = 0; stack[sp++] = 0;
+        while (sp) {
+            const Node &nd = nodes[stack[--sp]];
+            if (box_d2(p, nd.lo, nd.hi) >= best) continue;
+            if (nd.tri >= 0) {
+                const V3 q = closest_on_triangle(p, vtx(nd.tri, 0), vtx(nd.tri, 1), vtx(nd.tri, 2));
+                const V3 d = p - q; const double d2 = dot(d, d);
+                if (d2 < best) { best = d2; c = q; tri = nd.tri; }
+                continue;
+            }
+            const double dl = box_d2(p, nodes[nd.left].lo, nodes[nd.left].hi);
+            const double dr = box_d2(p, nodes[nd.right].lo, nodes[nd.right].hi);
+            if (dl < dr) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+            else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+        }
+        return best;
+    }
     double closest_brute(const V3 &p, V3 &c, int &tri) const {
         double best = 1e300; tri = -1;
         for (int t = 0; t < ntri(); t++) {

@@ -150,7 +150,7 @@ struct EvalOut {
 // ---------------------------------------------------------------------------------------------
 // grad_cost_p (hpp:766-824): one pose against the occupied voxels in its AABB.
 inline bool grad_cost_p(const Params &P, const Grid &G, const Shape &S, const V3 &pos, const M3 &R, const double quat[4],
-                        V3 &gradp, double grad_quat[4], double &costp, long long *npairs) {
+                        V3 &gradp, double grad_quat[4], double &costp, long long *npairs, bool fair = false) {
     costp = 0.0; gradp = V3(); for (int k = 0; k < 4; k++) grad_quat[k] = 0.0;
     std::vector<V3> ob;
     G.points_in_aabb(pos, P.bd / 2, P.bd / 2, P.bd / 2, ob);
@@ -159,8 +159,10 @@ inline bool grad_cost_p(const Params &P, const Grid &G, const Shape &S, const V3
         const V3 prel = mulT(R, d);
         if (std::abs(prel.x) > P.bd / 2 || std::abs(prel.y) > P.bd / 2 || std::abs(prel.z) > P.bd / 2) continue;
         V3 grel;
-        const double sdf = S.sdf_grad(prel, grel);  // getSDFWithGradWhenRobotAtState (swm:537-541)
+        double sdf;
         if (npairs) (*npairs)++;
+        if (fair) { if (!S.sdf_grad_reach(prel, P.safety_hor, sdf, grel)) continue; }   // exact culls of the "fair CPU" arm
+        else sdf = S.sdf_grad(prel, grel);  // getSDFWithGradWhenRobotAtState (swm:537-541)
         double sdf_cost = 0, grad_out = 0.0;
         smoothedL1(P.safety_hor - sdf, P.smooth_fac, sdf_cost, grad_out);
         if (sdf_cost > 0) {
@@ -178,7 +180,7 @@ inline bool grad_cost_p(const Params &P, const Grid &G, const Shape &S, const V3
 struct SampleContribution { double gdC[18]; double gdT; double cost; int piece; };
 
 inline void eval_sample(const Params &P, const Grid *G, const Shape *S, const Flat &F, const Traj &tr, int count,
-                        SampleContribution &out, long long *npairs) {
+                        SampleContribution &out, long long *npairs, bool fair = false) {
     const int K = P.integral_res;
     const int j = count % (K + 1), i = count / (K + 1);
     const double integralFrac = 1.0 / K;
@@ -214,7 +216,7 @@ inline void eval_sample(const Params &P, const Grid *G, const Shape *S, const Fl
     }
     if (P.with_collision && G && S) {
         V3 gp; double gq[4], cp;
-        if (grad_cost_p(P, *G, *S, pos, R, quat, gp, gq, cp, npairs)) {  // wired as hpp:619-626
+        if (grad_cost_p(P, *G, *S, pos, R, quat, gp, gq, cp, npairs, fair)) {  // wired as hpp:619-626
             gradPos += P.weight_p * gp;
             for (int k = 0; k < 4; k++) gradQuat[k] += P.weight_p * gq[k];
             pena += P.weight_p * cp;
@@ -236,7 +238,10 @@ inline void eval_sample(const Params &P, const Grid *G, const Shape *S, const Fl
 // use_omp = false: serial, deterministic order (THE ORACLE).  use_omp = true: the reference's
 // `parallel for schedule(dynamic)` + `critical` structure (the CPU baseline; nondeterministic order).
 // rank/world: evaluate only samples with count % world == rank (partial sums; test harness for the multi-GPU sharding)
-inline void eval_discrete(const Params &P, const Grid *G, const Shape *S, const Traj &tr, EvalOut &out, bool use_omp, int rank = 0, int world = 1) {
+// fair = true (with use_omp): the "fair CPU" arm of BASELINE.md §2 — per-thread accumulators merged once instead of the critical section,
+// and the exact culls of Shape::sdf_grad_reach; same cost and gradient up to summation order.
+inline void eval_discrete(const Params &P, const Grid *G, const Shape *S, const Traj &tr, EvalOut &out, bool use_omp, int rank = 0, int world = 1,
+                          bool fair = false) {
     Flat F; F.reset(P.mass, P.grav, P.dh, P.dv, P.cp, P.veps);
     const int N = tr.N, K = P.integral_res, total = N * (K + 1);
     out.gradC.assign((size_t)18 * N, 0.0); out.gradT.assign(N, 0.0); out.cost = 0; out.n_pairs = 0;
@@ -250,6 +255,36 @@ inline void eval_discrete(const Params &P, const Grid *G, const Shape *S, const 
         for (int count = 0; count < total; count++) {
             if (count % world != rank) continue;
             SampleContribution c; eval_sample(P, G, S, F, tr, count, c, &out.n_pairs); accumulate(c);
+        }
+        return;
+    }
+    if (fair) {
+#ifdef _OPENMP
+#pragma omp parallel num_threads(P.threads)
+#endif
+        {
+            std::vector<double> lg((size_t)19 * N + 1, 0.0);   // thread-local [gradC | gradT | cost]
+            long long lnp = 0;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4) nowait
+#endif
+            for (int count = 0; count < total; count++) {
+                if (count % world != rank) continue;
+                SampleContribution c;
+                eval_sample(P, G, S, F, tr, count, c, &lnp, true);
+                for (int ax = 0; ax < 3; ax++)
+                    for (int k = 0; k < 6; k++) lg[(size_t)ax * 6 * N + 6 * c.piece + k] += c.gdC[ax * 6 + k];
+                lg[(size_t)18 * N + c.piece] += c.gdT;
+                lg[(size_t)19 * N] += c.cost;
+            }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+            {
+                for (size_t k = 0; k < (size_t)18 * N; k++) out.gradC[k] += lg[k];
+                for (int k = 0; k < N; k++) out.gradT[k] += lg[(size_t)18 * N + k];
+                out.cost += lg[(size_t)19 * N]; out.n_pairs += lnp;
+            }
         }
         return;
     }

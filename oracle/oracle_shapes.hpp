@@ -242,6 +242,34 @@ struct Shape {
         g = grad(p);    // helperfunc (Shape.hpp:58-81) / Box::getSDFwithGrad1 (Shape.hpp:2378-2388)
         return sdf(p);
     }
+
+    // "fair CPU" variant: the value is needed only where sdf < reach (the hinge's support), so the culls the GPU kernels
+    // use are applied here as well — all EXACT, i.e. they never change the cost or the gradient:
+    //   mesh     : outside the AABB inflated by reach -> inactive; BVH search bounded by reach; a point with no triangle within reach is
+    //              inactive unless it is inside (winding number), in which case the full search runs;
+    //   analytic : the six finite-difference evaluations of getSDFwithGrad1 only when the hinge is active.
+    // Returns false when the pair is inactive (sdf >= reach).
+    bool sdf_grad_reach(const V3 &p, double reach, double &s_out, V3 &g) const {
+        if (kind == SK_MESH) {
+            const Mesh::Node &root = mesh->nodes[0];
+            for (int a = 0; a < 3; a++) if (p[a] < root.lo[a] - reach || p[a] > root.hi[a] + reach) return false;
+            V3 c; int tri;
+            double d2 = mesh->closest_within(p, reach * reach, c, tri);
+            double s;
+            if (tri < 0) {
+                if (mesh->sign(p) > 0) return false;
+                d2 = mesh->closest(p, c, tri); s = -1.0;
+            } else s = mesh->sign(p);
+            g = normalized(s * (-(c - p)));
+            s_out = s * std::sqrt(d2);
+            return s_out < reach;
+        }
+        if (kind == SK_BALL || kind == SK_POINT) { s_out = sdf_grad(p, g); return s_out < reach; }
+        s_out = sdf(p);
+        if (!(s_out < reach)) return false;
+        g = grad(p);
+        return true;
+    }
 };
 
 // Factory mirroring SweptVolumeManager::shapeConstructors + initShape (swm:74-123, 255-275):
