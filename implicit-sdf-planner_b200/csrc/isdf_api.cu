@@ -58,7 +58,7 @@ struct isdf_ctx {
     int warp_slots = 148 * 16;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
     int sm_count = 148, mesh_blocks = 4, analytic_blocks = 4;   // persistent grids: one CTA per resident slot
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
-    DevBuf<unsigned long long> d_counter, d_dbg;
+    DevBuf<unsigned long long> d_counter, d_dbg, d_trace;
     DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout;   // batched callback (isdf_minco.cuh)
     int minco_B = 0, minco_N = 0;
     bool dbg_on = false;
@@ -169,7 +169,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release(); c->d_cell_rec.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_piece_cost.release();
-    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_split_done.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release();
+    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_split_done.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release(); c->d_trace.release();
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
@@ -629,13 +629,16 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
         A.peer = c->peer; A.peer.epoch = c->peer.epoch + 1;   // committed below, once the exchange kernel is really enqueued
     }
     A.dbg = nullptr;
+    A.trace = nullptr;
     if (c->dbg_on) { CU_TRY(c->d_dbg.ensure((size_t)3 * S)); CU_TRY(cudaMemsetAsync(c->d_dbg.p, 0, sizeof(unsigned long long) * 3 * S, st)); A.dbg = c->d_dbg.p; }
     const long long M = (S - c->rank + c->world - 1) / c->world;
     CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
     // longest-first order from the previous evaluation of the same problem shape (first evaluation: natural order)
     const long long sig = ((long long)N << 20) ^ ((long long)c->rank << 10) ^ c->world ^ ((long long)K << 40);
     const bool mesh = (c->shape.kind == ISDF_SHAPE_MESH);
-    const int max_split = mesh ? (int)std::min<long long>(M / 4 + 1, MAX_SPLIT_SLOTS) : 0;   // only mesh samples have a heavy tail worth splitting
+    // only mesh samples have a heavy tail worth splitting. Every sample of a launch may be split (item trace at world = 8, profiles/r02_tuning.md:
+    // with M/4 slots the 515 heaviest samples were split and the NEXT heaviest — unsplit, 15-25 queries, 80-110 us — set the kernel time)
+    const int max_split = mesh ? (int)std::min<long long>(M, MAX_SPLIT_SLOTS) : 0;
     const size_t max_items = (size_t)M + (size_t)(ROW_CLASSES - 1) * max_split;
     CU_TRY(c->d_work.ensure((size_t)S));
     if (c->d_items.n < 3 * max_items + (size_t)M) { CU_TRY(c->d_items.ensure(3 * max_items + (size_t)M)); c->order_for = -1; }   // a regrown table holds no items yet
@@ -650,6 +653,7 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
         CU_TRY(cudaMemsetAsync(c->d_split_done.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
     }
     A.work = c->d_work.p;
+    if (c->dbg_on) { CU_TRY(c->d_trace.ensure(TRACE_STRIDE * max_items)); CU_TRY(cudaMemsetAsync(c->d_trace.p, 0, sizeof(unsigned long long) * TRACE_STRIDE * max_items, st)); A.trace = c->d_trace.p; }
     // a launch with far more samples than resident warps (batched callbacks: millions) balances itself through the persistent warps'
     // dynamic item counter: sorting / splitting would only cost a long single-CTA pass over the work array
     const bool want_items = !c->no_items && M <= 1024ll * ITEMS_CACHE * 4;
@@ -1228,6 +1232,12 @@ extern "C" int isdf_dbg_swept_stats(isdf_ctx *c, unsigned long long *out, long l
     if (!c || !out || (size_t)n > c->sv.d_dbg.n) return -1;
     cudaStreamSynchronize(c->stream);
     return cudaMemcpy(out, c->sv.d_dbg.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
+extern "C" int isdf_dbg_trace_stride(void) { return TRACE_STRIDE; }
+extern "C" int isdf_dbg_item_trace(isdf_ctx *c, unsigned long long *out, long long n) {
+    if (!c || !out || (size_t)n > c->d_trace.n) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -3;
+    return cudaMemcpy(out, c->d_trace.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
 extern "C" int isdf_dbg_sample_stats(isdf_ctx *c, unsigned long long *out, long long n) {
     if (!c || !out || (size_t)n > c->d_dbg.n) return -1;

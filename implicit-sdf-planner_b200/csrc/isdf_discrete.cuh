@@ -45,7 +45,7 @@ constexpr int DISC_THREADS = DISC_WARPS * 32;
 constexpr int QCAP = 64;
 constexpr int ROW_CLASSES = 32;         // a pose window's rows are summed in 32 interleaved classes (canonical order): row r -> class r % 32
 constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than this (work units: 64 per mesh query + 1 per culled pair)
-constexpr int MAX_SPLIT_SLOTS = 8192;   // split samples per launch (2 KB of class sums each)
+constexpr int MAX_SPLIT_SLOTS = 16384;  // split samples per launch (2 KB of class sums each)
 constexpr int WINDOW_AXIS_MAX = 1023;   // voxels per window axis: window offsets are packed 10 bits per axis
 // CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md, r02_tuning.md)
 constexpr int ANALYTIC_MIN_BLOCKS = 4;
@@ -69,6 +69,7 @@ struct DiscArgs {
     double *out;           // 19N+1: cost | gradC | gradT
     unsigned long long *pair_counter;  // may be null
     unsigned long long *dbg;           // may be null: per sample {cycles, pairs, work}
+    unsigned long long *trace;         // may be null: per work-item slot {begin, end} in ns of the global timer (+ 6 phase cycle counts with -DISDF_PHASE_TIMING)
     const int *items;                  // may be null: 3 ints per work item {local sample m, -1 = all classes or c0 | c1 << 8, split slot or -1}
     const int *item_count;             // number of valid items (device)
     int *item_cursor;                  // persistent warps draw items from this counter (zero on entry; the epilogue zeroes it again)
@@ -260,7 +261,15 @@ __device__ __forceinline__ void sample_epilogue(const DiscArgs &A, int i, int j,
 
 // ============================================================================================================================
 // Work item of a warp: {global sample, first class, one-past-last class, split slot}.
-struct Item { int s, c0, c1, hslot; };
+struct Item { int s, c0, c1, hslot, slot; };
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef ISDF_PHASE_TIMING
+constexpr int TRACE_STRIDE = 8;
+#define ISDF_PT(x) x
+#else
+constexpr int TRACE_STRIDE = 2;
+#define ISDF_PT(x)
+#endif
 
 // Persistent-warp scheduler: the warp's next work item, or false when the table is exhausted. Which warp takes which item
 // never touches the arithmetic, so results stay bit-reproducible.
@@ -271,6 +280,7 @@ __device__ __forceinline__ bool next_item(const DiscArgs &A, Item &it, int lane)
     int slot = 0;
     if (lane == 0) slot = atomicAdd(A.item_cursor, 1);
     slot = __shfl_sync(0xffffffffu, slot, 0);
+    it.slot = slot;
     if (A.items) {
         if (slot >= __ldg(A.item_count)) return false;
         const int m = __ldg(A.items + 3 * slot), part = __ldg(A.items + 3 * slot + 1);
@@ -513,6 +523,8 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
         const int s = it.s;
         const int i = s / (K + 1), j = s - i * (K + 1);
         const long long t_begin = A.dbg ? clock64() : 0;
+        if (A.trace && lane == 0) A.trace[TRACE_STRIDE * (size_t)it.slot] = global_ns();
+        ISDF_PT(long long pt_pose = 0; long long pt_cull = 0; long long pt_search = 0; long long pt_tail = 0; long long pt_t0 = clock64(); long long pt_all0 = pt_t0;)
         unsigned npairs = 0, nquery = 0;
         const bool whole = (it.c1 - it.c0) == ROW_CLASSES;
 
@@ -533,6 +545,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
             }
             for (int k = lane; k < ROW_CLASSES * 8; k += 32) (&sm.cacc[0][0])[k] = 0.0;
             __syncwarp();
+            ISDF_PT(pt_pose = clock64() - pt_t0;)
             const int ny = W.iy1 - W.iy0 + 1;
             const int nrows = (W.ix1 - W.ix0 + 1) * ny;
             const float inv_ny = 1.0f / (float)ny;
@@ -542,6 +555,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
             // contributions are then added to the class accumulators in voxel order by lanes 0..7 (one per component)
             auto flush_tails = [&]() __attribute__((always_inline)) {
                 __syncwarp();
+                ISDF_PT(const long long pt_a = clock64();)
                 bool active = false;
                 if (lane < nres) {
                     const QRes r = sm.qr[lane];
@@ -567,11 +581,13 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 }
                 __syncwarp();
                 nres = 0;
+                ISDF_PT(pt_tail += clock64() - pt_a;)
             };
 
             int nsv = 0;   // queued survivors (warp-uniform)
             // cull stage for the n oldest voxels of the ring (n <= 32): survivors are appended to the survivor queue
             auto cull = [&](int n) __attribute__((always_inline)) {
+                ISDF_PT(const long long pt_a = clock64();)
                 bool pass = false, box = false;
                 uint32_t code = 0;
                 d3 prel = mk3(0, 0, 0);
@@ -605,11 +621,13 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 }
                 nsv += __popc(bal);
                 __syncwarp();
+                ISDF_PT(pt_cull += clock64() - pt_a;)
             };
             // search stage for every queued survivor, in voxel order, software-pipelined ACROSS queries: while query k runs, the
             // first 32 candidate ids of query k+2 are being loaded and the triangle records of query k+1's first pass are
             // prefetched into L1 — the id -> record -> arithmetic chain of a query starts with its operands already close
             auto search_all = [&](bool final) __attribute__((always_inline)) {
+                ISDF_PT(const long long pt_a = clock64(); const long long pt_tail0 = pt_tail;)
                 nquery += nsv;
                 auto first_ids = [&](int k) -> int {
                     if (k >= nsv) return -1;
@@ -641,6 +659,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 } while (k < nsv);
                 __syncwarp();
                 nsv = 0;
+                ISDF_PT(pt_search += (clock64() - pt_a) - (pt_tail - pt_tail0);)
             };
 
             // Producer loop (one cull and one search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
@@ -751,6 +770,11 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
             }
         } else {
             sample_finish_whole(A, it, 0.0, 0u, t_begin, 0u);
+        }
+        if (A.trace && lane == 0) {
+            unsigned long long *tr = A.trace + TRACE_STRIDE * (size_t)it.slot;
+            tr[1] = global_ns();
+            ISDF_PT(tr[2] = pt_pose; tr[3] = pt_cull; tr[4] = pt_search; tr[5] = pt_tail; tr[6] = clock64() - pt_all0; tr[7] = ((unsigned long long)nquery << 32) | npairs;)
         }
         __syncwarp();
     }

@@ -23,13 +23,18 @@ else:
     import workloads as W
     R, t = W.rotation_from_poly_params(w["poly_params"])
     ev.set_shape_named(robot, R, t)
+for a in sys.argv:
+    if a.startswith("--shard="):   # --shard=rank/world: one rank's shard, no exchange
+        r_, w_ = a[8:].split("/")
+        ev.set_shard(int(r_), int(w_))
 if "--natural" in sys.argv:
     ev.dbg_schedule(natural_order=True)
-d_T, d_C = torch.from_numpy(T).to(dev), torch.from_numpy(Cc).to(dev)
+iters = B.make_iterates(w, T, Cc, steps)
+d_T, d_Cs = torch.from_numpy(T).to(dev), torch.from_numpy(iters).to(dev)
 d_out = torch.zeros(19 * N + 1, dtype=torch.float64, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
-for _ in range(steps):
-    ev.eval_discrete_device(N, d_T.data_ptr(), d_C.data_ptr(), d_out.data_ptr(), stream)
+for k in range(steps):
+    ev.eval_discrete_device(N, d_T.data_ptr(), d_Cs[k].data_ptr(), d_out.data_ptr(), stream)
     torch.cuda.synchronize()
 print("cost", float(d_out[0].item()))
 ev.close()
