@@ -53,18 +53,17 @@ struct isdf_ctx {
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_piece_cost;
     DevBuf<int> d_tickets;       // pieces_done counter of the epilogue kernel
-    DevBuf<double> d_tot;   // per-sample collision sums handed from the scan kernels to the epilogue
-    DevBuf<int> d_items; DevBuf<unsigned> d_work;   // analytic kernel: sample order (longest first) and the work each sample reported
-    // mesh path: survivor chunks handed from the cull kernel to the search kernel to the epilogue
-    DevBuf<double> d_pose, d_chunk_sum; DevBuf<int> d_sample_run; DevBuf<int4> d_chunk_hdr; DevBuf<SurvRec> d_chunk_rec;
-    long long chunks_per_sample = 4, chunk_cap_min = 0;   // capacity = max(8192, chunks_per_sample * local samples); grown after an overflow
-    int sm_count = 148, cull_blocks = 8, search_blocks = 5, analytic_blocks = 4;   // persistent grids: one CTA per resident slot
+    DevBuf<double> d_tot; DevBuf<unsigned> d_split_done;   // per-sample collision sums handed from the scan kernels to the epilogue
+    DevBuf<int> d_items, d_item_count; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
+    int warp_slots = 148 * 16;   // resident warps of the mesh kernel on this device (SMs x CTAs/SM x warps/CTA)
+    int sm_count = 148, mesh_blocks = 4, analytic_blocks = 4;   // persistent grids: one CTA per resident slot
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
-    DevBuf<unsigned long long> d_counter, d_dbg;
+    DevBuf<unsigned long long> d_counter, d_dbg, d_trace;
     DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout;   // batched callback (isdf_minco.cuh)
     int minco_B = 0, minco_N = 0;
     bool dbg_on = false;
-    bool no_items = false;       // diagnostics: analytic kernel always in natural sample order (isdf_dbg_schedule)
+    bool no_items = false;       // diagnostics: always launch in natural order, never split (isdf_dbg_schedule)
+    int warp_slots_override = 0; // diagnostics: pretend the device has this many resident warps (forces splitting)
     double *h_stage = nullptr;   // pinned
     size_t h_stage_n = 0;
     // swept volume
@@ -124,8 +123,8 @@ extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
     if (device < 0 || device >= ndev) return fail(ISDF_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
     CU_TRY(cudaSetDevice(device));
     // fail loudly if the sm_100a image cannot run here
-    int nb_cull = 0, nb_search = 0, nb_analytic = 0;
-    CU_TRY(discrete_resident_blocks(&nb_cull, &nb_search, &nb_analytic));
+    int nb_mesh = 0, nb_analytic = 0;
+    CU_TRY(discrete_resident_blocks(&nb_mesh, &nb_analytic));
     // pose-window offsets are packed 10 bits per axis (isdf_discrete.cuh); the inclusive index range of a window is at most
     // kernel_size + 2 voxels when the map resolution equals occupancy_resolution (isdf_set_map checks the resolution)
     if (cfg->kernel_size + 2 > WINDOW_AXIS_MAX) return fail(ISDF_ERR_UNSUPPORTED, "kernel_size too large (pose windows are limited to 1023 voxels per axis)");
@@ -133,9 +132,10 @@ extern "C" int isdf_create(const isdf_config *cfg, int device, isdf_ctx **out) {
     c->device = device; c->cfg = *cfg;
     {
         cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && nb_cull > 0 && nb_search > 0 && nb_analytic > 0) {
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && nb_mesh > 0 && nb_analytic > 0) {
             c->sm_count = prop.multiProcessorCount;
-            c->cull_blocks = nb_cull; c->search_blocks = nb_search; c->analytic_blocks = nb_analytic;
+            c->mesh_blocks = nb_mesh; c->analytic_blocks = nb_analytic;
+            c->warp_slots = prop.multiProcessorCount * nb_mesh * DISC_WARPS;
         }
     }
     std::memset(&c->stats, 0, sizeof(c->stats));
@@ -169,8 +169,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release(); c->d_cell_rec.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_piece_cost.release();
-    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_tot.release(); c->d_work.release(); c->d_dbg.release();
-    c->d_pose.release(); c->d_chunk_sum.release(); c->d_sample_run.release(); c->d_chunk_hdr.release(); c->d_chunk_rec.release();
+    c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_split_done.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release(); c->d_trace.release();
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
@@ -607,30 +606,19 @@ extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints,
 }
 
 // ---- discrete evaluation ------------------------------------------------------------------------------------
-// after a survivor-storage overflow (mesh path): clear the sticky flag and quadruple the capacity for the next attempt
-static int discrete_survivor_regrow(isdf_ctx *c) {
-    c->chunks_per_sample *= 4;
-    CU_TRY(cudaMemsetAsync(c->d_tickets.p + 4, 0, sizeof(int), c->stream));
-    return 0;
-}
-
-// local samples (s % world == rank) below sample index S0
-static long long local_count(long long S0, int rank, int world) { return S0 > rank ? (S0 - rank + world - 1) / world : 0; }
-
 static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *d_C, double *d_out, cudaStream_t st) {
     const int K = c->cfg.integral_intervs;
     const long long S = (long long)N * (K + 1);
     if (S > 0x7fffffffll) return fail(ISDF_ERR_UNSUPPORTED, "N * (integral_intervs + 1) must fit in 31 bits");
     CU_TRY(c->d_piece_cost.ensure(N));
-    if (c->d_tickets.n < 8) {   // [0] pieces_done of the epilogue, [1] item cursor of the persistent scan warps, [2] chunk counter, [3] search cursor, [4] overflow
-        CU_TRY(c->d_tickets.ensure(8));
-        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, 8 * sizeof(int), st));
+    if (c->d_tickets.n < 2) {   // [0] pieces_done of the epilogue, [1] work-item cursor of the persistent scan warps
+        CU_TRY(c->d_tickets.ensure(2));
+        CU_TRY(cudaMemsetAsync(c->d_tickets.p, 0, 2 * sizeof(int), st));
     }
+    CU_TRY(c->d_tot.ensure((size_t)S * 8));
     DiscArgs A;
-    std::memset(&A, 0, sizeof(A));
     A.cfg = c->dcfg; A.grid = c->grid; A.shape = c->shape; A.N = N; A.T = d_T; A.C = d_C;
-    A.pieces_done = c->d_tickets.p; A.item_cursor = c->d_tickets.p + 1;
-    A.chunk_counter = c->d_tickets.p + 2; A.search_cursor = c->d_tickets.p + 3; A.overflow = c->d_tickets.p + 4;
+    A.tot = c->d_tot.p; A.pieces_done = c->d_tickets.p; A.item_cursor = c->d_tickets.p + 1;
     A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
     A.rank = c->rank; A.world = c->world;
     A.peer = PeerArgs{};
@@ -641,63 +629,56 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
         A.peer = c->peer; A.peer.epoch = c->peer.epoch + 1;   // committed below, once the exchange kernel is really enqueued
     }
     A.dbg = nullptr;
+    A.trace = nullptr;
     if (c->dbg_on) { CU_TRY(c->d_dbg.ensure((size_t)3 * S)); CU_TRY(cudaMemsetAsync(c->d_dbg.p, 0, sizeof(unsigned long long) * 3 * S, st)); A.dbg = c->d_dbg.p; }
-    const long long M = local_count(S, c->rank, c->world);
+    const long long M = (S - c->rank + c->world - 1) / c->world;
     CU_TRY(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), st));
-    const bool mesh = (c->shape.kind == ISDF_SHAPE_MESH);
-    if (mesh) {
-        // ---- mesh robot: cull -> search -> epilogue, in slabs of whole pieces so that the survivor storage stays bounded (a batched
-        // callback concatenates millions of samples); a single trajectory is one slab
-        A.use_chunks = 1;
-        const long long slab_pieces = std::max<long long>(1, (long long)DISC_SLAB_SAMPLES * c->world / (K + 1));
-        for (long long p0 = 0; p0 < N; p0 += slab_pieces) {
-            const long long p1 = std::min<long long>(N, p0 + slab_pieces);
-            const long long m0 = local_count(p0 * (K + 1), c->rank, c->world), m1 = local_count(p1 * (K + 1), c->rank, c->world);
-            const long long Ms = m1 - m0;
-            const long long cap = std::max<long long>(c->chunk_cap_min, std::max<long long>(8192, c->chunks_per_sample * Ms));
-            if (cap > 0x3fffffffll) return fail(ISDF_ERR_UNSUPPORTED, "survivor storage too large");
-            CU_TRY(c->d_pose.ensure((size_t)16 * std::max<long long>(Ms, 1)));
-            CU_TRY(c->d_sample_run.ensure((size_t)2 * std::max<long long>(Ms, 1)));
-            CU_TRY(c->d_chunk_hdr.ensure((size_t)cap)); CU_TRY(c->d_chunk_rec.ensure((size_t)cap * CHUNK)); CU_TRY(c->d_chunk_sum.ensure((size_t)cap * 8));
-            A.p0 = (int)p0; A.m0 = (int)m0; A.m1 = (int)m1; A.chunk_cap = (int)std::min<long long>(cap, (long long)c->d_chunk_hdr.n);
-            A.pose = c->d_pose.p; A.sample_run = c->d_sample_run.p; A.chunk_hdr = c->d_chunk_hdr.p; A.chunk_rec = c->d_chunk_rec.p; A.chunk_sum = c->d_chunk_sum.p;
-            const long long res_cull = (long long)c->sm_count * c->cull_blocks, res_search = (long long)c->sm_count * c->search_blocks;
-            const unsigned g_cull = (unsigned)std::max<long long>(1, std::min((Ms + DISC_WARPS - 1) / DISC_WARPS, res_cull));
-            const unsigned g_search = (unsigned)std::max<long long>(1, std::min(Ms + DISC_WARPS, res_search));   // chunk count unknown on the host: <= one warp per sample is plenty for a small launch
-            CU_TRY(discrete_launch_mesh(A, g_cull, g_search, st));
-            CU_TRY(discrete_launch_epilogue(A, (int)(p1 - p0), st));
-            c->stats.kernel_launches += 3;
-        }
-        if (fused) c->peer.epoch = A.peer.epoch;
-        c->stats.evals_discrete++;
-        return 0;
-    }
-    // ---- analytic robots: one scan kernel (longest-first sample order learned from the previous evaluation) + epilogue
-    CU_TRY(c->d_tot.ensure((size_t)S * 8));
-    A.tot = c->d_tot.p; A.use_chunks = 0; A.p0 = 0; A.m0 = 0; A.m1 = (int)M;
+    // longest-first order from the previous evaluation of the same problem shape (first evaluation: natural order)
     const long long sig = ((long long)N << 20) ^ ((long long)c->rank << 10) ^ c->world ^ ((long long)K << 40);
+    const bool mesh = (c->shape.kind == ISDF_SHAPE_MESH);
+    // only mesh samples have a heavy tail worth splitting. Every sample of a launch may be split (item trace at world = 8, profiles/r02_tuning.md:
+    // with M/4 slots the 515 heaviest samples were split and the NEXT heaviest — unsplit, 15-25 queries, 80-110 us — set the kernel time)
+    const int max_split = mesh ? (int)std::min<long long>(M, MAX_SPLIT_SLOTS) : 0;
+    const size_t max_items = (size_t)M + (size_t)(ROW_CLASSES - 1) * max_split;
     CU_TRY(c->d_work.ensure((size_t)S));
-    if (c->d_items.n < (size_t)std::max<long long>(M, 1)) { CU_TRY(c->d_items.ensure((size_t)std::max<long long>(M, 1))); c->order_for = -1; }   // a regrown table holds no items yet
+    if (c->d_items.n < 3 * max_items + (size_t)M) { CU_TRY(c->d_items.ensure(3 * max_items + (size_t)M)); c->order_for = -1; }   // a regrown table holds no items yet
+    CU_TRY(c->d_item_count.ensure(1));
+    CU_TRY(c->d_subsum.ensure((size_t)std::max(max_split, 1) * ROW_CLASSES * 8));
+    if (c->d_split_work.n < (size_t)std::max(max_split, 1)) {
+        CU_TRY(c->d_split_work.ensure((size_t)std::max(max_split, 1)));
+        CU_TRY(cudaMemsetAsync(c->d_split_work.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
+    }
+    if (c->d_split_done.n < (size_t)std::max(max_split, 1)) {
+        CU_TRY(c->d_split_done.ensure((size_t)std::max(max_split, 1)));
+        CU_TRY(cudaMemsetAsync(c->d_split_done.p, 0, sizeof(unsigned) * std::max(max_split, 1), st));
+    }
     A.work = c->d_work.p;
-    const bool want_items = !c->no_items && M <= ITEMS_MAX_SAMPLES;
+    if (c->dbg_on) { CU_TRY(c->d_trace.ensure(TRACE_STRIDE * max_items)); CU_TRY(cudaMemsetAsync(c->d_trace.p, 0, sizeof(unsigned long long) * TRACE_STRIDE * max_items, st)); A.trace = c->d_trace.p; }
+    // a launch with far more samples than resident warps (batched callbacks: millions) balances itself through the persistent warps'
+    // dynamic item counter: sorting / splitting would only cost a long single-CTA pass over the work array
+    const bool want_items = !c->no_items && M <= 1024ll * ITEMS_CACHE * 4;
     const bool have_items = (c->order_for == sig) && want_items;
     A.items = have_items ? c->d_items.p : nullptr;
-    const long long resident = (long long)c->sm_count * c->analytic_blocks;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min((M + DISC_WARPS - 1) / DISC_WARPS, resident));
+    A.item_count = c->d_item_count.p; A.subsum = c->d_subsum.p; A.split_work = c->d_split_work.p; A.split_done = c->d_split_done.p;
+    // persistent grid: one CTA per resident slot (or fewer when there are fewer items than warps)
+    const long long want = ((have_items ? (long long)max_items : M) + DISC_WARPS - 1) / DISC_WARPS;
+    const long long resident = (long long)c->sm_count * (mesh ? c->mesh_blocks : c->analytic_blocks);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min(want, resident));
     if (c->items_pending) CU_TRY(cudaStreamWaitEvent(st, c->ev_items_done, 0));   // the table this launch reads (or overwrites next)
-    CU_TRY(discrete_launch_analytic(A, grid, st));
-    CU_TRY(discrete_launch_epilogue(A, N, st));
+    CU_TRY(discrete_launch_scan(A, mesh, grid, st));
+    CU_TRY(discrete_launch_epilogue(A, st));
     if (fused) c->peer.epoch = A.peer.epoch;
-    if (want_items) {   // the next evaluation's order, built on the aux stream: overlaps the caller's D2H / host work
+    // build the next evaluation's work items on the aux stream: overlaps the caller's D2H / all-reduce / host work
+    if (want_items) {
         CU_TRY(cudaEventRecord(c->ev_main_done, st));
         CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_main_done, 0));
-        CU_TRY(discrete_launch_build_items(c->d_work.p, c->rank, c->world, (int)M, c->d_items.p, c->aux_stream));
+        CU_TRY(discrete_launch_build_items(c->d_work.p, c->rank, c->world, (int)M, max_split, c->warp_slots_override > 0 ? c->warp_slots_override : c->warp_slots, c->d_items.p, c->d_item_count.p, c->aux_stream));
         CU_TRY(cudaEventRecord(c->ev_items_done, c->aux_stream));
         c->items_pending = true;
         c->order_for = sig;
-        c->stats.kernel_launches++;
+        c->stats.kernel_launches++;   // work-item builder
     }
-    c->stats.kernel_launches += 2;
+    c->stats.kernel_launches += 2;   // scan kernel, epilogue
     c->stats.evals_discrete++;
     return 0;
 }
@@ -734,23 +715,15 @@ extern "C" int isdf_eval_discrete(isdf_ctx *c, int N, const double *T, const dou
         std::memcpy(c->h_stage + N, coeffs, sizeof(double) * 18 * N);
         CU_TRY(cudaMemcpyAsync(c->d_T.p, c->h_stage, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage + N, sizeof(double) * 18 * N, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaEventRecord(c->ev0, c->stream));
+        int rr = launch_discrete(c, N, c->d_T.p, c->d_C.p, c->d_out.p, c->stream);
+        if (rr) return rr;
+        CU_TRY(cudaEventRecord(c->ev1, c->stream));
         double *h_out = c->h_stage + nin;
+        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
         unsigned long long pairs = 0;
-        for (int attempt = 0;; attempt++) {
-            CU_TRY(cudaEventRecord(c->ev0, c->stream));
-            int rr = launch_discrete(c, N, c->d_T.p, c->d_C.p, c->d_out.p, c->stream);
-            if (rr) return rr;
-            CU_TRY(cudaEventRecord(c->ev1, c->stream));
-            CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(cudaMemcpyAsync(&pairs, c->d_counter.p, sizeof(pairs), cudaMemcpyDeviceToHost, c->stream));
-            int over = 0;
-            CU_TRY(cudaMemcpyAsync(&over, c->d_tickets.p + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(cudaStreamSynchronize(c->stream));
-            if (!over) break;
-            // the mesh path's survivor storage was too small for this evaluation (result poisoned): grow it and evaluate again
-            if (attempt >= 8) return fail(ISDF_ERR_CUDA, "survivor storage overflow persists");
-            if (discrete_survivor_regrow(c)) return ISDF_ERR_CUDA;
-        }
+        CU_TRY(cudaMemcpyAsync(&pairs, c->d_counter.p, sizeof(pairs), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->stats.last_kernel_ms = ms; c->stats.last_pairs = (int64_t)pairs;
         *cost += h_out[0];                                   // accumulate like hpp:539-550
@@ -784,13 +757,13 @@ static int callback_batch_launch(isdf_ctx *c, int B, int N0, const double *d_hea
     MincoArgs M;
     M.B = B; M.N = N0; M.x = d_x; M.head = d_head; M.tail = d_tail; M.bc_stride = bc_stride; M.rho = rho;
     M.T = c->d_mT.p; M.C = c->d_mC.p; M.lu = c->d_mlu.p; M.energy = c->d_men.p; M.gC_e = c->d_mgC.p; M.gT_e = c->d_mgT.p;
-    M.disc_out = nullptr; M.piece_cost = nullptr; M.cost = d_cost; M.grad = d_grad; M.fail_flag = nullptr;
+    M.disc_out = nullptr; M.piece_cost = nullptr; M.cost = d_cost; M.grad = d_grad;
     CU_TRY(cudaFuncSetAttribute(k_minco_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(cudaFuncSetAttribute(k_minco_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_minco_forward<<<B, 32, smem, st>>>(M);
     int r = launch_discrete(c, (int)BN, M.T, M.C, c->d_mout.p, st);
     if (r) return r;
-    M.disc_out = c->d_mout.p; M.piece_cost = c->d_piece_cost.p; M.fail_flag = c->d_tickets.p + 4;
+    M.disc_out = c->d_mout.p; M.piece_cost = c->d_piece_cost.p;
     k_minco_backward<<<B, 32, smem, st>>>(M);
     c->stats.kernel_launches += 2;
     c->minco_B = B; c->minco_N = N0;
@@ -829,20 +802,13 @@ extern "C" int isdf_callback_batch(isdf_ctx *c, int B, int N0, const double *hea
         CU_TRY(cudaMemcpyAsync(c->d_mbc.p, head, sizeof(double) * nbc, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->d_mbc.p + nbc, tail, sizeof(double) * nbc, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(c->d_mcost.ensure(B)); CU_TRY(c->d_mgrad.ensure(dim * B));
-        for (int attempt = 0;; attempt++) {
-            CU_TRY(cudaEventRecord(c->ev0, c->stream));
-            int rr = callback_batch_launch(c, B, N0, c->d_mbc.p, c->d_mbc.p + nbc, per_problem_bc ? 9 : 0, rho, c->d_mx.p, c->d_mcost.p, c->d_mgrad.p, c->stream);
-            if (rr) return rr;
-            CU_TRY(cudaEventRecord(c->ev1, c->stream));
-            CU_TRY(cudaMemcpyAsync(cost, c->d_mcost.p, sizeof(double) * B, cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(cudaMemcpyAsync(grad, c->d_mgrad.p, sizeof(double) * dim * B, cudaMemcpyDeviceToHost, c->stream));
-            int over = 0;
-            CU_TRY(cudaMemcpyAsync(&over, c->d_tickets.p + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(cudaStreamSynchronize(c->stream));
-            if (!over) break;
-            if (attempt >= 8) return fail(ISDF_ERR_CUDA, "survivor storage overflow persists");
-            if (discrete_survivor_regrow(c)) return ISDF_ERR_CUDA;
-        }
+        CU_TRY(cudaEventRecord(c->ev0, c->stream));
+        int rr = callback_batch_launch(c, B, N0, c->d_mbc.p, c->d_mbc.p + nbc, per_problem_bc ? 9 : 0, rho, c->d_mx.p, c->d_mcost.p, c->d_mgrad.p, c->stream);
+        if (rr) return rr;
+        CU_TRY(cudaEventRecord(c->ev1, c->stream));
+        CU_TRY(cudaMemcpyAsync(cost, c->d_mcost.p, sizeof(double) * B, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(grad, c->d_mgrad.p, sizeof(double) * dim * B, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->stats.last_kernel_ms = ms;
         return 0;
@@ -1224,23 +1190,27 @@ extern "C" int isdf_get_swept_results(isdf_ctx *c, double *tstar, double *sdf, d
 
 // ---- internal diagnostics (not part of include/isdf.h) ------------------------------------------------------------
 extern "C" int isdf_dbg_enable(isdf_ctx *c, int on) { if (!c) return -1; c->dbg_on = on != 0; c->sv.dbg_on = on != 0; return 0; }
-// scheduling diagnostics: natural_order != 0 -> the analytic scan kernel always runs in natural sample order (the state of a context's
-// FIRST evaluation); chunks_per_sample > 0 -> size the mesh path's survivor storage as max(8192, chunks_per_sample * samples) chunks
-// (tests use 1 with a tiny map to provoke an overflow and check the NaN / regrow contract); 0 keeps the current value.
-extern "C" int isdf_dbg_schedule(isdf_ctx *c, int natural_order, int chunks_per_sample) {
+// scheduling diagnostics: natural_order != 0 -> every launch in natural sample order, nothing split (the state of a context's FIRST
+// evaluation); warp_slots > 0 -> build the work items as if the device had that many resident warps (huge values shrink the
+// balanced share per warp and force every non-trivial sample to be split, so tests can compare split parts against the oracle on one
+// GPU); 0 restores the device's own figure.
+extern "C" int isdf_dbg_schedule(isdf_ctx *c, int natural_order, int warp_slots) {
     if (!c) return -1;
-    c->no_items = natural_order != 0; c->order_for = -1;
-    if (chunks_per_sample > 0) c->chunks_per_sample = chunks_per_sample;
+    c->no_items = natural_order != 0; c->warp_slots_override = warp_slots > 0 ? warp_slots : 0; c->order_for = -1;
     return 0;
 }
-// mesh path, last discrete evaluation (its last slab): number of survivor chunks written, and whether the survivor storage overflowed
-extern "C" int isdf_dbg_item_stats(isdf_ctx *c, int *chunk_count, int *overflowed) {
-    if (!c || !chunk_count || !overflowed || c->d_tickets.n < 8) return -1;
+// number of work items / split samples of the table built by the last discrete evaluation
+extern "C" int isdf_dbg_item_stats(isdf_ctx *c, int *item_count, int *split_parts) {
+    if (!c || !item_count || !split_parts || !c->d_item_count.p) return -1;
     if (cudaSetDevice(c->device) != cudaSuccess) return -3;
-    cudaStreamSynchronize(c->stream);
-    int t[8];
-    if (cudaMemcpy(t, c->d_tickets.p, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
-    *chunk_count = t[5]; *overflowed = t[4];
+    cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->aux_stream);
+    int n = 0;
+    if (cudaMemcpy(&n, c->d_item_count.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    std::vector<int> it((size_t)3 * std::max(n, 1));
+    if (n > 0 && cudaMemcpy(it.data(), c->d_items.p, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    int parts = 0;
+    for (int k = 0; k < n; k++) if (it[3 * k + 2] >= 0) parts++;
+    *item_count = n; *split_parts = parts;
     return 0;
 }
 // the device flatness map and its adjoint as compiled into the epilogue kernel: vaj n x 9 (vel, acc, jer), grads n x 10
@@ -1262,6 +1232,12 @@ extern "C" int isdf_dbg_swept_stats(isdf_ctx *c, unsigned long long *out, long l
     if (!c || !out || (size_t)n > c->sv.d_dbg.n) return -1;
     cudaStreamSynchronize(c->stream);
     return cudaMemcpy(out, c->sv.d_dbg.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}
+extern "C" int isdf_dbg_trace_stride(void) { return TRACE_STRIDE; }
+extern "C" int isdf_dbg_item_trace(isdf_ctx *c, unsigned long long *out, long long n) {
+    if (!c || !out || (size_t)n > c->d_trace.n) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -3;
+    return cudaMemcpy(out, c->d_trace.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
 }
 extern "C" int isdf_dbg_sample_stats(isdf_ctx *c, unsigned long long *out, long long n) {
     if (!c || !out || (size_t)n > c->d_dbg.n) return -1;

@@ -1,5 +1,5 @@
-// Discrete collision cost/gradient kernels: scan kernels (persistent warps) and an epilogue kernel (thread per sample, CTA per piece)
-// per optimiser step.
+// Discrete collision cost/gradient kernels: a scan kernel (persistent warps drawing pose-sample work items) and an epilogue kernel
+// (thread per sample, CTA per piece) per optimiser step.
 //
 // Reference semantics: addTimeIntPenaltyParallel (back_end_optimizer.hpp:432-554) with grad_cost_p (hpp:766-824)
 // wired into the sample loop exactly as hpp:619-626 wires its swept-volume sibling; PCSmapManager::getPointsInAABB
@@ -7,29 +7,29 @@
 //
 // Mapping (B200-first, not the reference's OpenMP-over-samples + critical section):
 //   * the pose window is read from the BIT-packed occupancy: lane = (x,y) row, one or two 32-bit loads + funnel shift give the
-//     row's z-run; only the occupied voxels are enumerated, in the reference's (x, y, z) order, and compacted through a per-warp
-//     shared-memory ring so that every cull pass runs on 32 live voxels (the reference tests every voxel and heap-allocates a
-//     vector per sample, hpp:787);
-//   * PERSISTENT warps draw work items from one device counter: a warp that finishes a light item takes the next one at once
-//     instead of idling until its CTA's slowest warp is done;
-//   * mesh robots — k_discrete_mesh_cull (item = pose sample: pose, window scan, the exact culls: body-frame box, inflated mesh
-//     AABB, per-cell distance lower bound) writes the surviving voxels as CHUNKS of <= 8 voxels; k_discrete_mesh_search (item =
-//     chunk) answers them with WARP-COOPERATIVE nearest-triangle searches (the cell's exact candidate list near the surface, 32
+//     row's z-run; only the occupied voxels are enumerated, in the reference's (x, y, z) order per row, and compacted through a
+//     per-warp shared-memory queue so that every cull pass runs on 32 live voxels (the reference tests every voxel and
+//     heap-allocates a vector per sample, hpp:787);
+//   * PERSISTENT warps draw work items (longest first) from one device counter: a warp that finishes a light sample takes the
+//     next item at once instead of idling until its CTA's slowest warp is done;
+//   * work items: the per-sample work measured in the previous evaluation (an optimiser moves the trajectory only a little
+//     between steps) sorts the samples, and a sample that grazes an obstacle (dozens of mesh queries) is split into 2..32 items,
+//     each a contiguous range of the 32 interleaved ROW CLASSES (window row r belongs to class r % 32). The per-sample sum is
+//     ALWAYS formed class by class in the same order, whether one warp walks all classes or 32 warps take one each, so the split
+//     never changes a bit of the result;
+//   * k_discrete_analytic — two warp-level compaction queues keep lanes dense: queue A = voxels inside the body-frame
+//     cull box, queue B = voxels whose hinge is active (sdf < safety_hor) and therefore need the 6 extra finite-
+//     difference SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87). Evaluating those only for active voxels is exact
+//     because an inactive voxel contributes nothing (hpp:809-821);
+//   * k_discrete_mesh — voxels that survive the exact culls (body-frame box, inflated mesh AABB, per-cell distance lower
+//     bound) are answered by WARP-COOPERATIVE nearest-triangle searches (the cell's exact candidate list near the surface, 64
 //     candidates per pass with a division-free closest-point test; elsewhere the 32-ary tree seeded with the cell's nearest
-//     triangle), then evaluates sign, gradient, hinge and pose chain rule one voxel per lane and adds the chunk's contributions
-//     in voxel order. The search work — 57 % of the fused kernel's time and extremely uneven across samples (0 .. 500 queries) —
-//     is thereby cut into near-equal items without any learned schedule; the cull kernel runs at 64 registers / 32 warps per SM,
-//     the search kernel at 96 / 20, instead of one 128-register kernel at 16 warps per SM;
-//   * analytic robots — k_discrete_analytic, one kernel: two warp-level compaction queues keep lanes dense: queue A = voxels
-//     inside the body-frame cull box, queue B = voxels whose hinge is active (sdf < safety_hor) and therefore need the 6 extra
-//     finite-difference SDF evaluations of getSDFwithGrad1 (Shape.hpp:58-87). Evaluating those only for active voxels is exact
-//     because an inactive voxel contributes nothing (hpp:809-821). Samples are taken longest first (work reported by the
-//     previous evaluation; k_build_items);
+//     triangle); sign, gradient, hinge and pose chain rule of the answered voxels are DEFERRED and evaluated one voxel per lane;
+//     the warp-uniform pose (position, rotation, quaternion) lives in shared memory, not in 16 x 2 registers of every lane;
 //   * k_discrete_epilogue — the per-sample chain rule (penalties, flatness adjoint, beta-basis outer products) as one THREAD
-//     per sample (a mesh sample's collision sums = its chunks' partial sums added in chunk order), then a deterministic reduction
-//     inside the piece's CTA from shared memory: 20 threads add the partials in ascending sample order; the last CTA adds the
-//     piece costs in ascending order and (several GPUs) runs the peer-memory exchange — independent of scheduling, so results are
-//     bit-reproducible run to run and identical on every rank.
+//     per sample, then a deterministic reduction inside the piece's CTA from shared memory: 20 threads add the partials in
+//     ascending sample order; the last CTA adds the piece costs in ascending order and (several GPUs) runs the peer-memory
+//     exchange — independent of scheduling, so results are bit-reproducible run to run and identical on every rank.
 //
 // This header is included by two translation units: isdf_api.cu (argument block, host-side constants, the device helpers the
 // service kernels share) and isdf_discrete_tu.cu, which defines ISDF_DISCRETE_TU and is the only one that instantiates the
@@ -43,23 +43,18 @@ namespace isdf {
 constexpr int DISC_WARPS = 4;
 constexpr int DISC_THREADS = DISC_WARPS * 32;
 constexpr int QCAP = 64;
+constexpr int ROW_CLASSES = 32;         // a pose window's rows are summed in 32 interleaved classes (canonical order): row r -> class r % 32
+constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than this (work units: 64 per mesh query + 1 per culled pair)
+constexpr int MAX_SPLIT_SLOTS = 16384;  // split samples per launch (2 KB of class sums each)
 constexpr int WINDOW_AXIS_MAX = 1023;   // voxels per window axis: window offsets are packed 10 bits per axis
 // CTAs per SM the register allocator must leave room for — A/B-measured on B200 (profiles/r01_tuning.md, r02_tuning.md)
 constexpr int ANALYTIC_MIN_BLOCKS = 4;
-#ifndef ISDF_CULL_MIN_BLOCKS
-#define ISDF_CULL_MIN_BLOCKS 8
+#ifndef ISDF_MESH_MIN_BLOCKS
+#define ISDF_MESH_MIN_BLOCKS 4
 #endif
-#ifndef ISDF_SEARCH_MIN_BLOCKS
-#define ISDF_SEARCH_MIN_BLOCKS 5
-#endif
-constexpr int CULL_MIN_BLOCKS = ISDF_CULL_MIN_BLOCKS, SEARCH_MIN_BLOCKS = ISDF_SEARCH_MIN_BLOCKS;
-constexpr int CHUNK = 8;                // voxels per search work item (mesh path)
-constexpr int DISC_SLAB_SAMPLES = 1 << 20;   // mesh path: local samples per round of (cull, search, epilogue) launches
-// a voxel that passed the exact culls of the mesh path: body-frame point, its cell's candidate list (cnt bit 31: cell centre inside the mesh),
-// seed triangle (0xffffffff: outside the cell grid), voxel index (ix | iy << 16, iz)
-struct SurvRec { double px, py, pz; uint32_t off, cnt, seed, ixy, iz, pad; };
+constexpr int MESH_MIN_BLOCKS = ISDF_MESH_MIN_BLOCKS;
 constexpr int EPI_THREADS = 288;
-constexpr int ITEMS_MAX_SAMPLES = 1 << 17;   // analytic kernel: beyond this many local samples the persistent warps' dynamic counter balances by itself
+constexpr int ITEMS_CACHE = 24;   // k_build_items: samples per thread whose work value is kept in registers (M <= 24576: any single trajectory)
 
 struct DiscArgs {
     DevCfg cfg;
@@ -68,25 +63,19 @@ struct DiscArgs {
     int N;
     const double *T;       // N
     const double *C;       // 6N x 3 column-major
-    double *tot;           // S x 8: collision sums of a sample {costp, gradp(3), grad_quat(4)} (analytic kernel)
-    // mesh path (k_discrete_mesh_cull -> k_discrete_mesh_search -> epilogue), one slab of pieces [p0, p0 + gridDim) per round of launches:
-    int use_chunks;        // 1: the epilogue takes a sample's sums from its chunks' partial sums
-    int p0;                // first piece of the slab
-    int m0, m1;            // local samples of the slab: m0 <= m < m1, global s = rank + world * m
-    double *pose;          // (m1 - m0) x 16, written by the cull kernel
-    int4 *chunk_hdr;       // chunk -> {slab-local sample m - m0, voxels, first chunk of the sample's NEXT run or -1, chunks in that run}
-    SurvRec *chunk_rec;    // chunk x CHUNK
-    double *chunk_sum;     // chunk x 8 partial sums (search kernel)
-    int *sample_run;       // (m1 - m0) x 2: first chunk of the sample's first run (-1: none), chunks in it
-    int *chunk_counter, *search_cursor, *overflow;   // zero on entry; counters zeroed again by the epilogue, overflow is sticky
-    int chunk_cap;
+    double *tot;           // S x 8: collision sums of a sample evaluated as ONE work item {costp, gradp(3), grad_quat(4)}
     int *pieces_done;      // 1  (zero on entry, zero on exit)
     double *piece_cost;    // N
     double *out;           // 19N+1: cost | gradC | gradT
     unsigned long long *pair_counter;  // may be null
     unsigned long long *dbg;           // may be null: per sample {cycles, pairs, work}
-    const int *items;                  // may be null: local sample indices, longest first (analytic kernel)
+    unsigned long long *trace;         // may be null: per work-item slot {begin, end} in ns of the global timer (+ 6 phase cycle counts with -DISDF_PHASE_TIMING)
+    const int *items;                  // may be null: 3 ints per work item {local sample m, -1 = all classes or c0 | c1 << 8, split slot or -1}
+    const int *item_count;             // number of valid items (device)
     int *item_cursor;                  // persistent warps draw items from this counter (zero on entry; the epilogue zeroes it again)
+    double *subsum;                    // split slot x ROW_CLASSES x 8 class sums
+    unsigned *split_work;              // split slot -> work accumulated by the parts (zero on entry, zeroed by the sample's last part)
+    unsigned *split_done;              // split slot -> parts finished (zero on entry, zeroed by the sample's last part)
     unsigned *work;                    // may be null: per global sample, work measure written for the next evaluation
     int rank, world;       // this launch evaluates samples s with s % world == rank
     PeerArgs peer;         // peer.world > 1: the epilogue's last CTA also sums `out` over the ranks through peer memory (isdf_peer.cuh)
@@ -271,9 +260,16 @@ __device__ __forceinline__ void sample_epilogue(const DiscArgs &A, int i, int j,
 }
 
 // ============================================================================================================================
-// Work item of an analytic-kernel warp: a pose sample (longest first once the previous evaluation's work is known).
-struct Item { int s, slot; };
+// Work item of a warp: {global sample, first class, one-past-last class, split slot}.
+struct Item { int s, c0, c1, hslot, slot; };
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#ifdef ISDF_PHASE_TIMING
+constexpr int TRACE_STRIDE = 8;
+#define ISDF_PT(x) x
+#else
+constexpr int TRACE_STRIDE = 2;
+#define ISDF_PT(x)
+#endif
 
 // Persistent-warp scheduler: the warp's next work item, or false when the table is exhausted. Which warp takes which item
 // never touches the arithmetic, so results stay bit-reproducible.
@@ -285,12 +281,20 @@ __device__ __forceinline__ bool next_item(const DiscArgs &A, Item &it, int lane)
     if (lane == 0) slot = atomicAdd(A.item_cursor, 1);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     it.slot = slot;
+    if (A.items) {
+        if (slot >= __ldg(A.item_count)) return false;
+        const int m = __ldg(A.items + 3 * slot), part = __ldg(A.items + 3 * slot + 1);
+        it.s = A.rank + A.world * m;
+        it.c0 = part < 0 ? 0 : (part & 0xff); it.c1 = part < 0 ? ROW_CLASSES : (part >> 8);
+        it.hslot = __ldg(A.items + 3 * slot + 2);
+        return true;
+    }
     if (slot >= M) return false;
-    it.s = A.rank + A.world * (A.items ? __ldg(A.items + slot) : slot);
+    it.s = A.rank + A.world * slot; it.c0 = 0; it.c1 = ROW_CLASSES; it.hslot = -1;
     return true;
 }
 
-// Tail of the analytic scan kernel: lanes 0..7 hold the sample's eight collision sums.
+// Shared tail of both scan kernels for an item that covers the WHOLE sample: lanes 0..7 hold the eight collision sums.
 // The per-sample chain rule and the per-piece reduction run afterwards in k_discrete_epilogue with one THREAD per sample.
 __device__ __forceinline__ void sample_finish_whole(const DiscArgs &A, const Item &it, double mine, unsigned npairs, long long t_begin, unsigned work) {
     const int lane = threadIdx.x & 31;
@@ -311,7 +315,7 @@ __device__ __forceinline__ void sample_finish_whole(const DiscArgs &A, const Ite
 // the total cost in ascending piece order.
 __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_constant__ DiscArgs A) {
     __shared__ double sp[PARTIAL_STRIDE][EPI_THREADS + 1];   // component-major, padded: conflict-free writes, <= 2-way reads
-    const int K = A.cfg.K, N = A.N, i = A.p0 + blockIdx.x;
+    const int K = A.cfg.K, N = A.N, i = blockIdx.x;
     const int first_s = i * (K + 1), last_s = first_s + K;
     const int f0 = first_s + ((A.rank - first_s) % A.world + A.world) % A.world;  // first local sample >= first_s
     const int local_cnt = (f0 > last_s) ? 0 : ((last_s - f0) / A.world + 1);
@@ -322,22 +326,8 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
         if (idx < local_cnt) {
             const int s = f0 + idx * A.world;
             const int j = s - first_s;
-            double tot[8];   // the sample's collision sums
-            if (A.use_chunks) {   // mesh path: the chunks' partial sums added in chunk (= voxel) order, run by run
-#pragma unroll
-                for (int v = 0; v < 8; v++) tot[v] = 0.0;
-                const int mloc = (s - A.rank) / A.world - A.m0;
-                int run = A.sample_run[2 * (size_t)mloc], nch = A.sample_run[2 * (size_t)mloc + 1];
-                while (run >= 0) {
-                    const int4 hdr = __ldcg(A.chunk_hdr + run);
-                    for (int c = 0; c < nch; c++) {
-                        const double2 *tp = reinterpret_cast<const double2 *>(A.chunk_sum + (size_t)(run + c) * 8);
-                        const double2 t0 = __ldcg(tp), t1 = __ldcg(tp + 1), t2 = __ldcg(tp + 2), t3 = __ldcg(tp + 3);
-                        tot[0] += t0.x; tot[1] += t0.y; tot[2] += t1.x; tot[3] += t1.y; tot[4] += t2.x; tot[5] += t2.y; tot[6] += t3.x; tot[7] += t3.y;
-                    }
-                    run = hdr.z; nch = hdr.w;
-                }
-            } else {
+            double tot[8];   // the sample's collision sums (a split sample's row was finished by its last part, in class order)
+            {
                 const double2 *tp = reinterpret_cast<const double2 *>(A.tot + (size_t)s * 8);
                 const double2 t0 = __ldcg(tp), t1 = __ldcg(tp + 1), t2 = __ldcg(tp + 2), t3 = __ldcg(tp + 3);
                 tot[0] = t0.x; tot[1] = t0.y; tot[2] = t1.x; tot[3] = t1.y; tot[4] = t2.x; tot[5] = t2.y; tot[6] = t3.x; tot[7] = t3.y;
@@ -369,10 +359,6 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
         else if (comp == 18) A.out[1 + 18 * N + i] = run;
         else A.piece_cost[i] = run;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {   // the scan kernels of this slab are complete (stream order): rewind their counters
-        *A.item_cursor = 0;
-        if (A.use_chunks) { A.chunk_counter[3] = *A.chunk_counter; *A.chunk_counter = 0; *A.search_cursor = 0; }   // [3] = tickets[5]: last chunk count (diagnostics)
-    }
     // last CTA to finish: total cost = piece costs added in ascending order, then (multi-GPU) the exchange over peer memory
     __shared__ int s_last;
     __threadfence();
@@ -388,8 +374,7 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
             const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
             for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
         }
-        // survivor storage exhausted in this evaluation: a dropped voxel must never look like a result (header contract: failed => NaN cost)
-        if (lane == 0) { A.out[0] = (A.use_chunks && *A.overflow) ? __longlong_as_double(0x7ff8000000000000ll) : c; *A.pieces_done = 0; }
+        if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; *A.item_cursor = 0; }
     }
     if (A.peer.world > 1) {
         __threadfence();
@@ -498,25 +483,16 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
 }
 
 // ============================================================================================================================
-// mesh shapes — two kernels per evaluation:
-//   k_discrete_mesh_cull   : persistent warps, one pose SAMPLE per item (natural order: pose + window scan + exact culls cost about the
-//                            same for every sample). The voxels that survive the culls are written to global memory in CHUNKS of up to
-//                            CHUNK voxels of one sample (a sample's chunks are allocated in contiguous runs, in voxel order);
-//   k_discrete_mesh_search : persistent warps, one CHUNK per item: warp-cooperative nearest-triangle search per voxel, then sign, gradient,
-//                            hinge and pose chain rule one voxel per lane, summed in voxel order into the chunk's eight partial sums.
-// The epilogue adds a sample's chunk sums in chunk order. Which warp takes which sample or chunk never touches the arithmetic, so the
-// result is bit-reproducible — and the unit of search work is 1..CHUNK queries whatever the sample: a sample that grazes an obstacle
-// (hundreds of queries) no longer needs a learned schedule or row-class splitting to be spread over the machine, on one GPU or on eight.
-struct QRes { double ex, ey, ez, d2; int tri, feat; };          // an answered voxel awaiting its tail (search kernel, shared memory)
-struct CullWarpSmem {
+// mesh shapes
+struct QRes { double ex, ey, ez, d2; int tri, feat; uint32_t code; int cls; };   // an answered voxel awaiting its deferred tail
+struct Survivor { double px, py, pz; uint32_t off, cnt, seed, code; };   // a voxel that passed the exact culls: body-frame point, its cell's list (cnt bit 31: cell centre inside), seed triangle (0xffffffff: none)
+struct MeshWarpSmem {
     double pose[16];                     // warp-uniform pose: pos 0..2, R rows 3..11, q (w, x, y, z) 12..15
-    SurvRec sv[64];                      // culled voxels awaiting their flush into chunks
+    double cacc[ROW_CLASSES][8];         // class accumulators
+    double vals[32][8];                  // deferred tails: one voxel's eight contributions per lane
+    QRes qr[32];
+    Survivor sv[32];                     // culled voxels awaiting their search
     uint32_t vq[64];                     // ring of occupied-voxel codes (dx | dy << 10 | dz << 20, relative to the window origin)
-};
-struct SearchWarpSmem {
-    double pose[16];
-    double vals[CHUNK][8];
-    QRes qr[CHUNK];
     WideStack stk;
 };
 
@@ -531,8 +507,8 @@ __device__ __forceinline__ void row_split(int r, int ny, float inv_ny, int &rx, 
     if (ry < 0) { rx--; ry += ny; } else if (ry >= ny) { rx++; ry -= ny; }
 }
 
-__global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh_cull(const __grid_constant__ DiscArgs A) {
-    __shared__ CullWarpSmem wsm[DISC_WARPS];
+__global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
+    __shared__ MeshWarpSmem wsm[DISC_WARPS];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -540,23 +516,21 @@ __global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh
     const DevMesh &Mh = A.shape.mesh;
     const DevGrid &G = A.grid;
     const int K = cfg.K;
-    CullWarpSmem &sm = wsm[warp];
+    MeshWarpSmem &sm = wsm[warp];
     const double h = cfg.half_bd, sf = cfg.safety;
-    const int M = A.m1 - A.m0;                      // local samples of this launch: m0 <= m < m1, global s = rank + world * m
-    for (;;) {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(A.item_cursor, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= M) break;
-        const int s = A.rank + A.world * (A.m0 + slot);
+    Item it;
+    while (next_item(A, it, lane)) {
+        const int s = it.s;
         const int i = s / (K + 1), j = s - i * (K + 1);
         const long long t_begin = A.dbg ? clock64() : 0;
-        unsigned npairs = 0, nsurv_total = 0;
-        int first_run = -1, first_run_n = 0, prev_run = -1;   // chunk runs of this sample (warp-uniform)
+        if (A.trace && lane == 0) A.trace[TRACE_STRIDE * (size_t)it.slot] = global_ns();
+        ISDF_PT(long long pt_pose = 0; long long pt_cull = 0; long long pt_search = 0; long long pt_tail = 0; long long pt_t0 = clock64(); long long pt_all0 = pt_t0;)
+        unsigned npairs = 0, nquery = 0;
+        const bool whole = (it.c1 - it.c0) == ROW_CLASSES;
 
         if (cfg.flags & ISDF_WITH_COLLISION) {
             Window W;
-            {   // pose -> shared memory (every lane computes the same values) and to global memory for the search kernel
+            {   // pose -> shared memory (every lane computes the same values; lane 0 publishes them)
                 const double Ti = __ldg(A.T + i);
                 d3 pos; quat4 q; rot3 R;
                 sample_pose(A, i, j, Ti * (1.0 / K), pos, q, R);
@@ -568,41 +542,52 @@ __global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh
                     ps[9] = R.r2.x; ps[10] = R.r2.y; ps[11] = R.r2.z;
                     ps[12] = q.w; ps[13] = q.x; ps[14] = q.y; ps[15] = q.z;
                 }
-                __syncwarp();
-                if (lane < 16) A.pose[(size_t)slot * 16 + lane] = sm.pose[lane];   // slab-local sample index
             }
+            for (int k = lane; k < ROW_CLASSES * 8; k += 32) (&sm.cacc[0][0])[k] = 0.0;
+            __syncwarp();
+            ISDF_PT(pt_pose = clock64() - pt_t0;)
             const int ny = W.iy1 - W.iy0 + 1;
             const int nrows = (W.ix1 - W.ix0 + 1) * ny;
             const float inv_ny = 1.0f / (float)ny;
-            int nq = 0, head = 0, nsv = 0;   // voxel ring fill / head, buffered survivors (warp-uniform)
+            int nq = 0, head = 0, nres = 0;   // voxel ring fill / head, answered voxels awaiting their tail (warp-uniform)
 
-            // write the first `n` buffered survivors (n a multiple of CHUNK, or everything at the end of the sample) as one contiguous run
-            // of chunks; runs of one sample are linked through the first chunk of the previous run
-            auto flush_run = [&](int n) __attribute__((always_inline)) {
-                const int nch = (n + CHUNK - 1) / CHUNK;
-                int base = 0;
-                if (lane == 0) base = atomicAdd(A.chunk_counter, nch);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + nch <= A.chunk_cap) {
-                    for (int k = lane; k < n; k += 32) A.chunk_rec[(size_t)base * CHUNK + k] = sm.sv[k];
-                    if (lane < nch) A.chunk_hdr[base + lane] = make_int4(slot, min(CHUNK, n - lane * CHUNK), -1, 0);
-                    __syncwarp();
-                    if (lane == 0 && prev_run >= 0) { A.chunk_hdr[prev_run].z = base; A.chunk_hdr[prev_run].w = nch; }
-                    if (first_run < 0) { first_run = base; first_run_n = nch; }
-                    prev_run = base;
-                } else if (lane == 0) *A.overflow = 1;   // survivor storage exhausted: the epilogue poisons the result (cost = NaN)
+            // deferred tails: sign, gradient, hinge, chain rule onto (position, quaternion) — one answered voxel per lane; the
+            // contributions are then added to the class accumulators in voxel order by lanes 0..7 (one per component)
+            auto flush_tails = [&]() __attribute__((always_inline)) {
                 __syncwarp();
-                const int rest = nsv - n;                // move the unflushed tail to the front
-                SurvRec keep;
-                if (lane < rest) keep = sm.sv[n + lane];
+                ISDF_PT(const long long pt_a = clock64();)
+                bool active = false;
+                if (lane < nres) {
+                    const QRes r = sm.qr[lane];
+                    d3 g = mk3(0, 0, 0);
+                    const double sdf = mesh_finish(Mh, mk3(r.ex, r.ey, r.ez), r.d2, r.tri, r.feat, g);
+                    const double *ps = sm.pose;
+                    const d3 d = voxel_centre(G, W.ix0 + (int)(r.code & 0x3ffu), W.iy0 + (int)((r.code >> 10) & 0x3ffu), W.iz0 + (int)(r.code >> 20)) - smem_pos(ps);
+                    quat4 q; q.w = ps[12]; q.x = ps[13]; q.y = ps[14]; q.z = ps[15];
+                    PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};
+                    pair_accumulate(cfg, smem_rot(ps), q, d, sdf, g, one);
+                    active = one.c > 0.0;
+                    double *v = sm.vals[lane];
+                    v[0] = one.c; v[1] = one.gx; v[2] = one.gy; v[3] = one.gz; v[4] = one.q0; v[5] = one.q1; v[6] = one.q2; v[7] = one.q3;
+                }
+                unsigned act = __ballot_sync(0xffffffffu, active);
                 __syncwarp();
-                if (lane < rest) sm.sv[lane] = keep;
+                if (lane < 8) {
+                    while (act) {
+                        const int k = __ffs(act) - 1;
+                        act &= act - 1;
+                        sm.cacc[sm.qr[k].cls][lane] += sm.vals[k][lane];
+                    }
+                }
                 __syncwarp();
-                nsv = rest;
+                nres = 0;
+                ISDF_PT(pt_tail += clock64() - pt_a;)
             };
 
-            // cull stage for the n oldest voxels of the ring (n <= 32): survivors are appended to the survivor buffer
+            int nsv = 0;   // queued survivors (warp-uniform)
+            // cull stage for the n oldest voxels of the ring (n <= 32): survivors are appended to the survivor queue
             auto cull = [&](int n) __attribute__((always_inline)) {
+                ISDF_PT(const long long pt_a = clock64();)
                 bool pass = false, box = false;
                 uint32_t code = 0;
                 d3 prel = mk3(0, 0, 0);
@@ -630,20 +615,61 @@ __global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh
                 npairs += __popc(__ballot_sync(0xffffffffu, box));
                 const unsigned bal = __ballot_sync(0xffffffffu, pass);
                 if (pass) {
-                    SurvRec &v = sm.sv[nsv + __popc(bal & lt_mask)];
-                    v.px = prel.x; v.py = prel.y; v.pz = prel.z; v.off = rec.z; v.seed = rec.y;
+                    Survivor &v = sm.sv[nsv + __popc(bal & lt_mask)];
+                    v.px = prel.x; v.py = prel.y; v.pz = prel.z; v.off = rec.z; v.seed = rec.y; v.code = code;
                     v.cnt = rec.w | ((rec.y != 0xffffffffu && __uint_as_float(rec.x) < 0.0f) ? 0x80000000u : 0u);
-                    v.ixy = (uint32_t)(W.ix0 + (int)(code & 0x3ffu)) | ((uint32_t)(W.iy0 + (int)((code >> 10) & 0x3ffu)) << 16);
-                    v.iz = (uint32_t)(W.iz0 + (int)(code >> 20));
                 }
                 nsv += __popc(bal);
-                nsurv_total += __popc(bal);
                 __syncwarp();
+                ISDF_PT(pt_cull += clock64() - pt_a;)
+            };
+            // search stage for every queued survivor, in voxel order, software-pipelined ACROSS queries: while query k runs, the
+            // first 32 candidate ids of query k+2 are being loaded and the triangle records of query k+1's first pass are
+            // prefetched into L1 — the id -> record -> arithmetic chain of a query starts with its operands already close
+            auto search_all = [&](bool final) __attribute__((always_inline)) {
+                ISDF_PT(const long long pt_a = clock64(); const long long pt_tail0 = pt_tail;)
+                nquery += nsv;
+                auto first_ids = [&](int k) -> int {
+                    if (k >= nsv) return -1;
+                    const uint32_t cnt = sm.sv[k].cnt & 0x7fffffffu;
+                    return (lane < (int)cnt) ? (int)__ldg(Mh.cand + sm.sv[k].off + lane) : -1;
+                };
+                int ids0 = first_ids(0), ids1 = first_ids(1);
+                int k = 0;
+                do {
+                    if (k < nsv) {
+                        const int ids2 = first_ids(k + 2);
+                        const Survivor &v = sm.sv[k];
+                        const d3 p = mk3(v.px, v.py, v.pz);
+                        const uint32_t cnt_in = v.cnt, qcode = v.code;
+                        double d2; d3 c = mk3(0, 0, 0); int tri, feat;
+                        if (mesh_search_rec(Mh, p, sf, lane, &sm.stk, (int)(cnt_in & 0x7fffffffu), v.off, ids0, (int)v.seed, (cnt_in >> 31) != 0u, d2, c, tri, feat)) {
+                            if (lane == 0) {
+                                QRes r;
+                                r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.d2 = d2; r.tri = tri; r.feat = feat; r.code = qcode;
+                                r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu)) % ROW_CLASSES);
+                                sm.qr[nres] = r;
+                            }
+                            nres++;
+                        }
+                        ids0 = ids1; ids1 = ids2;
+                    }
+                    k++;
+                    if (nres == 32 || (final && k >= nsv && nres > 0)) flush_tails();   // the only call site
+                } while (k < nsv);
+                __syncwarp();
+                nsv = 0;
+                ISDF_PT(pt_search += (clock64() - pt_a) - (pt_tail - pt_tail0);)
             };
 
-            // Producer loop: batches of 32 window rows are loaded (lane = row) and their occupied voxels appended to the ring in (row, z)
-            // order — at once when the batch fits into the ring, otherwise row by row (dense walls) — and whenever 32 voxels are queued,
-            // or the window is exhausted, they are culled; whenever 32 survivors are buffered they are flushed as a run of chunks.
+            // Producer loop (one cull and one search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
+            // are appended to the ring, and whenever 32 voxels are queued — or the window is exhausted — they are processed.
+            //   whole sample: a batch is 32 consecutive rows = 32 different classes, so any emission order keeps every CLASS's
+            //                 voxels in (row, z) order: the batch is emitted at once (row-major) when it fits into the ring,
+            //                 otherwise round-robin, one voxel per lane and round (dense walls);
+            //   split part  : rows of the classes [c0, c1) only, emitted row by row so that a class's rows stay in ascending order.
+            const int w = it.c1 - it.c0;
+            const int nk = whole ? nrows : ((nrows + ROW_CLASSES - 1) / ROW_CLASSES) * w;   // row slots to visit per z-chunk
             int zs = W.iz0, kb = -32;
             uint32_t bits = 0, rowcode = 0;
             unsigned pending = 0;
@@ -652,26 +678,27 @@ __global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh
                 if (!finished) {
                     if (pending == 0u) {   // next batch of rows
                         kb += 32;
-                        if (kb >= nrows) { kb = 0; zs += 32; }
+                        if (kb >= nk) { kb = 0; zs += 32; }
                         if (zs > W.iz1) finished = true;
                         else {
                             const int nzc = min(32, W.iz1 - zs + 1);
                             const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
-                            const int r = kb + lane;
+                            const int k = kb + lane;
+                            const int r = whole ? k : (k / w) * ROW_CLASSES + it.c0 + (k % w);
                             bits = 0;
-                            if (r < nrows) {
+                            if (k < nk && r < nrows) {
                                 int rx, ry;
                                 row_split(r, ny, inv_ny, rx, ry);
                                 bits = row_bits(G, W.ix0 + rx, W.iy0 + ry, zs, zmask);
                                 rowcode = (uint32_t)rx | ((uint32_t)ry << 10) | ((uint32_t)(zs - W.iz0) << 20);
                             }
                             pending = __ballot_sync(0xffffffffu, bits != 0u);
-                            if (pending != 0u) {
+                            if (whole && pending != 0u) {
                                 int incl = __popc(bits);
 #pragma unroll
                                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
                                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                                if (nq + total <= 64) {   // the whole batch fits: emit it at once, row-major
+                                if (nq + total <= 64) {   // the whole batch fits: emit it at once
                                     int pos = head + nq + incl - __popc(bits);
                                     while (bits != 0u) {
                                         const int z = __ffs(bits) - 1;
@@ -684,7 +711,15 @@ __global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh
                                 }
                             }
                         }
-                    } else {               // one row: lane z emits voxel z of the lowest pending row
+                    } else if (whole) {    // one round: every lane that still has voxels emits its lowest one
+                        if (bits != 0u) {
+                            const int z = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            sm.vq[(head + nq + __popc(pending & lt_mask)) & 63] = rowcode + ((uint32_t)z << 20);
+                        }
+                        nq += __popc(pending);
+                        pending = __ballot_sync(0xffffffffu, bits != 0u);
+                    } else {               // one row: lane z emits voxel z of the row
                         const int src = __ffs(pending) - 1;
                         pending &= pending - 1;
                         const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
@@ -695,91 +730,66 @@ __global__ void __launch_bounds__(DISC_THREADS, CULL_MIN_BLOCKS) k_discrete_mesh
                     __syncwarp();
                 }
                 if (nq >= 32 || (finished && nq > 0)) cull(min(nq, 32));
+                // single call site; the final round runs even without survivors when answered voxels still await their tail
                 const bool last_round = finished && nq == 0;
-                if (nsv >= 32 || (last_round && nsv > 0)) flush_run(last_round ? nsv : (nsv / CHUNK) * CHUNK);   // single call site
+                if (nsv > 0 || (last_round && nres > 0)) {
+                    search_all(last_round);
+                }
                 if (last_round) break;
             }
-        }
-        if (lane == 0) {
-            A.sample_run[2 * (size_t)slot] = first_run; A.sample_run[2 * (size_t)slot + 1] = first_run_n;
-            if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
-            if (A.dbg) { A.dbg[3 * (size_t)s] = (unsigned long long)(clock64() - t_begin); A.dbg[3 * (size_t)s + 1] = npairs; A.dbg[3 * (size_t)s + 2] = nsurv_total; }
-        }
-        __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(DISC_THREADS, SEARCH_MIN_BLOCKS) k_discrete_mesh_search(const __grid_constant__ DiscArgs A) {
-    __shared__ SearchWarpSmem wsm[DISC_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const DevCfg &cfg = A.cfg;
-    const DevMesh &Mh = A.shape.mesh;
-    const DevGrid &G = A.grid;
-    SearchWarpSmem &sm = wsm[warp];
-    const double sf = cfg.safety;
-    const int nchunks = min(*A.chunk_counter, A.chunk_cap);
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(A.search_cursor, 1);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= nchunks) break;
-        const int4 hdr = __ldg(A.chunk_hdr + c);
-        const int mloc = hdr.x, n = hdr.y;
-        if (lane < 16) sm.pose[lane] = __ldcg(A.pose + (size_t)mloc * 16 + lane);
-        SurvRec mine;                                  // lane k < n keeps voxel k's record for the tail
-        if (lane < n) mine = A.chunk_rec[(size_t)c * CHUNK + lane];
-        __syncwarp();
-        unsigned found_mask = 0;
-        for (int k = 0; k < n; k++) {   // warp-cooperative searches, in voxel order
-            const d3 p = mk3(__shfl_sync(0xffffffffu, mine.px, k), __shfl_sync(0xffffffffu, mine.py, k), __shfl_sync(0xffffffffu, mine.pz, k));
-            const uint32_t cnt_in = __shfl_sync(0xffffffffu, mine.cnt, k), off = __shfl_sync(0xffffffffu, mine.off, k);
-            const int seed = (int)__shfl_sync(0xffffffffu, mine.seed, k);
-            const int cnt = (int)(cnt_in & 0x7fffffffu);
-            const int first_id = (lane < cnt) ? (int)__ldg(Mh.cand + off + lane) : -1;
-            double d2; d3 cp = mk3(0, 0, 0); int tri, feat;
-            if (mesh_search_rec(Mh, p, sf, lane, &sm.stk, cnt, off, first_id, seed, (cnt_in >> 31) != 0u, d2, cp, tri, feat)) {
-                found_mask |= 1u << k;
-                if (lane == 0) { QRes r; r.ex = p.x - cp.x; r.ey = p.y - cp.y; r.ez = p.z - cp.z; r.d2 = d2; r.tri = tri; r.feat = feat; sm.qr[k] = r; }
+            __syncwarp();
+            // sample (or part) total: class sums added in class order
+            if (whole) {
+                double mine = 0.0;
+                if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) mine += sm.cacc[c][lane];
+                sample_finish_whole(A, it, mine, npairs, t_begin, 64u * nquery + npairs);
+            } else {
+                // split part: publish this part's class sums; the LAST part of the sample to arrive (one ticket per split slot) adds
+                // all 32 class sums in class order — the same additions a whole-sample item performs — so that the epilogue sees
+                // one finished row per sample whether or not it was split
+                double *sub = A.subsum + (size_t)it.hslot * ROW_CLASSES * 8;
+                if (lane < 8) for (int c = it.c0; c < it.c1; c++) __stcg(sub + c * 8 + lane, sm.cacc[c][lane]);
+                __threadfence();
+                __syncwarp();
+                unsigned mywork = 64u * nquery + npairs, prev = 0;
+                if (lane == 0) {
+                    if (A.pair_counter && npairs) atomicAdd(A.pair_counter, (unsigned long long)npairs);
+                    atomicAdd(A.split_work + it.hslot, mywork);
+                    prev = atomicAdd(A.split_done + it.hslot, 1u);
+                }
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                if ((int)prev == ROW_CLASSES / w - 1) {   // last of the f = 32 / w parts
+                    __threadfence();
+                    double mine = 0.0;
+                    if (lane < 8) for (int c = 0; c < ROW_CLASSES; c++) mine += __ldcg(sub + c * 8 + lane);
+                    unsigned total_work = 0;
+                    if (lane == 0) { total_work = atomicExch(A.split_work + it.hslot, 0u); A.split_done[it.hslot] = 0u; }
+                    total_work = __shfl_sync(0xffffffffu, total_work, 0);
+                    sample_finish_whole(A, it, mine, 0u, t_begin, total_work);
+                }
             }
+        } else {
+            sample_finish_whole(A, it, 0.0, 0u, t_begin, 0u);
         }
-        __syncwarp();
-        // tails: sign, gradient, hinge, chain rule onto (position, quaternion) — one answered voxel per lane
-        bool active = false;
-        if (lane < n && ((found_mask >> lane) & 1u)) {
-            const QRes r = sm.qr[lane];
-            d3 g = mk3(0, 0, 0);
-            const double sdf = mesh_finish(Mh, mk3(r.ex, r.ey, r.ez), r.d2, r.tri, r.feat, g);
-            const double *ps = sm.pose;
-            const d3 d = voxel_centre(G, (int)(mine.ixy & 0xffffu), (int)(mine.ixy >> 16), (int)mine.iz) - smem_pos(ps);
-            quat4 q; q.w = ps[12]; q.x = ps[13]; q.y = ps[14]; q.z = ps[15];
-            PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};
-            pair_accumulate(cfg, smem_rot(ps), q, d, sdf, g, one);
-            active = one.c > 0.0;
-            double *v = sm.vals[lane];
-            v[0] = one.c; v[1] = one.gx; v[2] = one.gy; v[3] = one.gz; v[4] = one.q0; v[5] = one.q1; v[6] = one.q2; v[7] = one.q3;
-        }
-        unsigned act = __ballot_sync(0xffffffffu, active);
-        __syncwarp();
-        if (lane < 8) {   // the chunk's eight partial sums, added in voxel order
-            double sum = 0.0;
-            while (act) {
-                const int k = __ffs(act) - 1;
-                act &= act - 1;
-                sum += sm.vals[k][lane];
-            }
-            A.chunk_sum[(size_t)c * 8 + lane] = sum;
+        if (A.trace && lane == 0) {
+            unsigned long long *tr = A.trace + TRACE_STRIDE * (size_t)it.slot;
+            tr[1] = global_ns();
+            ISDF_PT(tr[2] = pt_pose; tr[3] = pt_cull; tr[4] = pt_search; tr[5] = pt_tail; tr[6] = clock64() - pt_all0; tr[7] = ((unsigned long long)nquery << 32) | npairs;)
         }
         __syncwarp();
     }
 }
 
 
-// Sample order for the next evaluation of the ANALYTIC kernel: bucket sort by the work (culled pairs) each sample reported, descending —
-// an optimiser moves the trajectory only a little between steps. Placement inside a bucket uses shared-memory atomics: the order only
-// decides WHICH warp takes WHICH sample, never the arithmetic. One CTA, off the critical path of the evaluation that produced `work`.
-// (The mesh path needs no learned schedule: its search work is cut into chunks of <= CHUNK queries whatever the sample.)
+// Work items for the next evaluation: bucket sort by reported work, descending. A sample is split into f = 2..32 items (each a
+// contiguous range of 32/f row classes, work/f each) only when it alone would outlast the launch's balanced share:
+// work > thr = 0.7 * total / warp_slots, f = the power of two that brings a part down to ~thr. With one GPU almost nothing is
+// split (splitting costs redundant pose work and sparse row scans); with the samples sharded over 8 GPUs the same trajectory has
+// 8x less work per GPU and its heavy samples are spread over up to 32 warps each. Placement inside a bucket uses shared-memory
+// atomics: the order only decides WHICH warp takes WHICH item, never the arithmetic, so results stay bit-reproducible.
+// One CTA, ~10 us, off the critical path of the evaluation that produced `work`.
 constexpr int ORDER_BUCKETS = 1024;
-__device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 1, (unsigned)ORDER_BUCKETS - 1u); }
+__device__ __forceinline__ int order_bucket(unsigned w) { return (int)min(w >> 3, (unsigned)ORDER_BUCKETS - 1u); }
 
 // inclusive scan of one int per thread over the 1024-thread block (warp scans + a scan of the 32 warp totals)
 __device__ __forceinline__ int block_scan_inclusive_1024(int v, int *warp_tot) {
@@ -800,32 +810,113 @@ __device__ __forceinline__ int block_scan_inclusive_1024(int v, int *warp_tot) {
     return r;
 }
 
-__global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int rank, int world, int M, int *items) {
+template <bool CACHED>
+__global__ void __launch_bounds__(1024) k_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots,
+                                                      int *items, int *item_count) {
     __shared__ int hist[ORDER_BUCKETS];
     __shared__ int cursor[ORDER_BUCKETS];
     __shared__ int warp_tot[32];
+    __shared__ int nsplit, first_over;
+    __shared__ unsigned long long total_work;
+    int *scratch = items + 3 * ((size_t)M + (size_t)(ROW_CLASSES - 1) * max_split);   // behind the item table: per sample (slot << 6) | f, or -1
     const int tid = threadIdx.x;
-    hist[tid] = 0;
+    unsigned wv[CACHED ? ITEMS_CACHE : 1];
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; wv[u] = (m < M) ? __ldcg(work + rank + (size_t)world * m) : 0u; }
+    }
+    auto work_of = [&](int u, int m) -> unsigned { return CACHED ? wv[u] : __ldcg(work + rank + (size_t)world * m); };
+    hist[tid] = 0; cursor[tid] = 0;
+    if (tid == 0) { nsplit = 0; total_work = 0ull; first_over = ORDER_BUCKETS; }
     __syncthreads();
-    for (int m = tid; m < M; m += 1024) atomicAdd(&hist[order_bucket(__ldcg(work + rank + (size_t)world * m))], 1);
+    {   // per-sample work histogram (cursor[]) and total work
+        unsigned long long mine = 0ull;
+        if (CACHED) {
+#pragma unroll
+            for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; if (m < M) { mine += wv[u]; atomicAdd(&cursor[order_bucket(wv[u])], 1); } }
+        } else {
+            for (int m = tid; m < M; m += 1024) { const unsigned w = work_of(0, m); mine += w; atomicAdd(&cursor[order_bucket(w)], 1); }
+        }
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((tid & 31) == 0) atomicAdd(&total_work, mine);
+    }
+    __syncthreads();
+    // balanced-share threshold, raised if needed so that only the max_split HEAVIEST samples qualify: walking the buckets from the
+    // top, b = the first bucket whose samples no longer fit into the split slots (thread t looks at bucket 1023 - t)
+    {
+        const int cum = block_scan_inclusive_1024(cursor[ORDER_BUCKETS - 1 - tid], warp_tot);
+        if (cum > max_split) atomicMin(&first_over, tid);
+    }
+    __syncthreads();
+    unsigned THR;
+    {
+        const unsigned long long t = (total_work * 7ull) / (10ull * (unsigned long long)max(warp_slots, 1));
+        THR = (unsigned)min(max(t, (unsigned long long)SPLIT_WORK_MIN), 0xffffffffull);
+        if (first_over < ORDER_BUCKETS) {
+            const int b = ORDER_BUCKETS - 1 - first_over;
+            THR = max(THR, (unsigned)(b + 1) << 3);           // buckets above b fit into the split slots
+            if (b == ORDER_BUCKETS - 1) THR = 0xffffffffu;     // even the top bucket alone overflows: no splitting
+        }
+    }
+    __syncthreads();
+    cursor[tid] = 0;
+    __syncthreads();
+    // pass 1: decide splits (first come first served up to max_split) and their factor, histogram the item keys
+    auto decide = [&](int m, unsigned w) {
+        int code = -1;
+        if (w >= THR) {
+            const int hs = atomicAdd(&nsplit, 1);
+            if (hs < max_split) {
+                int f = 2;
+                while (f < ROW_CLASSES && (unsigned long long)THR * (unsigned)f < (unsigned long long)w) f <<= 1;
+                code = (hs << 6) | f;
+                atomicAdd(&hist[order_bucket(w / (unsigned)f)], f);
+            }
+        }
+        if (code < 0) atomicAdd(&hist[order_bucket(w)], 1);
+        scratch[m] = code;
+    };
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; if (m < M) decide(m, wv[u]); }
+    } else {
+        for (int m = tid; m < M; m += 1024) decide(m, work_of(0, m));
+    }
     __syncthreads();
     {   // exclusive scan over buckets in DESCENDING bucket order
         const int b = ORDER_BUCKETS - 1 - tid;
         const int incl = block_scan_inclusive_1024(hist[b], warp_tot);
         cursor[b] = incl - hist[b];
+        if (tid == ORDER_BUCKETS - 1) *item_count = incl;
     }
     __syncthreads();
-    for (int m = tid; m < M; m += 1024) items[atomicAdd(&cursor[order_bucket(__ldcg(work + rank + (size_t)world * m))], 1)] = m;
+    auto place = [&](int m, unsigned w) {
+        const int code = scratch[m];
+        if (code >= 0) {
+            const int hs = code >> 6, f = code & 63, cw = ROW_CLASSES / f;
+            const int pos = atomicAdd(&cursor[order_bucket(w / (unsigned)f)], f);
+            for (int p = 0; p < f; p++) { items[3 * (pos + p)] = m; items[3 * (pos + p) + 1] = (p * cw) | ((p * cw + cw) << 8); items[3 * (pos + p) + 2] = hs; }
+        } else {
+            const int pos = atomicAdd(&cursor[order_bucket(w)], 1);
+            items[3 * pos] = m; items[3 * pos + 1] = -1; items[3 * pos + 2] = -1;
+        }
+    };
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < ITEMS_CACHE; u++) { const int m = tid + u * 1024; if (m < M) place(m, wv[u]); }
+    } else {
+        for (int m = tid; m < M; m += 1024) place(m, work_of(0, m));
+    }
 }
 #endif  // ISDF_DISCRETE_TU
 
 // ---- launch interface of the discrete translation unit (isdf_discrete_tu.cu) ------------------------------------------------------
-cudaError_t discrete_launch_analytic(const DiscArgs &A, unsigned grid, cudaStream_t st);
-cudaError_t discrete_launch_mesh(const DiscArgs &A, unsigned grid_cull, unsigned grid_search, cudaStream_t st);   // cull + search kernels
-cudaError_t discrete_launch_epilogue(const DiscArgs &A, int npieces, cudaStream_t st);                            // pieces [A.p0, A.p0 + npieces)
-cudaError_t discrete_launch_build_items(const unsigned *work, int rank, int world, int M, int *items, cudaStream_t st);
+cudaError_t discrete_launch_scan(const DiscArgs &A, bool mesh, unsigned grid, cudaStream_t st);
+cudaError_t discrete_launch_epilogue(const DiscArgs &A, cudaStream_t st);
+cudaError_t discrete_launch_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots, int *items,
+                                        int *item_count, cudaStream_t st);
 // resident CTAs per SM of the scan kernels (occupancy API); also the "can this image run here" probe of isdf_create
-cudaError_t discrete_resident_blocks(int *cull_blocks, int *search_blocks, int *analytic_blocks);
+cudaError_t discrete_resident_blocks(int *mesh_blocks, int *analytic_blocks);
 // diagnostics: the device flatness map / adjoint exactly as the epilogue compiles it (tests pin it to the reference's flatness.hpp)
 cudaError_t discrete_launch_dbg_flatness(const FlatParams &fp, int n, const double *vaj, const double *grads, double *out, cudaStream_t st);
 

@@ -1,5 +1,5 @@
-// Translation unit of the discrete-path kernels (isdf_discrete.cuh): k_discrete_mesh_cull, k_discrete_mesh_search, k_discrete_analytic,
-// k_discrete_epilogue, k_build_items. Compiled WITH FMA contraction (nvcc default): nothing on this path replays a sequential decision of the
+// Translation unit of the discrete-path kernels (isdf_discrete.cuh): k_discrete_mesh, k_discrete_analytic, k_discrete_epilogue,
+// k_build_items. Compiled WITH FMA contraction (nvcc default): nothing on this path replays a sequential decision of the
 // reference, its parity bar is the north star's 1e-6 (observed ~1e-15), and un-fused FP64 cost the mesh kernel ~12 % (ncu,
 // profiles/r01_p). The swept-volume search, whose accept/reject sequence must replay the reference's bit for bit, stays in
 // isdf_api.cu under -fmad=false. ISDF_FAST_TRI selects the division-free closest-point test (isdf_mesh.cuh) for this TU only.
@@ -13,34 +13,29 @@
 
 namespace isdf {
 
-cudaError_t discrete_launch_analytic(const DiscArgs &A, unsigned grid, cudaStream_t st) {
-    k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
+cudaError_t discrete_launch_scan(const DiscArgs &A, bool mesh, unsigned grid, cudaStream_t st) {
+    if (mesh) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
+    else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
     return cudaGetLastError();
 }
 
-cudaError_t discrete_launch_mesh(const DiscArgs &A, unsigned grid_cull, unsigned grid_search, cudaStream_t st) {
-    k_discrete_mesh_cull<<<grid_cull, DISC_THREADS, 0, st>>>(A);
-    k_discrete_mesh_search<<<grid_search, DISC_THREADS, 0, st>>>(A);
+cudaError_t discrete_launch_epilogue(const DiscArgs &A, cudaStream_t st) {
+    k_discrete_epilogue<<<(unsigned)A.N, EPI_THREADS, 0, st>>>(A);
     return cudaGetLastError();
 }
 
-cudaError_t discrete_launch_epilogue(const DiscArgs &A, int npieces, cudaStream_t st) {
-    k_discrete_epilogue<<<(unsigned)npieces, EPI_THREADS, 0, st>>>(A);
+cudaError_t discrete_launch_build_items(const unsigned *work, int rank, int world, int M, int max_split, int warp_slots, int *items,
+                                        int *item_count, cudaStream_t st) {
+    if (M <= 1024 * ITEMS_CACHE) k_build_items<true><<<1, 1024, 0, st>>>(work, rank, world, M, max_split, warp_slots, items, item_count);
+    else k_build_items<false><<<1, 1024, 0, st>>>(work, rank, world, M, max_split, warp_slots, items, item_count);
     return cudaGetLastError();
 }
 
-cudaError_t discrete_launch_build_items(const unsigned *work, int rank, int world, int M, int *items, cudaStream_t st) {
-    k_build_items<<<1, 1024, 0, st>>>(work, rank, world, M, items);
-    return cudaGetLastError();
-}
-
-cudaError_t discrete_resident_blocks(int *cull_blocks, int *search_blocks, int *analytic_blocks) {
+cudaError_t discrete_resident_blocks(int *mesh_blocks, int *analytic_blocks) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)k_discrete_analytic);   // fails loudly if the sm_100a image cannot run here
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(cull_blocks, k_discrete_mesh_cull, DISC_THREADS, 0);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(search_blocks, k_discrete_mesh_search, DISC_THREADS, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(mesh_blocks, k_discrete_mesh, DISC_THREADS, 0);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(analytic_blocks, k_discrete_analytic, DISC_THREADS, 0);
 }

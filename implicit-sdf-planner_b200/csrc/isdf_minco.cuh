@@ -30,7 +30,6 @@ struct MincoArgs {
     double *gC_e, *gT_e;      // energy partials, same layouts as C / T
     const double *disc_out;   // [cost | gradC 18BN | gradT BN] of the concatenated time-integral evaluation (null: none)
     const double *piece_cost; // B*N per-piece cost terms of that evaluation
-    const int *fail_flag;     // may be null: non-zero = the time-integral evaluation dropped work (survivor storage overflow) -> every cost NaN
     double *cost;             // B
     double *grad;             // B x (N + 3(N-1))
 };
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(32) k_minco_backward(const __grid_constant__ M
         double tsum = 0.0;
         for (int i = 0; i < N; i++) tsum += A.T[(size_t)b * N + i];
         cost += A.rho * tsum;
-        A.cost[b] = (A.fail_flag && *A.fail_flag) ? __longlong_as_double(0x7ff8000000000000ll) : cost;
+        A.cost[b] = cost;
     }
 }
 

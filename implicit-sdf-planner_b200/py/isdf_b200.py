@@ -355,21 +355,20 @@ class Evaluator:
         return s
 
     # ---- diagnostics (isdf_dbg_*: exported by the library, not part of include/isdf.h) ----
-    def dbg_schedule(self, natural_order=False, chunks_per_sample=0):
-        """natural_order: the analytic scan kernel always in natural sample order (a context's first evaluation); chunks_per_sample > 0: size the
-        mesh path's survivor storage as max(8192, chunks_per_sample * samples) chunks (1 provokes an overflow on a big workload)."""
+    def dbg_schedule(self, natural_order=False, warp_slots=0):
+        """natural_order: every launch as a context's first one (no work items, nothing split); warp_slots > 0: build the work items as
+        if the device had that many resident warps (huge values force every non-trivial sample to be split)."""
         vp = C.c_void_p
         self.lib.isdf_dbg_schedule.argtypes = [vp, C.c_int, C.c_int]
-        if self.lib.isdf_dbg_schedule(self.h, int(natural_order), int(chunks_per_sample)) != 0:
+        if self.lib.isdf_dbg_schedule(self.h, int(natural_order), int(warp_slots)) != 0:
             raise IsdfError(-1, "isdf_dbg_schedule failed")
 
     def dbg_item_stats(self):
-        """(survivor chunks written by the last discrete evaluation's last slab, overflow flag) — mesh path"""
-        n, over = C.c_int(0), C.c_int(0)
+        n, parts = C.c_int(0), C.c_int(0)
         self.lib.isdf_dbg_item_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-        if self.lib.isdf_dbg_item_stats(self.h, C.byref(n), C.byref(over)) != 0:
+        if self.lib.isdf_dbg_item_stats(self.h, C.byref(n), C.byref(parts)) != 0:
             raise IsdfError(-1, "isdf_dbg_item_stats failed")
-        return n.value, over.value
+        return n.value, parts.value
 
     def dbg_flatness(self, v, a, j, quat_grad, omg_grad, vel_grad):
         """device flatness map + adjoint as compiled into the epilogue kernel -> (quat, omg, gV, gA, gJ)"""

@@ -36,5 +36,5 @@ for world in (1, 2, 4, 8):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         items = ev.dbg_item_stats()
-        print(f"world {world} rank {rank}: {statistics.mean(ts)*1e3:7.1f} us (min {min(ts)*1e3:.1f})  ideal {statistics.mean(ts)*1e3 if world==1 else 0:.0f}  chunks {items}", flush=True)
+        print(f"world {world} rank {rank}: {statistics.mean(ts)*1e3:7.1f} us (min {min(ts)*1e3:.1f})  ideal {statistics.mean(ts)*1e3 if world==1 else 0:.0f}  items {items}", flush=True)
 ev.close()
