@@ -664,10 +664,10 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
 
             // Producer loop (one cull and one search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
             // are appended to the ring, and whenever 32 voxels are queued — or the window is exhausted — they are processed.
-            //   whole sample: a batch is 32 consecutive rows = 32 different classes, so any emission order keeps every CLASS's
-            //                 voxels in (row, z) order: the batch is emitted at once (row-major) when it fits into the ring,
-            //                 otherwise round-robin, one voxel per lane and round (dense walls);
-            //   split part  : rows of the classes [c0, c1) only, emitted row by row so that a class's rows stay in ascending order.
+            // A batch is emitted at once, lane by lane, when it fits into the ring (the common case); otherwise (dense walls)
+            //   whole sample: round-robin, one voxel per lane and round — 32 consecutive rows are 32 different classes, so every CLASS's
+            //                 voxels still come in (row, z) order;
+            //   split part  : row by row (rows of the classes [c0, c1) only), so that a class's rows stay in ascending order.
             const int w = it.c1 - it.c0;
             const int nk = whole ? nrows : ((nrows + ROW_CLASSES - 1) / ROW_CLASSES) * w;   // row slots to visit per z-chunk
             int zs = W.iz0, kb = -32;
@@ -693,7 +693,9 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                                 rowcode = (uint32_t)rx | ((uint32_t)ry << 10) | ((uint32_t)(zs - W.iz0) << 20);
                             }
                             pending = __ballot_sync(0xffffffffu, bits != 0u);
-                            if (whole && pending != 0u) {
+                            // lane order = (row block, class) order, so for every class its rows ascend with the lane: emitting the batch
+                            // lane by lane keeps each CLASS's voxels in (row, z) order for whole samples and for split parts alike
+                            if (pending != 0u) {
                                 int incl = __popc(bits);
 #pragma unroll
                                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
