@@ -6,6 +6,7 @@
 #include "isdf_swept.cuh"
 #include "isdf_minco.cuh"
 #include "isdf_frontend.cuh"
+#include "isdf_lbfgs.cuh"
 #include <queue>
 #include "isdf_host_mesh.cuh"
 #include <cstdio>
@@ -49,7 +50,7 @@ struct isdf_ctx {
     // shape
     bool have_shape = false;
     DevShape shape;
-    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt; DevBuf<uint4> d_cell_rec;
+    DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt; DevBuf<uint4> d_cell_rec; DevBuf<WnNode> d_wn;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_piece_cost;
     DevBuf<int> d_tickets;       // pieces_done counter of the epilogue kernel
@@ -61,6 +62,8 @@ struct isdf_ctx {
     DevBuf<unsigned long long> d_counter, d_dbg, d_trace;
     DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout;   // batched callback (isdf_minco.cuh)
     int minco_B = 0, minco_N = 0;
+    DevBuf<double> d_lb_x, d_lb_f, d_lb_grad, d_lb_state; DevBuf<int> d_lb_int, d_lb_head;   // device-resident lock-step L-BFGS (isdf_lbfgs.cuh)
+    int *h_lb_active = nullptr;  // pinned
     bool dbg_on = false;
     bool no_items = false;       // diagnostics: always launch in natural order, never split (isdf_dbg_schedule)
     int warp_slots_override = 0; // diagnostics: pretend the device has this many resident warps (forces splitting)
@@ -167,7 +170,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
-    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release(); c->d_cell_rec.release();
+    c->d_bits.release(); c->d_nodes.release(); c->d_wnodes.release(); c->d_tris.release(); c->d_pn.release(); c->d_obb.release(); c->d_cell_dist.release(); c->d_cell_seed.release(); c->d_cell_off.release(); c->d_cand.release(); c->d_cell_cnt.release(); c->d_cell_rec.release(); c->d_wn.release();
     c->d_T.release(); c->d_C.release(); c->d_out.release(); c->d_piece_cost.release();
     c->d_tickets.release(); c->d_counter.release(); c->d_items.release(); c->d_item_count.release(); c->d_tot.release(); c->d_split_done.release(); c->d_work.release(); c->d_split_work.release(); c->d_subsum.release(); c->d_dbg.release(); c->d_trace.release();
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
@@ -177,6 +180,8 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_lb_active) cudaFreeHost(c->h_lb_active);
+    c->d_lb_x.release(); c->d_lb_f.release(); c->d_lb_grad.release(); c->d_lb_state.release(); c->d_lb_int.release(); c->d_lb_head.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_main_done) cudaEventDestroy(c->ev_main_done);
@@ -268,13 +273,19 @@ extern "C" int isdf_set_shape_named(isdf_ctx *c, const char *name, const double 
 }
 
 extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const int32_t *F, int nF, const double *poly_params) {
+    return isdf_set_shape_mesh_ex(c, V, nV, F, nF, poly_params, ISDF_MESH_SIGN_AUTO);
+}
+
+extern "C" int isdf_set_shape_mesh_ex(isdf_ctx *c, const double *V, int nV, const int32_t *F, int nF, const double *poly_params, int sign_mode) {
     if (!c || !V || !F) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (sign_mode < 0 || sign_mode > 2) return fail(ISDF_ERR_INVALID, "bad sign_mode");
     if (set_device(c)) return ISDF_ERR_CUDA;
     HostMesh hm; std::string err;
     // the bitmap shortcut is sized for the smallest bound the kernels use: safety_hor (discrete) — the swept path uses
     // 2*safety_hor + 0.1 >= safety_hor
-    if (!build_host_mesh(V, nV, F, nF, poly_params, c->cfg.safety_hor, hm, err))
+    if (!build_host_mesh(V, nV, F, nF, poly_params, c->cfg.safety_hor, hm, err, sign_mode))
         return fail(err.find("not a closed") != std::string::npos ? ISDF_ERR_UNSUPPORTED : ISDF_ERR_INVALID, err);
+    if (!hm.wn.empty()) CU_TRY(c->d_wn.upload(hm.wn.data(), hm.wn.size(), c->stream));
     CU_TRY(c->d_nodes.upload(hm.nodes.data(), hm.nodes.size(), c->stream));
     CU_TRY(c->d_wnodes.upload(hm.wnodes.data(), hm.wnodes.size(), c->stream));
     CU_TRY(c->d_tris.upload(hm.tris.data(), hm.tris.size(), c->stream));
@@ -286,6 +297,7 @@ extern "C" int isdf_set_shape_mesh(isdf_ctx *c, const double *V, int nV, const i
     shape_common(c, nullptr, nullptr);
     DevMesh m = hm.view();
     m.nodes = c->d_nodes.p; m.wnodes = c->d_wnodes.p; m.tris = c->d_tris.p; m.pnormals = c->d_pn.p; m.leaf_obb = c->d_obb.p;
+    m.wn = hm.wn.empty() ? nullptr : c->d_wn.p;
     // per-cell signed distance + seed triangle, computed on the device with the freshly uploaded BVH
     const size_t ncell = (size_t)m.gdim[0] * m.gdim[1] * m.gdim[2];
     CU_TRY(c->d_cell_dist.ensure(ncell));
@@ -818,6 +830,107 @@ extern "C" int isdf_callback_batch(isdf_ctx *c, int B, int N0, const double *hea
     return r;
 }
 
+// ---- device-resident lock-step L-BFGS over the batched callback (isdf_lbfgs.cuh) ----------------------------------------
+static int lbfgs_check(const isdf_lbfgs_params *p) {
+    if (!p) return fail(ISDF_ERR_INVALID, "params is NULL");
+    if (p->mem_size <= 0 || p->mem_size > 64) return fail(ISDF_ERR_INVALID, "mem_size out of range (1..64)");
+    if (p->past < 0 || p->g_epsilon < 0.0 || p->delta < 0.0 || p->min_step < 0.0 || p->max_step < p->min_step || !(p->f_dec_coeff > 0.0 && p->f_dec_coeff < 1.0) ||
+        !(p->machine_prec > 0.0) || p->max_linesearch <= 0 || p->max_iterations < 0 || p->max_rounds < 0)
+        return fail(ISDF_ERR_INVALID, "L-BFGS parameter out of range");
+    return 0;
+}
+
+extern "C" int isdf_lbfgs_default_params(isdf_lbfgs_params *p) {
+    if (!p) return fail(ISDF_ERR_INVALID, "params is NULL");
+    // lbfgs_parameter_t defaults (lbfgs.hpp:40-142) with the back end's settings (config_CappedCone.yaml:99-102: mem 16, past 10, min_step 1e-32, g_epsilon 0)
+    p->mem_size = 16; p->past = 10; p->max_iterations = 0; p->max_linesearch = 64; p->max_rounds = 0;
+    p->g_epsilon = 0.0; p->delta = 1.0e-6; p->min_step = 1.0e-32; p->max_step = 1.0e+20; p->f_dec_coeff = 1.0e-4; p->cautious_factor = 1.0e-6; p->machine_prec = 1.0e-16;
+    return 0;
+}
+
+// d_x: B x n (in: starting points, out: solutions); d_f: B; d_ret / d_iterations / d_evaluations: B ints (any of the three may be null).
+// Synchronous with respect to the host (one 4-byte read per round decides termination), all data stays on the device.
+extern "C" int isdf_lbfgs_batch_device(isdf_ctx *c, int B, int N0, const double *d_head, const double *d_tail, int per_problem_bc, double rho,
+                                       const isdf_lbfgs_params *prm, double *d_x, double *d_f, int *d_ret, int *d_iterations, int *d_evaluations,
+                                       int *rounds_out, void *cuda_stream) {
+    int r = callback_batch_check(c, B, N0);
+    if (r) return r;
+    if ((r = lbfgs_check(prm))) return r;
+    if (!d_head || !d_tail || !d_x || !d_f) return fail(ISDF_ERR_INVALID, "NULL device pointer");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int n = 4 * N0 - 3, m = prm->mem_size, npf = prm->past > 1 ? prm->past : 1;
+    const size_t per = (size_t)4 * n + npf + 2 * (size_t)m + 2 * (size_t)m * n + LB_NSCALAR;   // doubles of state per instance
+    CU_TRY(c->d_lb_state.ensure(per * B)); CU_TRY(c->d_lb_grad.ensure((size_t)B * n)); CU_TRY(c->d_lb_int.ensure((size_t)B * LB_NINT + 4));
+    if (!c->h_lb_active) CU_TRY(cudaMallocHost((void **)&c->h_lb_active, sizeof(int)));
+    CU_TRY(cudaMemsetAsync(c->d_lb_state.p, 0, sizeof(double) * per * B, st));
+    CU_TRY(cudaMemsetAsync(c->d_lb_int.p, 0, sizeof(int) * ((size_t)B * LB_NINT + 4), st));   // phase = WANT_INIT
+    LbfgsArgs L;
+    L.B = B; L.n = n;
+    L.pr.mem_size = m; L.pr.past = prm->past; L.pr.max_iterations = prm->max_iterations; L.pr.max_linesearch = prm->max_linesearch;
+    L.pr.g_epsilon = prm->g_epsilon; L.pr.delta = prm->delta; L.pr.min_step = prm->min_step; L.pr.max_step = prm->max_step;
+    L.pr.f_dec_coeff = prm->f_dec_coeff; L.pr.cautious_factor = prm->cautious_factor; L.pr.machine_prec = prm->machine_prec;
+    double *p = c->d_lb_state.p;
+    L.x = d_x; L.f = d_f; L.grad = c->d_lb_grad.p;
+    L.xp = p; p += (size_t)B * n; L.g = p; p += (size_t)B * n; L.gp = p; p += (size_t)B * n; L.d = p; p += (size_t)B * n;
+    L.pf = p; p += (size_t)B * npf; L.alpha = p; p += (size_t)B * m; L.ys = p; p += (size_t)B * m;
+    L.S = p; p += (size_t)B * m * n; L.Y = p; p += (size_t)B * m * n; L.sc = p;
+    L.st = c->d_lb_int.p; L.active = c->d_lb_int.p + (size_t)B * LB_NINT;
+    // olddnorm starts at 1 (lbfgs.hpp:541): scalar slot 2 of every instance
+    {
+        std::vector<double> init((size_t)B * LB_NSCALAR, 0.0);
+        for (int b = 0; b < B; b++) init[(size_t)b * LB_NSCALAR + 2] = 1.0;
+        CU_TRY(cudaMemcpyAsync(L.sc, init.data(), sizeof(double) * init.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    int rounds = 0;
+    for (;;) {
+        // every instance's requested point is evaluated (finished instances ride along unchanged: their state is frozen)
+        r = callback_batch_launch(c, B, N0, d_head, d_tail, per_problem_bc ? 9 : 0, rho, d_x, d_f, c->d_lb_grad.p, st);
+        if (r) return r;
+        CU_TRY(cudaMemsetAsync(L.active, 0, sizeof(int), st));
+        k_lbfgs_feed<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(L);
+        c->stats.kernel_launches++;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(c->h_lb_active, L.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        ++rounds;
+        if (*c->h_lb_active == 0) break;
+        if (prm->max_rounds > 0 && rounds >= prm->max_rounds) break;
+    }
+    // results: f = fx of every instance (scalar slot 0), return codes and counters
+    CU_TRY(cudaMemcpy2DAsync(d_f, sizeof(double), L.sc, sizeof(double) * LB_NSCALAR, sizeof(double), B, cudaMemcpyDeviceToDevice, st));
+    if (d_ret) CU_TRY(cudaMemcpy2DAsync(d_ret, sizeof(int), L.st + 1, sizeof(int) * LB_NINT, sizeof(int), B, cudaMemcpyDeviceToDevice, st));
+    if (d_iterations) CU_TRY(cudaMemcpy2DAsync(d_iterations, sizeof(int), L.st + 8, sizeof(int) * LB_NINT, sizeof(int), B, cudaMemcpyDeviceToDevice, st));
+    if (d_evaluations) CU_TRY(cudaMemcpy2DAsync(d_evaluations, sizeof(int), L.st + 9, sizeof(int) * LB_NINT, sizeof(int), B, cudaMemcpyDeviceToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (rounds_out) *rounds_out = rounds;
+    return 0;
+}
+
+extern "C" int isdf_lbfgs_batch(isdf_ctx *c, int B, int N0, const double *head, const double *tail, int per_problem_bc, double rho,
+                                const isdf_lbfgs_params *prm, double *x, double *f, int *ret, int *iterations, int *evaluations, int *rounds_out) {
+    int r = callback_batch_check(c, B, N0);
+    if (r) return r;
+    if (!head || !tail || !x || !f) return fail(ISDF_ERR_INVALID, "NULL argument");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    const size_t n = (size_t)4 * N0 - 3, nbc = per_problem_bc ? (size_t)9 * B : 9;
+    CU_TRY(c->d_lb_x.upload(x, n * B, c->stream));
+    CU_TRY(c->d_mbc.ensure(2 * nbc));
+    CU_TRY(cudaMemcpyAsync(c->d_mbc.p, head, sizeof(double) * nbc, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->d_mbc.p + nbc, tail, sizeof(double) * nbc, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c->d_lb_f.ensure(B)); CU_TRY(c->d_lb_head.ensure((size_t)3 * B));
+    r = isdf_lbfgs_batch_device(c, B, N0, c->d_mbc.p, c->d_mbc.p + nbc, per_problem_bc, rho, prm, c->d_lb_x.p, c->d_lb_f.p, c->d_lb_head.p, c->d_lb_head.p + B,
+                                c->d_lb_head.p + 2 * (size_t)B, rounds_out, c->stream);
+    if (r) return r;
+    CU_TRY(cudaMemcpy(x, c->d_lb_x.p, sizeof(double) * n * B, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(f, c->d_lb_f.p, sizeof(double) * B, cudaMemcpyDeviceToHost));
+    if (ret) CU_TRY(cudaMemcpy(ret, c->d_lb_head.p, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    if (iterations) CU_TRY(cudaMemcpy(iterations, c->d_lb_head.p + B, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    if (evaluations) CU_TRY(cudaMemcpy(evaluations, c->d_lb_head.p + 2 * (size_t)B, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int isdf_get_batch_trajectories(isdf_ctx *c, double *T, double *coeffs, double *energy) {
     if (!c) return fail(ISDF_ERR_INVALID, "ctx is NULL");
     if (c->minco_B <= 0) return fail(ISDF_ERR_STATE, "no batched callback evaluated yet");
@@ -1098,6 +1211,9 @@ extern "C" int isdf_set_points(isdf_ctx *c, const double *pts, int P) {
 static int swept_common(isdf_ctx *c, int N, const double *d_T, const double *d_C, double *d_out, cudaStream_t st,
                         const double *g_t, const double *g_s, const double *g_g) {
     if (c->sv.P <= 0) return fail(ISDF_ERR_STATE, "obstacle points not set (isdf_set_points)");
+    if (c->shape.kind == ISDF_SHAPE_MESH && c->shape.mesh.sign_mode == MESH_SIGN_WINDING)
+        return fail(ISDF_ERR_UNSUPPORTED, "the swept-volume search prunes with distance brackets that need a true distance function: winding-sign meshes "
+                                          "(open meshes / soups, ISDF_MESH_SIGN_WINDING) are supported by the discrete path and isdf_shape_query only");
     int launches = 0;
     cudaError_t e = c->sv.launch(c->dcfg, c->shape, N, d_T, d_C, d_out, c->rank, c->world, st, g_t, g_s, g_g, &launches);
     c->stats.kernel_launches += launches;

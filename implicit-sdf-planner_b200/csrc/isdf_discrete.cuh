@@ -507,6 +507,7 @@ __device__ __forceinline__ void row_split(int r, int ny, float inv_ny, int &rx, 
     if (ry < 0) { rx--; ry += ny; } else if (ry >= ny) { rx++; ry -= ny; }
 }
 
+template <bool WINDING>
 __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh(const __grid_constant__ DiscArgs A) {
     __shared__ MeshWarpSmem wsm[DISC_WARPS];
 
@@ -560,9 +561,9 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 if (lane < nres) {
                     const QRes r = sm.qr[lane];
                     d3 g = mk3(0, 0, 0);
-                    const double sdf = mesh_finish(Mh, mk3(r.ex, r.ey, r.ez), r.d2, r.tri, r.feat, g);
                     const double *ps = sm.pose;
                     const d3 d = voxel_centre(G, W.ix0 + (int)(r.code & 0x3ffu), W.iy0 + (int)((r.code >> 10) & 0x3ffu), W.iz0 + (int)(r.code >> 20)) - smem_pos(ps);
+                    const double sdf = mesh_finish_t<WINDING>(Mh, rot_applyT(smem_rot(ps), d), mk3(r.ex, r.ey, r.ez), r.d2, r.tri, r.feat, g);
                     quat4 q; q.w = ps[12]; q.x = ps[13]; q.y = ps[14]; q.z = ps[15];
                     PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};
                     pair_accumulate(cfg, smem_rot(ps), q, d, sdf, g, one);
@@ -599,15 +600,17 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                     prel = rot_applyT(smem_rot(ps), d);
                     box = !(fabs(prel.x) > h || fabs(prel.y) > h || fabs(prel.z) > h);  // hpp:800
                     // exact skips: outside the mesh AABB inflated by safety_hor, or in a cell whose every point is >= safety_hor away
-                    pass = box && !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
-                                    prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf);
+                    // (with the un-thresholded winding sign s = 1 - 2 w no distance bound decides the hinge: every voxel in the box is answered)
+                    constexpr bool wn = WINDING;
+                    pass = box && (wn || !(prel.x < Mh.blo[0] - sf || prel.x > Mh.bhi[0] + sf || prel.y < Mh.blo[1] - sf || prel.y > Mh.bhi[1] + sf ||
+                                           prel.z < Mh.blo[2] - sf || prel.z > Mh.bhi[2] + sf));
                     if (pass) {
                         const int cx = (int)floor((prel.x - Mh.glo[0]) * Mh.inv_gcell), cy = (int)floor((prel.y - Mh.glo[1]) * Mh.inv_gcell),
                                   cz = (int)floor((prel.z - Mh.glo[2]) * Mh.inv_gcell);
-                        if (cx < 0 || cy < 0 || cz < 0 || cx >= Mh.gdim[0] || cy >= Mh.gdim[1] || cz >= Mh.gdim[2]) pass = !(sf <= Mh.gpad);   // outside the grid: >= gpad away
+                        if (cx < 0 || cy < 0 || cz < 0 || cx >= Mh.gdim[0] || cy >= Mh.gdim[1] || cz >= Mh.gdim[2]) pass = wn || !(sf <= Mh.gpad);   // outside the grid: >= gpad away
                         else {
                             rec = __ldg(Mh.cell_rec + ((size_t)(cx * Mh.gdim[1] + cy) * Mh.gdim[2] + cz));
-                            pass = !((double)__uint_as_float(rec.x) - Mh.ghd >= sf);
+                            pass = wn || !((double)__uint_as_float(rec.x) - Mh.ghd >= sf);
                         }
                     }
                 }

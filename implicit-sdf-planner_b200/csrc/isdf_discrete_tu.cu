@@ -14,7 +14,8 @@
 namespace isdf {
 
 cudaError_t discrete_launch_scan(const DiscArgs &A, bool mesh, unsigned grid, cudaStream_t st) {
-    if (mesh) k_discrete_mesh<<<grid, DISC_THREADS, 0, st>>>(A);
+    if (mesh && A.shape.mesh.sign_mode == MESH_SIGN_WINDING) k_discrete_mesh<true><<<grid, DISC_THREADS, 0, st>>>(A);
+    else if (mesh) k_discrete_mesh<false><<<grid, DISC_THREADS, 0, st>>>(A);
     else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);
     return cudaGetLastError();
 }
@@ -35,7 +36,7 @@ cudaError_t discrete_resident_blocks(int *mesh_blocks, int *analytic_blocks) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, (const void *)k_discrete_analytic);   // fails loudly if the sm_100a image cannot run here
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(mesh_blocks, k_discrete_mesh, DISC_THREADS, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(mesh_blocks, k_discrete_mesh<false>, DISC_THREADS, 0);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(analytic_blocks, k_discrete_analytic, DISC_THREADS, 0);
 }

@@ -18,6 +18,10 @@ struct HostMesh {
     std::vector<BvhNode> nodes;
     std::vector<WideNode> wnodes;
     std::vector<double> tris, pnormals, leaf_obb;
+    std::vector<WnNode> wn;
+    int sign_mode = MESH_SIGN_PSEUDONORMAL;
+    bool closed = true;
+    double wn_beta2 = 256.0;   // beta = 16: measured max |w_tree - w_exact| ~1e-4 on a 3800-triangle mesh (tests/host_mesh_check.cu); the reference's FP32 order-2 tree at beta = 2 is at 1e-4..1e-3
     int ntris = 0;
     int gdim[3] = {0, 0, 0};
     double glo[3] = {0, 0, 0}, gcell = 0, ghd = 0, gpad = 0, sign_radius = 0;
@@ -25,6 +29,7 @@ struct HostMesh {
     DevMesh view() const {  // host pointers; same code path as the device for the bitmap construction
         DevMesh m;
         m.nodes = nodes.data(); m.wnodes = wnodes.data(); m.tris = tris.data(); m.pnormals = pnormals.data(); m.leaf_obb = leaf_obb.empty() ? nullptr : leaf_obb.data(); m.cell_dist = nullptr; m.cell_seed = nullptr; m.cell_off = nullptr; m.cell_cnt = nullptr; m.cand = nullptr; m.cell_rec = nullptr;
+        m.sign_mode = sign_mode; m.wn = wn.empty() ? nullptr : wn.data(); m.wn_beta2 = wn_beta2;
         m.ntris = ntris;
         for (int a = 0; a < 3; a++) { m.gdim[a] = gdim[a]; m.glo[a] = glo[a]; m.blo[a] = blo[a]; m.bhi[a] = bhi[a]; }
         m.gcell = gcell; m.inv_gcell = gcell > 0 ? 1.0 / gcell : 0.0; m.ghd = ghd; m.gpad = gpad; m.sign_radius = sign_radius;
@@ -65,8 +70,10 @@ inline int build_rec(std::vector<BuildNode> &bn, std::vector<int> &order, int b,
 
 // V: nV x 3, F: nF x 3 (row-major). poly_params {tx,ty,tz, roll,pitch,yaw [deg]} or nullptr (Shape.cpp:38-50).
 // sign_reach: smallest query bound the kernels will use with the bitmap shortcut (safety_hor).
+// want_sign: 0 = automatic (closed, consistently oriented mesh -> exact ±1 from pseudonormals; anything else -> winding number),
+//            1 = exact ±1 required (fails for open meshes / soups), 2 = winding number s = 1 - 2 w (the reference's form) even when closed.
 inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF, const double *poly_params, double sign_reach,
-                            HostMesh &out, std::string &err) {
+                            HostMesh &out, std::string &err, int want_sign = 0) {
     if (nV < 3 || nF < 1) { err = "mesh needs at least 3 vertices and 1 face"; return false; }
     for (int i = 0; i < 3 * nF; i++) if (F[i] < 0 || F[i] >= nV) { err = "face index out of range"; return false; }
     std::vector<std::array<double, 3>> V(nV);
@@ -121,12 +128,14 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
             for (int k = 0; k < 3; k++) directed[{fi[t][k], fi[t][(k + 1) % 3]}]++;
         for (const auto &e : directed) {
             const auto rev = directed.find({e.first.second, e.first.first});
-            if (e.first.first == e.first.second || e.second != 1 || rev == directed.end() || rev->second != 1) {
-                err = "mesh is not a closed, consistently oriented 2-manifold (open, duplicated or flipped edge); the winding-number "
-                      "sign of soups / open meshes is not supported by this build";
-                return false;
-            }
+            if (e.first.first == e.first.second || e.second != 1 || rev == directed.end() || rev->second != 1) { out.closed = false; break; }
         }
+        if (!out.closed && want_sign == 1) {
+            err = "mesh is not a closed, consistently oriented 2-manifold (open, duplicated or flipped edge): the exact ±1 sign needs one — "
+                  "use the automatic or the winding-number sign mode";
+            return false;
+        }
+        out.sign_mode = (want_sign == 2 || !out.closed) ? MESH_SIGN_WINDING : MESH_SIGN_PSEUDONORMAL;
     }
     // BVH
     std::vector<int> order(nF);
@@ -157,6 +166,39 @@ inline bool build_host_mesh(const double *Vin, int nV, const int32_t *F, int nF,
             for (int a = 0; a < 3; a++) Pn[3 + 3 * k + a] = e[a];
         }
         for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) Pn[12 + 3 * k + a] = vn[fi[t][k]][a];
+    }
+    // winding-number tree over the same nodes: vector area, first-moment tensor and radius about the area-weighted centroid
+    if (out.sign_mode == MESH_SIGN_WINDING) {
+        out.wn.resize(bn.size());
+        for (size_t i = 0; i < bn.size(); i++) {
+            WnNode &w = out.wn[i];
+            const auto &b = bn[i];
+            w.left = b.left; w.right = b.right; w.first = b.first; w.count = b.count;
+            double asum = 0, c[3] = {0, 0, 0};
+            for (int t = b.first; t < b.first + b.count; t++) {
+                const double *T = &out.tris[(size_t)TRI_STRIDE * t];
+                const double nx = T[4] * T[8] - T[5] * T[7], ny = T[5] * T[6] - T[3] * T[8], nz = T[3] * T[7] - T[4] * T[6];   // ab x ac = 2 a_t n_t
+                const double ar = 0.5 * std::sqrt(nx * nx + ny * ny + nz * nz);
+                for (int a = 0; a < 3; a++) c[a] += ar * (T[a] + (T[3 + a] + T[6 + a]) / 3.0);
+                asum += ar;
+            }
+            for (int a = 0; a < 3; a++) w.c[a] = asum > 0 ? c[a] / asum : 0.5 * (b.lo[a] + b.hi[a]);
+            for (int a = 0; a < 3; a++) w.N[a] = 0;
+            for (int a = 0; a < 9; a++) w.M[a] = 0;
+            w.r2 = 0;
+            for (int t = b.first; t < b.first + b.count; t++) {
+                const double *T = &out.tris[(size_t)TRI_STRIDE * t];
+                const double an[3] = {0.5 * (T[4] * T[8] - T[5] * T[7]), 0.5 * (T[5] * T[6] - T[3] * T[8]), 0.5 * (T[3] * T[7] - T[4] * T[6])};   // a_t n_t
+                double dct[3];
+                for (int a = 0; a < 3; a++) { dct[a] = T[a] + (T[3 + a] + T[6 + a]) / 3.0 - w.c[a]; w.N[a] += an[a]; }
+                for (int a = 0; a < 3; a++) for (int q = 0; q < 3; q++) w.M[3 * a + q] += dct[a] * an[q];
+                for (int k = 0; k < 3; k++) {
+                    double d2 = 0;
+                    for (int a = 0; a < 3; a++) { const double v = T[a] + (k == 1 ? T[3 + a] : 0.0) + (k == 2 ? T[6 + a] : 0.0) - w.c[a]; d2 += v * v; }
+                    w.r2 = std::max(w.r2, d2);
+                }
+            }
+        }
     }
     // fat nodes: every internal node carries both children's boxes
     auto code_of = [&](int bi, const std::vector<int> &fat_index) -> int {

@@ -30,6 +30,16 @@ struct WideNode {           // 1664 bytes
     int child[32];          // >= 0: WideNode index; < 0: leaf, ~code with code = first_tri*8 + (count-1); WIDE_EMPTY: unused slot
 };
 
+// Node of the winding-number tree (same binary tree / triangle order as the BVH): first-order Barnes-Hut expansion of the solid angle the
+// node's triangles subtend (Barill et al. 2018, the scheme behind igl::fast_winding_number): vector area N = sum a_t n_t about the
+// area-weighted centroid c, first-moment tensor M = sum a_t (x_t - c) (x) n_t, and the squared radius of the node about c.
+struct WnNode {
+    double c[3], N[3], M[9], r2;
+    int left, right;        // node indices; left < 0: leaf
+    int first, count;       // triangle range (leaf order)
+};
+enum { MESH_SIGN_PSEUDONORMAL = 0, MESH_SIGN_WINDING = 1 };
+
 struct DevMesh {
     const BvhNode *nodes;   // nodes[0] is the root (a single-leaf mesh still gets one node with right = left)
     const WideNode *wnodes; // wnodes[0] is the root of the 32-ary tree
@@ -62,6 +72,12 @@ struct DevMesh {
     double gpad;            // padding of the grid around the AABB: a point outside the grid is at least gpad away
     double sign_radius;     // a point with no triangle within this distance shares its cell centre's sign (0 = unusable)
     double blo[3], bhi[3];  // mesh AABB
+    // sign source. PSEUDONORMAL: s = ±1 from the angle-weighted pseudonormal of the closest feature — exact inside/outside for closed,
+    // consistently oriented meshes. WINDING: s = 1 - 2 w with the generalised winding number w evaluated hierarchically and NOT thresholded —
+    // the reference's form (Shape.cpp:110-111), the only meaningful one for open meshes and triangle soups.
+    int sign_mode;
+    const WnNode *wn;       // winding-number tree (root 0); null when sign_mode == PSEUDONORMAL
+    double wn_beta2;        // a node is expanded in the far field when |q - c|^2 > wn_beta2 * r2
 };
 
 // Triangle record, TRI_STRIDE doubles (128 B = four 32-byte sectors, 32-byte aligned), in leaf order:
@@ -204,6 +220,54 @@ ISDF_HD bool mesh_far(const DevMesh &M, d3 p, double reach, int &cell) {
 }
 ISDF_HD bool mesh_cell_inside(const DevMesh &M, int cell) { return cell >= 0 && M.cell_dist[cell] < 0.0f; }
 
+// signed solid angle of triangle record T seen from q (van Oosterom & Strackee 1983), positive for an outward triangle seen from inside
+ISDF_HD double tri_solid_angle(d3 q, const double *T) {
+    const d3 A = mk3(T[0] - q.x, T[1] - q.y, T[2] - q.z), B = mk3(A.x + T[3], A.y + T[4], A.z + T[5]), C = mk3(A.x + T[6], A.y + T[7], A.z + T[8]);
+    const double la = len3(A), lb = len3(B), lc = len3(C);
+    const double num = dot3(A, cross3(B, C));
+    const double den = la * lb * lc + dot3(A, B) * lc + dot3(B, C) * la + dot3(C, A) * lb;
+    return 2.0 * atan2(num, den);
+}
+
+// Generalised winding number of the mesh at q: Barnes-Hut traversal of the WnNode tree — far nodes contribute their first-order expansion
+// (dipole + first-moment term), near leaves the exact solid angles of their triangles. One query per thread.
+__host__ __device__ inline double mesh_winding(const DevMesh &M, d3 q) {
+    double om = 0.0;
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const WnNode &nd = M.wn[stack[--sp]];
+        const d3 r = mk3(nd.c[0] - q.x, nd.c[1] - q.y, nd.c[2] - q.z);
+        const double d2 = dot3(r, r);
+        if (d2 > M.wn_beta2 * nd.r2 && d2 > 0.0) {
+            const double inv = 1.0 / sqrt(d2), inv3 = inv * inv * inv;
+            const double Nr = nd.N[0] * r.x + nd.N[1] * r.y + nd.N[2] * r.z;
+            const double tr = nd.M[0] + nd.M[4] + nd.M[8];
+            const double rMr = r.x * (nd.M[0] * r.x + nd.M[1] * r.y + nd.M[2] * r.z) + r.y * (nd.M[3] * r.x + nd.M[4] * r.y + nd.M[5] * r.z) +
+                               r.z * (nd.M[6] * r.x + nd.M[7] * r.y + nd.M[8] * r.z);
+            om += (Nr + tr) * inv3 - 3.0 * rMr * inv3 * inv * inv;
+        } else if (nd.left < 0) {
+            for (int t = nd.first; t < nd.first + nd.count; t++) om += tri_solid_angle(q, M.tris + TRI_STRIDE * (size_t)t);
+        } else if (sp + 2 <= 64) {
+            stack[sp++] = nd.left; stack[sp++] = nd.right;
+        }
+    }
+    return om / (4.0 * 3.14159265358979323846);
+}
+
+// sign factor of the SDF at p given the vector e = p - closest point and the closest feature
+__host__ __device__ inline double mesh_sign(const DevMesh &M, d3 p, d3 e, int tri, int feat) {
+    if (M.sign_mode == MESH_SIGN_WINDING) return 1.0 - 2.0 * mesh_winding(M, p);   // Shape.cpp:110-111: not thresholded
+    const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
+    double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
+    if (side == 0.0) {  // on the surface or numerically tangent: fall back to the face normal
+        const double *fn = M.pnormals + 21 * (size_t)tri;
+        side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2];
+    }
+    return (side < 0.0) ? -1.0 : 1.0;
+}
+
 // getSDFwithGrad1 for the mesh shape (Shape.cpp:139-151): sdf = s * dist, grad = normalise(s * (p - c)).
 // `reach` prunes the search: the caller only needs the value when sdf < reach (pass 1e300 for "always").
 // If nothing lies within reach the point is either farther out than reach (returns +reach, grad untouched => the
@@ -211,7 +275,8 @@ ISDF_HD bool mesh_cell_inside(const DevMesh &M, int cell) { return cell >= 0 && 
 __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double reach, d3 &g) {
     d3 c = mk3(0, 0, 0);
     int tri = -1, feat = 0, cell;
-    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+    // winding sign: s = 1 - 2 w is not ±1, so no distance bound can decide the hinge — every query is answered exactly
+    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius) && (M.sign_mode == MESH_SIGN_PSEUDONORMAL);
     const bool far = mesh_far(M, p, reach, cell);
     if (bounded && far) return reach;                                  // exact: every point of this cell is >= reach away
     if (cell >= 0 && M.cell_cnt && M.cell_cnt[cell] != 0) {
@@ -229,10 +294,7 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
             if (dd < bd) { bd = dd; c = q; tri = t; feat = f; }
         }
         const d3 e = p - c;
-        const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
-        double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
-        if (side == 0.0) { const double *fn = M.pnormals + 21 * (size_t)tri; side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2]; }
-        const double s = (side < 0.0) ? -1.0 : 1.0;
+        const double s = mesh_sign(M, p, e, tri, feat);
         g = unit3(s * e);
         return s * sqrt(bd);
     }
@@ -268,13 +330,7 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
         d2 = mesh_closest(M, p, 1e300, c, tri, feat);
     }
     const d3 e = p - c;
-    const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
-    double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
-    if (side == 0.0) {  // on the surface or numerically tangent: fall back to the face normal
-        const double *fn = M.pnormals + 21 * (size_t)tri;
-        side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2];
-    }
-    const double s = (side < 0.0) ? -1.0 : 1.0;
+    const double s = mesh_sign(M, p, e, tri, feat);
     g = unit3(s * e);
     return s * sqrt(d2);
 }
@@ -526,7 +582,7 @@ __device__ __forceinline__ bool mesh_search_rec(const DevMesh &M, d3 p, double r
         d2 = list_closest_pre(M, p, off, cnt, first_id, c, tri, feat, lane);
         return true;
     }
-    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius) && (M.sign_mode == MESH_SIGN_PSEUDONORMAL);
     double bound2 = bounded ? reach * reach : 1e300;
     for (;;) {   // one inlined copy of the tree search: first within `reach`, then (deep inside only) unbounded
 #ifdef ISDF_OUTLINE_TREE_SEARCH
@@ -542,14 +598,23 @@ __device__ __forceinline__ bool mesh_search_rec(const DevMesh &M, d3 p, double r
 
 // Sign + gradient half (Shape.cpp:139-151): e = p - closest point; sdf = s * dist, grad = normalise(s * e), s = ±1 from the
 // angle-weighted pseudonormal of the closest feature.
-__device__ __forceinline__ double mesh_finish(const DevMesh &M, d3 e, double d2, int tri, int feat, d3 &g) {
-    const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
-    double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
-    if (side == 0.0) {
-        const double *fn = M.pnormals + 21 * (size_t)tri;
-        side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2];
+__device__ __forceinline__ double mesh_finish(const DevMesh &M, d3 p, d3 e, double d2, int tri, int feat, d3 &g) {
+    const double s = mesh_sign(M, p, e, tri, feat);
+    g = unit3(s * e);
+    return s * sqrt(d2);
+}
+// compile-time choice of the sign source: the closed-mesh instantiation of a kernel carries no winding-number code at all (the discrete
+// scan kernel is sensitive to its code size: profiles/r02_tuning.md, v5)
+template <bool WINDING>
+__device__ __forceinline__ double mesh_finish_t(const DevMesh &M, d3 p, d3 e, double d2, int tri, int feat, d3 &g) {
+    double s;
+    if (WINDING) s = 1.0 - 2.0 * mesh_winding(M, p);
+    else {
+        const double *pn = M.pnormals + 21 * (size_t)tri + 3 * feat;
+        double side = e.x * pn[0] + e.y * pn[1] + e.z * pn[2];
+        if (side == 0.0) { const double *fn = M.pnormals + 21 * (size_t)tri; side = e.x * fn[0] + e.y * fn[1] + e.z * fn[2]; }
+        s = (side < 0.0) ? -1.0 : 1.0;
     }
-    const double s = (side < 0.0) ? -1.0 : 1.0;
     g = unit3(s * e);
     return s * sqrt(d2);
 }
@@ -566,7 +631,7 @@ __device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, dou
         if (bounded && far) return reach;
     }
     if (!mesh_search_warp(M, p, reach, lane, stk, cell, d2, c, tri, feat)) return reach;
-    return mesh_finish(M, p - c, d2, tri, feat, g);
+    return mesh_finish(M, p, p - c, d2, tri, feat, g);
 }
 
 }  // namespace isdf

@@ -20,14 +20,16 @@ NAMED_SHAPES = ["Ball", "Point", "Torus", "Torus_big", "Cappedtorus", "CappedCon
                 "SmoothIntersection", "SmoothIntersection_big", "CSG"]
 WITH_DYNAMICS, WITH_COLLISION = 1, 2
 QUERY_SDF, QUERY_GRAD, QUERY_SDF_GRAD = 0, 1, 2
+MESH_SIGN_AUTO, MESH_SIGN_EXACT, MESH_SIGN_WINDING = 0, 1, 2
 
 # every symbol include/isdf.h declares (tests assert the library exports all of them)
 ABI_SYMBOLS = ["isdf_default_config", "isdf_create", "isdf_destroy", "isdf_last_error", "isdf_get_stats", "isdf_set_shard",
-               "isdf_set_shape_analytic", "isdf_set_shape_named", "isdf_set_shape_mesh", "isdf_shape_query",
+               "isdf_set_shape_analytic", "isdf_set_shape_named", "isdf_set_shape_mesh", "isdf_set_shape_mesh_ex", "isdf_shape_query",
                "isdf_set_map_u8", "isdf_set_map_f64", "isdf_points_in_aabb", "isdf_eval_discrete",
                "isdf_eval_discrete_device", "isdf_set_points", "isdf_eval_swept", "isdf_eval_swept_device",
                "isdf_get_swept_results", "isdf_eval_swept_given", "isdf_get_piece_costs",
                "isdf_gather_obstacle_points", "isdf_callback_batch", "isdf_callback_batch_device", "isdf_get_batch_trajectories",
+               "isdf_lbfgs_default_params", "isdf_lbfgs_batch", "isdf_lbfgs_batch_device",
                "isdf_frontend_build_kernels", "isdf_frontend_get_kernels", "isdf_frontend_feasibility", "isdf_frontend_feasibility_device",
                "isdf_frontend_check_batch", "isdf_peer_export", "isdf_peer_connect", "isdf_peer_allreduce_device", "isdf_peer_status", "isdf_peer_disconnect"]
 
@@ -48,6 +50,12 @@ class Config(C.Structure):
         c = Config()
         C.memmove(C.byref(c), C.byref(self), C.sizeof(Config))
         return c
+
+
+class LbfgsParams(C.Structure):
+    """isdf_lbfgs_params"""
+    _fields_ = [(n, C.c_int32) for n in ["mem_size", "past", "max_iterations", "max_linesearch", "max_rounds", "reserved_"]] + \
+               [(n, C.c_double) for n in ["g_epsilon", "delta", "min_step", "max_step", "f_dec_coeff", "cautious_factor", "machine_prec"]]
 
 
 class Stats(C.Structure):
@@ -87,6 +95,7 @@ def load_library(path=None):
     lib.isdf_set_shape_analytic.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp]
     lib.isdf_set_shape_named.argtypes = [vp, C.c_char_p, dp, dp]
     lib.isdf_set_shape_mesh.argtypes = [vp, dp, C.c_int, ip, C.c_int, dp]
+    lib.isdf_set_shape_mesh_ex.argtypes = [vp, dp, C.c_int, ip, C.c_int, dp, C.c_int]
     lib.isdf_shape_query.argtypes = [vp, dp, C.c_int, dp, dp, C.c_int]
     lib.isdf_set_map_u8.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, dp, C.c_double]
     lib.isdf_set_map_f64.argtypes = [vp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_double]
@@ -102,6 +111,9 @@ def load_library(path=None):
     lib.isdf_callback_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, C.c_double, dp, dp, dp]
     lib.isdf_callback_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, vp, vp, vp, vp]
     lib.isdf_get_batch_trajectories.argtypes = [vp, dp, dp, dp]
+    lib.isdf_lbfgs_default_params.argtypes = [C.POINTER(LbfgsParams)]
+    lib.isdf_lbfgs_batch.argtypes = [vp, C.c_int, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(LbfgsParams), dp, dp, ip, ip, ip, ip]
+    lib.isdf_lbfgs_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_double, C.POINTER(LbfgsParams), vp, vp, vp, vp, vp, ip, vp]
     lib.isdf_frontend_build_kernels.argtypes = [vp, C.POINTER(KernelConfig), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.isdf_frontend_get_kernels.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int]
     lib.isdf_frontend_feasibility.argtypes = [vp, C.POINTER(C.c_uint32)]
@@ -173,11 +185,11 @@ class Evaluator:
         t = _f64(trans).reshape(3) if trans is not None else None
         self._check(self.lib.isdf_set_shape_analytic(self.h, int(kind), _dp(p) if p.size else None, p.size, _dp(r), _dp(t)))
 
-    def set_shape_mesh(self, V, F, poly_params=None):
+    def set_shape_mesh(self, V, F, poly_params=None, sign_mode=MESH_SIGN_AUTO):
         V = _f64(V).reshape(-1, 3)
         F = np.ascontiguousarray(F, dtype=np.int32).reshape(-1, 3)
         pp = _f64(poly_params).reshape(6) if poly_params is not None else None
-        self._check(self.lib.isdf_set_shape_mesh(self.h, _dp(V), V.shape[0], F.ctypes.data_as(C.POINTER(C.c_int32)), F.shape[0], _dp(pp)))
+        self._check(self.lib.isdf_set_shape_mesh_ex(self.h, _dp(V), V.shape[0], F.ctypes.data_as(C.POINTER(C.c_int32)), F.shape[0], _dp(pp), int(sign_mode)))
 
     def shape_query(self, p, what=QUERY_SDF_GRAD):
         p = _f64(p).reshape(-1, 3)
@@ -247,6 +259,32 @@ class Evaluator:
 
     def callback_batch_device(self, B, N0, d_head, d_tail, per_problem_bc, rho, d_x, d_cost, d_grad, stream=None):
         self._check(self.lib.isdf_callback_batch_device(self.h, B, N0, d_head, d_tail, int(per_problem_bc), float(rho), d_x, d_cost, d_grad, stream))
+
+    def lbfgs_params(self, **kw):
+        p = LbfgsParams()
+        self._check(self.lib.isdf_lbfgs_default_params(C.byref(p)))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def lbfgs_batch(self, head, tail, rho, X, params=None):
+        """device-resident lock-step L-BFGS over the batched callback: X (B, 4*N0-3) starting points -> dict(x, f, ret, iterations, evaluations, rounds)"""
+        X = _f64(X)
+        B, dim = X.shape
+        N0 = (dim + 3) // 4
+        head, tail = np.asarray(head, dtype=np.float64), np.asarray(tail, dtype=np.float64)
+        per = int(head.ndim == 3)
+        colmajor = (lambda a: np.ascontiguousarray(np.swapaxes(a, -1, -2)).reshape(-1))
+        h, t = colmajor(head), colmajor(tail)
+        x = np.ascontiguousarray(X).copy().reshape(-1)
+        f = np.zeros(B)
+        ret, it, evs = (np.zeros(B, dtype=np.int32) for _ in range(3))
+        rounds = C.c_int32(0)
+        ip = C.POINTER(C.c_int32)
+        p = params if params is not None else self.lbfgs_params()
+        self._check(self.lib.isdf_lbfgs_batch(self.h, B, N0, _dp(h), _dp(t), per, float(rho), C.byref(p), _dp(x), _dp(f), ret.ctypes.data_as(ip), it.ctypes.data_as(ip),
+                                              evs.ctypes.data_as(ip), C.byref(rounds)))
+        return dict(x=x.reshape(B, dim), f=f, ret=ret, iterations=it, evaluations=evs, rounds=rounds.value)
 
     def batch_trajectories(self, B, N0):
         T, Cc, en = np.zeros(B * N0), np.zeros(18 * B * N0), np.zeros(B)

@@ -105,10 +105,20 @@ int isdf_set_shape_analytic(isdf_ctx *ctx, int kind, const double *params, int n
                             const double *rotate_rowmajor, const double *trans);
 /* factory keyed by the OBJ basename like shapeConstructors (swm:74-123): "Torus", "CSG", ...; plus "Ball", "Point" */
 int isdf_set_shape_named(isdf_ctx *ctx, const char *name, const double *rotate_rowmajor, const double *trans);
-/* triangle mesh (V: nV x 3 row-major, F: nF x 3 row-major, consistently outward-oriented, closed);
- * poly_params = {tx,ty,tz, roll,pitch,yaw in degrees} pre-transform as Shape.cpp:38-50, NULL = none.
- * SDF = s * dist (Shape.cpp:105-151) with s = ±1 the exact inside/outside sign (see DESIGN.md "mesh sign"). */
+/* triangle mesh (V: nV x 3 row-major, F: nF x 3 row-major); poly_params = {tx,ty,tz, roll,pitch,yaw in degrees} pre-transform as
+ * Shape.cpp:38-50, NULL = none. SDF = s * dist (Shape.cpp:105-151); the distance is exact, the sign factor s depends on the mode:
+ *   ISDF_MESH_SIGN_AUTO    closed, consistently oriented mesh -> ISDF_MESH_SIGN_EXACT, anything else (open mesh, triangle soup) ->
+ *                          ISDF_MESH_SIGN_WINDING (as igl::fast_winding_number accepts any soup);
+ *   ISDF_MESH_SIGN_EXACT   s = ±1, the exact inside/outside classification (angle-weighted pseudonormals); ISDF_ERR_UNSUPPORTED if the mesh
+ *                          is not closed. This is what the reference's s = 1 - 2 w rounds to; DESIGN.md "mesh sign" reports the deviation;
+ *   ISDF_MESH_SIGN_WINDING s = 1 - 2 w with w the generalised winding number, NOT thresholded — the reference's form (Shape.cpp:110-111).
+ *                          w is evaluated hierarchically in FP64 (first-order expansion, exact near field), i.e. closer to the true winding
+ *                          number than the reference's FP32 tree, not bit-equal to it. Discrete path, isdf_shape_query and the front end
+ *                          support this mode; the swept-volume entry points return ISDF_ERR_UNSUPPORTED for it.
+ * isdf_set_shape_mesh = isdf_set_shape_mesh_ex(..., ISDF_MESH_SIGN_AUTO). */
+typedef enum isdf_mesh_sign { ISDF_MESH_SIGN_AUTO = 0, ISDF_MESH_SIGN_EXACT = 1, ISDF_MESH_SIGN_WINDING = 2 } isdf_mesh_sign;
 int isdf_set_shape_mesh(isdf_ctx *ctx, const double *V, int nV, const int32_t *F, int nF, const double *poly_params);
+int isdf_set_shape_mesh_ex(isdf_ctx *ctx, const double *V, int nV, const int32_t *F, int nF, const double *poly_params, int sign_mode);
 /* the BasicShape virtual surface (Shape.hpp:469-472) for n body-frame points (n x 3 row-major); sdf/grad may be NULL */
 int isdf_shape_query(isdf_ctx *ctx, const double *p_rel, int n, double *sdf, double *grad, int what);
 
@@ -160,6 +170,29 @@ int isdf_callback_batch_device(isdf_ctx *ctx, int B, int N0, const double *d_hea
 /* the trajectories of the last batched callback: durations (B*N0), coefficient block (6*B*N0 x 3 column-major, piece b*N0+i),
  * jerk energies (B); any may be NULL */
 int isdf_get_batch_trajectories(isdf_ctx *ctx, double *T, double *coeffs, double *energy);
+
+/* ---- device-resident lock-step L-BFGS over the batched callback ------------------------------------------------
+ * B independent instances of the reference's patched LBFGS-Lite fork (utils/include/utils/lbfgs.hpp:480-830: Lewis-Overton bracketing that
+ * returns on Armijo :290-430, cautious update + two-loop recursion :742-786, the fork's direction reset :788-811, stop tests :656-690; same
+ * return codes :148-197) advanced together: every round is ONE isdf_callback_batch_device evaluation of all instances' requested points plus
+ * one bookkeeping kernel; iterates and histories never leave the device. Each instance's iterates, counts and return code are bit-identical
+ * to the sequential driver host/isdf_lbfgs.hpp run on the same callback. The reference's own driver is single-instance (and its live LMBM
+ * shim non-re-entrant, lmbm/lmbm.cpp:4-6). */
+typedef struct isdf_lbfgs_params {     /* lbfgs_parameter_t (lbfgs.hpp:40-142); with_tole_ls / cast_x_range off as in the shipped configs */
+    int32_t mem_size, past, max_iterations, max_linesearch;
+    int32_t max_rounds;                /* 0 = until every instance has stopped; otherwise a cap on batched evaluations */
+    int32_t reserved_;
+    double g_epsilon, delta, min_step, max_step, f_dec_coeff, cautious_factor, machine_prec;
+} isdf_lbfgs_params;
+int isdf_lbfgs_default_params(isdf_lbfgs_params *p);   /* config_CappedCone.yaml:99-102: mem 16, past 10, min_step 1e-32, g_epsilon 0, delta 1e-6 */
+/* x: B x (4*N0-3) in/out; f: B; ret / iterations / evaluations: B (any may be NULL); rounds: batched evaluations used (may be NULL).
+ * head / tail / rho / per_problem_bc as isdf_callback_batch. */
+int isdf_lbfgs_batch(isdf_ctx *ctx, int B, int N0, const double *head, const double *tail, int per_problem_bc, double rho,
+                     const isdf_lbfgs_params *params, double *x, double *f, int32_t *ret, int32_t *iterations, int32_t *evaluations, int32_t *rounds);
+/* device-resident variant (all pointers on ctx's device; returns when every instance has stopped — one 4-byte read per round) */
+int isdf_lbfgs_batch_device(isdf_ctx *ctx, int B, int N0, const double *d_head, const double *d_tail, int per_problem_bc, double rho,
+                            const isdf_lbfgs_params *params, double *d_x, double *d_f, int32_t *d_ret, int32_t *d_iterations, int32_t *d_evaluations,
+                            int32_t *rounds, void *cuda_stream);
 
 /* ---- multi-GPU reduction through NVLink / NVSwitch peer memory (optional; ncclAllReduce over the same 19N+1 doubles is the
  * library alternative). One process per GPU. Sequence on every rank:

@@ -87,6 +87,34 @@ int main(int argc, char **argv) {
                 if (exact > 0) worst = fmax(worst, (sqrt(exact) - sqrt(fmax(ob, ab))));
             }
     }
-    printf("HOST MESH OK tris %d leaves %d wide nodes %zu max bound slack %.4f\n", hm.ntris, nleaf, hm.wnodes.size(), worst);
+    // 4. winding-number tree (ISDF_MESH_SIGN_WINDING): the hierarchical evaluation against the brute-force sum of exact solid angles, on the
+    //    closed mesh (w in {0, 1}) and on the same mesh with every 7th face removed (an open surface: fractional w, the soup case)
+    double wn_worst = 0.0;
+    for (int open = 0; open < 2; open++) {
+        std::vector<int32_t> F2;
+        for (int t = 0; t < nF; t++) if (!open || t % 7 != 3) { F2.push_back(F[3 * t]); F2.push_back(F[3 * t + 1]); F2.push_back(F[3 * t + 2]); }
+        HostMesh hw; std::string e2;
+        if (!build_host_mesh(V.data(), nV, F2.data(), (int)F2.size() / 3, poly, 0.866, hw, e2, 2)) { printf("winding build failed: %s\n", e2.c_str()); return 1; }
+        if (hw.sign_mode != MESH_SIGN_WINDING || hw.closed != (open == 0)) { printf("sign mode / closedness wrong (open %d closed %d)\n", open, (int)hw.closed); return 1; }
+        HostMesh ha; std::string e3;
+        if (!build_host_mesh(V.data(), nV, F2.data(), (int)F2.size() / 3, poly, 0.866, ha, e3, 0)) { printf("auto build failed: %s\n", e3.c_str()); return 1; }
+        if ((ha.sign_mode == MESH_SIGN_WINDING) != (open == 1)) { printf("automatic sign mode wrong for open = %d\n", open); return 1; }
+        HostMesh hx; std::string e4;
+        if (build_host_mesh(V.data(), nV, F2.data(), (int)F2.size() / 3, poly, 0.866, hx, e4, 1) != (open == 0)) { printf("exact-sign mode must refuse exactly the open mesh\n"); return 1; }
+        const DevMesh W = hw.view();
+        std::mt19937_64 r2(7 + open);
+        std::uniform_real_distribution<double> u01(0.0, 1.0);
+        auto u = [&](std::mt19937_64 &g) { return u01(g); };
+        for (int it = 0; it < 400; it++) {
+            const d3 q = mk3(W.blo[0] - 0.7 + (W.bhi[0] - W.blo[0] + 1.4) * u(r2), W.blo[1] - 0.7 + (W.bhi[1] - W.blo[1] + 1.4) * u(r2), W.blo[2] - 0.7 + (W.bhi[2] - W.blo[2] + 1.4) * u(r2));
+            double om = 0.0;
+            for (int t = 0; t < hw.ntris; t++) om += tri_solid_angle(q, &hw.tris[(size_t)TRI_STRIDE * t]);
+            const double w_exact = om / (4.0 * 3.14159265358979323846), w_tree = mesh_winding(W, q);
+            wn_worst = fmax(wn_worst, fabs(w_tree - w_exact));
+            if (!open && fabs(w_exact - round(w_exact)) > 1e-9) { printf("closed mesh: exact winding number %.12f is not an integer\n", w_exact); return 1; }
+        }
+    }
+    if (wn_worst > 2.5e-4) { printf("winding tree deviates from the exact winding number by %.3e\n", wn_worst); return 1; }
+    printf("HOST MESH OK tris %d leaves %d wide nodes %zu max bound slack %.4f winding tree max error %.2e\n", hm.ntris, nleaf, hm.wnodes.size(), worst, wn_worst);
     return 0;
 }
