@@ -477,6 +477,21 @@ def batch_callback_bench(ev, w, cfg, dev, rank, world, B, barrier, max_over_rank
                         "mean_cost_start": float(c[:nb].mean()), "mean_cost_end": float(fl.mean()), "max_iterations": 12}
         except Exception as e:
             lockstep = {"error": repr(e)}
+        try:   # the same restarts under the DEVICE-RESIDENT lock-step driver (isdf_lbfgs_batch: iterates never leave the GPU)
+            nb = min(B, 32)
+            prm = ev.lbfgs_params(max_iterations=12)
+            hh3 = heads[:nb].reshape(nb, 3, 3).transpose(0, 2, 1)
+            tt3 = tails[:nb].reshape(nb, 3, 3).transpose(0, 2, 1)
+            t0 = time.perf_counter()
+            rd = ev.lbfgs_batch(hh3, tt3, 20.0, xs[:nb], prm)
+            dt = time.perf_counter() - t0
+            lockstep["device_resident"] = {"problems": nb, "rounds": int(rd["rounds"]), "iterations_total": int(rd["iterations"].sum()), "evaluations_total": int(rd["evaluations"].sum()),
+                                           "seconds": dt, "iters_per_s": float(rd["iterations"].sum() / dt), "callback_evals_per_s": float(rd["evaluations"].sum() / dt),
+                                           "batched_evals_per_s_incl_finished_instances": float(nb * rd["rounds"] / dt), "mean_cost_end": float(rd["f"].mean()),
+                                           "identical_to_host_lockstep": bool(np.array_equal(rd["x"].reshape(-1), Xl) and np.array_equal(rd["f"], fl))}
+        except Exception as e:
+            if isinstance(lockstep, dict):
+                lockstep["device_resident"] = {"error": repr(e)}
     return {"callbacks_per_s": world * B * 1e3 / ms, "host_adapter_one_at_a_time": per_problem, "lockstep_lbfgs": lockstep, "ms_per_batch_max_over_ranks": ms, "problems_per_gpu": B, "problems_total": world * B,
             "scaling": "weak", "finite_costs": bool(np.all(np.isfinite(c))), "mean_cost": float(c.mean()),
             "what": f"BASELINE configs[4]: {world * B} random-restart problems ({N0} pieces x {w['samples_per_piece']} samples, shared {X}^3 map, mesh robot), "
@@ -1011,6 +1026,26 @@ def run_batch(args):
             e2e.append(max_over_ranks(dt))
     clocks = sampler.stop() if sampler else None
     fin = bool(np.all(np.isfinite(c)))
+    # BASELINE metric (ii): L-BFGS iterations/s — every rank optimises its own problems with the device-resident lock-step driver
+    lb = None
+    try:
+        prm = ev.lbfgs_params(max_iterations=args.lbfgs_iterations)
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        rd = ev.lbfgs_batch(hh, tt, 20.0, xs, prm)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        tot = torch.tensor([float(rd["iterations"].sum()), float(rd["evaluations"].sum()), float(rd["f"].sum()), float(c.sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tot)
+        tot = tot.cpu().numpy()
+        lb = {"iters_per_s": tot[0] / dt, "callback_evals_per_s": tot[1] / dt, "iterations_total": int(tot[0]), "evaluations_total": int(tot[1]), "seconds_max_over_ranks": dt,
+              "rounds_rank0": int(rd["rounds"]), "max_iterations": args.lbfgs_iterations, "mean_cost_start": tot[3] / Btot, "mean_cost_end": tot[2] / Btot,
+              "what": f"{Btot} restarts, each under the reference fork's L-BFGS (mem 16, past 10), lock-step on the device: one batched callback per round, "
+                      "iterates and histories resident in HBM; problems sharded over the ranks, no collective"}
+    except Exception as e:
+        lb = {"error": repr(e)}
     if rank == 0:
         ms, ms_e2e = statistics.mean(times), statistics.mean(e2e)
         S = Btot * N0 * (w["samples_per_piece"] + 1)
@@ -1026,7 +1061,7 @@ def run_batch(args):
                         "api": "isdf_callback_batch (host buffers: decision vectors in, costs and gradients out)"},
                 "roofline": {"bound": "hbm", "achieved": ab / world / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": ab / world / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "peak_source": peak_src, "kernel": "k_discrete_mesh", "algorithmic_bytes_per_launch": ab // world},
-                "extra": {"finite_costs": fin}}
+                "extra": {"finite_costs": fin, "lbfgs": lb}}
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as O
@@ -1120,6 +1155,7 @@ def main():
     ap.add_argument("--workload", default="discrete", choices=["discrete", "swept", "batch1024"],
                     help="discrete = BASELINE configs[2] (headline); swept = configs[3]; batch1024 = configs[4] — each a strong-scaling workload of its own")
     ap.add_argument("--batch-total", type=int, default=1024, help="--workload batch1024: total problems (sharded over the ranks)")
+    ap.add_argument("--lbfgs-iterations", type=int, default=8, help="--workload batch1024: iteration cap of the device-resident L-BFGS measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args) if args.workload == "discrete" else run_reference_other(args)

@@ -423,7 +423,7 @@ extern "C" int isdf_shape_query(isdf_ctx *c, const double *p_rel, int n, double 
     if (what < 0 || what > 2) return fail(ISDF_ERR_INVALID, "bad query kind");
     if (n == 0) return 0;
     if (set_device(c)) return ISDF_ERR_CUDA;
-    DevBuf<double> dp, ds, dg;
+    ScopedDevBuf<double> dp, ds, dg;
     CU_TRY(dp.upload(p_rel, (size_t)3 * n, c->stream));
     CU_TRY(ds.ensure(n)); CU_TRY(dg.ensure((size_t)3 * n));
     k_shape_query<<<(n + 127) / 128, 128, 0, c->stream>>>(c->shape, dp.p, n, ds.p, dg.p, what);
@@ -435,7 +435,6 @@ extern "C" int isdf_shape_query(isdf_ctx *c, const double *p_rel, int n, double 
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (sdf && what != ISDF_QUERY_GRAD) std::memcpy(sdf, hs.data(), sizeof(double) * n);
     if (grad && what != ISDF_QUERY_SDF) std::memcpy(grad, hg.data(), sizeof(double) * 3 * n);
-    dp.release(); ds.release(); dg.release();
     return 0;
 }
 
@@ -443,10 +442,11 @@ extern "C" int isdf_shape_query(isdf_ctx *c, const double *p_rel, int n, double 
 template <typename T>
 __global__ void k_pack_bits(const T *occ, uint32_t *bits, int rows, int Z, int Zw) {
     // one warp per 32-voxel word: ballot of "voxel != 0"
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const long long nwords = (long long)rows * Zw;
     if (gw >= nwords) return;
-    const int row = gw / Zw, w = gw - row * Zw;
+    const int row = (int)(gw / Zw), w = (int)(gw - (long long)row * Zw);
     const int z = w * 32 + lane;
     const bool o = (z < Z) && (occ[(size_t)row * Z + z] != (T)0);
     const unsigned b = __ballot_sync(0xffffffffu, o);
@@ -459,6 +459,10 @@ static int set_map_impl(isdf_ctx *c, const T *occ, int X, int Y, int Z, const do
     if (X < 1 || Y < 1 || Z < 1 || !(res > 0)) return fail(ISDF_ERR_INVALID, "bad map size");
     if ((long long)X * Y >= (1ll << 31) / ((Z + 31) / 32)) return fail(ISDF_ERR_INVALID, "map too large");
     if (Z > 65535) return fail(ISDF_ERR_UNSUPPORTED, "Z > 65535");
+    // a pose window spans 2 * half_bd / res + 2 voxels per axis of THIS map (its resolution need not equal occupancy_resolution); the scan
+    // kernels pack window offsets into 10 bits per axis
+    if (c && 2.0 * c->dcfg.half_bd / res + 2.0 > (double)WINDOW_AXIS_MAX)
+        return fail(ISDF_ERR_UNSUPPORTED, "map resolution too fine for kernel_size * occupancy_resolution: a pose window would exceed 1023 voxels per axis");
     if (set_device(c)) return ISDF_ERR_CUDA;
     const size_t nvox = (size_t)X * Y * Z;
     T *d_occ = nullptr;
@@ -514,7 +518,7 @@ extern "C" int isdf_points_in_aabb(isdf_ctx *c, const double *centre, double hal
     if (!c || !centre || !n || cap < 0 || (cap > 0 && !out_points)) return fail(ISDF_ERR_INVALID, "bad argument");
     if (!c->have_map) return fail(ISDF_ERR_STATE, "map not set");
     if (set_device(c)) return ISDF_ERR_CUDA;
-    DevBuf<double> d; DevBuf<int> dn;
+    ScopedDevBuf<double> d; ScopedDevBuf<int> dn;
     CU_TRY(d.ensure((size_t)3 * (cap > 0 ? cap : 1))); CU_TRY(dn.ensure(1));
     k_points_in_aabb<<<1, 32, 0, c->stream>>>(c->grid, centre[0], centre[1], centre[2], half_extent, d.p, cap, dn.p);
     c->stats.kernel_launches++;
@@ -525,7 +529,6 @@ extern "C" int isdf_points_in_aabb(isdf_ctx *c, const double *centre, double hal
     const int m = cnt < cap ? cnt : cap;
     if (m > 0) CU_TRY(cudaMemcpy(out_points, d.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
     *n = cnt;
-    d.release(); dn.release();
     return 0;
 }
 
@@ -589,7 +592,7 @@ extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints,
     if (!c || !waypoints || nQ < 1 || !n || cap < 0 || (cap > 0 && !out_points && !set_as_points)) return fail(ISDF_ERR_INVALID, "bad argument");
     if (!c->have_map) return fail(ISDF_ERR_STATE, "map not set");
     if (set_device(c)) return ISDF_ERR_CUDA;
-    DevBuf<double> dw, dout; DevBuf<GatherBox> db; DevBuf<int> dn;
+    ScopedDevBuf<double> dw, dout; ScopedDevBuf<GatherBox> db; ScopedDevBuf<int> dn;
     const int capd = cap > 0 ? cap : 1;
     CU_TRY(dw.upload(waypoints, (size_t)3 * nQ, c->stream));
     CU_TRY(dout.ensure((size_t)3 * capd)); CU_TRY(db.ensure(nQ)); CU_TRY(dn.ensure(1));
@@ -613,7 +616,6 @@ extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints,
             if (e != cudaSuccess) rc = fail(ISDF_ERR_CUDA, cudaGetErrorString(e));
         }
     }
-    dw.release(); dout.release(); db.release(); dn.release();
     return rc;
 }
 
@@ -736,6 +738,7 @@ extern "C" int isdf_eval_discrete(isdf_ctx *c, int N, const double *T, const dou
         unsigned long long pairs = 0;
         CU_TRY(cudaMemcpyAsync(&pairs, c->d_counter.p, sizeof(pairs), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
+        if (c->peer_fused && c->peer.world > 1 && c->world > 1 && isdf_peer_status(c) != ISDF_OK) return ISDF_ERR_CUDA;   // exchange timed out: the vector is NaN
         float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->stats.last_kernel_ms = ms; c->stats.last_pairs = (int64_t)pairs;
         *cost += h_out[0];                                   // accumulate like hpp:539-550
@@ -966,6 +969,7 @@ extern "C" int isdf_peer_export(isdf_ctx *c, int world, int max_doubles, unsigne
 extern "C" int isdf_peer_connect(isdf_ctx *c, int world, int rank, const unsigned char *handles, int fuse_into_eval) {
     if (!c || !handles || rank < 0 || rank >= world) return fail(ISDF_ERR_INVALID, "bad argument");
     if (!c->peer_buf || world != c->peer_world_alloc) return fail(ISDF_ERR_STATE, "isdf_peer_export with the same world first");
+    if (c->peer.world != 0) return fail(ISDF_ERR_STATE, "already connected: isdf_peer_disconnect first");
     if (set_device(c)) return ISDF_ERR_CUDA;
     PeerArgs P = {};
     P.world = world; P.rank = rank; P.cap = c->peer_cap; P.epoch = 0; P.status = c->d_peer_status.p;
@@ -995,10 +999,11 @@ extern "C" int isdf_peer_allreduce_device(isdf_ctx *c, double *d_vec, int n, voi
     if (n > c->peer.cap) return fail(ISDF_ERR_INVALID, "vector longer than the exchange buffer");
     if (set_device(c)) return ISDF_ERR_CUDA;
     PeerArgs P = c->peer;
-    P.epoch = ++c->peer.epoch;
+    P.epoch = c->peer.epoch + 1;
     k_peer_allreduce<<<1, 512, 0, (cudaStream_t)cuda_stream>>>(P, d_vec, n);
     c->stats.kernel_launches++;
     CU_TRY(cudaGetLastError());
+    c->peer.epoch = P.epoch;
     return 0;
 }
 
@@ -1223,10 +1228,11 @@ static int swept_common(isdf_ctx *c, int N, const double *d_T, const double *d_C
         if (c->peer.world != c->world || c->peer.rank != c->rank) return fail(ISDF_ERR_STATE, "peer group does not match isdf_set_shard");
         if (19 * N + 1 > c->peer.cap) return fail(ISDF_ERR_INVALID, "peer exchange buffer too small for this N (isdf_peer_export max_doubles)");
         PeerArgs P = c->peer;
-        P.epoch = ++c->peer.epoch;
+        P.epoch = c->peer.epoch + 1;
         k_peer_allreduce<<<1, 512, 0, st>>>(P, d_out, 19 * N + 1);
         c->stats.kernel_launches++;
         CU_TRY(cudaGetLastError());
+        c->peer.epoch = P.epoch;   // committed only once the exchange is enqueued: a local failure must not leave this rank one epoch ahead
     }
     return 0;
 }
@@ -1255,7 +1261,7 @@ static int eval_swept_host(isdf_ctx *c, int N, const double *T, const double *co
         std::memcpy(c->h_stage + N, coeffs, sizeof(double) * 18 * N);
         CU_TRY(cudaMemcpyAsync(c->d_T.p, c->h_stage, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage + N, sizeof(double) * 18 * N, cudaMemcpyHostToDevice, c->stream));
-        DevBuf<double> dgt, dgs, dgg;
+        ScopedDevBuf<double> dgt, dgs, dgg;
         if (g_t) {
             CU_TRY(dgt.upload(g_t, c->sv.P, c->stream)); CU_TRY(dgs.upload(g_s, c->sv.P, c->stream));
             CU_TRY(dgg.upload(g_g, (size_t)3 * c->sv.P, c->stream));
@@ -1269,7 +1275,7 @@ static int eval_swept_host(isdf_ctx *c, int N, const double *T, const double *co
         unsigned long long nsdf = 0;
         CU_TRY(cudaMemcpyAsync(&nsdf, c->sv.d_counter.p, sizeof(nsdf), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        dgt.release(); dgs.release(); dgg.release();
+        if (c->peer_fused && c->peer.world > 1 && c->world > 1 && isdf_peer_status(c) != ISDF_OK) return ISDF_ERR_CUDA;   // exchange timed out: the vector is NaN
         float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->stats.last_kernel_ms = ms; c->stats.last_sdf_evals = (int64_t)nsdf;
         *cost += h_out[0];                                   // accumulate like hpp:640-645
@@ -1334,14 +1340,13 @@ extern "C" int isdf_dbg_item_stats(isdf_ctx *c, int *item_count, int *split_part
 extern "C" int isdf_dbg_flatness(isdf_ctx *c, int n, const double *vaj, const double *grads, double *out) {
     if (!c || n < 1 || !vaj || !grads || !out) return -1;
     if (cudaSetDevice(c->device) != cudaSuccess) return -3;
-    DevBuf<double> dv, dg, dout;
+    ScopedDevBuf<double> dv, dg, dout;
     cudaError_t e = dv.upload(vaj, (size_t)9 * n, c->stream);
     if (e == cudaSuccess) e = dg.upload(grads, (size_t)10 * n, c->stream);
     if (e == cudaSuccess) e = dout.ensure((size_t)16 * n);
     if (e == cudaSuccess) e = discrete_launch_dbg_flatness(c->dcfg.fp, n, dv.p, dg.p, dout.p, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout.p, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    dv.release(); dg.release(); dout.release();
     return e == cudaSuccess ? 0 : -3;
 }
 extern "C" int isdf_dbg_swept_stats(isdf_ctx *c, unsigned long long *out, long long n) {

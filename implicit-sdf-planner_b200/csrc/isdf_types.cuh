@@ -46,6 +46,15 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// function-local scratch buffer: released on EVERY exit path (the CU_TRY early returns of the query entry points included)
+template <typename T>
+struct ScopedDevBuf : DevBuf<T> {
+    ScopedDevBuf() = default;
+    ScopedDevBuf(const ScopedDevBuf &) = delete;
+    ScopedDevBuf &operator=(const ScopedDevBuf &) = delete;
+    ~ScopedDevBuf() { this->release(); }
+};
+
 constexpr int PARTIAL_STRIDE = 20;  // per sample / per point: 18 gradC entries (axis*6+k), gradT term, cost term
 
 }  // namespace isdf
