@@ -60,7 +60,7 @@ struct isdf_ctx {
     int sm_count = 148, mesh_blocks = 4, analytic_blocks = 4;   // persistent grids: one CTA per resident slot
     long long order_for = -1;    // (N, rank, world) signature the order array is valid for
     DevBuf<unsigned long long> d_counter, d_dbg, d_trace;
-    DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout;   // batched callback (isdf_minco.cuh)
+    DevBuf<double> d_mx, d_mbc, d_mT, d_mC, d_mlu, d_men, d_mgC, d_mgT, d_mcost, d_mgrad, d_mout, d_mCpp, d_msv;   // batched callback (isdf_minco.cuh)
     int minco_B = 0, minco_N = 0;
     DevBuf<double> d_lb_x, d_lb_f, d_lb_grad, d_lb_state; DevBuf<int> d_lb_int, d_lb_head;   // device-resident lock-step L-BFGS (isdf_lbfgs.cuh)
     int *h_lb_active = nullptr;  // pinned
@@ -177,7 +177,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
     c->d_fe_rot.release(); c->d_fe_kernels.release(); c->d_fe_order.release(); c->d_fe_ok.release(); c->d_fe_masks.release(); c->d_fe_out.release(); c->d_fe_ind.release(); c->d_fe_father.release(); c->d_fe_child.release();
-    c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release();
+    c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release(); c->d_mCpp.release(); c->d_msv.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_lb_active) cudaFreeHost(c->h_lb_active);
@@ -495,23 +495,50 @@ extern "C" int isdf_set_map_f64(isdf_ctx *c, const double *grid_map, int X, int 
     return set_map_impl<double>(c, grid_map, X, Y, Z, bmin, res);
 }
 
-// getPointsInAABB (pcs:148-170): one thread per voxel of the clamped index box, ordered output via a single-thread scan
-__global__ void k_points_in_aabb(const DevGrid G, double cx, double cy, double cz, double h, double *out, int cap, int *count) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// getPointsInAABB (pcs:148-170): one CTA; thread = (x, y) row of the clamped index box — popcount of the row's z-run, block-wide exclusive scan
+// for the row's output offset, then every thread writes its row's voxel centres in z order: the reference's x -> y -> z output order
+__global__ void __launch_bounds__(256) k_points_in_aabb(const DevGrid G, double cx, double cy, double cz, double h, double *out, int cap, int *count) {
+    __shared__ int warp_tot[8];
+    __shared__ int running;
     const int ix0 = grid_axis_index(cx - h, G.bmin[0], G.bmax[0], G.res, G.X), ix1 = grid_axis_index(cx + h, G.bmin[0], G.bmax[0], G.res, G.X);
     const int iy0 = grid_axis_index(cy - h, G.bmin[1], G.bmax[1], G.res, G.Y), iy1 = grid_axis_index(cy + h, G.bmin[1], G.bmax[1], G.res, G.Y);
     const int iz0 = grid_axis_index(cz - h, G.bmin[2], G.bmax[2], G.res, G.Z), iz1 = grid_axis_index(cz + h, G.bmin[2], G.bmax[2], G.res, G.Z);
-    int n = 0;
-    for (int i = ix0; i <= ix1; i++)
-        for (int j = iy0; j <= iy1; j++)
-            for (int k = iz0; k <= iz1; k++) {
-                const uint32_t w = G.bits[((size_t)i * G.Y + j) * G.Zw + (k >> 5)];
-                if ((w >> (k & 31)) & 1u) {
-                    if (n < cap) { out[3 * n] = (i + 0.5) * G.res + G.bmin[0]; out[3 * n + 1] = (j + 0.5) * G.res + G.bmin[1]; out[3 * n + 2] = (k + 0.5) * G.res + G.bmin[2]; }
-                    n++;
-                }
+    const int ny = iy1 - iy0 + 1, nrows = (ix1 - ix0 + 1) * ny;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < nrows; base += blockDim.x) {
+        const int r = base + threadIdx.x;
+        int i = 0, j = 0, cnt = 0;
+        if (r < nrows) {
+            i = ix0 + r / ny; j = iy0 + r % ny;
+            const uint32_t *row = G.bits + ((size_t)i * G.Y + j) * G.Zw;
+            for (int wz = iz0 >> 5; wz <= (iz1 >> 5); wz++) {
+                uint32_t w = row[wz];
+                if (wz == (iz0 >> 5)) w &= 0xffffffffu << (iz0 & 31);
+                if (wz == (iz1 >> 5) && (iz1 & 31) != 31) w &= (1u << ((iz1 & 31) + 1)) - 1u;
+                cnt += __popc(w);
             }
-    *count = n;
+        }
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int off = running + incl - cnt;
+        for (int w = 0; w < warp; w++) off += warp_tot[w];
+        if (r < nrows && cnt > 0) {
+            const uint32_t *row = G.bits + ((size_t)i * G.Y + j) * G.Zw;
+            for (int k = iz0; k <= iz1; k++)
+                if ((row[k >> 5] >> (k & 31)) & 1u) {
+                    if (off < cap) { out[3 * off] = (i + 0.5) * G.res + G.bmin[0]; out[3 * off + 1] = (j + 0.5) * G.res + G.bmin[1]; out[3 * off + 2] = (k + 0.5) * G.res + G.bmin[2]; }
+                    off++;
+                }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_tot[w]; running += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = running;
 }
 
 extern "C" int isdf_points_in_aabb(isdf_ctx *c, const double *centre, double half_extent, double *out_points, int cap, int *n) {
@@ -520,7 +547,7 @@ extern "C" int isdf_points_in_aabb(isdf_ctx *c, const double *centre, double hal
     if (set_device(c)) return ISDF_ERR_CUDA;
     ScopedDevBuf<double> d; ScopedDevBuf<int> dn;
     CU_TRY(d.ensure((size_t)3 * (cap > 0 ? cap : 1))); CU_TRY(dn.ensure(1));
-    k_points_in_aabb<<<1, 32, 0, c->stream>>>(c->grid, centre[0], centre[1], centre[2], half_extent, d.p, cap, dn.p);
+    k_points_in_aabb<<<1, 256, 0, c->stream>>>(c->grid, centre[0], centre[1], centre[2], half_extent, d.p, cap, dn.p);
     c->stats.kernel_launches++;
     CU_TRY(cudaGetLastError());
     int cnt = 0;
@@ -539,52 +566,62 @@ __device__ __forceinline__ bool gather_includes(const DevGrid &G, const GatherBo
     if (!(i > b.l1[0] || i < b.l0[0] || j > b.l1[1] || j < b.l0[1] || k > b.l1[2] || k < b.l0[2])) return false;
     return (G.bits[((size_t)i * G.Y + j) * G.Zw + (k >> 5)] >> (k & 31)) & 1u;
 }
-// one CTA; waypoints processed in order, a voxel is emitted by the FIRST waypoint that includes it; block-level ordered compaction
-__global__ void __launch_bounds__(256) k_gather_points(const DevGrid G, const double *wps, int nQ, double h, double ox, double oy, double oz,
-                                                       GatherBox *boxes, double *out, int cap, int *count) {
+// Obstacle gather, one CTA per waypoint, three launches: k_gather_boxes (index boxes of every waypoint), k_gather_points<false> (how many
+// voxels each waypoint emits: a voxel belongs to the FIRST waypoint whose box includes it) and, after an exclusive scan over the waypoints
+// inside the kernel, k_gather_points<true> (ordered compaction inside the CTA at the waypoint's offset). Output order = the reference's:
+// waypoint by waypoint, each box in x -> y -> z order.
+__global__ void k_gather_boxes(const DevGrid G, const double *wps, int nQ, double h, double ox, double oy, double oz, GatherBox *boxes) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nQ) return;
+    GatherBox b;
+    const double c[3] = {wps[3 * q] + ox, wps[3 * q + 1] + oy, wps[3 * q + 2] + oz};
+    const double l[3] = {q == 0 ? 999.0 : wps[3 * (q - 1)], q == 0 ? 999.0 : wps[3 * (q - 1) + 1], q == 0 ? 999.0 : wps[3 * (q - 1) + 2]};
+    const int dims[3] = {G.X, G.Y, G.Z};
+    for (int a = 0; a < 3; a++) {
+        b.a0[a] = grid_axis_index(c[a] - h, G.bmin[a], G.bmax[a], G.res, dims[a]); b.a1[a] = grid_axis_index(c[a] + h, G.bmin[a], G.bmax[a], G.res, dims[a]);
+        b.l0[a] = grid_axis_index(l[a] - h, G.bmin[a], G.bmax[a], G.res, dims[a]); b.l1[a] = grid_axis_index(l[a] + h, G.bmin[a], G.bmax[a], G.res, dims[a]);
+    }
+    boxes[q] = b;
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_gather_points(const DevGrid G, int nQ, const GatherBox *boxes, int *counts, double *out, int cap, int *count) {
     __shared__ int warp_cnt[8];
     __shared__ int running;
-    for (int q = threadIdx.x; q < nQ; q += blockDim.x) {
-        GatherBox b;
-        const double c[3] = {wps[3 * q] + ox, wps[3 * q + 1] + oy, wps[3 * q + 2] + oz};
-        const double l[3] = {q == 0 ? 999.0 : wps[3 * (q - 1)], q == 0 ? 999.0 : wps[3 * (q - 1) + 1], q == 0 ? 999.0 : wps[3 * (q - 1) + 2]};
-        const int dims[3] = {G.X, G.Y, G.Z};
-        for (int a = 0; a < 3; a++) {
-            b.a0[a] = grid_axis_index(c[a] - h, G.bmin[a], G.bmax[a], G.res, dims[a]); b.a1[a] = grid_axis_index(c[a] + h, G.bmin[a], G.bmax[a], G.res, dims[a]);
-            b.l0[a] = grid_axis_index(l[a] - h, G.bmin[a], G.bmax[a], G.res, dims[a]); b.l1[a] = grid_axis_index(l[a] + h, G.bmin[a], G.bmax[a], G.res, dims[a]);
-        }
-        boxes[q] = b;
-    }
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
+    const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = 0; q < nQ; q++) {
-        const GatherBox b = boxes[q];
-        const int ny = b.a1[1] - b.a0[1] + 1, nz = b.a1[2] - b.a0[2] + 1;
-        const int nvox = (b.a1[0] - b.a0[0] + 1) * ny * nz;
-        for (int base = 0; base < nvox; base += blockDim.x) {
-            const int v = base + threadIdx.x;
-            bool emit = false; int i = 0, j = 0, k = 0;
-            if (v < nvox) {
-                i = b.a0[0] + v / (ny * nz); j = b.a0[1] + (v / nz) % ny; k = b.a0[2] + v % nz;
-                emit = gather_includes(G, b, i, j, k);
-                for (int p = 0; emit && p < q; p++) if (gather_includes(G, boxes[p], i, j, k)) emit = false;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, emit);
-            if (lane == 0) warp_cnt[warp] = __popc(bal);
-            __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        if (WRITE) { for (int p = 0; p < q; p++) off += counts[p]; if (q == nQ - 1) *count = off + counts[q]; }
+        running = off;
+    }
+    __syncthreads();
+    const GatherBox b = boxes[q];
+    const int ny = b.a1[1] - b.a0[1] + 1, nz = b.a1[2] - b.a0[2] + 1;
+    const int nvox = (b.a1[0] - b.a0[0] + 1) * ny * nz;
+    for (int base = 0; base < nvox; base += blockDim.x) {
+        const int v = base + threadIdx.x;
+        bool emit = false; int i = 0, j = 0, k = 0;
+        if (v < nvox) {
+            i = b.a0[0] + v / (ny * nz); j = b.a0[1] + (v / nz) % ny; k = b.a0[2] + v % nz;
+            emit = gather_includes(G, b, i, j, k);
+            for (int p = 0; emit && p < q; p++) if (gather_includes(G, boxes[p], i, j, k)) emit = false;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        if (WRITE) {
             int off = running;
             for (int w = 0; w < warp; w++) off += warp_cnt[w];
             if (emit) {
                 const int pos = off + __popc(bal & ((1u << lane) - 1u));
                 if (pos < cap) { out[3 * pos] = (i + 0.5) * G.res + G.bmin[0]; out[3 * pos + 1] = (j + 0.5) * G.res + G.bmin[1]; out[3 * pos + 2] = (k + 0.5) * G.res + G.bmin[2]; }
             }
-            __syncthreads();
-            if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_cnt[w]; running += t; }
-            __syncthreads();
         }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += warp_cnt[w]; running += t; }
+        __syncthreads();
     }
-    if (threadIdx.x == 0) *count = running;
+    if (!WRITE && threadIdx.x == 0) counts[q] = running;
 }
 
 extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints, int nQ, double half_extent, const double *offset,
@@ -595,10 +632,12 @@ extern "C" int isdf_gather_obstacle_points(isdf_ctx *c, const double *waypoints,
     ScopedDevBuf<double> dw, dout; ScopedDevBuf<GatherBox> db; ScopedDevBuf<int> dn;
     const int capd = cap > 0 ? cap : 1;
     CU_TRY(dw.upload(waypoints, (size_t)3 * nQ, c->stream));
-    CU_TRY(dout.ensure((size_t)3 * capd)); CU_TRY(db.ensure(nQ)); CU_TRY(dn.ensure(1));
+    CU_TRY(dout.ensure((size_t)3 * capd)); CU_TRY(db.ensure(nQ)); CU_TRY(dn.ensure((size_t)nQ + 1));
     const double ox = offset ? offset[0] : 0.0, oy = offset ? offset[1] : 0.0, oz = offset ? offset[2] : 0.0;
-    k_gather_points<<<1, 256, 0, c->stream>>>(c->grid, dw.p, nQ, half_extent, ox, oy, oz, db.p, dout.p, capd, dn.p);
-    c->stats.kernel_launches++;
+    k_gather_boxes<<<(nQ + 127) / 128, 128, 0, c->stream>>>(c->grid, dw.p, nQ, half_extent, ox, oy, oz, db.p);
+    k_gather_points<false><<<nQ, 256, 0, c->stream>>>(c->grid, nQ, db.p, dn.p + 1, nullptr, 0, dn.p);
+    k_gather_points<true><<<nQ, 256, 0, c->stream>>>(c->grid, nQ, db.p, dn.p + 1, dout.p, capd, dn.p);
+    c->stats.kernel_launches += 3;
     CU_TRY(cudaGetLastError());
     int cnt = 0;
     CU_TRY(cudaMemcpyAsync(&cnt, dn.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -773,9 +812,27 @@ static int callback_batch_launch(isdf_ctx *c, int B, int N0, const double *d_hea
     M.B = B; M.N = N0; M.x = d_x; M.head = d_head; M.tail = d_tail; M.bc_stride = bc_stride; M.rho = rho;
     M.T = c->d_mT.p; M.C = c->d_mC.p; M.lu = c->d_mlu.p; M.energy = c->d_men.p; M.gC_e = c->d_mgC.p; M.gT_e = c->d_mgT.p;
     M.disc_out = nullptr; M.piece_cost = nullptr; M.cost = d_cost; M.grad = d_grad;
+    // per-problem obstacle point sets registered for exactly this batch (isdf_set_points_batch): the LIVE composition of costFunctionLmbm
+    // (hpp:386-405) — swept-volume term, then time-integral term
+    const bool with_swept = (c->sv.B == B);
+    M.Cpp = nullptr; M.sv_out = nullptr;
+    if (with_swept) {
+        if (c->shape.kind == ISDF_SHAPE_MESH && c->shape.mesh.sign_mode == MESH_SIGN_WINDING)
+            return fail(ISDF_ERR_UNSUPPORTED, "swept-volume term with a winding-sign mesh (see isdf_set_shape_mesh_ex)");
+        CU_TRY(c->d_mCpp.ensure(18 * BN)); CU_TRY(c->d_msv.ensure((size_t)B * (19 * (size_t)N0 + 1)));
+        M.Cpp = c->d_mCpp.p;
+    }
     CU_TRY(cudaFuncSetAttribute(k_minco_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(cudaFuncSetAttribute(k_minco_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_minco_forward<<<B, 32, smem, st>>>(M);
+    if (with_swept) {
+        int launches = 0;
+        cudaError_t e = c->sv.launch_batch(c->dcfg, c->shape, N0, M.T, M.Cpp, c->d_msv.p, st, &launches);
+        c->stats.kernel_launches += launches;
+        c->stats.evals_swept++;
+        if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? ISDF_ERR_INVALID : ISDF_ERR_CUDA, std::string("batched swept: ") + cudaGetErrorString(e));
+        M.sv_out = c->d_msv.p;
+    }
     int r = launch_discrete(c, (int)BN, M.T, M.C, c->d_mout.p, st);
     if (r) return r;
     M.disc_out = c->d_mout.p; M.piece_cost = c->d_piece_cost.p;
@@ -1209,7 +1266,20 @@ extern "C" int isdf_frontend_check_batch(isdf_ctx *c, int n, const int32_t *ind,
 extern "C" int isdf_set_points(isdf_ctx *c, const double *pts, int P) {
     if (!c || P < 0 || (P > 0 && !pts)) return fail(ISDF_ERR_INVALID, "bad argument");
     if (set_device(c)) return ISDF_ERR_CUDA;
+    c->sv.B = 0;   // a single point set replaces any per-problem sets
     CU_TRY(c->sv.set_points(pts, P, c->stream));
+    return 0;
+}
+
+extern "C" int isdf_set_points_batch(isdf_ctx *c, int B, const int32_t *offsets, const double *pts) {
+    if (!c || B < 0 || (B > 0 && !offsets)) return fail(ISDF_ERR_INVALID, "bad argument");
+    if (set_device(c)) return ISDF_ERR_CUDA;
+    if (B == 0) { c->sv.B = 0; return 0; }
+    if (offsets[0] != 0) return fail(ISDF_ERR_INVALID, "offsets[0] must be 0");
+    for (int b = 0; b < B; b++) if (offsets[b + 1] < offsets[b]) return fail(ISDF_ERR_INVALID, "offsets must be non-decreasing");
+    if (offsets[B] > 0 && !pts) return fail(ISDF_ERR_INVALID, "pts is NULL");
+    if (offsets[B] == 0) return fail(ISDF_ERR_INVALID, "no points at all: use B = 0 to switch the batched swept-volume term off");
+    CU_TRY(c->sv.set_points_batch(B, offsets, pts, c->stream));
     return 0;
 }
 

@@ -25,6 +25,8 @@ struct MincoArgs {
     double rho;
     double *T;                // B*N durations (concatenated)
     double *C;                // 18*B*N coefficients: column-major over the 6*B*N rows
+    double *Cpp;              // may be null: B x 18N, the same coefficients as one column-major 6N x 3 block PER PROBLEM (swept-volume kernels)
+    const double *sv_out;     // may be null: B x (19N+1), per problem [cost | gradC 18N | gradT N] of the batched swept-volume term
     double *lu;               // B x 78N: factored band of every problem (kept for the adjoint solve)
     double *energy;           // B
     double *gC_e, *gT_e;      // energy partials, same layouts as C / T
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(32) k_minco_forward(const __grid_constant__ Mi
     for (int k = lane; k < 3 * n; k += 32) {
         const int ax = k / n, row = k - ax * n;
         A.C[(size_t)ax * rows + (size_t)6 * b * N + row] = rhs[k];
+        if (A.Cpp) A.Cpp[(size_t)b * 18 * N + k] = rhs[k];
     }
     for (int k = lane; k < 13 * n; k += 32) A.lu[(size_t)b * 13 * n + k] = a[k];
     // energy partials (minco.hpp:550-582); the energy itself is summed in the reference's (piece, axis) order by lane 0
@@ -177,7 +180,9 @@ __global__ void __launch_bounds__(32) k_minco_backward(const __grid_constant__ M
     for (int k = lane; k < 3 * n; k += 32) {
         const int ax = k / n, row = k - ax * n;
         const size_t g = (size_t)ax * rows + (size_t)6 * b * N + row;
-        lam[k] = A.gC_e[g] + (A.disc_out ? A.disc_out[1 + g] : 0.0);
+        double v = A.gC_e[g];                                                   // accumulation order of costFunctionLmbm (hpp:386-405): energy partials,
+        if (A.sv_out) v += A.sv_out[(size_t)b * (19 * N + 1) + 1 + k];         // + swept-volume term,
+        lam[k] = v + (A.disc_out ? A.disc_out[1 + g] : 0.0);                    // + time-integral term
     }
     __syncwarp();
     // ---- solveAdj (minco.hpp:168-197) -----------------------------------------------------------------------------------
@@ -230,7 +235,9 @@ __global__ void __launch_bounds__(32) k_minco_backward(const __grid_constant__ M
                 s -= dval[1] * L[n - 3] + dval[2] * L[n - 2] + dval[3] * L[n - 1];
             }
         }
-        const double gT = A.gT_e[(size_t)b * N + i] + (A.disc_out ? A.disc_out[1 + 18 * BN + (size_t)b * N + i] : 0.0);
+        double gT = A.gT_e[(size_t)b * N + i];
+        if (A.sv_out) gT += A.sv_out[(size_t)b * (19 * N + 1) + 1 + 18 * N + i];
+        gT += (A.disc_out ? A.disc_out[1 + 18 * BN + (size_t)b * N + i] : 0.0);
         double gt = s + gT;
         gt += A.rho;
         gtm[i] = gt;
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(32) k_minco_backward(const __grid_constant__ M
     }
     if (lane == 0) {
         double cost = A.energy[b];
+        if (A.sv_out) cost += A.sv_out[(size_t)b * (19 * N + 1)];
         if (A.piece_cost) {
             double c = 0.0;
             for (int i = 0; i < N; i++) c += A.piece_cost[(size_t)b * N + i];

@@ -22,6 +22,8 @@
 #include "isdf_types.cuh"
 #include <cuda/barrier>
 #include <cuda/ptx>
+#include <vector>
+#include <algorithm>
 
 namespace isdf {
 
@@ -112,7 +114,8 @@ struct SvArgs {
 };
 
 // ---- k_sv_table ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sv_table(const __grid_constant__ SvArgs A) {
+__device__ __forceinline__ void sv_table_body(const SvArgs &A, const int bx) {
+    (void)bx;
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
 #pragma nv_diag_suppress static_var_with_dynamic_init
@@ -324,7 +327,7 @@ __device__ __forceinline__ void sv_point_tail(const SvArgs &A, const double *sC,
 }
 
 // ---- k_sv_points: one warp per obstacle point, analytic shapes ----------------------------------------------------------
-__global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant__ SvArgs A) {
+__device__ __forceinline__ void sv_points_body(const SvArgs &A, const int bx) {
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
     __shared__ uint32_t sflags[SV_WARPS][SV_FLAG_WORDS];
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant_
     const TrajView tr = {sT, sC, A.N};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Mloc = (A.P - A.rank + A.world - 1) / A.world;
-    const int m = blockIdx.x * SV_WARPS + warp;
+    const int m = bx * SV_WARPS + warp;
     if (m >= Mloc) return;
     const int pk = A.rank + A.world * m;
     const d3 p = mk3(A.pts[3 * pk], A.pts[3 * pk + 1], A.pts[3 * pk + 2]);
@@ -559,7 +562,8 @@ __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr,
 // MESH = false: analytic shapes through the same CTA-per-point structure — the scans are 256 samples wide and exact (an analytic
 // SDF is cheap, no bracket pass), the sign descent is the lane-speculative sv_gradient_descent on warp 0.
 template <bool MESH>
-__global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta(const __grid_constant__ SvArgs A) {
+__device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx) {
+    if (A.rank + A.world * bx >= A.P) return;   // batched launch: this problem has fewer points than the grid is wide (whole CTA leaves)
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
     __shared__ SvmShared S;
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta(const __grid_cons
     stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
     const TrajView tr = {sT, sC, A.N};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pk = A.rank + A.world * blockIdx.x;     // grid = number of points of this rank
+    const int pk = A.rank + A.world * bx;     // grid.x >= number of points of this rank (batched launches: the largest problem's)
     const DevMesh &M = A.shape.mesh;
     WideStack *stk = &S.stk[warp];
     const d3 p = mk3(A.pts[3 * pk], A.pts[3 * pk + 1], A.pts[3 * pk + 2]);
@@ -791,8 +795,8 @@ __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta(const __grid_cons
 }
 
 // ---- reductions --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sv_reduce(const __grid_constant__ SvArgs A) {
-    const int i = blockIdx.x;
+__device__ __forceinline__ void sv_reduce_body(const SvArgs &A, const int bx) {
+    const int i = bx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int Mloc = (A.P - A.rank + A.world - 1) / A.world;
     double acc[PARTIAL_STRIDE];
@@ -820,14 +824,59 @@ __global__ void __launch_bounds__(256) k_sv_reduce(const __grid_constant__ SvArg
     }
 }
 
-__global__ void k_sv_finish(const __grid_constant__ SvArgs A) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void sv_finish_body(const SvArgs &A, const int bx) {
+    if (threadIdx.x != 0 || bx != 0) return;
     double c = 0.0;
     for (int i = 0; i < A.N; i++) c += A.piece_cost[i];
     A.out[0] = c;
     double run = 0.0;  // gradT(j) += gdT for all j < i (hpp:642-645)  <=>  gradT(j) = sum over pieces i > j
     for (int i = A.N - 1; i >= 0; i--) { A.out[1 + 18 * A.N + i] = run; run += A.piece_gdt[i]; }
 }
+
+// ---- kernels: single problem (arguments in the constant bank) and batched (blockIdx.y = problem; the problem's argument view is built in
+// shared memory from the batch description) — both run the SAME bodies, so a problem's swept-volume term is bit-identical whether it is
+// evaluated alone or as one of B --------------------------------------------------------------------------------------------------------
+struct SvBatch {
+    SvArgs base;              // pointers = problem 0 / point 0; base.P unused
+    int B;
+    const int *pt_off;        // B + 1: problem b owns points [pt_off[b], pt_off[b+1])
+    long long out_stride;     // doubles between two problems' out vectors (19N + 1)
+};
+__device__ __forceinline__ void sv_make_view(const SvBatch &Bt, int b, SvArgs &V) {
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&Bt.base);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&V);
+    for (int k = threadIdx.x; k < (int)(sizeof(SvArgs) / 8); k += blockDim.x) dst[k] = src[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int N = Bt.base.N, p0 = Bt.pt_off[b];
+        V.P = Bt.pt_off[b + 1] - p0;
+        V.T = Bt.base.T + (size_t)b * N; V.C = Bt.base.C + (size_t)b * 18 * N;
+        V.pts = Bt.base.pts + (size_t)3 * p0; V.tstar = Bt.base.tstar + p0; V.sdf = Bt.base.sdf + p0; V.grel = Bt.base.grel + (size_t)3 * p0;
+        V.times = Bt.base.times + (size_t)b * SV_MAX_COARSE; V.poses = Bt.base.poses + (size_t)b * 12 * SV_MAX_COARSE;
+        V.meta = Bt.base.meta + (size_t)b * 4; V.state = Bt.base.state + (size_t)b * 4;
+        V.partial = Bt.base.partial + (size_t)p0 * PARTIAL_STRIDE; V.piece = Bt.base.piece + p0;
+        V.piece_gdt = Bt.base.piece_gdt + (size_t)b * N; V.piece_cost = Bt.base.piece_cost + (size_t)b * N;
+        V.out = Bt.base.out + (size_t)b * Bt.out_stride;
+        if (V.dbg) V.dbg = Bt.base.dbg + (size_t)8 * p0;
+    }
+    __syncthreads();
+}
+static_assert(sizeof(SvArgs) % 8 == 0, "SvArgs is copied as 64-bit words");
+
+__global__ void __launch_bounds__(256) k_sv_table(const __grid_constant__ SvArgs A) { sv_table_body(A, blockIdx.x); }
+__global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant__ SvArgs A) { sv_points_body(A, blockIdx.x); }
+template <bool MESH>
+__global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta(const __grid_constant__ SvArgs A) { sv_points_cta_body<MESH>(A, blockIdx.x); }
+__global__ void __launch_bounds__(256) k_sv_reduce(const __grid_constant__ SvArgs A) { sv_reduce_body(A, blockIdx.x); }
+__global__ void k_sv_finish(const __grid_constant__ SvArgs A) { sv_finish_body(A, blockIdx.x); }
+
+__global__ void __launch_bounds__(256) k_sv_table_b(const __grid_constant__ SvBatch Bt) { __shared__ SvArgs V; sv_make_view(Bt, blockIdx.y, V); sv_table_body(V, blockIdx.x); }
+template <bool MESH>
+__global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta_b(const __grid_constant__ SvBatch Bt) {
+    __shared__ SvArgs V; sv_make_view(Bt, blockIdx.y, V); sv_points_cta_body<MESH>(V, blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_sv_reduce_b(const __grid_constant__ SvBatch Bt) { __shared__ SvArgs V; sv_make_view(Bt, blockIdx.y, V); sv_reduce_body(V, blockIdx.x); }
+__global__ void k_sv_finish_b(const __grid_constant__ SvBatch Bt) { __shared__ SvArgs V; sv_make_view(Bt, blockIdx.y, V); sv_finish_body(V, blockIdx.x); }
 
 // ---- host-side state ----------------------------------------------------------------------------------------------
 struct SweptState {
@@ -907,7 +956,62 @@ struct SweptState {
         *launches = 3 + (grid > 0 ? 1 : 0);
         return cudaGetLastError();
     }
+    // ---- batched: B problems, each with its own obstacle point set (concatenated; offsets), its own trajectory (T: B x N, C: B x 18N,
+    // per-problem column-major blocks) and its own output vector (B x (19N+1)); one launch per stage, grid.y = problem -------------------
+    int B = 0, maxP = 0;
+    std::vector<int> h_off;
+    DevBuf<int> d_off;
+    cudaError_t set_points_batch(int nB, const int *off, const double *pts, cudaStream_t st) {
+        B = 0;
+        cudaError_t e = set_points(pts, off[nB], st);
+        if (e != cudaSuccess) return e;
+        if ((e = d_off.upload(off, (size_t)nB + 1, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        h_off.assign(off, off + nB + 1);
+        maxP = 0;
+        for (int b = 0; b < nB; b++) maxP = std::max(maxP, off[b + 1] - off[b]);
+        B = nB;
+        return cudaSuccess;
+    }
+    cudaError_t launch_batch(const DevCfg &cfg, const DevShape &shape, int N, const double *d_T, const double *d_Cpp, double *d_out, cudaStream_t st, int *launches) {
+        cudaError_t e;
+        if ((e = d_times.ensure((size_t)B * SV_MAX_COARSE)) != cudaSuccess) return e;
+        if ((e = d_poses.ensure((size_t)12 * B * SV_MAX_COARSE)) != cudaSuccess) return e;
+        if ((e = d_meta.ensure((size_t)4 * B)) != cudaSuccess) return e;
+        if (d_state.n < (size_t)4 * B) {   // traj_duration of every problem persists across evaluations (updateTraj quirk, swm:287-296): starts at 0
+            if ((e = d_state.ensure((size_t)4 * B)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(d_state.p, 0, sizeof(double) * 4 * B, st)) != cudaSuccess) return e;
+        }
+        if (d_counter.n == 0) { if ((e = d_counter.ensure(2)) != cudaSuccess) return e; }
+        if ((e = d_piece_gdt.ensure((size_t)B * N)) != cudaSuccess) return e;
+        if ((e = d_piece_cost.ensure((size_t)B * N)) != cudaSuccess) return e;
+        SvBatch Bt;
+        SvArgs &A = Bt.base;
+        A.cfg = cfg; A.shape = shape; A.N = N; A.T = d_T; A.C = d_Cpp; A.P = 0; A.pts = d_pts.p;
+        A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
+        A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
+        A.out = d_out; A.counter = d_counter.p; A.rank = 0; A.world = 1; A.g_t = nullptr; A.g_s = nullptr; A.g_g = nullptr; A.dbg = nullptr;
+        Bt.B = B; Bt.pt_off = d_off.p; Bt.out_stride = 19ll * N + 1;
+        const size_t sm = sizeof(double) * 19 * (size_t)N;
+        if (sm > 200 * 1024) return cudaErrorInvalidValue;
+        if ((e = cudaMemsetAsync(d_counter.p, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
+        if (sm > 48 * 1024) {
+            cudaFuncSetAttribute(k_sv_table_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points_cta_b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            cudaFuncSetAttribute(k_sv_points_cta_b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        }
+        k_sv_table_b<<<dim3(1, B), 256, sm, st>>>(Bt);
+        if (maxP > 0) {
+            if (shape.kind == ISDF_SHAPE_MESH) k_sv_points_cta_b<true><<<dim3(maxP, B), SVM_THREADS, sm, st>>>(Bt);
+            else k_sv_points_cta_b<false><<<dim3(maxP, B), SVM_THREADS, sm, st>>>(Bt);
+        }
+        k_sv_reduce_b<<<dim3(N, B), 256, 0, st>>>(Bt);
+        k_sv_finish_b<<<dim3(1, B), 32, 0, st>>>(Bt);
+        *launches = 3 + (maxP > 0 ? 1 : 0);
+        return cudaGetLastError();
+    }
     void release() {
+        d_off.release();
         d_pts.release(); d_tstar.release(); d_sdf.release(); d_grel.release(); d_times.release(); d_poses.release(); d_state.release();
         d_partial.release(); d_piece_gdt.release(); d_piece_cost.release(); d_piece.release(); d_meta.release(); d_counter.release(); d_dbg.release();
     }

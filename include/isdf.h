@@ -161,7 +161,13 @@ int isdf_get_piece_costs(isdf_ctx *ctx, double *piece_cost, int n);
  *   propogateGrad (:584-654) -> + rho*sum(T) -> backwardGradT / backwardGradP (hpp:283-330).
  * head / tail: 3x3 column-major (columns p, v, a), one pair shared by the batch (per_problem_bc = 0) or B pairs (= 1).
  * x: B x (4*N0-3) row-major; cost: B; grad: B x (4*N0-3). On failure every cost[b] is NaN. N0 <= 290.
- * Multi-GPU: shard by problem (each rank calls this with its own problems and isdf_set_shard(ctx, 0, 1)); no collective. */
+ * Multi-GPU: shard by problem (each rank calls this with its own problems and isdf_set_shard(ctx, 0, 1)); no collective.
+ * With per-problem obstacle point sets registered for the same B (isdf_set_points_batch) the callback is the LIVE composition of the
+ * reference — swept-volume term (addSaftyPenaOnSweptVolumeParallel, hpp:386-391) then time-integral term (hpp:399-405) — for every problem,
+ * each stage one launch over the whole batch (grid.y = problem). */
+/* problem b owns the points [offsets[b], offsets[b+1]) of pts (offsets: B+1 ints, offsets[0] = 0; what plan_manager.cpp:232-254 builds per plan);
+ * t* of every point starts at 0 and persists across evaluations like lastTstar. B = 0 switches the batched swept-volume term off again. */
+int isdf_set_points_batch(isdf_ctx *ctx, int B, const int32_t *offsets, const double *pts);
 int isdf_callback_batch(isdf_ctx *ctx, int B, int N0, const double *head, const double *tail, int per_problem_bc, double rho,
                         const double *x, double *cost, double *grad);
 /* device-resident variant (all pointers on ctx's device, asynchronous on cuda_stream) */

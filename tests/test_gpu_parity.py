@@ -233,13 +233,15 @@ def test_errors_surface_as_status_and_nan_cost():
     with pytest.raises(I.IsdfError):
         ev.set_shard(3, 2)
     V, F = W.box_mesh()
-    with pytest.raises(I.IsdfError) as e:      # open mesh: the winding-number sign is not defined by a closed surface
-        ev.set_shape_mesh(V, F[:-1])
+    with pytest.raises(I.IsdfError) as e:      # open mesh: the exact ±1 sign needs a closed surface ...
+        ev.set_shape_mesh(V, F[:-1], None, I.MESH_SIGN_EXACT)
     assert e.value.code == -4
-    with pytest.raises(I.IsdfError) as e:      # one flipped triangle: inconsistent orientation
+    with pytest.raises(I.IsdfError) as e:      # ... and a consistently oriented one (one flipped triangle)
         F2 = F.copy(); F2[0] = F2[0][::-1]
-        ev.set_shape_mesh(V, F2)
+        ev.set_shape_mesh(V, F2, None, I.MESH_SIGN_EXACT)
     assert e.value.code == -4
+    ev.set_shape_mesh(V, F[:-1])               # the automatic mode accepts both with the winding-number sign (tests/test_gpu_soup.py)
+    ev.set_shape_mesh(V, F2)
     ev.close()
 
 
