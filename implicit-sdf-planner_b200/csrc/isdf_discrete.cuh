@@ -14,7 +14,8 @@
 //     next item at once instead of idling until its CTA's slowest warp is done;
 //   * work items: the per-sample work measured in the previous evaluation (an optimiser moves the trajectory only a little
 //     between steps) sorts the samples, and a sample that grazes an obstacle (dozens of mesh queries) is split into 2..32 items,
-//     each a contiguous range of the 32 interleaved ROW CLASSES (window row r belongs to class r % 32). The per-sample sum is
+//     each a contiguous range of the 32 interleaved voxel CLASSES (window voxel (row r, z offset dz) belongs to class (r + 5 dz) % 32).
+//     The per-sample sum is
 //     ALWAYS formed class by class in the same order, whether one warp walks all classes or 32 warps take one each, so the split
 //     never changes a bit of the result;
 //   * k_discrete_analytic — two warp-level compaction queues keep lanes dense: queue A = voxels inside the body-frame
@@ -43,7 +44,7 @@ namespace isdf {
 constexpr int DISC_WARPS = 4;
 constexpr int DISC_THREADS = DISC_WARPS * 32;
 constexpr int QCAP = 64;
-constexpr int ROW_CLASSES = 32;         // a pose window's rows are summed in 32 interleaved classes (canonical order): row r -> class r % 32
+constexpr int ROW_CLASSES = 32;         // a pose window's voxels are summed in 32 interleaved classes (canonical order): (row r, z offset dz) -> class (r + 5 dz) % 32
 constexpr unsigned SPLIT_WORK_MIN = 256u;  // never split a sample lighter than this (work units: 64 per mesh query + 1 per culled pair)
 constexpr int MAX_SPLIT_SLOTS = 16384;  // split samples per launch (2 KB of class sums each)
 constexpr int WINDOW_AXIS_MAX = 1023;   // voxels per window axis: window offsets are packed 10 bits per axis
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                             if (lane == 0) {
                                 QRes r;
                                 r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.d2 = d2; r.tri = tri; r.feat = feat; r.code = qcode;
-                                r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu)) % ROW_CLASSES);
+                                r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu) + 5u * (qcode >> 20)) % ROW_CLASSES);   // (r + 5 dz) % 32
                                 sm.qr[nres] = r;
                             }
                             nres++;
@@ -667,12 +668,13 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
 
             // Producer loop (one cull and one search call site): batches of 32 window rows are loaded (lane = row), their occupied voxels
             // are appended to the ring, and whenever 32 voxels are queued — or the window is exhausted — they are processed.
-            // A batch is emitted at once, lane by lane, when it fits into the ring (the common case); otherwise (dense walls)
-            //   whole sample: round-robin, one voxel per lane and round — 32 consecutive rows are 32 different classes, so every CLASS's
-            //                 voxels still come in (row, z) order;
-            //   split part  : row by row (rows of the classes [c0, c1) only), so that a class's rows stay in ascending order.
+            // Voxel (row r, z offset dz) of the window belongs to class (r + 5 dz) % 32: the voxels an obstacle patch puts near the robot
+            // — a few rows x a few z, the ones that cost mesh queries — land in ~as many different classes as there are voxels, so the
+            // parts of a split sample get near-equal numbers of queries (row-interleaved classes gave a wall patch to 5 of 32 classes:
+            // item timeline in profiles/r02_tuning.md). A split part scans the same rows and keeps its classes' voxels (a bit filter).
+            // Lanes are rows in ascending order and a lane emits its voxels z-ascending, so emitting a batch lane by lane — at once when it
+            // fits into the ring, else row by row (dense walls) — keeps every CLASS's voxels in (row, z) order for whole samples and parts.
             const int w = it.c1 - it.c0;
-            const int nk = whole ? nrows : ((nrows + ROW_CLASSES - 1) / ROW_CLASSES) * w;   // row slots to visit per z-chunk
             int zs = W.iz0, kb = -32;
             uint32_t bits = 0, rowcode = 0;
             unsigned pending = 0;
@@ -681,23 +683,26 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                 if (!finished) {
                     if (pending == 0u) {   // next batch of rows
                         kb += 32;
-                        if (kb >= nk) { kb = 0; zs += 32; }
+                        if (kb >= nrows) { kb = 0; zs += 32; }
                         if (zs > W.iz1) finished = true;
                         else {
                             const int nzc = min(32, W.iz1 - zs + 1);
                             const uint32_t zmask = (nzc == 32) ? 0xffffffffu : ((1u << nzc) - 1u);
-                            const int k = kb + lane;
-                            const int r = whole ? k : (k / w) * ROW_CLASSES + it.c0 + (k % w);
+                            const int r = kb + lane;
                             bits = 0;
-                            if (k < nk && r < nrows) {
+                            if (r < nrows) {
                                 int rx, ry;
                                 row_split(r, ny, inv_ny, rx, ry);
                                 bits = row_bits(G, W.ix0 + rx, W.iy0 + ry, zs, zmask);
                                 rowcode = (uint32_t)rx | ((uint32_t)ry << 10) | ((uint32_t)(zs - W.iz0) << 20);
+                                if (!whole && bits != 0u) {   // keep the voxels of the classes [c0, c1)
+                                    uint32_t keep = 0u;
+                                    unsigned cls = (unsigned)(r + 5 * (zs - W.iz0)) & 31u;
+                                    for (int k = 0; k < nzc; k++) { keep |= (((cls - (unsigned)it.c0) & 31u) < (unsigned)w ? 1u : 0u) << k; cls = (cls + 5u) & 31u; }
+                                    bits &= keep;
+                                }
                             }
                             pending = __ballot_sync(0xffffffffu, bits != 0u);
-                            // lane order = (row block, class) order, so for every class its rows ascend with the lane: emitting the batch
-                            // lane by lane keeps each CLASS's voxels in (row, z) order for whole samples and for split parts alike
                             if (pending != 0u) {
                                 int incl = __popc(bits);
 #pragma unroll
@@ -716,15 +721,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                                 }
                             }
                         }
-                    } else if (whole) {    // one round: every lane that still has voxels emits its lowest one
-                        if (bits != 0u) {
-                            const int z = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            sm.vq[(head + nq + __popc(pending & lt_mask)) & 63] = rowcode + ((uint32_t)z << 20);
-                        }
-                        nq += __popc(pending);
-                        pending = __ballot_sync(0xffffffffu, bits != 0u);
-                    } else {               // one row: lane z emits voxel z of the row
+                    } else {               // one row: lane z emits voxel z of the lowest pending row
                         const int src = __ffs(pending) - 1;
                         pending &= pending - 1;
                         const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
