@@ -10,6 +10,7 @@
 #include <queue>
 #include "isdf_host_mesh.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <string>
@@ -314,10 +315,13 @@ extern "C" int isdf_set_shape_mesh_ex(isdf_ctx *c, const double *V, int nV, cons
     }
     m.cell_dist = c->d_cell_dist.p; m.cell_seed = c->d_cell_seed.p;
     m.cell_off = nullptr; m.cell_cnt = nullptr; m.cand = nullptr;
-    // exact candidate lists for the cells the discrete path queries (centre within safety_hor + a cell diagonal of the surface)
+    // exact candidate lists for every cell a query can land in and not be settled by the cell's distance bracket alone: the discrete
+    // path queries within safety_hor of the surface, the swept-volume path within its range bound 2*safety_hor + 0.1 (swm:383) — a
+    // flat pass over ~100 listed triangles answers such a query in a tenth of the time of a far-field tree search, and the sign
+    // descent of the swept-volume path is a CHAIN of them (profiles/r02_tuning.md, swept path)
     {
         const double hd = 0.5 * std::sqrt(3.0) * m.gcell;
-        const double list_reach = c->cfg.safety_hor + 2.0 * m.ghd;
+        const double list_reach = std::max(c->cfg.safety_hor, 2.0 * c->cfg.safety_hor + 0.1) + 2.0 * m.ghd;
         CU_TRY(c->d_cell_cnt.ensure(ncell)); CU_TRY(c->d_cell_off.ensure(ncell));
         const unsigned warps_grid = (unsigned)((ncell + 3) / 4);
         k_mesh_cell_lists<<<warps_grid, 128, 0, c->stream>>>(m, (long long)ncell, hd, list_reach, c->d_cell_cnt.p, nullptr, nullptr);
@@ -337,6 +341,11 @@ extern "C" int isdf_set_shape_mesh_ex(isdf_ctx *c, const double *V, int nV, cons
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaStreamSynchronize(c->stream));
             m.cell_off = c->d_cell_off.p; m.cell_cnt = c->d_cell_cnt.p; m.cand = c->d_cand.p;
+        }
+        if (getenv("ISDF_VERBOSE")) {
+            size_t listed = 0; for (size_t i = 0; i < ncell; i++) listed += cnt[i] != 0;
+            fprintf(stderr, "[isdf] mesh cell grid %d x %d x %d (cell %.3f m), %zu cells with a candidate list, %zu candidates (%.1f MB)\n", m.gdim[0], m.gdim[1], m.gdim[2],
+                    m.gcell, listed, total, total * 4e-6);
         }
     }
     // fused 16-byte cell records for the discrete scan kernel's cull stage
@@ -377,7 +386,7 @@ __global__ void k_mesh_cells(const __grid_constant__ DevMesh M, int nx, int ny, 
 
 // Candidate lists (one warp per cell). Pass 1 (cand == nullptr): count the triangles within d_c + 2 hd of the cell centre and
 // store the count (0 for cells that are too far, too deep or whose list would exceed LIST_CAP). Pass 2: fill the lists.
-constexpr int LIST_CAP = 160;
+constexpr int LIST_CAP = MESH_LIST_CAP;
 __global__ void __launch_bounds__(128) k_mesh_cell_lists(const __grid_constant__ DevMesh M, long long ncell, double hd, double list_reach,
                                                          uint16_t *cnt, const uint32_t *off, uint32_t *cand) {
     __shared__ WideStack stk[4];

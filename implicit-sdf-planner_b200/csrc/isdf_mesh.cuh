@@ -544,6 +544,39 @@ __device__ __forceinline__ double list_closest_pre(const DevMesh &M, d3 p, uint3
     return best;
 }
 
+// Latency-oriented list pass for callers that run ONE query at a time on an otherwise idle SM (the swept-volume path's descent and
+// fine-scan chains): all of this lane's candidate ids are requested at once, the 128-byte records of every pass after the first are
+// prefetched into L1 while the first pass computes — one DRAM/L2 round trip for the whole list instead of one per pass. Same
+// arithmetic, same pass order and tie-breaking as list_closest_pre.
+constexpr int MESH_LIST_CAP = 160;                       // longest candidate list a cell may carry (longer: the cell has none)
+constexpr int MESH_LIST_PASSES = MESH_LIST_CAP / 32;
+__device__ __forceinline__ double list_closest_lat(const DevMesh &M, d3 p, uint32_t off, int cnt, d3 &cbest, int &tri, int &feat, int lane) {
+    int ids[MESH_LIST_PASSES];
+#pragma unroll
+    for (int k = 0; k < MESH_LIST_PASSES; k++) { const int i = k * 32 + lane; ids[k] = (i < cnt) ? (int)__ldg(M.cand + off + i) : -1; }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int k = 1; k < MESH_LIST_PASSES; k++)
+        if (ids[k] >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(M.tris + TRI_STRIDE * (size_t)ids[k]));
+#endif
+    double best = 1e300;
+    tri = -1; feat = 0;
+#pragma unroll
+    for (int k = 0; k < MESH_LIST_PASSES; k++) {
+        if (k * 32 >= cnt) break;
+        const int t = ids[k];
+        double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0;
+        if (t >= 0) {
+            const double *T = M.tris + TRI_STRIDE * (size_t)t;
+            q = tri_closest_rec(p, T, f);
+            const d3 e = p - q;
+            dd = dot3(e, e);
+        }
+        warp_argmin_update(dd, q, t, f, best, cbest, tri, feat);
+    }
+    return best;
+}
+
 #ifdef ISDF_OUTLINE_TREE_SEARCH
 // Out-of-line copy of the tree search for the discrete scan kernel, where candidate lists answer almost every query: the kernel's
 // hot loop then stays small (instruction cache) — the call's spills are paid only on the rare tree path.
@@ -631,6 +664,29 @@ __device__ __forceinline__ double mesh_sdf_grad_warp(const DevMesh &M, d3 p, dou
         if (bounded && far) return reach;
     }
     if (!mesh_search_warp(M, p, reach, lane, stk, cell, d2, c, tri, feat)) return reach;
+    return mesh_finish(M, p, p - c, d2, tri, feat, g);
+}
+
+// The same query for latency-bound callers: the cell's fused 16-byte record (one load instead of three dependent ones) and the
+// latency-oriented list pass. Identical results (same search, same order).
+__device__ __forceinline__ double mesh_sdf_grad_warp_lat(const DevMesh &M, d3 p, double reach, d3 &g, int lane, WideStack *stk) {
+    if (!M.cell_rec || M.gdim[0] <= 0) return mesh_sdf_grad_warp(M, p, reach, g, lane, stk);
+    const int cell = mesh_cell_index(M, p);
+    const bool bounded = (reach < 1e150) && (M.sign_radius > 0.0) && (reach >= M.sign_radius);
+    d3 c = mk3(0, 0, 0);
+    int tri, feat;
+    double d2;
+    if (cell < 0) {
+        if (bounded && reach <= M.gpad) return reach;
+        if (!mesh_search_warp(M, p, reach, lane, stk, cell, d2, c, tri, feat)) return reach;
+    } else {
+        const uint4 rec = __ldg(M.cell_rec + cell);
+        const float dc = __uint_as_float(rec.x);
+        if (bounded && (double)dc - M.ghd >= reach) return reach;
+        const int cnt = (int)rec.w;
+        if (cnt != 0 && cnt <= MESH_LIST_CAP) d2 = list_closest_lat(M, p, rec.z, cnt, c, tri, feat, lane);
+        else if (!mesh_search_warp(M, p, reach, lane, stk, cell, d2, c, tri, feat)) return reach;
+    }
     return mesh_finish(M, p, p - c, d2, tri, feat, g);
 }
 

@@ -63,12 +63,29 @@ struct TrajView { const double *T; const double *C; int N; };
 // locatePieceIdx (trajectory.hpp:545-563): sequential subtraction, strict '>', clamps past the end
 __device__ __forceinline__ int traj_locate(const TrajView &tr, double &t) {
     int idx = 0;
-    for (; idx < tr.N; idx++) {
+    const int N = tr.N;
+    // eight pieces per trip: the durations are loaded together and the subtractions run ahead speculatively, so the dependent chain is
+    // the eight subtractions themselves — same operations in the same order as the reference's loop, the first failing comparison wins
+    while (idx + 8 <= N) {
+        double d[8], s[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = tr.T[idx + k];
+        s[0] = t;
+#pragma unroll
+        for (int k = 1; k < 8; k++) s[k] = s[k - 1] - d[k - 1];
+        int stop = 8;
+        double tsel = s[7] - d[7];
+#pragma unroll
+        for (int k = 7; k >= 0; k--) if (!(s[k] > d[k])) { stop = k; tsel = s[k]; }
+        t = tsel; idx += stop;
+        if (stop < 8) return idx;
+    }
+    for (; idx < N; idx++) {
         const double dur = tr.T[idx];
         if (!(t > dur)) break;
         t -= dur;
     }
-    if (idx == tr.N) { idx--; t += tr.T[idx]; }
+    if (idx == N) { idx--; t += tr.T[idx]; }
     return idx;
 }
 
@@ -110,32 +127,50 @@ struct SvArgs {
     unsigned long long *counter;  // reference-equivalent SDF evaluation count
     int rank, world;
     const double *g_t, *g_s, *g_g;  // tier-T1: given t*, sdf*, g_rel (null = search)
+    // longest-first schedule of the point CTAs: work[pk] = cycles point pk took in this evaluation; order = this rank's points sorted by
+    // the previous evaluation's work (null: natural order). A launch is a few waves of CTAs and ends with its slowest point — started
+    // first, that point overlaps the others instead of trailing them. Results do not depend on the order (per-point outputs).
+    unsigned *work;
+    int *order;
+    int use_order;
+    unsigned long long *dbg2;       // -DISDF_PHASE_TIMING: 4 per point, descent sub-phases of warp 0
     unsigned long long *dbg;        // -DISDF_PHASE_TIMING: 8 per point {total, coarse, bracket pass, exact pass, descent, intervals, exact searches, -}
 };
 
 // ---- k_sv_table ---------------------------------------------------------------------------------------------------
+constexpr int SV_TABLE_THREADS = 256;
+constexpr int SV_TABLE_CTAS = SV_MAX_COARSE / SV_TABLE_THREADS;
+// CTA bx computes the poses of coarse samples [256 bx, 256 bx + 256). The coarse time grid is a chain of repeated additions
+// (choiceTInit's loop variable, swm:392): thread 0 of every CTA walks the whole chain (a few microseconds) and keeps its own slice.
 __device__ __forceinline__ void sv_table_body(const SvArgs &A, const int bx) {
-    (void)bx;
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
 #pragma nv_diag_suppress static_var_with_dynamic_init
     __shared__ cuda::barrier<cuda::thread_scope_block> bar;
     stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
     __shared__ int s_nc;
+    __shared__ double s_times[SV_TABLE_THREADS];
+    const int k0 = bx * SV_TABLE_THREADS;
     if (threadIdx.x == 0) {
         double td = 0.0;
         for (int k = 0; k < A.N; k++) td += sT[k];         // getTotalDuration (trajectory.hpp:457-466)
-        if (td < 3 * 1e2) A.state[0] = td;                 // updateTraj (swm:287-296)
-        const double dur = A.state[0];
+        const double dur = (td < 3 * 1e2) ? td : A.state[0];   // updateTraj (swm:287-296): longer trajectories keep the previous duration
         int nc = 0;
-        for (double t = 0; t < dur && nc < SV_MAX_COARSE; t += 0.2) A.times[nc++] = t;  // choiceTInit's coarse loop (swm:392)
-        A.meta[0] = nc; s_nc = nc;
+        for (double t = 0; t < dur && nc < SV_MAX_COARSE; t += 0.2) {   // choiceTInit's coarse loop (swm:392)
+            if (nc >= k0 && nc < k0 + SV_TABLE_THREADS) s_times[nc - k0] = t;
+            nc++;
+        }
+        s_nc = nc;
+        if (bx == 0) { A.meta[0] = nc; if (td < 3 * 1e2) A.state[0] = td; }
     }
     __syncthreads();
     const TrajView tr = {sT, sC, A.N};
-    for (int k = threadIdx.x; k < s_nc; k += blockDim.x) {
+    const int k = k0 + (int)threadIdx.x;
+    if (k < s_nc) {
+        const double t = s_times[threadIdx.x];
+        A.times[k] = t;
         d3 x, v, a, j;
-        traj_pvaj(tr, A.times[k], x, v, a, j);
+        traj_pvaj(tr, t, x, v, a, j);
         const rot3 R = quat_rot(flat_quat_only(A.cfg.fp, v, a));
         double *o = A.poses + 12 * (size_t)k;
         o[0] = x.x; o[1] = x.y; o[2] = x.z;
@@ -153,6 +188,23 @@ __device__ __forceinline__ void mesh_bracket(const DevMesh &M, d3 prel, double &
     if (cell < 0) { lo = M.gpad; return; }
     const double dc = (double)__ldg(M.cell_dist + cell);
     lo = dc - M.ghd; hi = dc + M.ghd;
+}
+
+// Upper bound of the mesh SDF at a body-frame point without a search: the cell bracket's upper end, tightened by the exact distance
+// to the cell's seed triangle (the triangle nearest to the cell centre — for most points of the cell THE nearest triangle). The
+// signed distance never exceeds the distance to any one triangle.
+__device__ __forceinline__ double mesh_upper(const DevMesh &M, d3 prel) {
+    if (M.gdim[0] <= 0) return 1e300;
+    const int cell = mesh_cell_index(M, prel);
+    if (cell < 0) return 1e300;
+    double hi = (double)__ldg(M.cell_dist + cell) + M.ghd;
+    const int seed = (int)__ldg(M.cell_seed + cell);
+    if (seed >= 0 && seed < M.ntris) {
+        int f;
+        const d3 e = prel - tri_closest_rec(prel, M.tris + TRI_STRIDE * (size_t)seed, f);
+        hi = fmin(hi, sqrt(dot3(e, e)) * (1.0 + 1e-12));
+    }
+    return hi;
 }
 
 __device__ __forceinline__ d3 sv_body_point(const SvArgs &A, const TrajView &tr, d3 p, double t) {
@@ -173,7 +225,7 @@ __device__ __forceinline__ double mesh_sdf_each(const DevMesh &M, bool need, d3 
         todo &= todo - 1;
         const d3 q = mk3(__shfl_sync(0xffffffffu, prel.x, src), __shfl_sync(0xffffffffu, prel.y, src), __shfl_sync(0xffffffffu, prel.z, src));
         d3 g;
-        const double v = mesh_sdf_grad_warp(M, q, reach, g, lane, stk);
+        const double v = mesh_sdf_grad_warp_lat(M, q, reach, g, lane, stk);
         if (lane == src) out = v;
     }
     return out;
@@ -484,6 +536,10 @@ struct SvmShared {
     int red_i[SVM_WARPS];
     double cand_f[9], cand_x[9], cand_g[9][3], cand_q[9][3];
     double bc[4];
+#ifdef ISDF_PHASE_TIMING
+    unsigned dbg_rounds, dbg_exact, dbg_requery;   // descent candidate batches; fine-scan samples that needed an exact search; descent re-queries at x
+    long long dbg_t[4];               // descent, warp 0: pose at x, re-query at x, candidate (pose + query), wait + replay
+#endif
 };
 
 __device__ __forceinline__ bool same_bits(d3 a, d3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
@@ -500,23 +556,35 @@ __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr,
     x = x0;
     g = mk3(0, 0, 0); gq = mk3(0, 0, 0);
     double fval = 0.0;
+#ifdef ISDF_PHASE_TIMING
+    long long dt_mark = clock64();
+#define DT_ADD(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); S.dbg_t[i] += n_ - dt_mark; dt_mark = n_; } } while (0)
+#else
+#define DT_ADD(i) ((void)0)
+#endif
     while (iter < 300 && !stop && fabs(x - prev_x) > tol) {
+        DT_ADD(3);
         d3 xt, v, a, j;
         traj_pvaj(tr, x, xt, v, a, j);
         FlatState fs;
         flat_state(A.cfg.fp, v, a, j, fs);
         const rot3 R = quat_rot(flat_quat(fs));
         const d3 tmp = rot_applyT(R, p - xt);
+        DT_ADD(0);
         if (!(have && same_bits(tmp, gq))) {          // CTA-uniform: every thread computed the same tmp
+#ifdef ISDF_PHASE_TIMING
+            if (threadIdx.x == 0) S.dbg_requery++;
+#endif
             if (warp == 0) {
                 d3 g0 = mk3(0, 0, 0);
-                const double f0 = mesh_sdf_grad_warp(M, tmp, 1e300, g0, lane, stk);
+                const double f0 = mesh_sdf_grad_warp_lat(M, tmp, 1e300, g0, lane, stk);
                 if (lane == 0) { S.bc[0] = f0; S.bc[1] = g0.x; S.bc[2] = g0.y; S.bc[3] = g0.z; }
             }
             __syncthreads();
             fval = S.bc[0]; g = mk3(S.bc[1], S.bc[2], S.bc[3]); gq = tmp; have = true;
             __syncthreads();
         }
+        DT_ADD(1);
         if (iter == 0) { fx = fval; if (warp == 0) nevals++; }
         const d3 omg = flat_omega(fs);
         const d3 rv = rot_applyT(R, v), wx = cross3(omg, tmp);
@@ -525,6 +593,9 @@ __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr,
         prev_x = x;
         bool accepted = false;
         for (int b0 = 1; b0 < 10 && !accepted; b0 += SVM_WARPS) {
+#ifdef ISDF_PHASE_TIMING
+            if (threadIdx.x == 0) S.dbg_rounds++;
+#endif
             const int mydiv = b0 + warp;
             if (mydiv < 10) {
                 double tau = alpha;
@@ -532,13 +603,14 @@ __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr,
                 const double xc = fmax(fmin(x - tau * sgn, t_max), t_min);
                 const d3 qc = sv_body_point(A, tr, p, xc);
                 d3 g2 = mk3(0, 0, 0);
-                const double fc = mesh_sdf_grad_warp(M, qc, 1e300, g2, lane, stk);
+                const double fc = mesh_sdf_grad_warp_lat(M, qc, 1e300, g2, lane, stk);
                 if (lane == 0) {
                     S.cand_f[mydiv - 1] = fc; S.cand_x[mydiv - 1] = xc;
                     S.cand_g[mydiv - 1][0] = g2.x; S.cand_g[mydiv - 1][1] = g2.y; S.cand_g[mydiv - 1][2] = g2.z;
                     S.cand_q[mydiv - 1][0] = qc.x; S.cand_q[mydiv - 1][1] = qc.y; S.cand_q[mydiv - 1][2] = qc.z;
                 }
             }
+            DT_ADD(2);
             __syncthreads();
             const int dend = min(b0 + SVM_WARPS, 10);
             for (int div = b0; div < dend; div++) {      // the reference's sequential loop over the halvings
@@ -564,6 +636,7 @@ __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr,
 template <bool MESH>
 __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx) {
     if (A.rank + A.world * bx >= A.P) return;   // batched launch: this problem has fewer points than the grid is wide (whole CTA leaves)
+    const long long work_begin = clock64();
     extern __shared__ __align__(16) double smem[];
     double *sC = smem, *sT = smem + 18 * A.N;
     __shared__ SvmShared S;
@@ -572,7 +645,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
     stage_traj_block(sC, sT, A.C, A.T, A.N, &bar);
     const TrajView tr = {sT, sC, A.N};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pk = A.rank + A.world * bx;     // grid.x >= number of points of this rank (batched launches: the largest problem's)
+    const int pk = A.use_order ? A.order[bx] : A.rank + A.world * bx;     // grid.x >= number of points of this rank (batched launches: the largest problem's)
     const DevMesh &M = A.shape.mesh;
     WideStack *stk = &S.stk[warp];
     const d3 p = mk3(A.pts[3 * pk], A.pts[3 * pk + 1], A.pts[3 * pk + 2]);
@@ -586,6 +659,8 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
     unsigned nevals = 0;      // per warp; lane 0 of every warp adds its share to the counter
     bool found = false;
 #ifdef ISDF_PHASE_TIMING
+    if (threadIdx.x == 0) { S.dbg_rounds = 0; S.dbg_exact = 0; S.dbg_requery = 0; S.dbg_t[0] = S.dbg_t[1] = S.dbg_t[2] = S.dbg_t[3] = 0; }
+    __syncthreads();
     const long long pt_begin = clock64();
     long long pt_coarse = 0, pt_p1 = 0, pt_p2 = 0, pt_gd = 0, pt_mark = 0;
     unsigned pt_intervals = 0;
@@ -602,8 +677,12 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
     } else {
         // ---- coarse scan (swm:392-421): in-range bitmap; the cell bracket settles all but a thin band around `inf` ---------
         PT_MARK();
+        // consecutive samples go to different warps (an obstacle point's undecided samples — the thin band around `inf` — are
+        // consecutive in time and each costs a cooperative search: spread, they run on all warps at once)
+        for (int w = tid; w < SV_FLAG_WORDS; w += SVM_THREADS) S.flags[w] = 0u;
+        __syncthreads();
         for (int base = 0; base < nc; base += SVM_THREADS) {
-            const int k = base + tid;
+            const int k = base + lane * SVM_WARPS + warp;
             bool in = false, undecided = false;
             d3 prel = mk3(0, 0, 0);
             if (k < nc) {
@@ -623,9 +702,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                 const double v = mesh_sdf_each(M, undecided, prel, inf, inf, lane, stk);
                 if (undecided) in = v < inf;
             }
-            const unsigned b = __ballot_sync(0xffffffffu, in);
-            const int w = (base >> 5) + warp;
-            if (lane == 0 && w < SV_FLAG_WORDS) S.flags[w] = b;
+            if (in) atomicOr(&S.flags[k >> 5], 1u << (k & 31));
         }
         __syncthreads();
         PT_ADD(pt_coarse);
@@ -645,7 +722,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
             if (MESH) {
                 if (warp == 0) {
                     d3 g_;
-                    const double v = mesh_sdf_grad_warp(M, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, stk);
+                    const double v = mesh_sdf_grad_warp_lat(M, sv_body_point(A, tr, p, A.times[last_entry]), inf, g_, lane, stk);
                     if (lane == 0) S.bc[0] = v;
                 }
                 __syncthreads();
@@ -685,9 +762,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                     double t = lb;
                     for (int q = 0; q < first; q++) t += 0.02;
                     while (t < ub) {
-                        double blo, bhi;
-                        mesh_bracket(M, sv_body_point(A, tr, p, t), blo, bhi);
-                        cut = fmin(cut, bhi);
+                        cut = fmin(cut, mesh_upper(M, sv_body_point(A, tr, p, t)));
                         for (int q = 0; q < SVM_THREADS; q++) t += 0.02;
                     }
 #pragma unroll
@@ -717,6 +792,9 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                                 mesh_bracket(M, prel, blo, bhi);
                                 need = blo <= cut;
                             }
+#ifdef ISDF_PHASE_TIMING
+                            if (need) atomicAdd(&S.dbg_exact, 1u);
+#endif
                             dis = mesh_sdf_each(M, need, prel, inf, 1e300, lane, stk);
                         } else if (valid) dis = sv_sdf_at(A, tr, p, t);
                         nevals += __popc(__ballot_sync(0xffffffffu, valid));
@@ -773,7 +851,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                 else {
                     if (warp == 0) {
                         d3 g0 = mk3(0, 0, 0);
-                        if (MESH) mesh_sdf_grad_warp(M, qf, 1e300, g0, lane, stk);
+                        if (MESH) mesh_sdf_grad_warp_lat(M, qf, 1e300, g0, lane, stk);
                         else g0 = warp_grad(A.shape, qf, lane);
                         if (lane == 0) { S.bc[1] = g0.x; S.bc[2] = g0.y; S.bc[3] = g0.z; }
                     }
@@ -787,11 +865,35 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
     if (A.dbg && tid == 0) {
         unsigned long long *o = A.dbg + 8 * (size_t)pk;
         o[0] = (unsigned long long)(clock64() - pt_begin); o[1] = pt_coarse; o[2] = pt_p1; o[3] = pt_p2; o[4] = pt_gd;
-        o[5] = pt_intervals; o[6] = 0; o[7] = 0;
+        o[5] = pt_intervals | ((unsigned long long)S.dbg_requery << 16); o[6] = S.dbg_exact; o[7] = S.dbg_rounds;
+        if (A.dbg2) { unsigned long long *o2 = A.dbg2 + 4 * (size_t)pk; for (int q = 0; q < 4; q++) o2[q] = (unsigned long long)S.dbg_t[q]; }
     }
 #endif
     if (lane == 0 && A.counter && nevals) atomicAdd(A.counter, (unsigned long long)nevals);
     if (tid == 0) sv_point_tail(A, sC, tr, pk, p, found, tstar, sdf_value, grel);
+    if (tid == 0 && A.work) A.work[pk] = (unsigned)min((clock64() - work_begin) >> 4, 0xffffffffll);
+}
+
+// one CTA: this rank's points bucketed by the work they just reported (half-octave buckets), heaviest bucket first
+__device__ __forceinline__ int sv_work_bucket(unsigned w) {
+    if (w == 0) return 0;
+    const int e = 31 - __clz(w);
+    return min(63, 2 * e + (e > 0 ? (int)((w >> (e - 1)) & 1u) : 0));
+}
+__device__ __forceinline__ void sv_order_body(const SvArgs &A) {
+    __shared__ unsigned hist[64], base[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) hist[tid] = 0;
+    __syncthreads();
+    const int Mloc = (A.P - A.rank + A.world - 1) / A.world;
+    for (int i = tid; i < Mloc; i += blockDim.x) atomicAdd(&hist[sv_work_bucket(A.work[A.rank + A.world * i])], 1u);
+    __syncthreads();
+    if (tid == 0) { unsigned run = 0; for (int b = 63; b >= 0; b--) { base[b] = run; run += hist[b]; } }
+    __syncthreads();
+    for (int i = tid; i < Mloc; i += blockDim.x) {
+        const int pk = A.rank + A.world * i;
+        A.order[atomicAdd(&base[sv_work_bucket(A.work[pk])], 1u)] = pk;
+    }
 }
 
 // ---- reductions --------------------------------------------------------------------------------------------------
@@ -867,7 +969,7 @@ __global__ void __launch_bounds__(256) k_sv_table(const __grid_constant__ SvArgs
 __global__ void __launch_bounds__(SV_THREADS) k_sv_points(const __grid_constant__ SvArgs A) { sv_points_body(A, blockIdx.x); }
 template <bool MESH>
 __global__ void __launch_bounds__(SVM_THREADS) k_sv_points_cta(const __grid_constant__ SvArgs A) { sv_points_cta_body<MESH>(A, blockIdx.x); }
-__global__ void __launch_bounds__(256) k_sv_reduce(const __grid_constant__ SvArgs A) { sv_reduce_body(A, blockIdx.x); }
+__global__ void __launch_bounds__(256) k_sv_reduce(const __grid_constant__ SvArgs A) { if ((int)blockIdx.x == A.N) sv_order_body(A); else sv_reduce_body(A, blockIdx.x); }
 __global__ void k_sv_finish(const __grid_constant__ SvArgs A) { sv_finish_body(A, blockIdx.x); }
 
 __global__ void __launch_bounds__(256) k_sv_table_b(const __grid_constant__ SvBatch Bt) { __shared__ SvArgs V; sv_make_view(Bt, blockIdx.y, V); sv_table_body(V, blockIdx.x); }
@@ -884,6 +986,8 @@ struct SweptState {
     DevBuf<double> d_pts, d_tstar, d_sdf, d_grel, d_times, d_poses, d_state, d_partial, d_piece_gdt, d_piece_cost;
     DevBuf<int> d_piece, d_meta;
     DevBuf<unsigned long long> d_counter, d_dbg;
+    DevBuf<unsigned> d_work; DevBuf<int> d_order;
+    bool order_ready = false; int order_rank = -1, order_world = -1;
     bool dbg_on = false;
 
     cudaError_t set_points(const double *pts, int n, cudaStream_t st) {
@@ -896,6 +1000,9 @@ struct SweptState {
         if ((e = d_grel.ensure((size_t)3 * n)) != cudaSuccess) return e;
         if ((e = d_partial.ensure((size_t)n * PARTIAL_STRIDE)) != cudaSuccess) return e;
         if ((e = d_piece.ensure(n)) != cudaSuccess) return e;
+        if ((e = d_work.ensure(n)) != cudaSuccess) return e;
+        if ((e = d_order.ensure(n)) != cudaSuccess) return e;
+        order_ready = false;
         if ((e = cudaMemsetAsync(d_tstar.p, 0, sizeof(double) * n, st)) != cudaSuccess) return e;  // lastTstar := zeros (plan_manager.cpp:254)
         if ((e = cudaMemsetAsync(d_sdf.p, 0, sizeof(double) * n, st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(d_grel.p, 0, sizeof(double) * 3 * n, st)) != cudaSuccess) return e;
@@ -928,11 +1035,15 @@ struct SweptState {
         A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
         A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
         A.out = d_out; A.counter = d_counter.p; A.rank = rank; A.world = world; A.g_t = g_t; A.g_s = g_s; A.g_g = g_g;
-        A.dbg = nullptr;
+        // longest-first schedule (searching evaluations of a mesh robot only: the other kernels' points are cheap and uniform)
+        const bool record = (g_t == nullptr) && shape.kind == ISDF_SHAPE_MESH;
+        if (order_rank != rank || order_world != world) { order_ready = false; order_rank = rank; order_world = world; }
+        A.work = record ? d_work.p : nullptr; A.order = d_order.p; A.use_order = (record && order_ready) ? 1 : 0;
+        A.dbg = nullptr; A.dbg2 = nullptr;
         if (dbg_on) {
-            if ((e = d_dbg.ensure((size_t)8 * P)) != cudaSuccess) return e;
-            if ((e = cudaMemsetAsync(d_dbg.p, 0, sizeof(unsigned long long) * 8 * P, st)) != cudaSuccess) return e;
-            A.dbg = d_dbg.p;
+            if ((e = d_dbg.ensure((size_t)12 * P)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(d_dbg.p, 0, sizeof(unsigned long long) * 12 * P, st)) != cudaSuccess) return e;
+            A.dbg = d_dbg.p; A.dbg2 = d_dbg.p + 8 * (size_t)P;
         }
         const size_t sm = sizeof(double) * 19 * (size_t)N;
         if (sm > 200 * 1024) return cudaErrorInvalidValue;
@@ -943,7 +1054,7 @@ struct SweptState {
             cudaFuncSetAttribute(k_sv_points_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             cudaFuncSetAttribute(k_sv_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         }
-        k_sv_table<<<1, 256, sm, st>>>(A);
+        k_sv_table<<<SV_TABLE_CTAS, SV_TABLE_THREADS, sm, st>>>(A);
         const int Mloc = (P - rank + world - 1) / world;
         const unsigned grid = (unsigned)((Mloc + SV_WARPS - 1) / SV_WARPS);
         if (grid > 0) {
@@ -951,7 +1062,8 @@ struct SweptState {
             else if (SV_ANALYTIC_CTA) k_sv_points_cta<false><<<(unsigned)Mloc, SVM_THREADS, sm, st>>>(A);
             else k_sv_points<<<grid, SV_THREADS, sm, st>>>(A);
         }
-        k_sv_reduce<<<N, 256, 0, st>>>(A);
+        k_sv_reduce<<<N + ((record && grid > 0) ? 1 : 0), 256, 0, st>>>(A);   // + one CTA that sorts the points for the next evaluation
+        if (record && grid > 0) order_ready = true;
         k_sv_finish<<<1, 32, 0, st>>>(A);
         *launches = 3 + (grid > 0 ? 1 : 0);
         return cudaGetLastError();
@@ -990,7 +1102,8 @@ struct SweptState {
         A.cfg = cfg; A.shape = shape; A.N = N; A.T = d_T; A.C = d_Cpp; A.P = 0; A.pts = d_pts.p;
         A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
         A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
-        A.out = d_out; A.counter = d_counter.p; A.rank = 0; A.world = 1; A.g_t = nullptr; A.g_s = nullptr; A.g_g = nullptr; A.dbg = nullptr;
+        A.out = d_out; A.counter = d_counter.p; A.rank = 0; A.world = 1; A.g_t = nullptr; A.g_s = nullptr; A.g_g = nullptr; A.dbg = nullptr; A.dbg2 = nullptr;
+        A.work = nullptr; A.order = nullptr; A.use_order = 0;
         Bt.B = B; Bt.pt_off = d_off.p; Bt.out_stride = 19ll * N + 1;
         const size_t sm = sizeof(double) * 19 * (size_t)N;
         if (sm > 200 * 1024) return cudaErrorInvalidValue;
@@ -1000,7 +1113,7 @@ struct SweptState {
             cudaFuncSetAttribute(k_sv_points_cta_b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             cudaFuncSetAttribute(k_sv_points_cta_b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         }
-        k_sv_table_b<<<dim3(1, B), 256, sm, st>>>(Bt);
+        k_sv_table_b<<<dim3(SV_TABLE_CTAS, B), SV_TABLE_THREADS, sm, st>>>(Bt);
         if (maxP > 0) {
             if (shape.kind == ISDF_SHAPE_MESH) k_sv_points_cta_b<true><<<dim3(maxP, B), SVM_THREADS, sm, st>>>(Bt);
             else k_sv_points_cta_b<false><<<dim3(maxP, B), SVM_THREADS, sm, st>>>(Bt);
@@ -1013,7 +1126,7 @@ struct SweptState {
     void release() {
         d_off.release();
         d_pts.release(); d_tstar.release(); d_sdf.release(); d_grel.release(); d_times.release(); d_poses.release(); d_state.release();
-        d_partial.release(); d_piece_gdt.release(); d_piece_cost.release(); d_piece.release(); d_meta.release(); d_counter.release(); d_dbg.release();
+        d_partial.release(); d_piece_gdt.release(); d_piece_cost.release(); d_piece.release(); d_meta.release(); d_counter.release(); d_dbg.release(); d_work.release(); d_order.release();
     }
 };
 
