@@ -77,6 +77,7 @@ struct isdf_ctx {
     // front end attitude kernels (isdf_frontend.cuh)
     DevBuf<double> d_fe_rot; DevBuf<uint8_t> d_fe_kernels, d_fe_order, d_fe_ok; DevBuf<uint32_t> d_fe_masks, d_fe_out;
     DevBuf<int> d_fe_ind; DevBuf<double> d_fe_father, d_fe_child;
+    DevBuf<uint2> d_fe_core, d_fe_urows, d_fe_surv; int fe_nurow = 0; DevBuf<unsigned> d_fe_count; int fe_ncore = 0;
     bool fe_ready = false;
     int fe_xk = 0, fe_yk = 0, fe_ks = 0;
     double fe_max_roll = 0, fe_max_pitch = 0, fe_ang_res = 0, fe_margin = 0;
@@ -177,7 +178,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
-    c->d_fe_rot.release(); c->d_fe_kernels.release(); c->d_fe_order.release(); c->d_fe_ok.release(); c->d_fe_masks.release(); c->d_fe_out.release(); c->d_fe_ind.release(); c->d_fe_father.release(); c->d_fe_child.release();
+    c->d_fe_rot.release(); c->d_fe_kernels.release(); c->d_fe_order.release(); c->d_fe_ok.release(); c->d_fe_masks.release(); c->d_fe_out.release(); c->d_fe_ind.release(); c->d_fe_father.release(); c->d_fe_child.release(); c->d_fe_core.release(); c->d_fe_urows.release(); c->d_fe_surv.release(); c->d_fe_count.release();
     c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release(); c->d_mCpp.release(); c->d_msv.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1124,6 +1125,7 @@ static FrontArgs front_args(isdf_ctx *c) {
     A.res = c->cfg.occupancy_resolution; A.margin = c->fe_margin;
     A.att_rot = c->d_fe_rot.p; A.kernels = c->d_fe_kernels.p; A.offset_masks = c->d_fe_masks.p; A.order = c->d_fe_order.p;
     A.max_roll = c->fe_max_roll; A.max_pitch = c->fe_max_pitch; A.ang_res = c->fe_ang_res;
+    A.core_rows = c->d_fe_core.p; A.ncore = c->fe_ncore; A.urows = c->d_fe_urows.p; A.nurow = c->fe_nurow; A.surv = c->d_fe_surv.p; A.surv_count = c->d_fe_count.p;
     return A;
 }
 
@@ -1188,6 +1190,31 @@ extern "C" int isdf_frontend_build_kernels(isdf_ctx *c, const isdf_kernel_config
     c->stats.kernel_launches += 2;
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(c->stream));
+    // the kernel core (offsets every attitude occupies), row by row, densest rows first: pass 1 of the two-pass feasibility kernel
+    {
+        std::vector<uint32_t> om((size_t)4 * n3);
+        CU_TRY(cudaMemcpy(om.data(), c->d_fe_masks.p, sizeof(uint32_t) * om.size(), cudaMemcpyDeviceToHost));
+        uint32_t valid[4];
+        for (int k = 0; k < 4; k++) { const int lo = 32 * k; valid[k] = natt >= lo + 32 ? 0xffffffffu : (natt > lo ? ((1u << (natt - lo)) - 1u) : 0u); }
+        std::vector<uint2> rows, urows;
+        for (int a = 0; a < ks; a++)
+            for (int b = 0; b < ks; b++) {
+                uint32_t bits = 0, ubits = 0;
+                for (int cc = 0; cc < ks; cc++) {
+                    const uint32_t *m = &om[(size_t)4 * ((a * ks + b) * ks + cc)];
+                    if (m[0] == valid[0] && m[1] == valid[1] && m[2] == valid[2] && m[3] == valid[3]) bits |= 1u << cc;
+                    if (m[0] | m[1] | m[2] | m[3]) ubits |= 1u << cc;
+                }
+                if (bits) rows.push_back(make_uint2((uint32_t)a | ((uint32_t)b << 8), bits));
+                if (ubits) urows.push_back(make_uint2((uint32_t)a | ((uint32_t)b << 8), ubits));
+            }
+        c->fe_nurow = (int)urows.size();
+        if (!urows.empty()) CU_TRY(c->d_fe_urows.upload(urows.data(), urows.size(), c->stream));
+        std::stable_sort(rows.begin(), rows.end(), [](const uint2 &p, const uint2 &q) { return __builtin_popcount(p.y) > __builtin_popcount(q.y); });
+        c->fe_ncore = (int)rows.size();
+        if (!rows.empty()) CU_TRY(c->d_fe_core.upload(rows.data(), rows.size(), c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
     c->fe_ready = true;
     if (xkernel_size) *xkernel_size = xk;
     if (ykernel_size) *ykernel_size = yk;
@@ -1222,8 +1249,20 @@ extern "C" int isdf_frontend_feasibility_device(isdf_ctx *c, uint32_t *d_masks, 
     CU_TRY(cudaFuncSetAttribute(k_frontend_feasibility, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long nrun = (long long)c->grid.X * c->grid.Y * ((c->grid.Z + FE_ZRUN - 1) / FE_ZRUN);
     const unsigned grid = (unsigned)std::min<long long>((nrun + 255) / 256, 148ll * 64);
-    k_frontend_feasibility<<<grid, 256, smem, (cudaStream_t)cuda_stream>>>(A);
-    c->stats.kernel_launches++;
+    if (c->fe_ncore > 0 && nrun < (1ll << 32) && !getenv("ISDF_FE_ONE_PASS")) {
+        // two passes: the kernel core settles most voxels of a cluttered map, the mask accumulation runs on the survivors only
+        CU_TRY(c->d_fe_surv.ensure((size_t)nrun));
+        CU_TRY(c->d_fe_count.ensure(1));
+        A.surv = c->d_fe_surv.p; A.surv_count = c->d_fe_count.p;
+        CU_TRY(cudaMemsetAsync(c->d_fe_count.p, 0, sizeof(unsigned), (cudaStream_t)cuda_stream));
+        CU_TRY(cudaFuncSetAttribute(k_frontend_survivors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_frontend_core<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(A);
+        k_frontend_survivors<<<148 * 16, 256, smem, (cudaStream_t)cuda_stream>>>(A);
+        c->stats.kernel_launches += 2;
+    } else {
+        k_frontend_feasibility<<<grid, 256, smem, (cudaStream_t)cuda_stream>>>(A);
+        c->stats.kernel_launches++;
+    }
     CU_TRY(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,7 @@
 //   k_frontend_kernels      one thread per (attitude, a, b, c): SDF at the rotated body point <= margin
 //   k_frontend_offset_masks one thread per (a, b, c): the 128-bit attitude set of that offset
 //   k_frontend_feasibility  one thread per run of 4 voxels along z: window scan + mask OR -> collision-free attitude masks
+//   k_frontend_core / k_frontend_survivors  the same masks in two passes: core rows settle most voxels, the full accumulation runs on the rest
 //   k_frontend_check        one thread per query: same mask, then the reference's visiting order (level pose, BFS from the father)
 #pragma once
 #include "isdf_types.cuh"
@@ -33,6 +34,13 @@ struct FrontArgs {
     uint8_t *kernels;        // natt x ks^3 booleans, address a*ks*ks + b*ks + c
     uint32_t *offset_masks;  // ks^3 x 4
     uint32_t *out;           // X*Y*Z x 4 (feasibility) — or n x 4 for the batched check
+    // two-pass feasibility: rows of the kernel CORE (offsets occupied in EVERY attitude's kernel), the survivor list and its counter
+    const uint2 *core_rows;  // ncore x {a | b << 8, bits over c}
+    int ncore;
+    const uint2 *urows;      // nurow x {a | b << 8, bits over c}: the kernel rows ANY attitude occupies (every other offset's mask is zero)
+    int nurow;
+    uint2 *surv;             // runs with at least one voxel that no core offset settles: {run index, bit j = voxel j of the run is open}
+    unsigned *surv_count;
     // batched check
     int nq;
     const int *q_ind;        // nq x 3
@@ -147,37 +155,145 @@ __global__ void __launch_bounds__(256) k_frontend_feasibility(const __grid_const
         const int z0 = iz0 - side;                                       // bit p of a row window = voxel z0 + p
         const int w0 = (z0 >= 0) ? (z0 >> 5) : -1;
         const int sh = z0 - 32 * w0;
-        bool done = false;
-        for (int a = 0; a < ks && !done; a++) {
-            const int x = ix + a - side;
-            if (x < 0 || x >= G.X) continue;
-            for (int b = 0; b < ks; b++) {
-                const int y = iy + b - side;
-                if (y < 0 || y >= G.Y) continue;
-                const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
-                const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
-                const uint32_t hi = (sh + wbits > 32 && w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
-                unsigned bits = (unsigned)(((((unsigned long long)hi << 32) | lo) >> sh) & wmask);
-                const uint4 *mrow = sm4 + (size_t)((a * ks + b) * ks);
-                while (bits) {
-                    const int p = __ffs((int)bits) - 1;
-                    bits &= bits - 1;
+        // only the kernel rows some attitude occupies can contribute (the masks of all other offsets are zero)
+        for (int k = 0; k < A.nurow; k++) {
+            const uint2 ur = __ldg(A.urows + k);
+            const int a = (int)(ur.x & 0xffu), b = (int)(ur.x >> 8);
+            const int x = ix + a - side, y = iy + b - side;
+            if (x < 0 || x >= G.X || y < 0 || y >= G.Y) continue;
+            const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+            const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
+            const uint32_t hi = (sh + wbits > 32 && w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
+            unsigned span = 0u;
 #pragma unroll
-                    for (int j = 0; j < FE_ZRUN; j++) {
-                        const int c = p - j;
-                        if (c >= 0 && c < ks) { const uint4 t = mrow[c]; m[j].x |= t.x; m[j].y |= t.y; m[j].z |= t.z; m[j].w |= t.w; }
-                    }
+            for (int j = 0; j < FE_ZRUN; j++) span |= ur.y << j;
+            unsigned bits = (unsigned)(((((unsigned long long)hi << 32) | lo) >> sh) & wmask) & span;
+            const uint4 *mrow = sm4 + (size_t)((a * ks + b) * ks);
+            while (bits) {
+                const int p = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+#pragma unroll
+                for (int j = 0; j < FE_ZRUN; j++) {
+                    const int c = p - j;
+                    if (c >= 0 && c < ks) { const uint4 t = mrow[c]; m[j].x |= t.x; m[j].y |= t.y; m[j].z |= t.z; m[j].w |= t.w; }
                 }
             }
-            done = true;                                                   // every attitude of every run voxel collides already?
-#pragma unroll
-            for (int j = 0; j < FE_ZRUN; j++)
-                done = done && ((m[j].x & valid.x) == valid.x) && ((m[j].y & valid.y) == valid.y) && ((m[j].z & valid.z) == valid.z) && ((m[j].w & valid.w) == valid.w);
         }
         uint4 *o = reinterpret_cast<uint4 *>(A.out) + ((size_t)ix * G.Y + iy) * G.Z + iz0;
 #pragma unroll
         for (int j = 0; j < FE_ZRUN; j++)
             if (iz0 + j < G.Z) o[j] = make_uint4(~m[j].x & valid.x, ~m[j].y & valid.y, ~m[j].z & valid.z, ~m[j].w & valid.w);
+    }
+}
+
+// ---- two-pass feasibility ---------------------------------------------------------------------------------------------------------
+// Most voxels of a cluttered map admit NO attitude, and most of those for one cheap reason: an occupied voxel sits on a kernel offset that
+// every attitude's kernel occupies (the core of the robot: offset mask == all attitudes). Pass 1 tests only the core rows — a few dozen
+// row reads and ANDs per run of voxels, no mask traffic — writes the all-colliding answer for the voxels it settles and appends the
+// others' runs to a list; pass 2 runs the full mask accumulation on the listed runs' open voxels alone. Same masks as the one-pass kernel, bit for bit.
+__global__ void __launch_bounds__(256) k_frontend_core(const __grid_constant__ FrontArgs A) {
+    const DevGrid &G = A.grid;
+    const int ks = A.ks, side = (ks - 1) / 2;
+    const int zruns = (G.Z + FE_ZRUN - 1) / FE_ZRUN;
+    const long long nrun = (long long)G.X * G.Y * zruns;
+    const int wbits = ks + FE_ZRUN - 1;
+    const unsigned long long wmask = (1ull << wbits) - 1ull;
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (nrun + stride - 1) / stride;
+    for (long long it = 0; it < rounds; it++) {                           // whole warps stay in the loop (the append is warp-wide)
+        const long long r = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned alive = 0u;                                              // bit j: voxel iz0 + j exists and no core offset is occupied
+        int ix = 0, iy = 0, iz0 = 0;
+        if (r < nrun) {
+            const int zr = (int)(r % zruns);
+            iy = (int)((r / zruns) % G.Y); ix = (int)(r / ((long long)zruns * G.Y));
+            iz0 = zr * FE_ZRUN;
+            alive = (iz0 + FE_ZRUN <= G.Z) ? ((1u << FE_ZRUN) - 1u) : ((1u << (G.Z - iz0)) - 1u);
+            const int z0 = iz0 - side;
+            const int w0 = (z0 >= 0) ? (z0 >> 5) : -1;
+            const int sh = z0 - 32 * w0;
+            for (int k = 0; k < A.ncore && alive; k++) {
+                const uint2 cr = __ldg(A.core_rows + k);
+                const int x = ix + (int)(cr.x & 0xffu) - side, y = iy + (int)(cr.x >> 8) - side;
+                if (x < 0 || x >= G.X || y < 0 || y >= G.Y) continue;
+                const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+                const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
+                const uint32_t hi = (sh + wbits > 32 && w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
+                const unsigned bits = (unsigned)(((((unsigned long long)hi << 32) | lo) >> sh) & wmask);
+#pragma unroll
+                for (int j = 0; j < FE_ZRUN; j++)
+                    if ((bits >> j) & cr.y) alive &= ~(1u << j);
+            }
+            const unsigned exist = (iz0 + FE_ZRUN <= G.Z) ? ((1u << FE_ZRUN) - 1u) : ((1u << (G.Z - iz0)) - 1u);
+            uint4 *o = reinterpret_cast<uint4 *>(A.out) + ((size_t)ix * G.Y + iy) * G.Z + iz0;
+#pragma unroll
+            for (int j = 0; j < FE_ZRUN; j++)
+                if (((exist & ~alive) >> j) & 1u) o[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // warp-wide append of the runs that still have an open voxel
+        const unsigned open = __ballot_sync(0xffffffffu, alive != 0u);
+        if (open == 0u) continue;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(A.surv_count, (unsigned)__popc(open));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (alive) A.surv[base + __popc(open & ((1u << lane) - 1u))] = make_uint2((unsigned)r, alive);
+    }
+}
+
+// pass 2: one thread per surviving run — the one-pass kernel's window scan, masks accumulated for the open voxels only
+__global__ void __launch_bounds__(256) k_frontend_survivors(const __grid_constant__ FrontArgs A) {
+    extern __shared__ __align__(16) uint32_t fe_sm[];
+    frontend_stage_masks(A, fe_sm);
+    const uint4 *sm4 = reinterpret_cast<const uint4 *>(fe_sm);
+    const DevGrid &G = A.grid;
+    const int ks = A.ks, side = (ks - 1) / 2;
+    const int zruns = (G.Z + FE_ZRUN - 1) / FE_ZRUN;
+    const unsigned n = *A.surv_count;
+    const uint4 valid = make_uint4(A.natt >= 32 ? 0xffffffffu : ((1u << A.natt) - 1u),
+                                   A.natt >= 64 ? 0xffffffffu : (A.natt > 32 ? ((1u << (A.natt - 32)) - 1u) : 0u),
+                                   A.natt >= 96 ? 0xffffffffu : (A.natt > 64 ? ((1u << (A.natt - 64)) - 1u) : 0u),
+                                   A.natt >= 128 ? 0xffffffffu : (A.natt > 96 ? ((1u << (A.natt - 96)) - 1u) : 0u));
+    const int wbits = ks + FE_ZRUN - 1;
+    const unsigned long long wmask = (1ull << wbits) - 1ull;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 sv = A.surv[i];
+        const unsigned r = sv.x, alive = sv.y;
+        const int zr = (int)(r % (unsigned)zruns), iy = (int)((r / (unsigned)zruns) % (unsigned)G.Y), ix = (int)(r / ((unsigned)zruns * (unsigned)G.Y));
+        const int iz0 = zr * FE_ZRUN;
+        uint4 m[FE_ZRUN];
+#pragma unroll
+        for (int j = 0; j < FE_ZRUN; j++) m[j] = ((alive >> j) & 1u) ? make_uint4(0u, 0u, 0u, 0u) : valid;   // settled voxels never hold the run back
+        const int z0 = iz0 - side;
+        const int w0 = (z0 >= 0) ? (z0 >> 5) : -1;
+        const int sh = z0 - 32 * w0;
+        for (int k = 0; k < A.nurow; k++) {
+            const uint2 ur = __ldg(A.urows + k);
+            const int a = (int)(ur.x & 0xffu), b = (int)(ur.x >> 8);
+            const int x = ix + a - side, y = iy + b - side;
+            if (x < 0 || x >= G.X || y < 0 || y >= G.Y) continue;
+            const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+            const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
+            const uint32_t hi = (sh + wbits > 32 && w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
+            unsigned span = 0u;                                  // the bits of this row that can touch an open voxel
+#pragma unroll
+            for (int j = 0; j < FE_ZRUN; j++) if ((alive >> j) & 1u) span |= ur.y << j;
+            unsigned bits = (unsigned)(((((unsigned long long)hi << 32) | lo) >> sh) & wmask) & span;
+            const uint4 *mrow = sm4 + (size_t)((a * ks + b) * ks);
+            while (bits) {
+                const int p = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+#pragma unroll
+                for (int j = 0; j < FE_ZRUN; j++) {
+                    const int c = p - j;
+                    if (c >= 0 && c < ks && ((alive >> j) & 1u)) { const uint4 t = mrow[c]; m[j].x |= t.x; m[j].y |= t.y; m[j].z |= t.z; m[j].w |= t.w; }
+                }
+            }
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(A.out) + ((size_t)ix * G.Y + iy) * G.Z + iz0;
+#pragma unroll
+        for (int j = 0; j < FE_ZRUN; j++)
+            if ((alive >> j) & 1u) o[j] = make_uint4(~m[j].x & valid.x, ~m[j].y & valid.y, ~m[j].z & valid.z, ~m[j].w & valid.w);
     }
 }
 

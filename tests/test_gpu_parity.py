@@ -636,3 +636,33 @@ def test_frontend_state_errors():
     with pytest.raises(RuntimeError):
         ev.frontend_check_batch([[0, 0, occ.shape[2]]], [[0.0, 0.0]])   # voxel outside the map
     ev.close()
+
+
+@pytest.mark.gpu
+def test_frontend_two_pass_equals_one_pass_ragged_z():
+    """the two-pass feasibility kernels (kernel core first, mask accumulation on the survivors) against the one-pass kernel and the
+    oracle, on a map whose z extent is not a multiple of the z-run length and that is dense enough for the core to settle most voxels"""
+    import os
+    cfg, _, _, _, _ = small_case(N=2, K=4, seed=3, kernel_size=7)
+    X, Y, Z = 37, 29, 27
+    occ = W.random_map(X, Y, Z, p=0.04, seed=9, slabs=1)
+    V, F = MESHES["rcone"]()
+    poly = [0.1, 0.0, -0.1, 120.0, 10.0, 0.0]
+    ev = I.Evaluator(cfg)
+    ev.set_map_u8(occ, [0, 0, 0], cfg.occupancy_resolution)
+    ev.set_shape_mesh(V, F, poly)
+    ev.frontend_build_kernels(45.0, 45.0, 9.0, 0.8)
+    two = ev.frontend_feasibility(X, Y, Z)
+    os.environ["ISDF_FE_ONE_PASS"] = "1"
+    try:
+        one = ev.frontend_feasibility(X, Y, Z)
+    finally:
+        del os.environ["ISDF_FE_ONE_PASS"]
+    assert np.array_equal(one, two)
+    fe = O.FrontEnd(O.Shape.mesh(V, F, poly), occ, ks=7, res=cfg.occupancy_resolution, front_end_safeh=0.8)
+    ix, iy, iz = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    ref = fe.feasibility(np.stack([ix, iy, iz], -1).reshape(-1, 3))
+    assert np.array_equal(two, ref)
+    settled = (two == 0).all(axis=1).mean()
+    assert 0.05 < settled < 1.0
+    ev.close()
