@@ -77,7 +77,7 @@ struct isdf_ctx {
     // front end attitude kernels (isdf_frontend.cuh)
     DevBuf<double> d_fe_rot; DevBuf<uint8_t> d_fe_kernels, d_fe_order, d_fe_ok; DevBuf<uint32_t> d_fe_masks, d_fe_out;
     DevBuf<int> d_fe_ind; DevBuf<double> d_fe_father, d_fe_child;
-    DevBuf<uint2> d_fe_core, d_fe_urows, d_fe_surv; int fe_nurow = 0; DevBuf<unsigned> d_fe_count; int fe_ncore = 0;
+    DevBuf<uint2> d_fe_core, d_fe_urows, d_fe_surv, d_fe_chunks; DevBuf<uint4> d_fe_tab; int fe_nurow = 0, fe_nchunk = 0, fe_ntab = 0; DevBuf<unsigned> d_fe_count; int fe_ncore = 0;
     bool fe_ready = false;
     int fe_xk = 0, fe_yk = 0, fe_ks = 0;
     double fe_max_roll = 0, fe_max_pitch = 0, fe_ang_res = 0, fe_margin = 0;
@@ -178,7 +178,7 @@ extern "C" int isdf_destroy(isdf_ctx *c) {
     for (int p = 0; p < PEER_MAX; p++) if (c->peer_open[p]) cudaIpcCloseMemHandle(c->peer_open[p]);
     if (c->peer_buf) cudaFree(c->peer_buf);
     c->d_peer_status.release();
-    c->d_fe_rot.release(); c->d_fe_kernels.release(); c->d_fe_order.release(); c->d_fe_ok.release(); c->d_fe_masks.release(); c->d_fe_out.release(); c->d_fe_ind.release(); c->d_fe_father.release(); c->d_fe_child.release(); c->d_fe_core.release(); c->d_fe_urows.release(); c->d_fe_surv.release(); c->d_fe_count.release();
+    c->d_fe_rot.release(); c->d_fe_kernels.release(); c->d_fe_order.release(); c->d_fe_ok.release(); c->d_fe_masks.release(); c->d_fe_out.release(); c->d_fe_ind.release(); c->d_fe_father.release(); c->d_fe_child.release(); c->d_fe_core.release(); c->d_fe_urows.release(); c->d_fe_surv.release(); c->d_fe_chunks.release(); c->d_fe_tab.release(); c->d_fe_count.release();
     c->d_mx.release(); c->d_mbc.release(); c->d_mT.release(); c->d_mC.release(); c->d_mlu.release(); c->d_men.release(); c->d_mgC.release(); c->d_mgT.release(); c->d_mcost.release(); c->d_mgrad.release(); c->d_mout.release(); c->d_mCpp.release(); c->d_msv.release();
     c->sv.release();
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1125,7 +1125,7 @@ static FrontArgs front_args(isdf_ctx *c) {
     A.res = c->cfg.occupancy_resolution; A.margin = c->fe_margin;
     A.att_rot = c->d_fe_rot.p; A.kernels = c->d_fe_kernels.p; A.offset_masks = c->d_fe_masks.p; A.order = c->d_fe_order.p;
     A.max_roll = c->fe_max_roll; A.max_pitch = c->fe_max_pitch; A.ang_res = c->fe_ang_res;
-    A.core_rows = c->d_fe_core.p; A.ncore = c->fe_ncore; A.urows = c->d_fe_urows.p; A.nurow = c->fe_nurow; A.surv = c->d_fe_surv.p; A.surv_count = c->d_fe_count.p;
+    A.core_rows = c->d_fe_core.p; A.ncore = c->fe_ncore; A.urows = c->d_fe_urows.p; A.nurow = c->fe_nurow; A.chunks = c->d_fe_chunks.p; A.nchunk = c->fe_nchunk; A.tab = c->d_fe_tab.p; A.ntab = c->fe_ntab; A.surv = c->d_fe_surv.p; A.surv_count = c->d_fe_count.p;
     return A;
 }
 
@@ -1210,6 +1210,26 @@ extern "C" int isdf_frontend_build_kernels(isdf_ctx *c, const isdf_kernel_config
             }
         c->fe_nurow = (int)urows.size();
         if (!urows.empty()) CU_TRY(c->d_fe_urows.upload(urows.data(), urows.size(), c->stream));
+        // pattern tables of the union rows, in chunks of <= FE_CHUNK_BITS offsets (pass 2 of the table-driven kernels)
+        std::vector<uint2> chunks; std::vector<uint4> tab;
+        for (const uint2 &ur : urows) {
+            const int a = (int)(ur.x & 0xffu), b = (int)(ur.x >> 8);
+            const int lo = __builtin_ctz(ur.y), hi = 31 - __builtin_clz(ur.y);
+            for (int c0 = lo; c0 <= hi; c0 += FE_CHUNK_BITS) {
+                const int len = std::min(FE_CHUNK_BITS, hi - c0 + 1);
+                if (((ur.y >> c0) & ((1u << len) - 1u)) == 0u) continue;
+                chunks.push_back(make_uint2(ur.x | ((uint32_t)c0 << 16) | ((uint32_t)len << 24), (uint32_t)tab.size()));
+                for (uint32_t pat = 0; pat < (1u << len); pat++) {
+                    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < len; i++)
+                        if ((pat >> i) & 1u) { const uint32_t *m = &om[(size_t)4 * ((a * ks + b) * ks + c0 + i)]; e.x |= m[0]; e.y |= m[1]; e.z |= m[2]; e.w |= m[3]; }
+                    tab.push_back(e);
+                }
+            }
+        }
+        c->fe_nchunk = (int)chunks.size(); c->fe_ntab = (int)tab.size();
+        if (getenv("ISDF_VERBOSE")) fprintf(stderr, "[isdf] front end: %d attitudes, kernel core %zu rows, union %zu rows, %zu chunks, %zu table entries (%.1f KB)\n", natt, rows.size(), urows.size(), chunks.size(), tab.size(), tab.size() * 16e-3);
+        if (!chunks.empty()) { CU_TRY(c->d_fe_chunks.upload(chunks.data(), chunks.size(), c->stream)); CU_TRY(c->d_fe_tab.upload(tab.data(), tab.size(), c->stream)); }
         std::stable_sort(rows.begin(), rows.end(), [](const uint2 &p, const uint2 &q) { return __builtin_popcount(p.y) > __builtin_popcount(q.y); });
         c->fe_ncore = (int)rows.size();
         if (!rows.empty()) CU_TRY(c->d_fe_core.upload(rows.data(), rows.size(), c->stream));
@@ -1255,9 +1275,22 @@ extern "C" int isdf_frontend_feasibility_device(isdf_ctx *c, uint32_t *d_masks, 
         CU_TRY(c->d_fe_count.ensure(1));
         A.surv = c->d_fe_surv.p; A.surv_count = c->d_fe_count.p;
         CU_TRY(cudaMemsetAsync(c->d_fe_count.p, 0, sizeof(unsigned), (cudaStream_t)cuda_stream));
-        CU_TRY(cudaFuncSetAttribute(k_frontend_survivors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_frontend_core<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(A);
-        k_frontend_survivors<<<148 * 16, 256, smem, (cudaStream_t)cuda_stream>>>(A);
+        const size_t tsmem = sizeof(uint4) * ((size_t)c->fe_ntab + (size_t)c->fe_nchunk);
+        if (c->fe_nchunk > 0 && tsmem <= 200 * 1024 && !getenv("ISDF_FE_NO_TABLES")) {
+            // throughput form: zero-filled output, bit-parallel core pass (32 voxels per thread), table-driven accumulation on the survivors
+            const long long nvox = (long long)c->grid.X * c->grid.Y * c->grid.Z;
+            CU_TRY(cudaMemsetAsync(d_masks, 0, sizeof(uint32_t) * 4 * (size_t)nvox, (cudaStream_t)cuda_stream));
+            const long long nword = (long long)c->grid.X * c->grid.Y * c->grid.Zw;
+            CU_TRY(cudaFuncSetAttribute(k_frontend_survivors_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            k_frontend_core_words<<<(unsigned)std::min<long long>((nword + 255) / 256, 148ll * 32), 256, 0, (cudaStream_t)cuda_stream>>>(A);
+            // 32 warps per SM hide the row reads: two CTAs of 512 threads when two tables fit into shared memory, else one of 1024
+            if (2 * (tsmem + 1024) <= 220 * 1024) k_frontend_survivors_tab<<<148 * 2, 512, tsmem, (cudaStream_t)cuda_stream>>>(A);
+            else k_frontend_survivors_tab<<<148, 1024, tsmem, (cudaStream_t)cuda_stream>>>(A);
+        } else {
+            CU_TRY(cudaFuncSetAttribute(k_frontend_survivors, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_frontend_core<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(A);
+            k_frontend_survivors<<<148 * 16, 256, smem, (cudaStream_t)cuda_stream>>>(A);
+        }
         c->stats.kernel_launches += 2;
     } else {
         k_frontend_feasibility<<<grid, 256, smem, (cudaStream_t)cuda_stream>>>(A);

@@ -37,6 +37,9 @@ struct FrontArgs {
     // two-pass feasibility: rows of the kernel CORE (offsets occupied in EVERY attitude's kernel), the survivor list and its counter
     const uint2 *core_rows;  // ncore x {a | b << 8, bits over c}
     int ncore;
+    // pattern tables (pass 2, table-driven): every union row is cut into chunks of <= FE_CHUNK_BITS offsets along c; tab[off + pattern] =
+    // OR of the offset masks of the pattern's set bits. chunks: {a | b << 8 | c0 << 16 | len << 24, off}
+    const uint2 *chunks; int nchunk; const uint4 *tab; int ntab;
     const uint2 *urows;      // nurow x {a | b << 8, bits over c}: the kernel rows ANY attitude occupies (every other offset's mask is zero)
     int nurow;
     uint2 *surv;             // runs with at least one voxel that no core offset settles: {run index, bit j = voxel j of the run is open}
@@ -288,6 +291,144 @@ __global__ void __launch_bounds__(256) k_frontend_survivors(const __grid_constan
                     const int c = p - j;
                     if (c >= 0 && c < ks && ((alive >> j) & 1u)) { const uint4 t = mrow[c]; m[j].x |= t.x; m[j].y |= t.y; m[j].z |= t.z; m[j].w |= t.w; }
                 }
+            }
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(A.out) + ((size_t)ix * G.Y + iy) * G.Z + iz0;
+#pragma unroll
+        for (int j = 0; j < FE_ZRUN; j++)
+            if ((alive >> j) & 1u) o[j] = make_uint4(~m[j].x & valid.x, ~m[j].y & valid.y, ~m[j].z & valid.z, ~m[j].w & valid.w);
+    }
+}
+
+// ---- the same two passes, restated for throughput ---------------------------------------------------------------------------------
+// Pass 1, bit-parallel along z: a thread owns one 32-voxel word of a z row and ORs, for every core offset, the occupancy row shifted by
+// that offset — two instructions settle 32 voxels against one offset. The output buffer is zero-filled beforehand (a settled voxel's
+// answer IS the zero mask), so pass 1 writes nothing but the list of runs that still have an open voxel.
+constexpr int FE_RUNS_PER_WORD = 32 / FE_ZRUN;
+static_assert(32 % FE_ZRUN == 0, "a z-run must not straddle a 32-voxel word");
+__global__ void __launch_bounds__(256) k_frontend_core_words(const __grid_constant__ FrontArgs A) {
+    const DevGrid &G = A.grid;
+    const int side = (A.ks - 1) / 2;
+    const int zruns = (G.Z + FE_ZRUN - 1) / FE_ZRUN;
+    const long long nword = (long long)G.X * G.Y * G.Zw;
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (nword + stride - 1) / stride;
+    for (long long it = 0; it < rounds; it++) {
+        const long long wi = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned open = 0u;                                               // bit z: voxel 32 zw + z exists and no core offset is occupied
+        int ix = 0, iy = 0, zw = 0;
+        if (wi < nword) {
+            zw = (int)(wi % G.Zw); iy = (int)((wi / G.Zw) % G.Y); ix = (int)(wi / ((long long)G.Zw * G.Y));
+            unsigned hit = 0u;
+            for (int k = 0; k < A.ncore; k++) {
+                const uint2 cr = __ldg(A.core_rows + k);
+                const int x = ix + (int)(cr.x & 0xffu) - side, y = iy + (int)(cr.x >> 8) - side;
+                if (x < 0 || x >= G.X || y < 0 || y >= G.Y) continue;
+                const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+                const uint32_t w0 = (zw > 0) ? __ldg(row + zw - 1) : 0u, w1 = __ldg(row + zw), w2 = (zw + 1 < G.Zw) ? __ldg(row + zw + 1) : 0u;
+                unsigned cb = cr.y;
+                while (cb) {                                              // uniform across the grid: the core is a constant
+                    const int d = (__ffs((int)cb) - 1) - side;            // offset along z: voxel z looks at z + d
+                    cb &= cb - 1;
+                    hit |= (d >= 0) ? __funnelshift_r(w1, w2, d) : __funnelshift_r(w0, w1, 32 + d);
+                }
+            }
+            const int zleft = G.Z - 32 * zw;
+            const unsigned exist = (zleft >= 32) ? 0xffffffffu : ((1u << zleft) - 1u);
+            open = ~hit & exist;
+        }
+        // runs of this word with an open voxel -> list
+        unsigned runs = 0u;                                               // bit q: run q of the word has an open voxel
+#pragma unroll
+        for (int q = 0; q < FE_RUNS_PER_WORD; q++) if ((open >> (q * FE_ZRUN)) & ((1u << FE_ZRUN) - 1u)) runs |= 1u << q;
+        const int n = __popc(runs);
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned base = 0;
+        if (lane == 31) base = atomicAdd(A.surv_count, (unsigned)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned pos = base + (unsigned)(incl - n);
+        const unsigned r0 = (unsigned)(((long long)ix * G.Y + iy) * zruns + (long long)zw * FE_RUNS_PER_WORD);
+        while (runs) {
+            const int q = __ffs((int)runs) - 1;
+            runs &= runs - 1;
+            A.surv[pos++] = make_uint2(r0 + (unsigned)q, (open >> (q * FE_ZRUN)) & ((1u << FE_ZRUN) - 1u));
+        }
+    }
+}
+
+// Pass 2, table-driven: for a chunk of <= FE_CHUNK_BITS consecutive offsets of a kernel row, the occupancy pattern under the chunk
+// indexes a table whose entry is the OR of the pattern's offset masks — one shared-memory load and four ORs per (chunk, open voxel)
+// whatever the pattern (the empty pattern reads the table's zero entry). No data-dependent loop, no branch.
+constexpr int FE_CHUNK_BITS = 8;
+__global__ void __launch_bounds__(1024) k_frontend_survivors_tab(const __grid_constant__ FrontArgs A) {
+    extern __shared__ __align__(16) uint32_t fe_sm[];
+    uint4 *tab = reinterpret_cast<uint4 *>(fe_sm);
+    // per chunk: {row offset in words relative to the window's first row, c0 | first chunk of its row << 8 | a << 16 | b << 24, pattern mask, table offset}
+    uint4 *chk = tab + A.ntab;
+    const DevGrid &G = A.grid;
+    for (int k = threadIdx.x; k < A.ntab; k += blockDim.x) tab[k] = A.tab[k];
+    for (int k = threadIdx.x; k < A.nchunk; k += blockDim.x) {
+        const uint2 c = A.chunks[k];
+        const unsigned a = c.x & 0xffu, b = (c.x >> 8) & 0xffu;
+        const unsigned first = (k == 0 || (A.chunks[k - 1].x & 0xffffu) != (c.x & 0xffffu)) ? 1u : 0u;
+        chk[k] = make_uint4((a * (unsigned)G.Y + b) * (unsigned)G.Zw, ((c.x >> 16) & 0xffu) | (first << 8) | (a << 16) | (b << 24), (1u << (c.x >> 24)) - 1u, c.y);
+    }
+    __syncthreads();
+    const int ks = A.ks, side = (ks - 1) / 2;
+    const int zruns = (G.Z + FE_ZRUN - 1) / FE_ZRUN;
+    const unsigned n = *A.surv_count;
+    const uint4 valid = make_uint4(A.natt >= 32 ? 0xffffffffu : ((1u << A.natt) - 1u),
+                                   A.natt >= 64 ? 0xffffffffu : (A.natt > 32 ? ((1u << (A.natt - 32)) - 1u) : 0u),
+                                   A.natt >= 96 ? 0xffffffffu : (A.natt > 64 ? ((1u << (A.natt - 64)) - 1u) : 0u),
+                                   A.natt >= 128 ? 0xffffffffu : (A.natt > 96 ? ((1u << (A.natt - 96)) - 1u) : 0u));
+    const int wbits = ks + FE_ZRUN - 1;
+    const unsigned wmask = (wbits >= 32) ? 0xffffffffu : ((1u << wbits) - 1u);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 sv = A.surv[i];
+        const unsigned r = sv.x, alive = sv.y;
+        const int zr = (int)(r % (unsigned)zruns), iy = (int)((r / (unsigned)zruns) % (unsigned)G.Y), ix = (int)(r / ((unsigned)zruns * (unsigned)G.Y));
+        const int iz0 = zr * FE_ZRUN;
+        uint4 m[FE_ZRUN];
+        unsigned am[FE_ZRUN];                                             // all ones for an open voxel: a settled voxel always reads entry 0
+#pragma unroll
+        for (int j = 0; j < FE_ZRUN; j++) { m[j] = make_uint4(0u, 0u, 0u, 0u); am[j] = 0u - ((alive >> j) & 1u); }
+        const int z0 = iz0 - side;
+        const int w0 = (z0 >= 0) ? (z0 >> 5) : -1;
+        const int sh = z0 - 32 * w0;
+        // interior runs (the whole window inside the map, both words of every row present): no bounds test per row
+        const bool interior = ix >= side && ix + side < G.X && iy >= side && iy + side < G.Y && w0 >= 0 && w0 + 1 < G.Zw;
+        const uint32_t *base = G.bits + ((long long)(ix - side) * G.Y + (long long)(iy - side)) * G.Zw + w0;   // dereferenced only when interior
+        asm volatile("" : "+l"(base));                                    // keep the pointer in registers: do not recompute it per row
+        unsigned bits = 0u;
+        for (int k = 0; k < A.nchunk; k++) {
+            const uint4 ck = chk[k];
+            if (ck.y & 0x100u) {                                          // first chunk of a kernel row: read the row's window
+                if (interior) {
+                    const uint32_t *rp = base + ck.x;
+                    bits = __funnelshift_r(__ldg(rp), __ldg(rp + 1), sh) & wmask;
+                } else {
+                    const int x = ix + (int)((ck.y >> 16) & 0xffu) - side, y = iy + (int)(ck.y >> 24) - side;
+                    bits = 0u;
+                    if (x >= 0 && x < G.X && y >= 0 && y < G.Y) {
+                        const uint32_t *row = G.bits + ((size_t)x * G.Y + y) * G.Zw;
+                        const uint32_t lo = (w0 >= 0 && w0 < G.Zw) ? __ldg(row + w0) : 0u;
+                        const uint32_t hi = (w0 + 1 >= 0 && w0 + 1 < G.Zw) ? __ldg(row + w0 + 1) : 0u;
+                        bits = (unsigned)((((unsigned long long)hi << 32) | lo) >> sh) & wmask;
+                    }
+                }
+            }
+            const unsigned bc = bits >> (ck.y & 0xffu);
+            const uint4 *t = tab + ck.w;
+            // no branch: pattern 0 (and every pattern of a settled voxel) reads entry 0, the zero mask
+#pragma unroll
+            for (int j = 0; j < FE_ZRUN; j++) {
+                const uint4 v = t[(bc >> j) & ck.z & am[j]];
+                m[j].x |= v.x; m[j].y |= v.y; m[j].z |= v.z; m[j].w |= v.w;
             }
         }
         uint4 *o = reinterpret_cast<uint4 *>(A.out) + ((size_t)ix * G.Y + iy) * G.Z + iz0;

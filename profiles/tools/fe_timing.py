@@ -11,7 +11,8 @@ dev = torch.device("cuda", 0)
 ev = I.Evaluator(cfg, device=0)
 ev.set_map_u8(occ, [0, 0, 0], 1.0)
 ev.set_shape_mesh(V, F, w["poly_params"])
-for mode in ("two-pass", "one-pass"):
+for mode in ("tables", "two-pass", "one-pass"):
+    if mode == "two-pass": os.environ["ISDF_FE_NO_TABLES"] = "1"
     if mode == "one-pass": os.environ["ISDF_FE_ONE_PASS"] = "1"
     r = B.frontend_bench(ev, w, occ, V, F, dev, False)
     print(mode, json.dumps({k: r[k] for k in ("ms", "voxels_per_s", "voxels_with_a_fitting_attitude")}), "frac", r["roofline"]["frac"], flush=True)

@@ -644,7 +644,7 @@ def test_frontend_two_pass_equals_one_pass_ragged_z():
     oracle, on a map whose z extent is not a multiple of the z-run length and that is dense enough for the core to settle most voxels"""
     import os
     cfg, _, _, _, _ = small_case(N=2, K=4, seed=3, kernel_size=7)
-    X, Y, Z = 37, 29, 27
+    X, Y, Z = 37, 29, 43                                   # z: one full 32-voxel word + a ragged one, not a multiple of the run length
     occ = W.random_map(X, Y, Z, p=0.04, seed=9, slabs=1)
     V, F = MESHES["rcone"]()
     poly = [0.1, 0.0, -0.1, 120.0, 10.0, 0.0]
@@ -652,13 +652,18 @@ def test_frontend_two_pass_equals_one_pass_ragged_z():
     ev.set_map_u8(occ, [0, 0, 0], cfg.occupancy_resolution)
     ev.set_shape_mesh(V, F, poly)
     ev.frontend_build_kernels(45.0, 45.0, 9.0, 0.8)
-    two = ev.frontend_feasibility(X, Y, Z)
+    two = ev.frontend_feasibility(X, Y, Z)                 # zero fill + bit-parallel core pass + table-driven accumulation
+    os.environ["ISDF_FE_NO_TABLES"] = "1"
+    try:
+        two_b = ev.frontend_feasibility(X, Y, Z)           # core pass per z-run + offset-mask accumulation
+    finally:
+        del os.environ["ISDF_FE_NO_TABLES"]
     os.environ["ISDF_FE_ONE_PASS"] = "1"
     try:
         one = ev.frontend_feasibility(X, Y, Z)
     finally:
         del os.environ["ISDF_FE_ONE_PASS"]
-    assert np.array_equal(one, two)
+    assert np.array_equal(one, two) and np.array_equal(one, two_b)
     fe = O.FrontEnd(O.Shape.mesh(V, F, poly), occ, ks=7, res=cfg.occupancy_resolution, front_end_safeh=0.8)
     ix, iy, iz = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
     ref = fe.feasibility(np.stack([ix, iy, iz], -1).reshape(-1, 3))
