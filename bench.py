@@ -910,7 +910,7 @@ def run_swept(args):
     launches = ev.stats().kernel_launches - l0
     e2e = []
     for it in range(n_warm + args.steps):
-        Ck = iters[n_warm + args.steps + it]
+        Ck = iters[it]                                      # the iterates of the device-timed loop, in the same order
         flush.zero_()
         torch.cuda.synchronize(); barrier()
         t0 = time.perf_counter()
