@@ -217,16 +217,16 @@ __device__ __forceinline__ d3 sv_body_point(const SvArgs &A, const TrajView &tr,
 // Exact mesh SDF for the lanes flagged in `need` (each with its own body-frame point): one warp-cooperative search per
 // flagged lane, in lane order. A lane-per-query search costs ~10x more here because the interesting queries sit 1-2 m from
 // the mesh, where a closest-triangle search prunes badly and 32 private traversals diverge.
-__device__ __forceinline__ double mesh_sdf_each(const DevMesh &M, bool need, d3 prel, double reach, double dflt, int lane, WideStack *stk) {
+__device__ __forceinline__ double mesh_sdf_each(const DevMesh &M, bool need, d3 prel, double reach, double dflt, int lane, WideStack *stk, d3 *gout = nullptr) {
     unsigned todo = __ballot_sync(0xffffffffu, need);
     double out = dflt;
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
         const d3 q = mk3(__shfl_sync(0xffffffffu, prel.x, src), __shfl_sync(0xffffffffu, prel.y, src), __shfl_sync(0xffffffffu, prel.z, src));
-        d3 g;
+        d3 g = mk3(0, 0, 0);
         const double v = mesh_sdf_grad_warp_lat(M, q, reach, g, lane, stk);
-        if (lane == src) out = v;
+        if (lane == src) { out = v; if (gout) *gout = g; }
     }
     return out;
 }
@@ -536,6 +536,7 @@ struct SvmShared {
     int red_i[SVM_WARPS];
     double cand_f[9], cand_x[9], cand_g[9][3], cand_q[9][3];
     double bc[4];
+    double bestg[SVM_WARPS][32][6];      // fine scan: gradient and body-frame point of every lane's best sample (the descent starts there)
 #ifdef ISDF_PHASE_TIMING
     unsigned dbg_rounds, dbg_exact, dbg_requery;   // descent candidate batches; fine-scan samples that needed an exact search; descent re-queries at x
     long long dbg_t[4];               // descent, warp 0: pose at x, re-query at x, candidate (pose + query), wait + replay
@@ -546,16 +547,19 @@ __device__ __forceinline__ bool same_bits(d3 a, d3 b) { return a.x == b.x && a.y
 
 // gradientDescent (swm:1000-1062) for one point, executed by the whole CTA. Returns sdf(x), x and the unit gradient g at the
 // body-frame point q of the final x.
+// have0: (f0, g0) are the mesh SDF and its gradient at the body-frame point q0, already computed by the fine scan at its best sample — if
+// that sample is the seed x0 (its body-frame point has the same bits), the descent's first search is that one and is not repeated.
 __device__ __forceinline__ void svm_descent(const SvArgs &A, const TrajView &tr, d3 p, double t_min, double t_max, double x0, SvmShared &S,
-                                            double &fx, double &x, d3 &g, d3 &gq, unsigned &nevals, int lane, int warp) {
+                                            double &fx, double &x, d3 &g, d3 &gq, unsigned &nevals, int lane, int warp,
+                                            bool have0, double f0, d3 g0, d3 q0) {
     const DevMesh &M = A.shape.mesh;
     WideStack *stk = &S.stk[warp];
     const double alpha = 0.02, tol = 1e-5;
-    int iter = 0; bool stop = false, have = false;
+    int iter = 0; bool stop = false, have = have0;
     double prev_x = 10000000.0;
     x = x0;
-    g = mk3(0, 0, 0); gq = mk3(0, 0, 0);
-    double fval = 0.0;
+    g = have0 ? g0 : mk3(0, 0, 0); gq = have0 ? q0 : mk3(0, 0, 0);
+    double fval = have0 ? f0 : 0.0;
 #ifdef ISDF_PHASE_TIMING
     long long dt_mark = clock64();
 #define DT_ADD(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); S.dbg_t[i] += n_ - dt_mark; dt_mark = n_; } } while (0)
@@ -775,6 +779,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                 }
                 PT_ADD(pt_p1);
                 PT_MARK();
+                bool seed_have = false; double seed_f = 0.0; d3 seed_g = mk3(0, 0, 0), seed_q = mk3(0, 0, 0);
                 {
                     double t = lb;
                     for (int q = 0; q < first; q++) t += 0.02;
@@ -795,7 +800,9 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
 #ifdef ISDF_PHASE_TIMING
                             if (need) atomicAdd(&S.dbg_exact, 1u);
 #endif
-                            dis = mesh_sdf_each(M, need, prel, inf, 1e300, lane, stk);
+                            d3 gl = mk3(0, 0, 0);
+                            dis = mesh_sdf_each(M, need, prel, inf, 1e300, lane, stk, &gl);
+                            if (dis < bd) { double *bg = S.bestg[warp][lane]; bg[0] = gl.x; bg[1] = gl.y; bg[2] = gl.z; bg[3] = prel.x; bg[4] = prel.y; bg[5] = prel.z; }
                         } else if (valid) dis = sv_sdf_at(A, tr, p, t);
                         nevals += __popc(__ballot_sync(0xffffffffu, valid));
                         if (dis < bd) { bd = dis; bi = mi; bt = t; }      // own samples come in increasing index order
@@ -817,6 +824,10 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                         const double od = S.red_d[w]; const int oi = S.red_i[w];
                         if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = S.red_t[w]; }
                     }
+                    if (MESH && bd < range_mindis && bd < inf && bi != 0x7fffffff) {   // the seed is this scan's best sample: its search result starts the descent
+                        const double *bg = S.bestg[bi % SVM_WARPS][(bi % SVM_THREADS) / SVM_WARPS];
+                        seed_have = true; seed_f = bd; seed_g = mk3(bg[0], bg[1], bg[2]); seed_q = mk3(bg[3], bg[4], bg[5]);
+                    }
                     __syncthreads();
                     if (bd < range_mindis) { range_mindis = bd; range_time_seed = bt; }
                 }
@@ -826,7 +837,7 @@ __device__ __forceinline__ void sv_points_cta_body(const SvArgs &A, const int bx
                 const double tmin_ = fmax(0.0, lb), tmax_ = fmin(ub, dur);
                 double sdf_star = 1e1, t_star = 0;
                 d3 g_s = mk3(0, 0, 0), q_s = mk3(1e300, 1e300, 1e300);
-                if (MESH) svm_descent(A, tr, p, tmin_, tmax_, range_time_seed, S, sdf_star, t_star, g_s, q_s, nevals, lane, warp);
+                if (MESH) svm_descent(A, tr, p, tmin_, tmax_, range_time_seed, S, sdf_star, t_star, g_s, q_s, nevals, lane, warp, seed_have, seed_f, seed_g, seed_q);
                 else {
                     if (warp == 0) {
                         sv_gradient_descent(A, tr, p, tmin_, tmax_, range_time_seed, sdf_star, t_star, nevals, lane);
