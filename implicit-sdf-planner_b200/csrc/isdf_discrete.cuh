@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(DISC_THREADS, ANALYTIC_MIN_BLOCKS) k_discrete_
 
 // ============================================================================================================================
 // mesh shapes
-struct QRes { double ex, ey, ez, d2; int tri, feat; uint32_t code; int cls; };   // an answered voxel awaiting its deferred tail
+struct QRes { double ex, ey, ez; int tri; uint32_t code; int fc; };   // an answered voxel awaiting its deferred tail: e = p - closest point, triangle, voxel code, feature | class << 8 (40 bytes: with the float bounds of WideStack the kernel's shared memory fits the 132 KB carve-out at 4 CTAs/SM, i.e. 124 KB of L1 instead of 92)
 struct Survivor { double px, py, pz; uint32_t off, cnt, seed, code; };   // a voxel that passed the exact culls: body-frame point, its cell's list (cnt bit 31: cell centre inside), seed triangle (0xffffffff: none)
 struct MeshWarpSmem {
     double pose[16];                     // warp-uniform pose: pos 0..2, R rows 3..11, q (w, x, y, z) 12..15
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                     d3 g = mk3(0, 0, 0);
                     const double *ps = sm.pose;
                     const d3 d = voxel_centre(G, W.ix0 + (int)(r.code & 0x3ffu), W.iy0 + (int)((r.code >> 10) & 0x3ffu), W.iz0 + (int)(r.code >> 20)) - smem_pos(ps);
-                    const double sdf = mesh_finish_t<WINDING>(Mh, rot_applyT(smem_rot(ps), d), mk3(r.ex, r.ey, r.ez), r.d2, r.tri, r.feat, g);
+                    const double sdf = mesh_finish_t<WINDING>(Mh, rot_applyT(smem_rot(ps), d), mk3(r.ex, r.ey, r.ez), r.ex * r.ex + r.ey * r.ey + r.ez * r.ez, r.tri, r.fc & 0xff, g);
                     quat4 q; q.w = ps[12]; q.x = ps[13]; q.y = ps[14]; q.z = ps[15];
                     PairAcc one = {0, 0, 0, 0, 0, 0, 0, 0};
                     pair_accumulate(cfg, smem_rot(ps), q, d, sdf, g, one);
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                     while (act) {
                         const int k = __ffs(act) - 1;
                         act &= act - 1;
-                        sm.cacc[sm.qr[k].cls][lane] += sm.vals[k][lane];
+                        sm.cacc[sm.qr[k].fc >> 8][lane] += sm.vals[k][lane];
                     }
                 }
                 __syncwarp();
@@ -650,8 +650,8 @@ __global__ void __launch_bounds__(DISC_THREADS, MESH_MIN_BLOCKS) k_discrete_mesh
                         if (mesh_search_rec(Mh, p, sf, lane, &sm.stk, (int)(cnt_in & 0x7fffffffu), v.off, ids0, (int)v.seed, (cnt_in >> 31) != 0u, d2, c, tri, feat)) {
                             if (lane == 0) {
                                 QRes r;
-                                r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.d2 = d2; r.tri = tri; r.feat = feat; r.code = qcode;
-                                r.cls = (int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu) + 5u * (qcode >> 20)) % ROW_CLASSES);   // (r + 5 dz) % 32
+                                r.ex = p.x - c.x; r.ey = p.y - c.y; r.ez = p.z - c.z; r.tri = tri; r.code = qcode;
+                                r.fc = feat | ((int)(((qcode & 0x3ffu) * (uint32_t)ny + ((qcode >> 10) & 0x3ffu) + 5u * (qcode >> 20)) % ROW_CLASSES) << 8);   // class = (r + 5 dz) % 32
                                 sm.qr[nres] = r;
                             }
                             nres++;

@@ -14,6 +14,14 @@
 namespace isdf {
 
 cudaError_t discrete_launch_scan(const DiscArgs &A, bool mesh, unsigned grid, cudaStream_t st) {
+#ifdef ISDF_CARVEOUT
+    static bool carved = false;   // A/B: ask for the smallest shared-memory carve-out that still holds 4 CTAs/SM (132 KB -> 124 KB of L1)
+    if (!carved) {
+        carved = true;
+        cudaFuncSetAttribute(k_discrete_mesh<false>, cudaFuncAttributePreferredSharedMemoryCarveout, ISDF_CARVEOUT);
+        cudaFuncSetAttribute(k_discrete_mesh<true>, cudaFuncAttributePreferredSharedMemoryCarveout, ISDF_CARVEOUT);
+    }
+#endif
     if (mesh && A.shape.mesh.sign_mode == MESH_SIGN_WINDING) k_discrete_mesh<true><<<grid, DISC_THREADS, 0, st>>>(A);
     else if (mesh) k_discrete_mesh<false><<<grid, DISC_THREADS, 0, st>>>(A);
     else k_discrete_analytic<<<grid, DISC_THREADS, 0, st>>>(A);

@@ -340,7 +340,8 @@ __host__ __device__ inline double mesh_sdf_grad(const DevMesh &M, d3 p, double r
 // 32 at a time (8 leaves x 4 slots), the winner is found with a butterfly arg-min. All lanes return identical results.
 // `stk` is a per-warp shared-memory scratch of WIDE_STACK (node, d2) pairs.
 constexpr int WIDE_STACK = 96;
-struct WideStack { int node[WIDE_STACK]; double d2[WIDE_STACK]; int leaf[32]; double leaf_d2[32]; };
+// the stacked bounds are floats ROUNDED DOWN: still lower bounds, so pruning stays exact (a node is at worst opened needlessly)
+struct WideStack { int node[WIDE_STACK]; float d2[WIDE_STACK]; int leaf[32]; float leaf_d2[32]; };
 
 __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bound2, int seed, d3 &cbest, int &tri, int &feat,
                                                int lane, WideStack *stk) {
@@ -379,12 +380,12 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
             const bool is_leaf = alive && ch < 0;
             const unsigned leafmask = __ballot_sync(0xffffffffu, is_leaf);
             const int nleaf = __popc(leafmask);
-            if (is_leaf) { const int r = __popc(leafmask & lt_mask); stk->leaf[r] = ch; stk->leaf_d2[r] = d2; }
+            if (is_leaf) { const int r = __popc(leafmask & lt_mask); stk->leaf[r] = ch; stk->leaf_d2[r] = __double2float_rd(d2); }
             __syncwarp();
             for (int base = 0; base < nleaf; base += 8) {
                 const int idx = base + (lane >> 2), slot = lane & 3;
                 double dd = 1e300; d3 q = mk3(0, 0, 0); int f = 0, t = -1;
-                if (idx < nleaf && stk->leaf_d2[idx] < best) {
+                if (idx < nleaf && (double)stk->leaf_d2[idx] < best) {
                     const int code = ~stk->leaf[idx];
                     const int first = code >> 3, cnt = (code & 7) + 1;
                     for (int k = slot; k < cnt; k += 4) {   // leaves of up to 8 triangles: slots take triangle k and k+4
@@ -425,7 +426,7 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
                 const int sl = (int)(kmax & 31u);
                 const int snode = __shfl_sync(0xffffffffu, ch, sl);
                 const double sd2 = __shfl_sync(0xffffffffu, d2, sl);
-                if (lane == 0 && sp < WIDE_STACK) { stk->node[sp] = snode; stk->d2[sp] = sd2; }
+                if (lane == 0 && sp < WIDE_STACK) { stk->node[sp] = snode; stk->d2[sp] = __double2float_rd(sd2); }
                 sp = min(sp + 1, WIDE_STACK);
                 imask &= ~(1u << sl);
             }
@@ -433,7 +434,7 @@ __device__ __forceinline__ double wide_closest(const DevMesh &M, d3 p, double bo
         }
         if (sp == 0) return best;
         --sp;
-        cur = stk->node[sp]; cur_d2 = stk->d2[sp];
+        cur = stk->node[sp]; cur_d2 = (double)stk->d2[sp];
         __syncwarp();
     }
 }
