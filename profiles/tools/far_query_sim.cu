@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <random>
 #include <algorithm>
+#include <functional>
+#include <array>
 using namespace isdf;
 
 static double obb_dist2(const double *o, d3 p) {
@@ -18,6 +20,48 @@ static double obb_dist2(const double *o, d3 p) {
     return e0 * e0 + e1 * e1 + e2 * e2;
 }
 struct Count { long nodes = 0, passes = 0, tris = 0, leaves = 0; };
+
+// oriented box of a set of triangles, same recipe as the leaves' (isdf_host_mesh.cuh): axis 0 = area-weighted mean normal
+static void make_obb(const HostMesh &hm, const std::vector<int> &tris, double *o) {
+    double n[3] = {0, 0, 0};
+    std::vector<std::array<double, 3>> pts;
+    for (int t : tris) {
+        const double *T = &hm.tris[(size_t)TRI_STRIDE * t];
+        pts.push_back({T[0], T[1], T[2]}); pts.push_back({T[0] + T[3], T[1] + T[4], T[2] + T[5]}); pts.push_back({T[0] + T[6], T[1] + T[7], T[2] + T[8]});
+        n[0] += T[4] * T[8] - T[5] * T[7]; n[1] += T[5] * T[6] - T[3] * T[8]; n[2] += T[3] * T[7] - T[4] * T[6];
+    }
+    double ax[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    const double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (nl > 1e-12) {
+        for (int a = 0; a < 3; a++) n[a] /= nl;
+        // in-plane axis: direction of largest spread of the points projected into the plane (power iteration on the 2x2-in-3D covariance)
+        double c[3] = {0, 0, 0};
+        for (auto &q : pts) for (int a = 0; a < 3; a++) c[a] += q[a] / pts.size();
+        double u[3] = {n[1], -n[0], 0};
+        if (fabs(u[0]) + fabs(u[1]) < 1e-9) { u[0] = 1; u[1] = 0; u[2] = 0; }
+        for (int it = 0; it < 30; it++) {
+            double v[3] = {0, 0, 0};
+            for (auto &q : pts) {
+                double d[3] = {q[0] - c[0], q[1] - c[1], q[2] - c[2]};
+                const double dn = d[0] * n[0] + d[1] * n[1] + d[2] * n[2];
+                for (int a = 0; a < 3; a++) d[a] -= dn * n[a];
+                const double s = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+                for (int a = 0; a < 3; a++) v[a] += s * d[a];
+            }
+            const double vl = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            if (vl < 1e-300) break;
+            for (int a = 0; a < 3; a++) u[a] = v[a] / vl;
+        }
+        const double w[3] = {n[1] * u[2] - n[2] * u[1], n[2] * u[0] - n[0] * u[2], n[0] * u[1] - n[1] * u[0]};
+        for (int a = 0; a < 3; a++) { ax[0][a] = n[a]; ax[1][a] = u[a]; ax[2][a] = w[a]; }
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (auto &q : pts) for (int k = 0; k < 3; k++) { const double pr = q[0] * ax[k][0] + q[1] * ax[k][1] + q[2] * ax[k][2]; lo[k] = std::min(lo[k], pr); hi[k] = std::max(hi[k], pr); }
+    for (int a = 0; a < 3; a++) { o[a] = 0; for (int k = 0; k < 3; k++) o[a] += 0.5 * (lo[k] + hi[k]) * ax[k][a]; }
+    for (int k = 0; k < 3; k++) { for (int a = 0; a < 3; a++) o[3 + 3 * k + a] = ax[k][a]; o[12 + k] = 0.5 * (hi[k] - lo[k]) + 1e-9; }
+}
+static std::vector<double> g_node_obb;   // 15 per wide node (index = wide node id), built in main
+static bool g_use_node_obb = false;
 
 static double tri_d2(const HostMesh &hm, d3 p, int t) {
     const double *T = &hm.tris[(size_t)TRI_STRIDE * t];
@@ -43,6 +87,7 @@ static double sim(const HostMesh &hm, d3 p, int seed, bool sort_leaves, Count &C
                 d2[k] = ex * ex + ey * ey + ez * ez;
                 alive[k] = ch != WIDE_EMPTY && d2[k] < best;
                 if (alive[k] && ch < 0) { d2[k] = fmax(d2[k], obb_dist2(&hm.leaf_obb[(size_t)15 * ((~ch) >> 3)], p)); alive[k] = d2[k] < best; }
+                if (g_use_node_obb && alive[k] && ch >= 0 && ch != WIDE_EMPTY) { d2[k] = fmax(d2[k], obb_dist2(&g_node_obb[(size_t)15 * ch], p)); alive[k] = d2[k] < best; }
                 if (alive[k] && ch < 0) leaves.push_back({d2[k], ch});
             }
             if (sort_leaves) std::sort(leaves.begin(), leaves.end());
@@ -83,6 +128,19 @@ int main(int argc, char **argv) {
     if (!build_host_mesh(V.data(), nV, F.data(), nF, poly, 0.866, hm, err)) { printf("build failed: %s\n", err.c_str()); return 1; }
     const DevMesh M = hm.view();
     printf("tris %d wide nodes %zu  bbox [%.2f %.2f %.2f]..[%.2f %.2f %.2f] gpad %.3f gcell %.3f\n", hm.ntris, hm.wnodes.size(), M.blo[0], M.blo[1], M.blo[2], M.bhi[0], M.bhi[1], M.bhi[2], M.gpad, M.gcell);
+    // oriented boxes of the internal nodes
+    g_node_obb.assign((size_t)15 * hm.wnodes.size(), 0.0);
+    {
+        std::function<void(int, std::vector<int> &)> collect = [&](int nd, std::vector<int> &out) {
+            for (int k = 0; k < 32; k++) {
+                const int ch = hm.wnodes[nd].child[k];
+                if (ch == WIDE_EMPTY) continue;
+                if (ch < 0) { const int code = ~ch, first = code >> 3, cnt = (code & 7) + 1; for (int t = first; t < first + cnt; t++) out.push_back(t); }
+                else collect(ch, out);
+            }
+        };
+        for (size_t nd = 0; nd < hm.wnodes.size(); nd++) { std::vector<int> tr; collect((int)nd, tr); make_obb(hm, tr, &g_node_obb[15 * nd]); }
+    }
     std::mt19937_64 rng(5);
     std::uniform_real_distribution<double> U(-1.0, 1.0);
     for (double dist : {0.3, 0.9, 1.4, 1.9}) {
@@ -99,13 +157,14 @@ int main(int argc, char **argv) {
             const d3 pn = p + mk3(0.012, -0.009, 0.011);   // the neighbouring query (~2 cm away)
             int tn; sim(hm, pn, -1, false, tmp, tn);
             int t1, t2, t3, t4;
-            const double r0 = sim(hm, p, -1, false, a, t1), r1 = sim(hm, p, tn, false, b, t2), r2 = sim(hm, p, tn, true, c, t3), r3 = sim(hm, p, -1, true, d_, t4);
+            const double r0 = sim(hm, p, -1, false, a, t1), r1 = sim(hm, p, tn, false, b, t2), r3 = sim(hm, p, -1, true, d_, t4);
+            g_use_node_obb = true; const double r2 = sim(hm, p, tn, false, c, t3); g_use_node_obb = false;
             if (r0 != r1 || r0 != r2 || r0 != r3) { printf("MISMATCH\n"); return 1; }
             n++;
         }
         auto pr = [&](const char *nm, const Count &C) { printf("  %-28s nodes %.2f  leaf passes %.2f  alive leaves %.1f  triangle tests %.1f\n", nm, C.nodes / (double)n, C.passes / (double)n, C.leaves / (double)n, C.tris / (double)n); };
         printf("distance %.1f m:\n", dist);
-        pr("no seed", a); pr("no seed, leaves sorted", d_); pr("seed = neighbour's triangle", b); pr("seed + leaves sorted", c);
+        pr("no seed", a); pr("no seed, leaves sorted", d_); pr("seed = neighbour's triangle", b); pr("seed + internal-node OBBs", c);
     }
     return 0;
 }
