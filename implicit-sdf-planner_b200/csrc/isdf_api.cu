@@ -54,6 +54,7 @@ struct isdf_ctx {
     DevBuf<BvhNode> d_nodes; DevBuf<WideNode> d_wnodes; DevBuf<double> d_tris, d_pn, d_obb; DevBuf<float> d_cell_dist; DevBuf<uint32_t> d_cell_seed, d_cell_off, d_cand; DevBuf<uint16_t> d_cell_cnt; DevBuf<uint4> d_cell_rec; DevBuf<WnNode> d_wn;
     // evaluation scratch
     DevBuf<double> d_T, d_C, d_out, d_piece_cost;
+    double *count_out_dev = nullptr;   // host entry points: where the epilogue drops the pair count (behind the result vector)
     DevBuf<int> d_tickets;       // pieces_done counter of the epilogue kernel
     DevBuf<double> d_tot; DevBuf<unsigned> d_split_done;   // per-sample collision sums handed from the scan kernels to the epilogue
     DevBuf<int> d_items, d_item_count; DevBuf<unsigned> d_work, d_split_work; DevBuf<double> d_subsum;   // work items (longest first, heavy samples split)
@@ -682,7 +683,7 @@ static int launch_discrete(isdf_ctx *c, int N, const double *d_T, const double *
     DiscArgs A;
     A.cfg = c->dcfg; A.grid = c->grid; A.shape = c->shape; A.N = N; A.T = d_T; A.C = d_C;
     A.tot = c->d_tot.p; A.pieces_done = c->d_tickets.p; A.item_cursor = c->d_tickets.p + 1;
-    A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p;
+    A.piece_cost = c->d_piece_cost.p; A.out = d_out; A.pair_counter = c->d_counter.p; A.count_out = c->count_out_dev;
     A.rank = c->rank; A.world = c->world;
     A.peer = PeerArgs{};
     const bool fused = c->peer_fused && c->peer.world > 1 && c->world > 1;   // an unsharded call (isdf_set_shard(ctx, 0, 1)) stays local
@@ -772,21 +773,23 @@ extern "C" int isdf_eval_discrete(isdf_ctx *c, int N, const double *T, const dou
     auto body = [&]() -> int {
         if (set_device(c)) return ISDF_ERR_CUDA;
         const size_t nin = (size_t)19 * N, nout = (size_t)19 * N + 1;
-        if (ensure_stage(c, nin + nout)) return ISDF_ERR_CUDA;
-        CU_TRY(c->d_T.ensure(N)); CU_TRY(c->d_C.ensure((size_t)18 * N)); CU_TRY(c->d_out.ensure(nout));
-        std::memcpy(c->h_stage, T, sizeof(double) * N);
-        std::memcpy(c->h_stage + N, coeffs, sizeof(double) * 18 * N);
-        CU_TRY(cudaMemcpyAsync(c->d_T.p, c->h_stage, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage + N, sizeof(double) * 18 * N, cudaMemcpyHostToDevice, c->stream));
+        // one pinned staging block, ONE copy each way: [coefficients 18N | durations N] in, [cost | gradC | gradT | pair count] out
+        if (ensure_stage(c, nin + nout + 1)) return ISDF_ERR_CUDA;
+        CU_TRY(c->d_C.ensure(nin)); CU_TRY(c->d_out.ensure(nout + 1));
+        std::memcpy(c->h_stage, coeffs, sizeof(double) * 18 * N);
+        std::memcpy(c->h_stage + 18 * (size_t)N, T, sizeof(double) * N);
+        CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage, sizeof(double) * nin, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaEventRecord(c->ev0, c->stream));
-        int rr = launch_discrete(c, N, c->d_T.p, c->d_C.p, c->d_out.p, c->stream);
+        c->count_out_dev = c->d_out.p + nout;
+        int rr = launch_discrete(c, N, c->d_C.p + 18 * (size_t)N, c->d_C.p, c->d_out.p, c->stream);
+        c->count_out_dev = nullptr;
         if (rr) return rr;
         CU_TRY(cudaEventRecord(c->ev1, c->stream));
         double *h_out = c->h_stage + nin;
-        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
-        unsigned long long pairs = 0;
-        CU_TRY(cudaMemcpyAsync(&pairs, c->d_counter.p, sizeof(pairs), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * (nout + 1), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
+        unsigned long long pairs = 0;
+        std::memcpy(&pairs, h_out + nout, sizeof(pairs));
         if (c->peer_fused && c->peer.world > 1 && c->world > 1 && isdf_peer_status(c) != ISDF_OK) return ISDF_ERR_CUDA;   // exchange timed out: the vector is NaN
         float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->stats.last_kernel_ms = ms; c->stats.last_pairs = (int64_t)pairs;
@@ -1406,26 +1409,27 @@ static int eval_swept_host(isdf_ctx *c, int N, const double *T, const double *co
     auto body = [&]() -> int {
         if (set_device(c)) return ISDF_ERR_CUDA;
         const size_t nin = (size_t)19 * N, nout = (size_t)19 * N + 1;
-        if (ensure_stage(c, nin + nout)) return ISDF_ERR_CUDA;
-        CU_TRY(c->d_T.ensure(N)); CU_TRY(c->d_C.ensure((size_t)18 * N)); CU_TRY(c->d_out.ensure(nout));
-        std::memcpy(c->h_stage, T, sizeof(double) * N);
-        std::memcpy(c->h_stage + N, coeffs, sizeof(double) * 18 * N);
-        CU_TRY(cudaMemcpyAsync(c->d_T.p, c->h_stage, sizeof(double) * N, cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage + N, sizeof(double) * 18 * N, cudaMemcpyHostToDevice, c->stream));
+        if (ensure_stage(c, nin + nout + 1)) return ISDF_ERR_CUDA;
+        CU_TRY(c->d_C.ensure(nin)); CU_TRY(c->d_out.ensure(nout + 1));
+        std::memcpy(c->h_stage, coeffs, sizeof(double) * 18 * N);
+        std::memcpy(c->h_stage + 18 * (size_t)N, T, sizeof(double) * N);
+        CU_TRY(cudaMemcpyAsync(c->d_C.p, c->h_stage, sizeof(double) * nin, cudaMemcpyHostToDevice, c->stream));
         ScopedDevBuf<double> dgt, dgs, dgg;
         if (g_t) {
             CU_TRY(dgt.upload(g_t, c->sv.P, c->stream)); CU_TRY(dgs.upload(g_s, c->sv.P, c->stream));
             CU_TRY(dgg.upload(g_g, (size_t)3 * c->sv.P, c->stream));
         }
         CU_TRY(cudaEventRecord(c->ev0, c->stream));
-        int rr = swept_common(c, N, c->d_T.p, c->d_C.p, c->d_out.p, c->stream, dgt.p, dgs.p, dgg.p);
+        c->sv.count_out = c->d_out.p + nout;
+        int rr = swept_common(c, N, c->d_C.p + 18 * (size_t)N, c->d_C.p, c->d_out.p, c->stream, dgt.p, dgs.p, dgg.p);
+        c->sv.count_out = nullptr;
         if (rr) return rr;
         CU_TRY(cudaEventRecord(c->ev1, c->stream));
         double *h_out = c->h_stage + nin;
-        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->stream));
-        unsigned long long nsdf = 0;
-        CU_TRY(cudaMemcpyAsync(&nsdf, c->sv.d_counter.p, sizeof(nsdf), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * (nout + 1), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
+        unsigned long long nsdf = 0;
+        std::memcpy(&nsdf, h_out + nout, sizeof(nsdf));
         if (c->peer_fused && c->peer.world > 1 && c->world > 1 && isdf_peer_status(c) != ISDF_OK) return ISDF_ERR_CUDA;   // exchange timed out: the vector is NaN
         float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->stats.last_kernel_ms = ms; c->stats.last_sdf_evals = (int64_t)nsdf;

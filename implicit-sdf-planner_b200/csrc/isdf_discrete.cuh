@@ -69,6 +69,7 @@ struct DiscArgs {
     double *piece_cost;    // N
     double *out;           // 19N+1: cost | gradC | gradT
     unsigned long long *pair_counter;  // may be null
+    double *count_out;                 // host entry point only: the pair count (bit pattern) lands behind the result vector, one D2H copy fetches both
     unsigned long long *dbg;           // may be null: per sample {cycles, pairs, work}
     unsigned long long *trace;         // may be null: per work-item slot {begin, end} in ns of the global timer (+ 6 phase cycle counts with -DISDF_PHASE_TIMING)
     const int *items;                  // may be null: 3 ints per work item {local sample m, -1 = all classes or c0 | c1 << 8, split slot or -1}
@@ -375,7 +376,10 @@ __global__ void __launch_bounds__(EPI_THREADS) k_discrete_epilogue(const __grid_
             const double v = (base + lane < N) ? __ldcg(A.piece_cost + base + lane) : 0.0;
             for (int u = 0; u < 32 && base + u < N; u++) c += __shfl_sync(0xffffffffu, v, u);
         }
-        if (lane == 0) { A.out[0] = c; *A.pieces_done = 0; *A.item_cursor = 0; }
+        if (lane == 0) {
+            A.out[0] = c; *A.pieces_done = 0; *A.item_cursor = 0;
+            if (A.count_out) *A.count_out = __longlong_as_double(A.pair_counter ? (long long)*(volatile unsigned long long *)A.pair_counter : 0ll);
+        }
     }
     if (A.peer.world > 1) {
         __threadfence();

@@ -125,6 +125,7 @@ struct SvArgs {
     double *piece_gdt, *piece_cost;  // N each
     double *out;                  // 19N+1
     unsigned long long *counter;  // reference-equivalent SDF evaluation count
+    double *count_out;            // host entry point only: the count (bit pattern) lands behind the result vector, one D2H copy fetches both
     int rank, world;
     const double *g_t, *g_s, *g_g;  // tier-T1: given t*, sdf*, g_rel (null = search)
     // longest-first schedule of the point CTAs: work[pk] = cycles point pk took in this evaluation; order = this rank's points sorted by
@@ -944,6 +945,7 @@ __device__ __forceinline__ void sv_finish_body(const SvArgs &A, const int bx) {
     A.out[0] = c;
     double run = 0.0;  // gradT(j) += gdT for all j < i (hpp:642-645)  <=>  gradT(j) = sum over pieces i > j
     for (int i = A.N - 1; i >= 0; i--) { A.out[1 + 18 * A.N + i] = run; run += A.piece_gdt[i]; }
+    if (A.count_out) *A.count_out = __longlong_as_double(A.counter ? (long long)*(volatile unsigned long long *)A.counter : 0ll);
 }
 
 // ---- kernels: single problem (arguments in the constant bank) and batched (blockIdx.y = problem; the problem's argument view is built in
@@ -999,6 +1001,7 @@ struct SweptState {
     DevBuf<unsigned long long> d_counter, d_dbg;
     DevBuf<unsigned> d_work; DevBuf<int> d_order;
     bool order_ready = false; int order_rank = -1, order_world = -1;
+    double *count_out = nullptr;   // set by the host entry point around one launch
     bool dbg_on = false;
 
     cudaError_t set_points(const double *pts, int n, cudaStream_t st) {
@@ -1045,7 +1048,7 @@ struct SweptState {
         A.cfg = cfg; A.shape = shape; A.N = N; A.T = d_T; A.C = d_C; A.P = P; A.pts = d_pts.p;
         A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
         A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
-        A.out = d_out; A.counter = d_counter.p; A.rank = rank; A.world = world; A.g_t = g_t; A.g_s = g_s; A.g_g = g_g;
+        A.out = d_out; A.counter = d_counter.p; A.count_out = count_out; A.rank = rank; A.world = world; A.g_t = g_t; A.g_s = g_s; A.g_g = g_g;
         // longest-first schedule (searching evaluations of a mesh robot only: the other kernels' points are cheap and uniform)
         const bool record = (g_t == nullptr) && shape.kind == ISDF_SHAPE_MESH;
         if (order_rank != rank || order_world != world) { order_ready = false; order_rank = rank; order_world = world; }
@@ -1113,7 +1116,7 @@ struct SweptState {
         A.cfg = cfg; A.shape = shape; A.N = N; A.T = d_T; A.C = d_Cpp; A.P = 0; A.pts = d_pts.p;
         A.tstar = d_tstar.p; A.sdf = d_sdf.p; A.grel = d_grel.p; A.times = d_times.p; A.poses = d_poses.p; A.meta = d_meta.p;
         A.state = d_state.p; A.partial = d_partial.p; A.piece = d_piece.p; A.piece_gdt = d_piece_gdt.p; A.piece_cost = d_piece_cost.p;
-        A.out = d_out; A.counter = d_counter.p; A.rank = 0; A.world = 1; A.g_t = nullptr; A.g_s = nullptr; A.g_g = nullptr; A.dbg = nullptr; A.dbg2 = nullptr;
+        A.out = d_out; A.counter = d_counter.p; A.count_out = nullptr; A.rank = 0; A.world = 1; A.g_t = nullptr; A.g_s = nullptr; A.g_g = nullptr; A.dbg = nullptr; A.dbg2 = nullptr;
         A.work = nullptr; A.order = nullptr; A.use_order = 0;
         Bt.B = B; Bt.pt_off = d_off.p; Bt.out_stride = 19ll * N + 1;
         const size_t sm = sizeof(double) * 19 * (size_t)N;
