@@ -3,13 +3,18 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 // build, link, import or execute anything in this directory. The product (libisdf_b200.so) never does.
 //
-// Parity status: the reference ships no golden vectors, known-answer tests or fixtures for this path
-//  and cannot be built here (needs Eigen/ROS/PCL/gfortran), so this oracle is pinned by
-//   (i) finite-difference checks of cost vs gradient (tests/test_oracle_fd.py),
-//   (ii) the one reference file that does compile here — igl/FastWindingNumberForSoups.h — built into
-//        oracle/_ref/ as the known-answer source for winding numbers (tests/test_oracle_mesh.py),
-//   (iii) brute-force point–triangle distance as known answer for the BVH query.
-// For everything else: "parity unpinned" by reference-owned vectors.
+// Parity status: the reference ships no golden vectors, known-answer tests or fixtures for this path and its build
+// cannot run here (needs Eigen/ROS/PCL/gfortran). Pinned against REFERENCE-COMPILED code (oracle/Makefile `ref`, outputs in oracle/_ref/):
+//   - igl/FastWindingNumberForSoups.h, unmodified                              -> winding numbers, oracle mode WN_REF (tests/test_oracle_mesh.py)
+//   - utils/flatness.hpp, unmodified, against the element-access Eigen stand-in -> flatness forward / adjoint, bit-identical / 7e-16
+//   - utils/minco.hpp, unmodified, against the eager Eigen stand-in              -> orc::Minco: coefficients, dE/dC, adjoint solve bit-identical,
+//                                                                                  sums (energy, gradByTimes) to the ulp (tests/test_reference_pins.py)
+//   - utils/lbfgs.hpp, unmodified, against the eager Eigen stand-in              -> the product's host L-BFGS driver: every evaluated point, value,
+//                                                                                  return code and evaluation count identical
+// (the eager stand-in adds reductions left to right where Eigen adds packet-wise: what those two pins fix is the reference's logic and operation
+// order, see oracle/_shim_dyn/Eigen/Eigen). Otherwise by (i) finite-difference checks of cost vs gradient (tests/test_oracle_fd.py) and
+// (ii) brute-force point-triangle distance as known answer for the BVH query. The penalty loops themselves (hpp:432-649, 766-866), the swept-volume
+// search (swm) and the Shape.hpp shape classes need the real Eigen: "parity unpinned" by reference-owned vectors for those.
 //
 // Reference shorthand used in citations (all under /root/reference/src):
 //   hpp:   planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp

@@ -4,7 +4,9 @@ Run in the build container (where /root/reference exists):  python tests/golden/
   ref_meshes.npz     — the robot meshes the reference ships and loads down its mesh Generalshape path (src/plan_manager/shapes/
                        {Lthick,drone,kuang,box,RoundedCone,mybox}.obj; INPUT data, read with the product's OBJ reader), the
                        poly_params of the config that names them, seeded query points, and the winding numbers the
-                       reference-compiled igl/FastWindingNumberForSoups.h returns for them (order 2, accuracy scale 2.0: Shape.cpp:86,110)."""
+                       reference-compiled igl/FastWindingNumberForSoups.h returns for them (order 2, accuracy scale 2.0: Shape.cpp:86,110);
+  minco_reference.npz — outputs of the reference's utils/minco.hpp (MINCO_S3NU forward, energy gradients, propogateGrad) on seeded problems;
+  lbfgs_reference.npz — what the reference's utils/lbfgs.hpp does on seeded problems: every evaluated point, solution, value, return code."""
 import os
 import sys
 import numpy as np
@@ -15,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "implicit-sdf-planner_b200", "py"))
 import isdf_b200 as I          # noqa: E402
 import oracle_lib as O         # noqa: E402
-from test_reference_pins import flat_inputs   # noqa: E402
+from test_reference_pins import flat_inputs, _minco_cases, _lbfgs_problems   # noqa: E402
 
 
 REF_SHAPES = "/root/reference/src/plan_manager/shapes"
@@ -53,6 +55,22 @@ def main():
     b = ref.backward(v, a, j, pg, vg, qg, og)
     np.savez(os.path.join(HERE, "flat_reference.npz"), par=ref.par, v=v, a=a, j=j, pg=pg, vg=vg, qg=qg, og=og, quat=q, omg=o, back=b)
     print("flat_reference.npz written")
+    rm = O.RefMinco()
+    out = {}
+    for k, (N, head, tail, inPs, T, gC, gT) in enumerate(_minco_cases()):
+        co, e, gc, gt = rm.forward(head, tail, inPs, T)
+        gp, gto = rm.backward(head, tail, inPs, T, gC, gT)
+        out.update({f"c{k}_coeffs": co, f"c{k}_energy": np.array(e), f"c{k}_gdC": gc, f"c{k}_gdT": gt, f"c{k}_gradP": np.asarray(gp), f"c{k}_gradT": gto})
+    np.savez_compressed(os.path.join(HERE, "minco_reference.npz"), ncases=np.array(len(_minco_cases())), **out)
+    print("minco_reference.npz written")
+    rl = O.RefLbfgs()
+    out = {}
+    for k, (name, fun, x0, kw) in enumerate(_lbfgs_problems()):
+        r = rl.minimize(fun, x0, **kw)
+        out.update({f"p{k}_trace": np.array(r["trace"]), f"p{k}_x": r["x"], f"p{k}_f": np.array(r["f"]), f"p{k}_ret": np.array(r["ret"]), f"p{k}_evals": np.array(r["evaluations"])})
+        print(name, r["ret"], r["evaluations"])
+    np.savez_compressed(os.path.join(HERE, "lbfgs_reference.npz"), nproblems=np.array(len(_lbfgs_problems())), **out)
+    print("lbfgs_reference.npz written")
 
 
 if __name__ == "__main__":

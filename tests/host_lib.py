@@ -49,8 +49,11 @@ def lbfgs_minimize(fun, x0, mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_
     n = x.size
     count = [0]
 
+    trace = []
+
     def cb(_inst, xp, gp, nn, pc):
         xv = np.ctypeslib.as_array(xp, shape=(nn,))
+        trace.append(xv.copy())
         fv, gv = fun(xv.copy())
         np.ctypeslib.as_array(gp, shape=(nn,))[:] = gv
         count[0] += 1
@@ -59,7 +62,7 @@ def lbfgs_minimize(fun, x0, mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_
     fx, it, ev = C.c_double(0), C.c_int(0), C.c_int(0)
     r = lib().isdf_host_lbfgs_generic(n, _p(x), C.byref(fx), C.cast(cfn, C.c_void_p), None, mem_size, past, delta, g_epsilon, max_iterations,
                                       C.byref(it), C.byref(ev))
-    return dict(ret=r, x=x, f=fx.value, iterations=it.value, evaluations=ev.value)
+    return dict(ret=r, x=x, f=fx.value, iterations=it.value, evaluations=ev.value, trace=trace)
 
 
 EVAL_BATCH_T = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_int), dp, dp, dp)   # lbfgs_eval_batch_t

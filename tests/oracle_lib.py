@@ -10,6 +10,8 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_FWN = os.path.join(ORACLE_DIR, "_ref", "libref_fwn.so")
 REF_FLAT = os.path.join(ORACLE_DIR, "_ref", "libref_flat.so")
+REF_LBFGS = os.path.join(os.path.dirname(REF_FLAT), "libref_lbfgs.so")
+REF_MINCO = os.path.join(os.path.dirname(REF_FLAT), "libref_minco.so")
 
 WN_EXACT, WN_BH, WN_RAW, WN_REF = 0, 1, 2, 3
 
@@ -18,7 +20,7 @@ def build(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".hpp", ".cpp"))]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/src/utils/include/igl") and not (os.path.exists(REF_FWN) and os.path.exists(REF_FLAT)):
+    if os.path.isdir("/root/reference/src/utils/include/igl") and not all(os.path.exists(p) for p in (REF_FWN, REF_FLAT, REF_LBFGS, REF_MINCO)):
         subprocess.call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -218,6 +220,71 @@ def flat_backward_batch(cfg, v, a, j, pos_grad, vel_grad, quat_grad, omg_grad):
     lib().orc_flat_backward_batch(C.byref(cfg), n, _p(v), _p(a), _p(j), _p(f64(pos_grad).reshape(-1, 3)), _p(f64(vel_grad).reshape(-1, 3)),
                                   _p(f64(quat_grad).reshape(-1, 4)), _p(f64(omg_grad).reshape(-1, 3)), _p(out))
     return out
+
+
+class RefMinco:
+    """oracle/_ref/libref_minco.so: the reference's own utils/minco.hpp (BandedSystem, MINCO_S3NU) compiled unmodified against the eager
+    Eigen stand-in — kind "reference". Same calling convention as minco_forward / minco_backward below."""
+
+    def __init__(self):
+        self.L = C.CDLL(REF_MINCO)
+        self.L.ref_minco_forward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
+        self.L.ref_minco_backward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
+        self.L.ref_minco_trajectory.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp]
+
+    @staticmethod
+    def _in(head, tail, inPs, T):
+        T = f64(T).reshape(-1)
+        return T.size, np.asfortranarray(f64(head)), np.asfortranarray(f64(tail)), np.asfortranarray(f64(inPs).reshape(3, -1)), T
+
+    def forward(self, head, tail, inPs, T):
+        N, h, t, ip, T = self._in(head, tail, inPs, T)
+        co, gc, gt, e = np.zeros(18 * N), np.zeros(18 * N), np.zeros(N), C.c_double(0)
+        self.L.ref_minco_forward(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(co), C.byref(e), _p(gc), _p(gt))
+        return co, e.value, gc, gt
+
+    def backward(self, head, tail, inPs, T, gradC, gradT):
+        N, h, t, ip, T = self._in(head, tail, inPs, T)
+        gp, gt = np.zeros((3, N - 1), order="F"), np.zeros(N)
+        self.L.ref_minco_backward(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(f64(gradC)), _p(f64(gradT)),
+                                  gp.ctypes.data_as(dp), _p(gt))
+        return gp, gt
+
+    def trajectory(self, head, tail, inPs, T):
+        N, h, t, ip, T = self._in(head, tail, inPs, T)
+        dur, cm = np.zeros(N), np.zeros(18 * N)
+        self.L.ref_minco_trajectory(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(dur), _p(cm))
+        return dur, cm.reshape(N, 6, 3).transpose(0, 2, 1)          # per piece 3 x 6, highest power first
+
+
+class RefLbfgs:
+    """oracle/_ref/libref_lbfgs.so: the reference's own utils/lbfgs.hpp (lbfgs_optimize, line_search_lewisoverton) compiled unmodified
+    against the eager dynamic-vector Eigen stand-in (left-to-right reductions) — kind "reference"."""
+    EVAL_T = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, dp, dp)
+
+    def __init__(self):
+        self.L = C.CDLL(REF_LBFGS)
+        self.L.ref_lbfgs_optimize.argtypes = [C.c_int, dp, dp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                              C.POINTER(C.c_long)]
+        self.L.ref_lbfgs_optimize.restype = C.c_int
+
+    def minimize(self, fun, x0, mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_iterations=0, min_step=1e-32):
+        """fun(x) -> (f, grad); returns ret, x, f, evaluations and the list of every point the optimiser evaluated"""
+        x = f64(x0).copy()
+        n = x.size
+        trace = []
+
+        def cb(_u, nn, xp, gp):
+            xv = np.ctypeslib.as_array(xp, shape=(nn,)).copy()
+            trace.append(xv)
+            fv, gv = fun(xv.copy())
+            np.ctypeslib.as_array(gp, shape=(nn,))[:] = gv
+            return float(fv)
+        cfn = self.EVAL_T(cb)
+        fx, ev = C.c_double(0), C.c_long(0)
+        r = self.L.ref_lbfgs_optimize(n, _p(x), C.byref(fx), C.cast(cfn, C.c_void_p), None, mem_size, past, delta, g_epsilon, max_iterations, min_step,
+                                      C.byref(ev))
+        return dict(ret=r, x=x, f=fx.value, evaluations=ev.value, trace=trace)
 
 
 class RefFlat:

@@ -107,3 +107,128 @@ def test_obj_reader_forms(tmp_path):
     p.write_text("# c\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0 1.0\nvn 0 0 1\nvt 0 0\nf 1/1/1 2/1/1 3/1/1 4/1/1\nv 0 0 1\nf -1 1//1 2\nf 1/1 3/1 5/1\n")
     V, F = H.read_obj(str(p))
     assert V.shape == (5, 3) and np.array_equal(F, [[0, 1, 2], [0, 2, 3], [4, 0, 1], [0, 2, 4]])
+
+
+def _lbfgs_problems():
+    def rosen(x):
+        f = np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2)
+        g = np.zeros_like(x)
+        g[:-1] = -400 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+        g[1:] += 200 * (x[1:] - x[:-1] ** 2)
+        return f, g
+    A = np.diag([1.0, 10.0, 100.0, 3.0, 0.25])
+
+    def quad(x):
+        return 0.5 * x @ A @ x, A @ x
+
+    def hinge(x):       # smoothed-L1 like kink (the planner's penalty shape): piecewise cubic / linear, long line searches
+        f, g = 0.0, np.zeros_like(x)
+        for i, v in enumerate(x):
+            a = abs(v - 0.3 * i)
+            if a > 0.1:
+                f += a - 0.05; g[i] = np.sign(v - 0.3 * i)
+            else:
+                f += (0.2 - a) * a ** 3 / (2 * 0.1 ** 3) * 10; g[i] = np.sign(v - 0.3 * i) * (0.6 * a ** 2 - 4 * a ** 3) / (2 * 0.1 ** 3) * 10
+        return f + 0.05 * x @ x, g + 0.1 * x
+
+    def flat_then_nan(x):   # a callback that turns NaN away from the start: the drivers must fail the same way
+        if np.linalg.norm(x) > 3.0:
+            return float("nan"), x
+        return float(np.sum(np.cos(x))), -np.sin(x)
+    rng = np.random.default_rng(4)
+    return [("rosenbrock-6", rosen, np.array([-1.2, 1.0, -0.5, 0.8, 1.5, -0.3]), dict(mem_size=16, past=10, delta=1e-9, g_epsilon=0.0, max_iterations=300)),
+            ("rosenbrock-2 gtol", rosen, np.array([-1.2, 1.0]), dict(mem_size=8, past=0, delta=1e-6, g_epsilon=1e-8, max_iterations=2000)),
+            ("quadratic", quad, rng.normal(size=5), dict(mem_size=4, past=3, delta=1e-12, g_epsilon=1e-12, max_iterations=200)),
+            ("hinge", hinge, rng.normal(size=7) * 2, dict(mem_size=16, past=10, delta=1e-6, g_epsilon=0.0, max_iterations=150)),
+            ("iteration cap", rosen, np.array([-1.2, 1.0, 1.0, 1.0]), dict(mem_size=8, past=3, delta=1e-14, g_epsilon=0.0, max_iterations=7)),
+            ("nan away from the start", flat_then_nan, np.array([0.5, -0.4, 0.3]), dict(mem_size=8, past=3, delta=1e-6, g_epsilon=1e-9, max_iterations=50)),
+            ("stationary start", quad, np.zeros(5), dict(mem_size=8, past=3, delta=1e-6, g_epsilon=1e-5, max_iterations=50))]
+
+
+def test_lbfgs_host_driver_equals_reference_compiled_lbfgs_hpp():
+    """The product's sequential L-BFGS driver (host/isdf_lbfgs.hpp; the lock-step host and device drivers are tested bit-identical to it)
+    against the reference's own utils/lbfgs.hpp compiled unmodified (oracle/_ref/libref_lbfgs.so, eager Eigen stand-in with left-to-right
+    reductions): every point handed to the callback, in order, the solution, the value, the return code and the evaluation count are
+    IDENTICAL — Lewis-Overton line search, cautious update, the fork's direction-reset patches (one extra evaluation), stop tests."""
+    import host_lib as H
+    if not os.path.exists(O.REF_LBFGS):
+        pytest.skip("oracle/_ref/libref_lbfgs.so not built (needs /root/reference)")
+    ref = O.RefLbfgs()
+    for name, fun, x0, kw in _lbfgs_problems():
+        a = ref.minimize(fun, x0, **kw)
+        b = H.lbfgs_minimize(fun, x0, **kw)
+        assert a["ret"] == b["ret"], f"{name}: return code {a['ret']} (reference) vs {b['ret']}"
+        assert a["evaluations"] == b["evaluations"] == len(b["trace"]), f"{name}: evaluations {a['evaluations']} vs {b['evaluations']}"
+        for k, (p, q) in enumerate(zip(a["trace"], b["trace"])):
+            assert np.array_equal(p, q), f"{name}: evaluation {k} at different points (max diff {np.abs(p - q).max():.3e})"
+        assert np.array_equal(a["x"], b["x"]) and (a["f"] == b["f"] or (np.isnan(a["f"]) and np.isnan(b["f"]))), name
+
+
+def _minco_cases():
+    rng = np.random.default_rng(21)
+    out = []
+    for N in (2, 3, 8, 64):
+        head = np.stack([rng.normal(size=3) * 5, rng.normal(size=3), rng.normal(size=3) * 0.3], axis=1)
+        tail = np.stack([rng.normal(size=3) * 5 + 20, rng.normal(size=3), rng.normal(size=3) * 0.3], axis=1)
+        inPs = np.cumsum(rng.normal(size=(3, N - 1)) * 2 + 1.0, axis=1)
+        T = rng.uniform(0.4, 3.0, N)
+        out.append((N, head, tail, inPs, T, rng.normal(size=18 * N), rng.normal(size=N)))
+    return out
+
+
+def test_minco_oracle_and_host_port_equal_reference_compiled_minco_hpp():
+    """oracle_minco.hpp and host/isdf_minco.hpp against the reference's own utils/minco.hpp compiled unmodified (oracle/_ref/libref_minco.so, eager
+    Eigen stand-in): banded LU + substitution (coefficients), energy and its partial gradients, the adjoint solve and propogateGrad. The ORACLE
+    is bit-identical wherever no reduction is involved (coefficients, dE/dC, gradByPoints) and agrees to the last ulps where a sum's order is the
+    stand-in's (energy, dE/dT, gradByTimes); the product's host port (device kernels bit-identical to it) agrees to 1e-12."""
+    import host_lib as H
+    if not os.path.exists(O.REF_MINCO):
+        pytest.skip("oracle/_ref/libref_minco.so not built (needs /root/reference)")
+    ref = O.RefMinco()
+    for N, head, tail, inPs, T, gC, gT in _minco_cases():
+        rc, re, rgc, rgt = ref.forward(head, tail, inPs, T)
+        rgp, rgto = ref.backward(head, tail, inPs, T, gC, gT)
+        # the oracle follows the reference's operation order: identical bits wherever no reduction is involved
+        c, e, gc, gt = O.minco_forward(head, tail, inPs, T)
+        assert np.array_equal(c, rc), f"oracle N={N}: coefficients differ from the reference-compiled solve by {np.abs(c - rc).max():.3e}"
+        assert np.array_equal(gc, rgc), f"oracle N={N}: dE/dC"
+        assert abs(e - re) <= 4e-16 * abs(re) * 6 * N and np.allclose(gt, rgt, rtol=1e-14, atol=0), f"oracle N={N}: energy / dE/dT"
+        gp, gto = O.minco_backward(head, tail, inPs, T, gC, gT)
+        assert np.array_equal(np.asarray(gp).reshape(-1), np.asarray(rgp).reshape(-1)), f"oracle N={N}: gradByPoints (adjoint solve) differs by {np.abs(np.asarray(gp) - rgp).max():.3e}"
+        assert np.allclose(gto, rgto, rtol=1e-13, atol=1e-13 * np.abs(rgto).max()), f"oracle N={N}: gradByTimes"
+        # the product's host MINCO (the device kernels are bit-identical to it) keeps the band factored with reciprocal pivots: same
+        # solution to rounding
+        c, e, gc, gt = H.minco_forward(head, tail, inPs, T)
+        scale = np.abs(rc).max()
+        assert np.abs(c - rc).max() <= 1e-12 * scale, f"host N={N}: coefficients {np.abs(c - rc).max():.3e}"
+        assert np.allclose(gc, rgc, rtol=0, atol=1e-11 * np.abs(rgc).max()) and abs(e - re) <= 1e-12 * abs(re) and np.allclose(gt, rgt, rtol=0, atol=1e-11 * np.abs(rgt).max())
+        gp, gto = H.minco_backward(head, tail, inPs, T, gC, gT)
+        assert np.allclose(np.asarray(gp).reshape(-1), np.asarray(rgp).reshape(-1), rtol=0, atol=1e-11 * np.abs(rgp).max()), f"host N={N}: gradByPoints"
+        assert np.allclose(gto, rgto, rtol=0, atol=1e-11 * np.abs(rgto).max()), f"host N={N}: gradByTimes"
+    # getTrajectory: the 3 x 6 coefficient matrices are the coefficient block transposed, highest power first
+    N, head, tail, inPs, T, _, _ = _minco_cases()[2]
+    dur, cm = ref.trajectory(head, tail, inPs, T)
+    co = ref.forward(head, tail, inPs, T)[0].reshape(3, 6 * N)
+    assert np.array_equal(dur, T)
+    for i in range(N):
+        assert np.array_equal(cm[i], co[:, 6 * i:6 * i + 6][:, ::-1])
+
+
+def test_minco_and_lbfgs_equal_committed_reference_outputs():
+    """the same two pins against the COMMITTED outputs of the reference-compiled libraries (tests/golden/make_reference_golden.py), so that they hold
+    where /root/reference — and with it oracle/_ref — is absent"""
+    import host_lib as H
+    zm = np.load(os.path.join(G, "minco_reference.npz"))
+    for k, (N, head, tail, inPs, T, gC, gT) in enumerate(_minco_cases()):
+        c, e, gc, gt = O.minco_forward(head, tail, inPs, T)
+        gp, gto = O.minco_backward(head, tail, inPs, T, gC, gT)
+        assert np.array_equal(c, zm[f"c{k}_coeffs"]) and np.array_equal(gc, zm[f"c{k}_gdC"]) and np.array_equal(np.asarray(gp), zm[f"c{k}_gradP"])
+        assert abs(e - float(zm[f"c{k}_energy"])) <= 1e-14 * abs(e) and np.allclose(gt, zm[f"c{k}_gdT"], rtol=1e-14, atol=0)
+        assert np.allclose(gto, zm[f"c{k}_gradT"], rtol=0, atol=1e-13 * np.abs(gto).max())
+    zl = np.load(os.path.join(G, "lbfgs_reference.npz"))
+    for k, (name, fun, x0, kw) in enumerate(_lbfgs_problems()):
+        b = H.lbfgs_minimize(fun, x0, **kw)
+        assert b["ret"] == int(zl[f"p{k}_ret"]) and b["evaluations"] == int(zl[f"p{k}_evals"]), name
+        assert np.array_equal(np.array(b["trace"]), zl[f"p{k}_trace"]) and np.array_equal(b["x"], zl[f"p{k}_x"]), name
+        f_ref = float(zl[f"p{k}_f"])
+        assert b["f"] == f_ref or (np.isnan(b["f"]) and np.isnan(f_ref)), name
