@@ -223,6 +223,22 @@ int orc_minco_backward(int N, const double *headPVA, const double *tailPVA, cons
     return 0;
 }
 
+// Trajectory::getPos_Vel_Acc_Jerk / locatePieceIdx / getTotalDuration of the oracle (oracle_planner.hpp Traj) on a coefficient block:
+// out nt x 12 (pos, vel, acc, jerk), piece nt, tloc nt — the same outputs as oracle/ref_minco_wrap.cpp's ref_traj_eval
+void orc_traj_eval(int N, const double *T, const double *coeffs, int nt, const double *times, double *out, int *piece, double *tloc, double *total) {
+    Traj tr; tr.N = N; tr.T = T; tr.C = coeffs;
+    *total = tr.total();
+    for (int q = 0; q < nt; q++) {
+        V3 p, v, a, j;
+        tr.pvaj(times[q], p, v, a, j);
+        const V3 *src[4] = {&p, &v, &a, &j};
+        for (int b = 0; b < 4; b++) { out[12 * q + 3 * b] = src[b]->x; out[12 * q + 3 * b + 1] = src[b]->y; out[12 * q + 3 * b + 2] = src[b]->z; }
+        double t = times[q];
+        piece[q] = tr.locate(t);
+        tloc[q] = t;
+    }
+}
+
 // ---- front end: attitude kernels (oracle_frontend.hpp) --------------------------------------------------------------------
 void *orc_frontend_create(void *shape, double max_roll, double max_pitch, double ang_res, double front_end_safeh, double res, int ks,
                           const uint8_t *occ, int X, int Y, int Z, int *xk, int *yk) {

@@ -9,6 +9,8 @@
 //   - utils/flatness.hpp, unmodified, against the element-access Eigen stand-in -> flatness forward / adjoint, bit-identical / 7e-16
 //   - utils/minco.hpp, unmodified, against the eager Eigen stand-in              -> orc::Minco: coefficients, dE/dC, adjoint solve bit-identical,
 //                                                                                  sums (energy, gradByTimes) to the ulp (tests/test_reference_pins.py)
+//   - utils/trajectory.hpp, unmodified, same stand-in (root_finder.hpp: declarations only) -> orc::Traj: piece search, local time, pos / vel / acc / jerk
+//                                                                                  bit-identical, junctions and out-of-range times included
 //   - utils/lbfgs.hpp, unmodified, against the eager Eigen stand-in              -> the product's host L-BFGS driver: every evaluated point, value,
 //                                                                                  return code and evaluation count identical
 // (the eager stand-in adds reductions left to right where Eigen adds packet-wise: what those two pins fix is the reference's logic and operation

@@ -5,7 +5,8 @@ Run in the build container (where /root/reference exists):  python tests/golden/
                        {Lthick,drone,kuang,box,RoundedCone,mybox}.obj; INPUT data, read with the product's OBJ reader), the
                        poly_params of the config that names them, seeded query points, and the winding numbers the
                        reference-compiled igl/FastWindingNumberForSoups.h returns for them (order 2, accuracy scale 2.0: Shape.cpp:86,110);
-  minco_reference.npz — outputs of the reference's utils/minco.hpp (MINCO_S3NU forward, energy gradients, propogateGrad) on seeded problems;
+  minco_reference.npz — outputs of the reference's utils/minco.hpp (MINCO_S3NU forward, energy gradients, propogateGrad) on seeded problems, and
+                        of its utils/trajectory.hpp (getPos_Vel_Acc_Jerk, locatePieceIdx, getTotalDuration) on the resulting trajectories;
   lbfgs_reference.npz — what the reference's utils/lbfgs.hpp does on seeded problems: every evaluated point, solution, value, return code."""
 import os
 import sys
@@ -17,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "implicit-sdf-planner_b200", "py"))
 import isdf_b200 as I          # noqa: E402
 import oracle_lib as O         # noqa: E402
-from test_reference_pins import flat_inputs, _minco_cases, _lbfgs_problems   # noqa: E402
+from test_reference_pins import flat_inputs, _minco_cases, _lbfgs_problems, _traj_times   # noqa: E402
 
 
 REF_SHAPES = "/root/reference/src/plan_manager/shapes"
@@ -61,6 +62,9 @@ def main():
         co, e, gc, gt = rm.forward(head, tail, inPs, T)
         gp, gto = rm.backward(head, tail, inPs, T, gC, gT)
         out.update({f"c{k}_coeffs": co, f"c{k}_energy": np.array(e), f"c{k}_gdC": gc, f"c{k}_gdT": gt, f"c{k}_gradP": np.asarray(gp), f"c{k}_gradT": gto})
+        times = _traj_times(T, np.random.default_rng(100 + k))
+        ev, piece, tloc, total = rm.traj_eval(head, tail, inPs, T, times)
+        out.update({f"c{k}_times": times, f"c{k}_pvaj": ev, f"c{k}_piece": piece, f"c{k}_tloc": tloc, f"c{k}_total": np.array(total)})
     np.savez_compressed(os.path.join(HERE, "minco_reference.npz"), ncases=np.array(len(_minco_cases())), **out)
     print("minco_reference.npz written")
     rl = O.RefLbfgs()

@@ -231,6 +231,7 @@ class RefMinco:
         self.L.ref_minco_forward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         self.L.ref_minco_backward.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
         self.L.ref_minco_trajectory.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp]
+        self.L.ref_traj_eval.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, dp, C.POINTER(C.c_int), dp, dp]
 
     @staticmethod
     def _in(head, tail, inPs, T):
@@ -249,6 +250,15 @@ class RefMinco:
         self.L.ref_minco_backward(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(f64(gradC)), _p(f64(gradT)),
                                   gp.ctypes.data_as(dp), _p(gt))
         return gp, gt
+
+    def traj_eval(self, head, tail, inPs, T, times):
+        """MINCO -> the reference's Trajectory<5> -> getPos_Vel_Acc_Jerk / locatePieceIdx at absolute times"""
+        N, h, t, ip, T = self._in(head, tail, inPs, T)
+        times = f64(times).reshape(-1)
+        out, piece, tloc, total = np.zeros((times.size, 12)), np.zeros(times.size, dtype=np.int32), np.zeros(times.size), C.c_double(0)
+        self.L.ref_traj_eval(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), times.size, _p(times), _p(out),
+                             piece.ctypes.data_as(C.POINTER(C.c_int)), _p(tloc), C.byref(total))
+        return out, piece, tloc, total.value
 
     def trajectory(self, head, tail, inPs, T):
         N, h, t, ip, T = self._in(head, tail, inPs, T)
@@ -384,6 +394,16 @@ def minco_forward(head, tail, inPs, T):
     co, gc, gt, e = np.zeros(18 * N), np.zeros(18 * N), np.zeros(N), C.c_double(0)
     lib().orc_minco_forward(N, h.ctypes.data_as(dp), t.ctypes.data_as(dp), ip.ctypes.data_as(dp), _p(T), _p(co), C.byref(e), _p(gc), _p(gt))
     return co, e.value, gc, gt
+
+
+def traj_eval(T, coeffs, times):
+    """the oracle's Trajectory evaluation on a 6N x 3 column-major coefficient block"""
+    T, coeffs, times = f64(T).reshape(-1), f64(coeffs).reshape(-1), f64(times).reshape(-1)
+    L = lib()
+    L.orc_traj_eval.argtypes = [C.c_int, dp, dp, C.c_int, dp, dp, C.POINTER(C.c_int), dp, dp]
+    out, piece, tloc, total = np.zeros((times.size, 12)), np.zeros(times.size, dtype=np.int32), np.zeros(times.size), C.c_double(0)
+    L.orc_traj_eval(T.size, _p(T), _p(coeffs), times.size, _p(times), _p(out), piece.ctypes.data_as(C.POINTER(C.c_int)), _p(tloc), C.byref(total))
+    return out, piece, tloc, total.value
 
 
 def minco_backward(head, tail, inPs, T, gradC, gradT):

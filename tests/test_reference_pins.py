@@ -225,6 +225,8 @@ def test_minco_and_lbfgs_equal_committed_reference_outputs():
         assert np.array_equal(c, zm[f"c{k}_coeffs"]) and np.array_equal(gc, zm[f"c{k}_gdC"]) and np.array_equal(np.asarray(gp), zm[f"c{k}_gradP"])
         assert abs(e - float(zm[f"c{k}_energy"])) <= 1e-14 * abs(e) and np.allclose(gt, zm[f"c{k}_gdT"], rtol=1e-14, atol=0)
         assert np.allclose(gto, zm[f"c{k}_gradT"], rtol=0, atol=1e-13 * np.abs(gto).max())
+        ev, piece, tloc, total = O.traj_eval(T, c, zm[f"c{k}_times"])
+        assert np.array_equal(ev, zm[f"c{k}_pvaj"]) and np.array_equal(piece, zm[f"c{k}_piece"]) and np.array_equal(tloc, zm[f"c{k}_tloc"]) and total == float(zm[f"c{k}_total"])
     zl = np.load(os.path.join(G, "lbfgs_reference.npz"))
     for k, (name, fun, x0, kw) in enumerate(_lbfgs_problems()):
         b = H.lbfgs_minimize(fun, x0, **kw)
@@ -232,3 +234,28 @@ def test_minco_and_lbfgs_equal_committed_reference_outputs():
         assert np.array_equal(np.array(b["trace"]), zl[f"p{k}_trace"]) and np.array_equal(b["x"], zl[f"p{k}_x"]), name
         f_ref = float(zl[f"p{k}_f"])
         assert b["f"] == f_ref or (np.isnan(b["f"]) and np.isnan(f_ref)), name
+
+
+def _traj_times(T, rng):
+    """absolute times that exercise locatePieceIdx: inside pieces, EXACTLY on junctions (strict '>' keeps a junction in the earlier piece), the
+    sums as the bench's sampling produces them, before 0 and past the end (clamped into the last piece, quirk Q12)"""
+    cs = np.cumsum(T)
+    return np.concatenate([rng.uniform(0, cs[-1], 200), cs, cs - 1e-13, cs + 1e-13, np.cumsum(np.full(40, cs[-1] / 40)), [0.0, -0.3, cs[-1] + 0.7, cs[-1] * 2]])
+
+
+def test_trajectory_evaluation_equals_reference_compiled_trajectory_hpp():
+    """orc::Traj (locatePieceIdx's sequential subtraction, Piece::getPos_Vel_Acc_Jerk's running powers) against the reference's own
+    utils/trajectory.hpp compiled unmodified and fed by the reference's own MINCO getTrajectory: piece index, local time, position, velocity,
+    acceleration and jerk IDENTICAL at every time, incl. junctions and out-of-range times. The device's traj_locate / traj_pvaj
+    (csrc/isdf_swept.cuh) follow orc::Traj operation by operation and are compared with it by the GPU parity tests."""
+    if not os.path.exists(O.REF_MINCO):
+        pytest.skip("oracle/_ref/libref_minco.so not built (needs /root/reference)")
+    ref = O.RefMinco()
+    rng = np.random.default_rng(8)
+    for N, head, tail, inPs, T, _, _ in _minco_cases():
+        times = _traj_times(T, rng)
+        r_out, r_piece, r_tloc, r_total = ref.traj_eval(head, tail, inPs, T, times)
+        coeffs = O.minco_forward(head, tail, inPs, T)[0]
+        o_out, o_piece, o_tloc, o_total = O.traj_eval(T, coeffs, times)
+        assert o_total == r_total and np.array_equal(o_piece, r_piece) and np.array_equal(o_tloc, r_tloc), f"N={N}: piece search"
+        assert np.array_equal(o_out, r_out), f"N={N}: pos/vel/acc/jerk differ by {np.abs(o_out - r_out).max():.3e}"
