@@ -191,6 +191,20 @@ int orc_points_in_aabb(const uint8_t *occ, int X, int Y, int Z, const double *bm
     return (int)v.size();
 }
 
+// getGridIndex / getGridCubeCenter / isInMap of the oracle grid for n points (same outputs as oracle/ref_grid_wrap.cpp's ref_grid_index)
+int orc_grid_index(int X, int Y, int Z, const double *bmin, double res, int n, const double *pts, int *idx, double *centre, int *inmap) {
+    Grid G; G.X = X; G.Y = Y; G.Z = Z; G.res = res; G.occ = nullptr;
+    G.bmin = V3(bmin[0], bmin[1], bmin[2]); G.bmax = V3(bmin[0] + X * res, bmin[1] + Y * res, bmin[2] + Z * res);
+    for (int q = 0; q < n; q++) {
+        const V3 p(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
+        G.grid_index(p, idx + 3 * q);
+        const V3 c = G.centre(idx[3 * q], idx[3 * q + 1], idx[3 * q + 2]);
+        centre[3 * q] = c.x; centre[3 * q + 1] = c.y; centre[3 * q + 2] = c.z;
+        inmap[q] = G.in_map(p) ? 1 : 0;
+    }
+    return 0;
+}
+
 // obstacle list (plan_manager.cpp:232-254); wps: nQ x 3; returns count, writes up to cap points
 int orc_gather_obstacle_points(const uint8_t *occ, int X, int Y, int Z, const double *bmin, double res, const double *wps, int nQ,
                                double half, const double *offset, double *out, int cap) {

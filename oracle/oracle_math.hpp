@@ -11,6 +11,8 @@
 //                                                                                  sums (energy, gradByTimes) to the ulp (tests/test_reference_pins.py)
 //   - utils/trajectory.hpp, unmodified, same stand-in (root_finder.hpp: declarations only) -> orc::Traj: piece search, local time, pos / vel / acc / jerk
 //                                                                                  bit-identical, junctions and out-of-range times included
+//   - map_manager/src/Gridmap3D.cpp, unmodified, same stand-in + ROS stand-ins    -> orc::Grid: getGridIndex (clamping quirk), cube centres, in-map test and
+//                                                                                  the AABB gather built on them bit-identical
 //   - utils/lbfgs.hpp, unmodified, against the eager Eigen stand-in              -> the product's host L-BFGS driver: every evaluated point, value,
 //                                                                                  return code and evaluation count identical
 // (the eager stand-in adds reductions left to right where Eigen adds packet-wise: what those two pins fix is the reference's logic and operation

@@ -12,6 +12,7 @@ REF_FWN = os.path.join(ORACLE_DIR, "_ref", "libref_fwn.so")
 REF_FLAT = os.path.join(ORACLE_DIR, "_ref", "libref_flat.so")
 REF_LBFGS = os.path.join(os.path.dirname(REF_FLAT), "libref_lbfgs.so")
 REF_MINCO = os.path.join(os.path.dirname(REF_FLAT), "libref_minco.so")
+REF_GRID = os.path.join(os.path.dirname(REF_FLAT), "libref_grid.so")
 
 WN_EXACT, WN_BH, WN_RAW, WN_REF = 0, 1, 2, 3
 
@@ -20,7 +21,7 @@ def build(force=False):
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".hpp", ".cpp"))]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/src/utils/include/igl") and not all(os.path.exists(p) for p in (REF_FWN, REF_FLAT, REF_LBFGS, REF_MINCO)):
+    if os.path.isdir("/root/reference/src/utils/include/igl") and not all(os.path.exists(p) for p in (REF_FWN, REF_FLAT, REF_LBFGS, REF_MINCO, REF_GRID)):
         subprocess.call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -220,6 +221,39 @@ def flat_backward_batch(cfg, v, a, j, pos_grad, vel_grad, quat_grad, omg_grad):
     lib().orc_flat_backward_batch(C.byref(cfg), n, _p(v), _p(a), _p(j), _p(f64(pos_grad).reshape(-1, 3)), _p(f64(vel_grad).reshape(-1, 3)),
                                   _p(f64(quat_grad).reshape(-1, 4)), _p(f64(omg_grad).reshape(-1, 3)), _p(out))
     return out
+
+
+def grid_index(dims, bmin, res, pts, L=None, name="orc_grid_index"):
+    """getGridIndex / getGridCubeCenter / isInMap for n points: the oracle's (default) or, with L = RefGrid().L, the reference-compiled grid's"""
+    L = L or lib()
+    pts = f64(pts).reshape(-1, 3)
+    n = pts.shape[0]
+    idx, ctr, inm = np.zeros((n, 3), dtype=np.int32), np.zeros((n, 3)), np.zeros(n, dtype=np.int32)
+    fn = getattr(L, name)
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_double, C.c_int, dp, C.POINTER(C.c_int), dp, C.POINTER(C.c_int)]
+    r = fn(int(dims[0]), int(dims[1]), int(dims[2]), _p(f64(bmin)), float(res), n, _p(pts), idx.ctypes.data_as(C.POINTER(C.c_int)), _p(ctr),
+           inm.ctypes.data_as(C.POINTER(C.c_int)))
+    assert r == 0, "grid dimensions do not survive createGridMap's ceil((max - min) / res)"
+    return idx, ctr, inm
+
+
+class RefGrid:
+    """oracle/_ref/libref_grid.so: the reference's own map_manager/src/Gridmap3D.cpp compiled unmodified (eager Eigen stand-in, ROS stand-ins) —
+    kind "reference"."""
+
+    def __init__(self):
+        self.L = C.CDLL(REF_GRID)
+        self.L.ref_points_in_aabb.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, dp, C.c_double, dp, C.c_double, dp, C.c_int]
+
+    def index(self, dims, bmin, res, pts):
+        return grid_index(dims, bmin, res, pts, L=self.L, name="ref_grid_index")
+
+    def points_in_aabb(self, occ, bmin, res, centre, half, cap=100000):
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        X, Y, Z = occ.shape
+        out = np.zeros((cap, 3))
+        n = self.L.ref_points_in_aabb(occ.ctypes.data_as(C.POINTER(C.c_uint8)), X, Y, Z, _p(f64(bmin)), float(res), _p(f64(centre)), float(half), _p(out), cap)
+        return out[:max(0, min(n, cap))].copy(), n
 
 
 class RefMinco:

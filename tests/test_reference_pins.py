@@ -259,3 +259,30 @@ def test_trajectory_evaluation_equals_reference_compiled_trajectory_hpp():
         o_out, o_piece, o_tloc, o_total = O.traj_eval(T, coeffs, times)
         assert o_total == r_total and np.array_equal(o_piece, r_piece) and np.array_equal(o_tloc, r_tloc), f"N={N}: piece search"
         assert np.array_equal(o_out, r_out), f"N={N}: pos/vel/acc/jerk differ by {np.abs(o_out - r_out).max():.3e}"
+
+
+def test_grid_oracle_equals_reference_compiled_gridmap3d():
+    """orc::Grid against the reference's own map_manager/src/Gridmap3D.cpp compiled unmodified: getGridIndex (with its clamping quirk: the
+    'iy < 0' and 'iz < 0' branches reset ix), getGridCubeCenter, isInMap — at points inside, on every face, outside on every side; and the AABB
+    gather PCSmapManager::getPointsInAABB built on them (projInMap + index box + isIndexOccupied + cube centres): same voxels, same order, same bits."""
+    if not os.path.exists(O.REF_GRID):
+        pytest.skip("oracle/_ref/libref_grid.so not built (needs /root/reference)")
+    ref = O.RefGrid()
+    rng = np.random.default_rng(12)
+    for dims, bmin, res in (((20, 16, 12), np.array([0.0, 0.0, 0.0]), 1.0), ((24, 10, 31), np.array([-3.0, 2.0, -7.5]), 0.5), ((9, 9, 9), np.array([1.0, -1.0, 0.25]), 0.25)):
+        dims = np.array(dims)
+        bmax = bmin + dims * res
+        pts = np.concatenate([bmin + rng.random((400, 3)) * (bmax - bmin),                       # inside
+                              bmin - 2 + rng.random((300, 3)) * (bmax - bmin + 4),               # in and around
+                              np.array([bmin, bmax, bmin + (bmax - bmin) * [1, 0, 0], bmin + (bmax - bmin) * [0, 1, 1], (bmin + bmax) / 2]),   # corners / faces
+                              bmin + np.floor(rng.random((100, 3)) * dims) * res])               # exactly on cell boundaries
+        ri, rc, rm = ref.index(dims, bmin, res, pts)
+        oi, oc, om = O.grid_index(dims, bmin, res, pts)
+        assert np.array_equal(ri, oi) and np.array_equal(rc, oc) and np.array_equal(rm, om), f"grid {dims} res {res}"
+        occ = (rng.random(tuple(dims)) < 0.2).astype(np.uint8)
+        for _ in range(25):
+            centre = bmin - 1 + rng.random(3) * (bmax - bmin + 2)
+            half = rng.choice([0.4, 1.3, 2.5, 6.5]) * res
+            rp, rn = ref.points_in_aabb(occ, bmin, res, centre, half)
+            op, on = O.points_in_aabb(occ, bmin, res, centre, half)
+            assert rn == on and np.array_equal(rp, op), f"AABB gather at {centre} half {half}: {rn} vs {on} voxels"
