@@ -7,7 +7,8 @@ Run in the build container (where /root/reference exists):  python tests/golden/
                        reference-compiled igl/FastWindingNumberForSoups.h returns for them (order 2, accuracy scale 2.0: Shape.cpp:86,110);
   minco_reference.npz — outputs of the reference's utils/minco.hpp (MINCO_S3NU forward, energy gradients, propogateGrad) on seeded problems, and
                         of its utils/trajectory.hpp (getPos_Vel_Acc_Jerk, locatePieceIdx, getTotalDuration) on the resulting trajectories;
-  lbfgs_reference.npz — what the reference's utils/lbfgs.hpp does on seeded problems: every evaluated point, solution, value, return code."""
+  lbfgs_reference.npz — what the reference's utils/lbfgs.hpp does on seeded problems: every evaluated point, solution, value, return code;
+  grid_reference.npz  — the reference's map_manager/src/Gridmap3D.cpp: grid indices, cube centres, in-map flags and AABB gathers on seeded grids."""
 import os
 import sys
 import numpy as np
@@ -18,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "implicit-sdf-planner_b200", "py"))
 import isdf_b200 as I          # noqa: E402
 import oracle_lib as O         # noqa: E402
-from test_reference_pins import flat_inputs, _minco_cases, _lbfgs_problems, _traj_times   # noqa: E402
+from test_reference_pins import flat_inputs, _minco_cases, _lbfgs_problems, _traj_times, _grid_cases   # noqa: E402
 
 
 REF_SHAPES = "/root/reference/src/plan_manager/shapes"
@@ -75,6 +76,16 @@ def main():
         print(name, r["ret"], r["evaluations"])
     np.savez_compressed(os.path.join(HERE, "lbfgs_reference.npz"), nproblems=np.array(len(_lbfgs_problems())), **out)
     print("lbfgs_reference.npz written")
+    rg = O.RefGrid()
+    out = {}
+    for k, (dims, bmin, res, pts, occ, boxes) in enumerate(_grid_cases()):
+        idx, ctr, inm = rg.index(dims, bmin, res, pts)
+        out.update({f"g{k}_idx": idx, f"g{k}_centre": ctr, f"g{k}_inmap": inm})
+        for b, (centre, half) in enumerate(boxes):
+            p_, n_ = rg.points_in_aabb(occ, bmin, res, centre, half)
+            out.update({f"g{k}_b{b}_pts": p_, f"g{k}_b{b}_n": np.array(n_)})
+    np.savez_compressed(os.path.join(HERE, "grid_reference.npz"), **out)
+    print("grid_reference.npz written")
 
 
 if __name__ == "__main__":

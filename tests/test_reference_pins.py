@@ -261,14 +261,9 @@ def test_trajectory_evaluation_equals_reference_compiled_trajectory_hpp():
         assert np.array_equal(o_out, r_out), f"N={N}: pos/vel/acc/jerk differ by {np.abs(o_out - r_out).max():.3e}"
 
 
-def test_grid_oracle_equals_reference_compiled_gridmap3d():
-    """orc::Grid against the reference's own map_manager/src/Gridmap3D.cpp compiled unmodified: getGridIndex (with its clamping quirk: the
-    'iy < 0' and 'iz < 0' branches reset ix), getGridCubeCenter, isInMap — at points inside, on every face, outside on every side; and the AABB
-    gather PCSmapManager::getPointsInAABB built on them (projInMap + index box + isIndexOccupied + cube centres): same voxels, same order, same bits."""
-    if not os.path.exists(O.REF_GRID):
-        pytest.skip("oracle/_ref/libref_grid.so not built (needs /root/reference)")
-    ref = O.RefGrid()
+def _grid_cases():
     rng = np.random.default_rng(12)
+    out = []
     for dims, bmin, res in (((20, 16, 12), np.array([0.0, 0.0, 0.0]), 1.0), ((24, 10, 31), np.array([-3.0, 2.0, -7.5]), 0.5), ((9, 9, 9), np.array([1.0, -1.0, 0.25]), 0.25)):
         dims = np.array(dims)
         bmax = bmin + dims * res
@@ -276,13 +271,34 @@ def test_grid_oracle_equals_reference_compiled_gridmap3d():
                               bmin - 2 + rng.random((300, 3)) * (bmax - bmin + 4),               # in and around
                               np.array([bmin, bmax, bmin + (bmax - bmin) * [1, 0, 0], bmin + (bmax - bmin) * [0, 1, 1], (bmin + bmax) / 2]),   # corners / faces
                               bmin + np.floor(rng.random((100, 3)) * dims) * res])               # exactly on cell boundaries
+        occ = (rng.random(tuple(dims)) < 0.2).astype(np.uint8)
+        boxes = [(bmin - 1 + rng.random(3) * (bmax - bmin + 2), float(rng.choice([0.4, 1.3, 2.5, 6.5]) * res)) for _ in range(25)]
+        out.append((dims, bmin, res, pts, occ, boxes))
+    return out
+
+
+def test_grid_oracle_equals_committed_reference_outputs():
+    z = np.load(os.path.join(G, "grid_reference.npz"))
+    for k, (dims, bmin, res, pts, occ, boxes) in enumerate(_grid_cases()):
+        oi, oc, om = O.grid_index(dims, bmin, res, pts)
+        assert np.array_equal(oi, z[f"g{k}_idx"]) and np.array_equal(oc, z[f"g{k}_centre"]) and np.array_equal(om, z[f"g{k}_inmap"])
+        for b, (centre, half) in enumerate(boxes):
+            op, on = O.points_in_aabb(occ, bmin, res, centre, half)
+            assert on == int(z[f"g{k}_b{b}_n"]) and np.array_equal(op, z[f"g{k}_b{b}_pts"])
+
+
+def test_grid_oracle_equals_reference_compiled_gridmap3d():
+    """orc::Grid against the reference's own map_manager/src/Gridmap3D.cpp compiled unmodified: getGridIndex (with its clamping quirk: the
+    'iy < 0' and 'iz < 0' branches reset ix), getGridCubeCenter, isInMap — at points inside, on every face, outside on every side; and the AABB
+    gather PCSmapManager::getPointsInAABB built on them (projInMap + index box + isIndexOccupied + cube centres): same voxels, same order, same bits."""
+    if not os.path.exists(O.REF_GRID):
+        pytest.skip("oracle/_ref/libref_grid.so not built (needs /root/reference)")
+    ref = O.RefGrid()
+    for dims, bmin, res, pts, occ, boxes in _grid_cases():
         ri, rc, rm = ref.index(dims, bmin, res, pts)
         oi, oc, om = O.grid_index(dims, bmin, res, pts)
         assert np.array_equal(ri, oi) and np.array_equal(rc, oc) and np.array_equal(rm, om), f"grid {dims} res {res}"
-        occ = (rng.random(tuple(dims)) < 0.2).astype(np.uint8)
-        for _ in range(25):
-            centre = bmin - 1 + rng.random(3) * (bmax - bmin + 2)
-            half = rng.choice([0.4, 1.3, 2.5, 6.5]) * res
+        for centre, half in boxes:
             rp, rn = ref.points_in_aabb(occ, bmin, res, centre, half)
             op, on = O.points_in_aabb(occ, bmin, res, centre, half)
             assert rn == on and np.array_equal(rp, op), f"AABB gather at {centre} half {half}: {rn} vs {on} voxels"
